@@ -1,0 +1,179 @@
+"""ctypes binding of libbdlm.so (include/bdlm.h).  No torch types cross this boundary.
+
+The library is loaded lazily; if it is missing, or no CUDA device is usable, every
+compute entry point raises -- there is no CPU path behind this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libbdlm.so")
+
+TIME_MAJOR, SERIES_MAJOR = 0, 1
+DEVICE, HOST = 0, 1
+PS_V, PS_W, PS_M0, PS_C0 = 1, 2, 4, 8
+TEXTBOOK_SMOOTHER, SVD_CONSISTENT_W = 1, 2
+ST_SINGULAR, ST_NOTCONVERGED, ST_NOTPD, ST_NONFINITE = 1, 2, 4, 8
+E_ARG, E_EMPTY, E_CUDA, E_NODEVICE = -1, -2, -3, -4
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+
+SYMBOLS = [
+    "bdlm_create", "bdlm_destroy", "bdlm_last_error", "bdlm_version", "bdlm_set_stream",
+    "bdlm_sync", "bdlm_launch_count", "bdlm_set_staging_bytes", "bdlm_kf_filter",
+    "bdlm_rts_smooth", "bdlm_kf_filter_smooth", "bdlm_loglik", "bdlm_ffbs",
+    "bdlm_svd_filter", "bdlm_svd_ffbs", "bdlm_gibbs_suffstats",
+]
+
+
+class Problem(C.Structure):
+    _fields_ = [("B", C.c_int64), ("T", C.c_int32), ("n", C.c_int32), ("p", C.c_int32),
+                ("layout", C.c_int32), ("mem", C.c_int32), ("keep_init", C.c_int32),
+                ("f_tv", C.c_int32), ("g_tv", C.c_int32), ("per_series", C.c_int32),
+                ("compat", C.c_int32),
+                ("F", C.c_void_p), ("G", C.c_void_p), ("times", C.c_void_p),
+                ("V", C.c_void_p), ("W", C.c_void_p), ("m0", C.c_void_p), ("C0", C.c_void_p),
+                ("y", C.c_void_p)]
+
+
+class KfOut(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ("m", "C", "a", "R", "f", "Q")]
+
+
+class SmoothOut(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ("s", "S")]
+
+
+class SvdOut(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ("m", "dc", "uc", "a", "dr", "ur", "f")]
+
+
+class GibbsStats(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ("ssy", "ny", "ssw", "scatter")]
+
+
+class BdlmError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libbdlm error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def load():
+    """Load libbdlm.so (built in-tree by bayesian_dlms_b200.build); raises if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: build it with `python -m bayesian_dlms_b200.build` "
+            "(the CUDA library is the only implementation; there is no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    lib.bdlm_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+    lib.bdlm_destroy.argtypes = [C.c_void_p]
+    lib.bdlm_destroy.restype = None
+    lib.bdlm_last_error.argtypes = [C.c_void_p]
+    lib.bdlm_last_error.restype = C.c_char_p
+    lib.bdlm_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+    lib.bdlm_sync.argtypes = [C.c_void_p]
+    lib.bdlm_launch_count.argtypes = [C.c_void_p]
+    lib.bdlm_launch_count.restype = C.c_int64
+    lib.bdlm_set_staging_bytes.argtypes = [C.c_void_p, C.c_int64]
+    PP = C.POINTER(Problem)
+    lib.bdlm_kf_filter.argtypes = [C.c_void_p, PP, C.POINTER(KfOut), C.c_void_p]
+    lib.bdlm_rts_smooth.argtypes = [C.c_void_p, PP, C.POINTER(KfOut), C.POINTER(SmoothOut),
+                                    C.c_void_p]
+    lib.bdlm_kf_filter_smooth.argtypes = [C.c_void_p, PP, C.POINTER(KfOut),
+                                          C.POINTER(SmoothOut), C.c_void_p]
+    lib.bdlm_loglik.argtypes = [C.c_void_p, PP, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.bdlm_ffbs.argtypes = [C.c_void_p, PP, C.c_void_p, C.c_void_p, C.POINTER(KfOut),
+                              C.POINTER(GibbsStats), C.c_void_p]
+    lib.bdlm_svd_filter.argtypes = [C.c_void_p, PP, C.POINTER(SvdOut), C.c_void_p]
+    lib.bdlm_svd_ffbs.argtypes = [C.c_void_p, PP, C.c_void_p, C.c_void_p, C.POINTER(SvdOut),
+                                  C.POINTER(GibbsStats), C.c_void_p]
+    lib.bdlm_gibbs_suffstats.argtypes = [C.c_void_p, PP, C.c_void_p, C.POINTER(GibbsStats)]
+    if hasattr(lib, "bdlm_scan_filter_smooth"):
+        lib.bdlm_scan_filter_smooth.argtypes = [C.c_void_p, PP, C.POINTER(KfOut),
+                                                C.POINTER(SmoothOut), C.c_void_p, C.c_void_p]
+    _lib = lib
+    return lib
+
+
+class Context:
+    """Owns one bdlm_ctx (one GPU, one stream)."""
+
+    def __init__(self, device: int = 0):
+        lib = load()
+        h = C.c_void_p()
+        rc = lib.bdlm_create(int(device), C.byref(h))
+        if rc != 0:
+            raise BdlmError(rc, lib.bdlm_last_error(None).decode())
+        self._h = h
+        self.device = device
+        self._keep = []
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load().bdlm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, rc):
+        if rc < 0:
+            raise BdlmError(rc, load().bdlm_last_error(self._h).decode())
+        return rc
+
+    def set_stream(self, cuda_stream_handle):
+        self.check(load().bdlm_set_stream(self._h, C.c_void_p(cuda_stream_handle or 0)))
+
+    def sync(self):
+        self.check(load().bdlm_sync(self._h))
+
+    def launch_count(self) -> int:
+        return int(load().bdlm_launch_count(self._h))
+
+    def set_staging_bytes(self, nbytes: int):
+        self.check(load().bdlm_set_staging_bytes(self._h, int(nbytes)))
+
+    @property
+    def handle(self):
+        return self._h
+
+
+def host_ptr(a):
+    """Pointer of a C-contiguous float64 numpy array (or None)."""
+    if a is None:
+        return None
+    assert isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags.c_contiguous
+    return a.ctypes.data
+
+
+def make_problem(*, B, T, n, p, layout, mem, keep_init, F, G, times, V, W, m0, C0, y,
+                 per_series=0, compat=0, f_tv=0, g_tv=0):
+    """F, G, times: host numpy arrays (kept alive by the caller).  V, W, m0, C0, y: raw
+    addresses (ints) in the memory space named by `mem`, or numpy arrays when shared."""
+    pr = Problem()
+    pr.B, pr.T, pr.n, pr.p = int(B), int(T), int(n), int(p)
+    pr.layout, pr.mem, pr.keep_init = int(layout), int(mem), int(bool(keep_init))
+    pr.f_tv, pr.g_tv, pr.per_series, pr.compat = int(f_tv), int(g_tv), int(per_series), int(compat)
+
+    def addr(x):
+        if x is None:
+            return None
+        return host_ptr(x) if isinstance(x, np.ndarray) else int(x)
+
+    pr.F, pr.G, pr.times = addr(F), addr(G), addr(times)
+    pr.V, pr.W, pr.m0, pr.C0, pr.y = addr(V), addr(W), addr(m0), addr(C0), addr(y)
+    return pr

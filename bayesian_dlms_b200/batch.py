@@ -1,0 +1,330 @@
+"""Batched entry points over libbdlm.so: many independent series / chains per call.
+
+This is the host-side shim a Scala facade would sit on: it flattens the
+model closures (``dlm.materialise``), picks the memory space from the arrays it is given
+(torch CUDA tensors -> device pointers, numpy arrays -> host pointers) and calls the C
+ABI.  PyTorch is used only to own device memory and streams.
+
+Array shapes (k = components per row, rows = T + keep_init):
+  layout TIME_MAJOR   : y (T, p, B)   outputs (rows, k, B)   per-series params (k, B)
+  layout SERIES_MAJOR : y (B, T, p)   outputs (B, rows, k)   per-series params (B, k)
+Matrices are column-major inside a row (Breeze ``DenseMatrix.data`` order).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, Optional, Sequence
+
+import numpy as np
+
+from . import _capi as capi
+from . import dlm as _dlm
+
+TIME_MAJOR, SERIES_MAJOR = capi.TIME_MAJOR, capi.SERIES_MAJOR
+
+KF_FIELDS = ("m", "C", "a", "R", "f", "Q")
+SVD_FIELDS = ("m", "dc", "uc", "a", "dr", "ur", "f")
+
+
+@dataclass
+class Model:
+    """Materialised ``Dlm`` for one time grid (see ``dlm.materialise``)."""
+
+    F: np.ndarray
+    G: np.ndarray
+    f_tv: bool
+    g_tv: bool
+    n: int
+    p: int
+    T: int
+    times: Optional[np.ndarray]  # None = regular grid 1..T
+
+    @staticmethod
+    def build(mod: _dlm.Dlm, times: Optional[Sequence[float]] = None, T: Optional[int] = None):
+        if times is None:
+            assert T is not None and T > 0, "give times or T"
+            tgrid = np.arange(1, T + 1, dtype=np.float64)
+        else:
+            tgrid = np.ascontiguousarray(times, dtype=np.float64)
+        if tgrid.size == 0:
+            raise ValueError("empty observation vector (NoSuchElementException in the reference)")
+        F, f_tv, G, g_tv, n, p = _dlm.materialise(mod, tgrid)
+        regular = times is None or np.array_equal(tgrid, np.arange(1, tgrid.size + 1))
+        return Model(np.ascontiguousarray(F.ravel()), np.ascontiguousarray(G.ravel()),
+                     bool(f_tv), bool(g_tv), n, p, int(tgrid.size),
+                     None if regular else tgrid)
+
+
+def _is_torch(x):
+    return type(x).__module__.startswith("torch")
+
+
+def _mem_and_ptr(x):
+    if x is None:
+        return None, None
+    if _is_torch(x):
+        assert x.is_contiguous() and str(x.dtype) in ("torch.float64", "torch.int32"), \
+            "contiguous fp64 tensors only"
+        return (capi.DEVICE if x.is_cuda else capi.HOST), x.data_ptr()
+    assert isinstance(x, np.ndarray) and x.flags.c_contiguous
+    return capi.HOST, x.ctypes.data
+
+
+def _shared_param(x, rows, cols):
+    """Shared (host) parameter -> flat column-major numpy array."""
+    a = np.asarray(x, dtype=np.float64)
+    if a.ndim == 2 and a.shape == (rows, cols):
+        return _dlm.cm(a)
+    a = np.ascontiguousarray(a.ravel())
+    assert a.size == rows * cols, (a.shape, rows, cols)
+    return a
+
+
+class Engine:
+    """One GPU context.  All methods return dicts of arrays in the caller's memory space."""
+
+    def __init__(self, device: int = 0):
+        self.ctx = capi.Context(device)
+        self.device = device
+
+    # ------------------------------------------------------------------ helpers
+    def use_torch_stream(self):
+        import torch
+        self.ctx.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _alloc(self, like, shape, dtype="float64", pinned=False):
+        if _is_torch(like):
+            import torch
+            dt = torch.float64 if dtype == "float64" else torch.int32
+            if like.is_cuda:
+                return torch.empty(shape, dtype=dt, device=like.device)
+            return torch.empty(shape, dtype=dt, pin_memory=pinned)
+        return np.empty(shape, dtype=np.float64 if dtype == "float64" else np.int32)
+
+    def _shape(self, layout, B, rows, k):
+        return (rows, k, B) if layout == TIME_MAJOR else (B, rows, k)
+
+    def _problem(self, model: Model, params: Dict, y, layout, keep_init, compat, B, mem):
+        n, p = model.n, model.p
+        per = 0
+        ptrs = {}
+        keep = []
+        for name, bit, r, c in (("V", capi.PS_V, p, p), ("W", capi.PS_W, n, n),
+                                ("m0", capi.PS_M0, n, 1), ("C0", capi.PS_C0, n, n)):
+            x = params.get(name)
+            if x is None:
+                ptrs[name] = None
+                continue
+            # per-series parameters are named explicitly: params["per_series"] = ("V", "W")
+            if name in params.get("per_series", ()):
+                expect = (r * c, B) if layout == TIME_MAJOR else (B, r * c)
+                assert tuple(x.shape) == expect, (name, tuple(x.shape), expect)
+                m_, ptr = _mem_and_ptr(x)
+                assert m_ == mem, f"{name} lives in a different memory space than y"
+                per |= bit
+                ptrs[name] = ptr
+            else:
+                a = _shared_param(x, r, c)
+                keep.append(a)
+                ptrs[name] = a
+        _, yptr = _mem_and_ptr(y)
+        pr = capi.make_problem(B=B, T=model.T, n=n, p=p, layout=layout, mem=mem,
+                               keep_init=keep_init, F=model.F, G=model.G, times=model.times,
+                               V=ptrs["V"], W=ptrs["W"], m0=ptrs["m0"], C0=ptrs["C0"], y=yptr,
+                               per_series=per, compat=compat, f_tv=model.f_tv, g_tv=model.g_tv)
+        return pr, keep
+
+    def _batch_of(self, model, y, layout):
+        shp = tuple(y.shape)
+        if layout == TIME_MAJOR:
+            assert shp[0] == model.T and shp[1] == model.p, (shp, model.T, model.p)
+            return shp[2]
+        assert shp[1] == model.T and shp[2] == model.p, (shp, model.T, model.p)
+        return shp[0]
+
+    def _outs(self, cls, fields, want, like, layout, B, rows, dims, pinned):
+        out, struct = {}, cls()
+        for name in fields:
+            if name in want:
+                out[name] = self._alloc(like, self._shape(layout, B, rows, dims[name]),
+                                        pinned=pinned)
+                setattr(struct, name, _mem_and_ptr(out[name])[1])
+            else:
+                setattr(struct, name, None)
+        return out, struct
+
+    def _kf_dims(self, model):
+        n, p = model.n, model.p
+        return dict(m=n, C=n * n, a=n, R=n * n, f=p, Q=p * p, s=n, S=n * n)
+
+    def _svd_dims(self, model):
+        n, p = model.n, model.p
+        return dict(m=n, dc=n, uc=n * n, a=n, dr=n, ur=n * n, f=p)
+
+    def _status(self, like, B, want):
+        if not want:
+            return None, None
+        st = self._alloc(like, (B,), dtype="int32")
+        return st, _mem_and_ptr(st)[1]
+
+    # ------------------------------------------------------------------ filter / smoother
+    def filter(self, model: Model, params: Dict, y, *, layout=TIME_MAJOR, keep_init=True,
+               want=KF_FIELDS, status=True, pinned=False):
+        """KalmanFilter.filterDlm / .filter batched (KalmanFilter.scala:291-294, Filter.scala:41-45)."""
+        mem, _ = _mem_and_ptr(y)
+        B = self._batch_of(model, y, layout)
+        rows = model.T + int(keep_init)
+        pr, keep = self._problem(model, params, y, layout, keep_init, 0, B, mem)
+        out, ko = self._outs(capi.KfOut, KF_FIELDS, want, y, layout, B, rows,
+                             self._kf_dims(model), pinned)
+        st, stp = self._status(y, B, status)
+        self.ctx.check(capi.load().bdlm_kf_filter(self.ctx.handle, pr, ko, stp))
+        if st is not None:
+            out["status"] = st
+        return out
+
+    def smooth(self, model: Model, params: Dict, filt: Dict, *, layout=TIME_MAJOR,
+               keep_init=True, textbook=False, status=True, pinned=False):
+        """Smoothing.backwardsSmoother batched (Smoothing.scala:57-64)."""
+        m = filt["m"]
+        mem, _ = _mem_and_ptr(m)
+        B = m.shape[2] if layout == TIME_MAJOR else m.shape[0]
+        rows = model.T + int(keep_init)
+        pr, keep = self._problem(model, params, None, layout, keep_init,
+                                 capi.TEXTBOOK_SMOOTHER if textbook else 0, B, mem)
+        ko = capi.KfOut()
+        for name in KF_FIELDS:
+            setattr(ko, name, _mem_and_ptr(filt[name])[1] if name in ("m", "C", "a", "R")
+                    and filt.get(name) is not None else None)
+        out, so = self._outs(capi.SmoothOut, ("s", "S"), ("s", "S"), m, layout, B, rows,
+                             self._kf_dims(model), pinned)
+        st, stp = self._status(m, B, status)
+        self.ctx.check(capi.load().bdlm_rts_smooth(self.ctx.handle, pr, ko, so, stp))
+        if st is not None:
+            out["status"] = st
+        return out
+
+    def filter_smooth(self, model: Model, params: Dict, y, *, layout=TIME_MAJOR, keep_init=True,
+                      want=KF_FIELDS + ("s", "S"), textbook=False, status=True, pinned=False,
+                      out: Optional[Dict] = None):
+        """Fused KalmanFilter(adv).filter + Smoothing.backwardsSmoother."""
+        mem, _ = _mem_and_ptr(y)
+        B = self._batch_of(model, y, layout)
+        rows = model.T + int(keep_init)
+        pr, keep = self._problem(model, params, y, layout, keep_init,
+                                 capi.TEXTBOOK_SMOOTHER if textbook else 0, B, mem)
+        dims = self._kf_dims(model)
+        if out is None:
+            res, ko = self._outs(capi.KfOut, KF_FIELDS, want, y, layout, B, rows, dims, pinned)
+            res2, so = self._outs(capi.SmoothOut, ("s", "S"), want, y, layout, B, rows, dims, pinned)
+            res.update(res2)
+            st, stp = self._status(y, B, status)
+            if st is not None:
+                res["status"] = st
+        else:  # caller-provided output buffers (benchmarks reuse them across steps)
+            res, ko, so = out, capi.KfOut(), capi.SmoothOut()
+            for name in KF_FIELDS:
+                setattr(ko, name, _mem_and_ptr(out[name])[1] if name in out else None)
+            for name in ("s", "S"):
+                setattr(so, name, _mem_and_ptr(out[name])[1] if name in out else None)
+            stp = _mem_and_ptr(out["status"])[1] if "status" in out else None
+        self.ctx.check(capi.load().bdlm_kf_filter_smooth(self.ctx.handle, pr, ko, so, stp))
+        return res
+
+    def loglik(self, model: Model, params: Dict, y, *, layout=TIME_MAJOR, status=True):
+        """KalmanFilter.likelihood (transition form, KalmanFilter.scala:299-306) and the
+        innovations form (conditionalLikelihood, :138-153) per series."""
+        mem, _ = _mem_and_ptr(y)
+        B = self._batch_of(model, y, layout)
+        pr, keep = self._problem(model, params, y, layout, True, 0, B, mem)
+        tr, inn = self._alloc(y, (B,)), self._alloc(y, (B,))
+        st, stp = self._status(y, B, status)
+        self.ctx.check(capi.load().bdlm_loglik(self.ctx.handle, pr, _mem_and_ptr(tr)[1],
+                                               _mem_and_ptr(inn)[1], stp))
+        out = dict(transition=tr, innovations=inn)
+        if st is not None:
+            out["status"] = st
+        return out
+
+    # ------------------------------------------------------------------ samplers
+    def _stats(self, like, layout, B, model, want):
+        if not want:
+            return {}, None
+        n, p = model.n, model.p
+        dims = dict(ssy=p, ny=p, ssw=n, scatter=n * n)
+        out, gs = {}, capi.GibbsStats()
+        for k, d in dims.items():
+            out[k] = self._alloc(like, (d, B) if layout == TIME_MAJOR else (B, d))
+            setattr(gs, k, _mem_and_ptr(out[k])[1])
+        return out, gs
+
+    def ffbs(self, model: Model, params: Dict, y, z, *, layout=TIME_MAJOR, want_kf=(),
+             stats=False, status=True, svd=False, consistent_w=False, pinned=False):
+        """Smoothing.ffbsDlm (Smoothing.scala:173-180) or, with svd=True, SvdSampler.ffbsDlm
+        (SvdSampler.scala:79-82), batched over chains, with injected normals z."""
+        mem, _ = _mem_and_ptr(y)
+        B = self._batch_of(model, y, layout)
+        rows = model.T + 1
+        assert tuple(z.shape) == self._shape(layout, B, rows, model.n), (z.shape, rows, model.n)
+        compat = capi.SVD_CONSISTENT_W if (svd and consistent_w) else 0
+        pr, keep = self._problem(model, params, y, layout, True, compat, B, mem)
+        theta = self._alloc(y, self._shape(layout, B, rows, model.n), pinned=pinned)
+        out = dict(theta=theta)
+        sout, gs = self._stats(y, layout, B, model, stats)
+        out.update(sout)
+        st, stp = self._status(y, B, status)
+        lib = capi.load()
+        if svd:
+            fo, so = self._outs(capi.SvdOut, SVD_FIELDS, want_kf, y, layout, B, rows,
+                                self._svd_dims(model), pinned)
+            out.update({"svd_" + k: v for k, v in fo.items()})
+            self.ctx.check(lib.bdlm_svd_ffbs(self.ctx.handle, pr, _mem_and_ptr(z)[1],
+                                             _mem_and_ptr(theta)[1], so, gs, stp))
+        else:
+            fo, ko = self._outs(capi.KfOut, KF_FIELDS, want_kf, y, layout, B, rows,
+                                self._kf_dims(model), pinned)
+            out.update(fo)
+            self.ctx.check(lib.bdlm_ffbs(self.ctx.handle, pr, _mem_and_ptr(z)[1],
+                                         _mem_and_ptr(theta)[1], ko, gs, stp))
+        if st is not None:
+            out["status"] = st
+        return out
+
+    def svd_filter(self, model: Model, params: Dict, y, *, layout=TIME_MAJOR, keep_init=True,
+                   want=SVD_FIELDS, consistent_w=False, status=True, pinned=False):
+        """SvdFilter.filterDlm / .filter batched (SvdFilter.scala:100-119,158-161)."""
+        mem, _ = _mem_and_ptr(y)
+        B = self._batch_of(model, y, layout)
+        rows = model.T + int(keep_init)
+        pr, keep = self._problem(model, params, y, layout, keep_init,
+                                 capi.SVD_CONSISTENT_W if consistent_w else 0, B, mem)
+        out, so = self._outs(capi.SvdOut, SVD_FIELDS, want, y, layout, B, rows,
+                             self._svd_dims(model), pinned)
+        st, stp = self._status(y, B, status)
+        self.ctx.check(capi.load().bdlm_svd_filter(self.ctx.handle, pr, so, stp))
+        if st is not None:
+            out["status"] = st
+        return out
+
+    def gibbs_stats(self, model: Model, y, theta, *, layout=TIME_MAJOR):
+        """Sufficient statistics of a given path (Gibbs.scala:29-43,63-73; GibbsWishart.scala:22-29)."""
+        mem, _ = _mem_and_ptr(y)
+        B = self._batch_of(model, y, layout)
+        pr, keep = self._problem(model, {}, y, layout, True, 0, B, mem)
+        out, gs = self._stats(y, layout, B, model, True)
+        self.ctx.check(capi.load().bdlm_gibbs_suffstats(self.ctx.handle, pr,
+                                                        _mem_and_ptr(theta)[1], gs))
+        return out
+
+    def sync(self):
+        self.ctx.sync()
+
+
+_default: Dict[int, Engine] = {}
+
+
+def default_engine(device: int = 0) -> Engine:
+    """Process-wide engine per device; raises if libbdlm.so or a CUDA device is missing."""
+    if device not in _default:
+        _default[device] = Engine(device)
+    return _default[device]

@@ -1,0 +1,658 @@
+// api.cu -- C ABI of libbdlm.so (include/bdlm.h): context, validation, model upload,
+// kernel selection, layout handling and the host-buffer slab pipeline.
+//
+// Kernel selection: n <= 4, p = 1 filter / smoother calls go to the register kernels of
+// kf_small.cu (device-native time-major SoA; series-major data is transposed on the
+// device through context workspace); everything else goes to the warp-per-series
+// kernels of kf_warp.cu, which address user arrays through strided views.
+//
+// There is no CPU path in this file: every entry point either launches CUDA kernels or
+// fails with an error code.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "launch.h"
+
+using namespace bdlm;
+
+struct bdlm_ctx {
+  int device = 0;
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  cudaStream_t s_in = nullptr, s_out = nullptr;
+  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr},
+              ev_out[2] = {nullptr, nullptr};
+  std::string err;
+  int64_t launches = 0;
+  char *arena = nullptr;
+  size_t arena_bytes = 0;
+  size_t staging_cap = (size_t)8 << 30;
+  size_t workspace_cap = (size_t)48 << 30;  // device-mode spill/transposes per launch
+};
+
+static std::string g_create_err;
+
+namespace {
+
+enum ApiOp { A_FILTER, A_SMOOTH, A_FILTER_SMOOTH, A_LOGLIK, A_FFBS, A_SVD_FILTER, A_SVD_FFBS,
+             A_STATS };
+
+int fail(bdlm_ctx *c, int code, const std::string &msg) {
+  if (c) c->err = msg; else g_create_err = msg;
+  return code;
+}
+
+#define CU(call)                                                                        \
+  do {                                                                                  \
+    cudaError_t e_ = (call);                                                            \
+    if (e_ != cudaSuccess)                                                              \
+      return fail(c, BDLM_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));  \
+  } while (0)
+
+size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+int ensure_arena(bdlm_ctx *c, size_t bytes) {
+  if (bytes <= c->arena_bytes) return 0;
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaStreamSynchronize(c->s_in));
+  CU(cudaStreamSynchronize(c->s_out));
+  if (c->arena) CU(cudaFree(c->arena));
+  c->arena = nullptr; c->arena_bytes = 0;
+  CU(cudaMalloc(&c->arena, bytes));
+  c->arena_bytes = bytes;
+  return 0;
+}
+
+struct Bump {
+  char *base; size_t off, cap;
+  template <class T> T *take(size_t count) {
+    off = align_up(off);
+    T *p = reinterpret_cast<T *>(base + off);
+    off += count * sizeof(T);
+    return p;
+  }
+};
+
+// One fully device-resident invocation over series [b0, b0 + Bc) of arrays whose batch
+// pitch is Bp.
+struct DevCall {
+  int op;
+  bdlm_problem pr;  // F, G, times: host; everything else device
+  int64_t b0, Bc, Bp;
+  bdlm_kf_out kf{};
+  bdlm_smooth_out sm{};
+  bdlm_svd_out svd{};
+  bdlm_gibbs_stats stats{};
+  const double *z = nullptr;
+  double *theta = nullptr;
+  double *ll_tr = nullptr, *ll_in = nullptr;
+  int32_t *status = nullptr;
+};
+
+int rows_of(const bdlm_problem &p) { return p.T + (p.keep_init ? 1 : 0); }
+
+View mk_view(double *ptr, int layout, int64_t b0, int64_t Bp, int64_t R, int64_t k) {
+  View v{nullptr, 0, 0, 0};
+  if (!ptr) return v;
+  if (layout == BDLM_TIME_MAJOR) { v.ptr = ptr + b0; v.sb = 1; v.sk = Bp; v.sr = k * Bp; }
+  else { v.ptr = ptr + b0 * R * k; v.sb = R * k; v.sr = k; v.sk = 1; }
+  return v;
+}
+CView mk_cview(const double *ptr, int layout, int64_t b0, int64_t Bp, int64_t R, int64_t k) {
+  View v = mk_view(const_cast<double *>(ptr), layout, b0, Bp, R, k);
+  return CView{v.ptr, v.sb, v.sr, v.sk};
+}
+View mk_rowview(double *ptr, int layout, int64_t b0, int64_t Bp, int64_t k) {
+  return mk_view(ptr, layout, b0, Bp, 1, k);  // one row per series
+}
+
+bool small_path(int op, const bdlm_problem &p) {
+  return (op == A_FILTER || op == A_SMOOTH || op == A_FILTER_SMOOTH) && small_supported(p.n, p.p);
+}
+
+int warp_op(int op) {
+  switch (op) {
+    case A_FILTER: return kOpFilter;
+    case A_SMOOTH: return kOpSmooth;
+    case A_FILTER_SMOOTH: return kOpFilterSmooth;
+    case A_LOGLIK: return kOpLoglik;
+    case A_FFBS: return kOpFfbs;
+    case A_SVD_FILTER: return kOpSvdFilter;
+    case A_SVD_FFBS: return kOpSvdFfbs;
+    default: return kOpStats;
+  }
+}
+
+// Per-series fields of a call, used for transposes (small path) and host staging.
+struct Field {
+  double **slot;  // address of the pointer inside the DevCall
+  int64_t rows;   // rows per series (1 for per-series parameters / statistics)
+  int64_t k;      // components per row
+  bool in, out;
+};
+
+void collect_fields(DevCall &d, std::vector<Field> &f) {
+  const bdlm_problem &p = d.pr;
+  const int64_t n = p.n, pp = p.p, R = rows_of(p);
+  auto add = [&](const double *const *slot, int64_t rows, int64_t k, bool in, bool out) {
+    if (*slot) f.push_back(Field{const_cast<double **>(slot), rows, k, in, out});
+  };
+  const bool smooth_in = d.op == A_SMOOTH;
+  if (d.op != A_SMOOTH) add(&d.pr.y, p.T, pp, true, false);
+  if (p.per_series & BDLM_PS_V) add(&d.pr.V, 1, pp * pp, true, false);
+  if (p.per_series & BDLM_PS_W) add(&d.pr.W, 1, n * n, true, false);
+  if (p.per_series & BDLM_PS_M0) add(&d.pr.m0, 1, n, true, false);
+  if (p.per_series & BDLM_PS_C0) add(&d.pr.C0, 1, n * n, true, false);
+  add((const double *const *)&d.kf.m, R, n, smooth_in, !smooth_in);
+  add((const double *const *)&d.kf.C, R, n * n, smooth_in, !smooth_in);
+  add((const double *const *)&d.kf.a, R, n, smooth_in, !smooth_in);
+  add((const double *const *)&d.kf.R, R, n * n, smooth_in, !smooth_in);
+  add((const double *const *)&d.kf.f, R, pp, false, true);
+  add((const double *const *)&d.kf.Q, R, pp * pp, false, true);
+  add((const double *const *)&d.sm.s, R, n, false, true);
+  add((const double *const *)&d.sm.S, R, n * n, false, true);
+  add((const double *const *)&d.svd.m, R, n, false, true);
+  add((const double *const *)&d.svd.dc, R, n, false, true);
+  add((const double *const *)&d.svd.uc, R, n * n, false, true);
+  add((const double *const *)&d.svd.a, R, n, false, true);
+  add((const double *const *)&d.svd.dr, R, n, false, true);
+  add((const double *const *)&d.svd.ur, R, n * n, false, true);
+  add((const double *const *)&d.svd.f, R, pp, false, true);
+  add(&d.z, R, n, true, false);
+  add((const double *const *)&d.theta, R, n, d.op == A_STATS, d.op != A_STATS);
+  add((const double *const *)&d.stats.ssy, 1, pp, false, true);
+  add((const double *const *)&d.stats.ny, 1, pp, false, true);
+  add((const double *const *)&d.stats.ssw, 1, n, false, true);
+  add((const double *const *)&d.stats.scatter, 1, n * n, false, true);
+  add((const double *const *)&d.ll_tr, 1, 1, false, true);
+  add((const double *const *)&d.ll_in, 1, 1, false, true);
+}
+
+// Device workspace (bytes) one run_dev call over Bc series needs beyond user arrays.
+size_t dev_workspace_bytes(const DevCall &d, int64_t Bc) {
+  const bdlm_problem &p = d.pr;
+  const int64_t n = p.n, R = rows_of(p);
+  size_t bytes = 0;
+  // model: F, G, dt + shared params
+  bytes += align_up(sizeof(double) * ((size_t)p.T * (n * p.p + n * n + 1) + 2 * n * n +
+                                      (size_t)p.p * p.p + n + 64)) + 4096;
+  if (small_path(d.op, p)) {
+    if (p.layout == BDLM_SERIES_MAJOR) {  // time-major mirrors of every field
+      DevCall tmp = d;
+      std::vector<Field> f;
+      collect_fields(tmp, f);
+      for (auto &x : f) bytes += align_up(sizeof(double) * (size_t)x.rows * x.k * Bc);
+    }
+    if (d.op == A_FILTER_SMOOTH) {
+      if (!d.kf.m) bytes += align_up(sizeof(double) * (size_t)R * n * Bc);
+      if (!d.kf.C) bytes += align_up(sizeof(double) * (size_t)R * n * n * Bc);
+    }
+  } else {
+    bytes += align_up(sizeof(double) * warp_spill_doubles_per_row(warp_op(d.op), n, p.p) *
+                      (size_t)R * Bc);
+  }
+  return bytes + 8192;
+}
+
+// Upload F, G, dt and shared parameters; fill the Batch description.
+int upload_model(bdlm_ctx *c, const DevCall &d, Bump &bump, Batch &bt,
+                 std::vector<double> &hG0, std::vector<double> &hF0) {
+  const bdlm_problem &p = d.pr;
+  const int n = p.n, pp = p.p, T = p.T;
+  std::vector<double> host;
+  auto push = [&](const double *src, size_t cnt) {
+    size_t o = host.size();
+    host.insert(host.end(), src, src + cnt);
+    return o;
+  };
+  const size_t oF = push(p.F, (size_t)(p.f_tv ? T : 1) * n * pp);
+  const size_t oG = push(p.G, (size_t)(p.g_tv ? T : 1) * n * n);
+  hF0.assign(p.F, p.F + (size_t)n * pp);
+  hG0.assign(p.G, p.G + (size_t)n * n);
+  size_t oDt = (size_t)-1;
+  if (p.times) {
+    double tmin = p.times[0];
+    for (int t = 1; t < T; ++t) tmin = std::fmin(tmin, p.times[t]);
+    double prev = tmin - 1.0;  // KalmanFilter.initialiseState, KalmanFilter.scala:116-117
+    bool all_one = true;
+    std::vector<double> dts(T);
+    for (int t = 0; t < T; ++t) {
+      dts[t] = p.times[t] - prev;
+      prev = p.times[t];
+      all_one = all_one && dts[t] == 1.0;
+    }
+    if (!all_one) oDt = push(dts.data(), T);
+  }
+  auto shared = [&](const double *src, int bit, size_t cnt) {
+    return ((p.per_series & bit) || !src) ? (size_t)-1 : push(src, cnt);
+  };
+  const size_t oV = shared(p.V, BDLM_PS_V, (size_t)pp * pp);
+  const size_t oW = shared(p.W, BDLM_PS_W, (size_t)n * n);
+  const size_t oM = shared(p.m0, BDLM_PS_M0, n);
+  const size_t oC = shared(p.C0, BDLM_PS_C0, (size_t)n * n);
+  double *dev = bump.take<double>(host.size());
+  CU(cudaMemcpyAsync(dev, host.data(), host.size() * sizeof(double), cudaMemcpyHostToDevice,
+                     c->stream));
+  bt.B = d.Bc; bt.T = T; bt.n = n; bt.p = pp; bt.keep_init = p.keep_init ? 1 : 0;
+  bt.compat = p.compat; bt.F = dev + oF; bt.G = dev + oG;
+  bt.dt = (oDt == (size_t)-1) ? nullptr : dev + oDt;
+  bt.f_tv = p.f_tv; bt.g_tv = p.g_tv;
+  auto pv = [&](const double *user, size_t off, int64_t k) {
+    PView v{nullptr, 0, 1};
+    if (off != (size_t)-1) { v.ptr = dev + off; v.sb = 0; v.sk = 1; }
+    else if (!user) { /* not needed by this op */ }
+    else if (p.layout == BDLM_TIME_MAJOR) { v.ptr = user + d.b0; v.sb = 1; v.sk = d.Bp; }
+    else { v.ptr = user + d.b0 * k; v.sb = k; v.sk = 1; }
+    return v;
+  };
+  bt.V = pv(p.V, oV, (int64_t)pp * pp);
+  bt.W = pv(p.W, oW, (int64_t)n * n);
+  bt.m0 = pv(p.m0, oM, n);
+  bt.C0 = pv(p.C0, oC, (int64_t)n * n);
+  bt.y = mk_cview(p.y, p.layout, d.b0, d.Bp, T, pp);
+  bt.status = d.status ? d.status + d.b0 : nullptr;
+  return 0;
+}
+
+// Run one device-resident call over [b0, b0 + Bc); workspace taken from `bump`.
+int run_dev(bdlm_ctx *c, DevCall d, Bump bump) {
+  const bdlm_problem &p = d.pr;
+  const int64_t n = p.n, R = rows_of(p);
+  Batch bt{};
+  std::vector<double> hG0, hF0;
+
+  if (small_path(d.op, p)) {
+    int layout = p.layout;
+    std::vector<Field> fields;
+    std::vector<double *> user_ptrs;
+    if (layout == BDLM_SERIES_MAJOR) {
+      // Mirror every per-series field in time-major workspace; transpose inputs in.
+      collect_fields(d, fields);
+      for (auto &f : fields) {
+        double *user = *f.slot + d.b0 * f.rows * f.k;
+        double *tm = bump.take<double>((size_t)f.rows * f.k * d.Bc);
+        user_ptrs.push_back(user);
+        if (f.in) {
+          CU(launch_transpose(user, tm, d.Bc, f.rows * f.k, c->stream));
+          ++c->launches;
+        }
+        *f.slot = tm;
+      }
+      if (d.status) d.status += d.b0;
+      d.pr.layout = BDLM_TIME_MAJOR;
+      d.b0 = 0; d.Bp = d.Bc;
+    }
+    int rc = upload_model(c, d, bump, bt, hG0, hF0);
+    if (rc) return rc;
+    auto uv = [&](double *ptr, int64_t k) {
+      return mk_view(ptr, BDLM_TIME_MAJOR, d.b0, d.Bp, R, k);
+    };
+    KfViews kv;
+    kv.m = uv(d.kf.m, n); kv.C = uv(d.kf.C, n * n);
+    kv.a = uv(d.kf.a, n); kv.R = uv(d.kf.R, n * n);
+    kv.f = uv(d.kf.f, p.p); kv.Q = uv(d.kf.Q, (int64_t)p.p * p.p);
+    View sv = uv(d.sm.s, n), Sv = uv(d.sm.S, n * n);
+    if (d.op == A_FILTER_SMOOTH) {
+      // (m, C) spill for the backward pass when the caller does not want them: dense
+      // [R][k][Bc] workspace (pitch Bc, offset 0), unlike user arrays (pitch Bp, offset b0)
+      if (!d.kf.m)
+        kv.m = mk_view(bump.take<double>((size_t)R * n * d.Bc), BDLM_TIME_MAJOR, 0, d.Bc, R, n);
+      if (!d.kf.C)
+        kv.C = mk_view(bump.take<double>((size_t)R * n * n * d.Bc), BDLM_TIME_MAJOR, 0, d.Bc, R,
+                       n * n);
+    }
+    CU(launch_kf_small(bt, hG0.data(), hF0.data(), kv, sv, Sv, d.op != A_SMOOTH,
+                       d.op != A_FILTER, c->stream));
+    ++c->launches;
+    if (layout == BDLM_SERIES_MAJOR) {
+      for (size_t i = 0; i < fields.size(); ++i)
+        if (fields[i].out) {
+          CU(launch_transpose(*fields[i].slot, user_ptrs[i], fields[i].rows * fields[i].k,
+                              d.Bc, c->stream));
+          ++c->launches;
+        }
+    }
+    return 0;
+  }
+
+  // ---- warp-per-series path ----
+  int rc = upload_model(c, d, bump, bt, hG0, hF0);
+  if (rc) return rc;
+  WarpArgs wa{};
+  wa.bt = bt;
+  const int L = p.layout;
+  wa.kf.m = mk_view(d.kf.m, L, d.b0, d.Bp, R, n);
+  wa.kf.C = mk_view(d.kf.C, L, d.b0, d.Bp, R, n * n);
+  wa.kf.a = mk_view(d.kf.a, L, d.b0, d.Bp, R, n);
+  wa.kf.R = mk_view(d.kf.R, L, d.b0, d.Bp, R, n * n);
+  wa.kf.f = mk_view(d.kf.f, L, d.b0, d.Bp, R, p.p);
+  wa.kf.Q = mk_view(d.kf.Q, L, d.b0, d.Bp, R, (int64_t)p.p * p.p);
+  wa.s = mk_view(d.sm.s, L, d.b0, d.Bp, R, n);
+  wa.S = mk_view(d.sm.S, L, d.b0, d.Bp, R, n * n);
+  wa.z = mk_cview(d.z, L, d.b0, d.Bp, R, n);
+  wa.theta = mk_view(d.theta, L, d.b0, d.Bp, R, n);
+  wa.svd.m = mk_view(d.svd.m, L, d.b0, d.Bp, R, n);
+  wa.svd.dc = mk_view(d.svd.dc, L, d.b0, d.Bp, R, n);
+  wa.svd.uc = mk_view(d.svd.uc, L, d.b0, d.Bp, R, n * n);
+  wa.svd.a = mk_view(d.svd.a, L, d.b0, d.Bp, R, n);
+  wa.svd.dr = mk_view(d.svd.dr, L, d.b0, d.Bp, R, n);
+  wa.svd.ur = mk_view(d.svd.ur, L, d.b0, d.Bp, R, n * n);
+  wa.svd.f = mk_view(d.svd.f, L, d.b0, d.Bp, R, p.p);
+  wa.stats.ssy = mk_rowview(d.stats.ssy, L, d.b0, d.Bp, p.p);
+  wa.stats.ny = mk_rowview(d.stats.ny, L, d.b0, d.Bp, p.p);
+  wa.stats.ssw = mk_rowview(d.stats.ssw, L, d.b0, d.Bp, n);
+  wa.stats.scatter = mk_rowview(d.stats.scatter, L, d.b0, d.Bp, n * n);
+  wa.ll_transition = d.ll_tr ? d.ll_tr + d.b0 : nullptr;
+  wa.ll_innov = d.ll_in ? d.ll_in + d.b0 : nullptr;
+  const int wop = warp_op(d.op);
+  wa.spill_k = (int64_t)warp_spill_doubles_per_row(wop, p.n, p.p);
+  wa.spill = wa.spill_k ? bump.take<double>((size_t)wa.spill_k * R * d.Bc) : nullptr;
+  CU(launch_warp(wop, wa, c->stream));
+  ++c->launches;
+  return 0;
+}
+
+int validate(bdlm_ctx *c, int op, const bdlm_problem *p) {
+  if (!c) return fail(nullptr, BDLM_E_ARG, "null context");
+  if (!p) return fail(c, BDLM_E_ARG, "null problem");
+  if (p->T == 0) return fail(c, BDLM_E_EMPTY, "T == 0: empty observation vector");
+  if (p->B < 0 || p->T < 0) return fail(c, BDLM_E_ARG, "negative B or T");
+  if (p->n < 1 || p->n > BDLM_MAX_N || p->p < 1 || p->p > BDLM_MAX_P)
+    return fail(c, BDLM_E_ARG, "unsupported n or p (1..32)");
+  if (p->layout != BDLM_TIME_MAJOR && p->layout != BDLM_SERIES_MAJOR)
+    return fail(c, BDLM_E_ARG, "bad layout");
+  if (p->mem != BDLM_DEVICE && p->mem != BDLM_HOST) return fail(c, BDLM_E_ARG, "bad mem");
+  if (!p->F || !p->G) return fail(c, BDLM_E_ARG, "null F or G");
+  if (op != A_STATS && (!p->V || !p->W)) return fail(c, BDLM_E_ARG, "null V or W");
+  if (op != A_SMOOTH && op != A_STATS && (!p->m0 || !p->C0))
+    return fail(c, BDLM_E_ARG, "null m0 or C0");
+  if (op != A_SMOOTH && !p->y) return fail(c, BDLM_E_ARG, "null y");
+  if ((op == A_FFBS || op == A_SVD_FFBS || op == A_STATS) && !p->keep_init)
+    return fail(c, BDLM_E_ARG, "FFBS keeps the initial state: keep_init must be 1");
+  return 0;
+}
+
+// Device-mode entry: loop over series chunks that fit the workspace cap.
+int run_device_mode(bdlm_ctx *c, DevCall d) {
+  const int64_t B = d.pr.B;
+  if (B == 0) return 0;
+  int64_t chunk = B;
+  while (chunk > 128 && dev_workspace_bytes(d, chunk) > c->workspace_cap)
+    chunk = ((chunk / 2 + 127) / 128) * 128;
+  // series-major small path transposes are addressed per chunk; any chunk size works
+  const size_t need = dev_workspace_bytes(d, chunk);
+  int rc = ensure_arena(c, need);
+  if (rc) return rc;
+  for (int64_t b0 = 0; b0 < B; b0 += chunk) {
+    DevCall s = d;
+    s.b0 = b0; s.Bc = std::min(chunk, B - b0); s.Bp = B;
+    Bump bump{c->arena, 0, c->arena_bytes};
+    rc = run_dev(c, s, bump);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+// Host-mode entry: stage slabs of series through the arena with two buffer sets so the
+// H2D copy of slab i+1, the kernels of slab i and the D2H copy of slab i-1 overlap.
+int run_host_mode(bdlm_ctx *c, DevCall d) {
+  const bdlm_problem &p = d.pr;
+  const int64_t B = p.B;
+  if (B == 0) return 0;
+  std::vector<Field> fields;
+  collect_fields(d, fields);
+  std::vector<double *> host_ptrs;
+  for (auto &f : fields) host_ptrs.push_back(*f.slot);
+  int32_t *host_status = d.status;
+  size_t per_series = sizeof(int32_t);
+  for (auto &f : fields) per_series += sizeof(double) * (size_t)f.rows * f.k;
+
+  // slab size: two staged sets + one device workspace within the staging cap
+  int64_t slab = std::min<int64_t>(B, 1 << 20);
+  auto total_for = [&](int64_t s) {
+    DevCall t = d; t.pr.mem = BDLM_DEVICE;
+    size_t staged = 0;
+    for (auto &f : fields) staged += align_up(sizeof(double) * (size_t)f.rows * f.k * s);
+    staged += align_up(sizeof(int32_t) * s);
+    return 2 * staged + dev_workspace_bytes(t, s) + 65536;
+  };
+  while (slab > 128 && total_for(slab) > c->staging_cap) slab = ((slab / 2 + 127) / 128) * 128;
+  int rc = ensure_arena(c, total_for(slab));
+  if (rc) return rc;
+
+  Bump bump{c->arena, 0, c->arena_bytes};
+  std::vector<double *> dev_ptrs[2];
+  int32_t *dev_status[2];
+  for (int s = 0; s < 2; ++s) {
+    for (auto &f : fields) dev_ptrs[s].push_back(bump.take<double>((size_t)f.rows * f.k * slab));
+    dev_status[s] = bump.take<int32_t>(slab);
+  }
+  const Bump work = bump;
+
+  auto copy = [&](const Field &f, double *host, double *dev, int64_t b0, int64_t Bs,
+                  bool to_dev, cudaStream_t st) -> cudaError_t {
+    const size_t rk = (size_t)f.rows * f.k;
+    if (p.layout == BDLM_SERIES_MAJOR) {
+      double *h = host + (size_t)b0 * rk;
+      return to_dev ? cudaMemcpyAsync(dev, h, rk * Bs * sizeof(double), cudaMemcpyHostToDevice, st)
+                    : cudaMemcpyAsync(h, dev, rk * Bs * sizeof(double), cudaMemcpyDeviceToHost, st);
+    }
+    double *h = host + b0;  // [rows*k][B] -> dense [rows*k][Bs]
+    return to_dev ? cudaMemcpy2DAsync(dev, Bs * sizeof(double), h, B * sizeof(double),
+                                      Bs * sizeof(double), rk, cudaMemcpyHostToDevice, st)
+                  : cudaMemcpy2DAsync(h, B * sizeof(double), dev, Bs * sizeof(double),
+                                      Bs * sizeof(double), rk, cudaMemcpyDeviceToHost, st);
+  };
+
+  int it = 0;
+  for (int64_t b0 = 0; b0 < B; b0 += slab, ++it) {
+    const int s = it & 1;
+    const int64_t Bs = std::min(slab, B - b0);
+    // the set's buffers are free once the D2H of the slab that used them has finished
+    if (it >= 2) CU(cudaStreamWaitEvent(c->s_in, c->ev_out[s], 0));
+    for (size_t i = 0; i < fields.size(); ++i)
+      if (fields[i].in) CU(copy(fields[i], host_ptrs[i], dev_ptrs[s][i], b0, Bs, true, c->s_in));
+    CU(cudaEventRecord(c->ev_in[s], c->s_in));
+    CU(cudaStreamWaitEvent(c->stream, c->ev_in[s], 0));
+    if (it >= 2) CU(cudaStreamWaitEvent(c->stream, c->ev_out[s], 0));
+    DevCall t = d;
+    t.pr.mem = BDLM_DEVICE; t.pr.B = Bs; t.b0 = 0; t.Bc = Bs; t.Bp = Bs;
+    {
+      std::vector<Field> tf;
+      collect_fields(t, tf);
+      for (size_t i = 0; i < tf.size(); ++i) *tf[i].slot = dev_ptrs[s][i];
+      t.status = host_status ? dev_status[s] : nullptr;
+      rc = run_dev(c, t, work);
+      if (rc) return rc;
+    }
+    CU(cudaEventRecord(c->ev_comp[s], c->stream));
+    CU(cudaStreamWaitEvent(c->s_out, c->ev_comp[s], 0));
+    for (size_t i = 0; i < fields.size(); ++i)
+      if (fields[i].out) CU(copy(fields[i], host_ptrs[i], dev_ptrs[s][i], b0, Bs, false, c->s_out));
+    if (host_status)
+      CU(cudaMemcpyAsync(host_status + b0, dev_status[s], Bs * sizeof(int32_t),
+                         cudaMemcpyDeviceToHost, c->s_out));
+    CU(cudaEventRecord(c->ev_out[s], c->s_out));
+  }
+  CU(cudaStreamSynchronize(c->s_out));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int dispatch(bdlm_ctx *c, DevCall &d) {
+  CU(cudaSetDevice(c->device));
+  d.b0 = 0; d.Bc = d.pr.B; d.Bp = d.pr.B;
+  return d.pr.mem == BDLM_HOST ? run_host_mode(c, d) : run_device_mode(c, d);
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------- C ABI
+
+extern "C" {
+
+int bdlm_version(void) { return BDLM_VERSION; }
+
+int bdlm_create(int device, bdlm_ctx **out) {
+  bdlm_ctx *c = nullptr;
+  if (!out) return fail(nullptr, BDLM_E_ARG, "null out pointer");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return fail(nullptr, BDLM_E_NODEVICE,
+                std::string("no CUDA device (there is no CPU fallback): ") +
+                    (e != cudaSuccess ? cudaGetErrorString(e) : "device count 0"));
+  if (device < 0 || device >= count) return fail(nullptr, BDLM_E_ARG, "bad device index");
+  e = cudaSetDevice(device);
+  if (e != cudaSuccess) return fail(nullptr, BDLM_E_CUDA, cudaGetErrorString(e));
+  c = new (std::nothrow) bdlm_ctx();
+  if (!c) return fail(nullptr, BDLM_E_ARG, "out of host memory");
+  c->device = device;
+  bool ok = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking) == cudaSuccess;
+  for (int i = 0; i < 2 && ok; ++i)
+    ok = cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&c->ev_comp[i], cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&c->ev_out[i], cudaEventDisableTiming) == cudaSuccess;
+  if (!ok) {
+    g_create_err = std::string("stream/event creation failed: ") +
+                   cudaGetErrorString(cudaGetLastError());
+    bdlm_destroy(c);
+    return BDLM_E_CUDA;
+  }
+  c->stream = c->own_stream;
+  *out = c;
+  return 0;
+}
+
+void bdlm_destroy(bdlm_ctx *c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->arena) cudaFree(c->arena);
+  for (int i = 0; i < 2; ++i) {
+    if (c->ev_in[i]) cudaEventDestroy(c->ev_in[i]);
+    if (c->ev_comp[i]) cudaEventDestroy(c->ev_comp[i]);
+    if (c->ev_out[i]) cudaEventDestroy(c->ev_out[i]);
+  }
+  if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  if (c->s_in) cudaStreamDestroy(c->s_in);
+  if (c->s_out) cudaStreamDestroy(c->s_out);
+  delete c;
+}
+
+const char *bdlm_last_error(bdlm_ctx *c) { return c ? c->err.c_str() : g_create_err.c_str(); }
+
+int bdlm_set_stream(bdlm_ctx *c, void *s) {
+  if (!c) return BDLM_E_ARG;
+  c->stream = s ? reinterpret_cast<cudaStream_t>(s) : c->own_stream;
+  return 0;
+}
+
+int bdlm_sync(bdlm_ctx *c) {
+  if (!c) return BDLM_E_ARG;
+  CU(cudaSetDevice(c->device));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int64_t bdlm_launch_count(bdlm_ctx *c) { return c ? c->launches : 0; }
+
+int bdlm_set_staging_bytes(bdlm_ctx *c, int64_t bytes) {
+  if (!c || bytes < ((int64_t)1 << 20)) return BDLM_E_ARG;
+  c->staging_cap = (size_t)bytes;
+  c->workspace_cap = std::max(c->workspace_cap, (size_t)bytes);
+  return 0;
+}
+
+int bdlm_kf_filter(bdlm_ctx *c, const bdlm_problem *p, const bdlm_kf_out *out,
+                   int32_t *status) {
+  int rc = validate(c, A_FILTER, p);
+  if (rc) return rc;
+  if (!out) return fail(c, BDLM_E_ARG, "null output struct");
+  DevCall d{}; d.op = A_FILTER; d.pr = *p; d.kf = *out; d.status = status;
+  return dispatch(c, d);
+}
+
+int bdlm_rts_smooth(bdlm_ctx *c, const bdlm_problem *p, const bdlm_kf_out *filt,
+                    const bdlm_smooth_out *out, int32_t *status) {
+  int rc = validate(c, A_SMOOTH, p);
+  if (rc) return rc;
+  if (!filt || !out || !filt->m || !filt->C)
+    return fail(c, BDLM_E_ARG, "smoother needs filtered m and C");
+  if (!out->s && !out->S) return fail(c, BDLM_E_ARG, "no smoother output requested");
+  DevCall d{}; d.op = A_SMOOTH; d.pr = *p; d.kf = *filt; d.kf.f = nullptr; d.kf.Q = nullptr;
+  d.sm = *out; d.status = status;
+  return dispatch(c, d);
+}
+
+int bdlm_kf_filter_smooth(bdlm_ctx *c, const bdlm_problem *p, const bdlm_kf_out *kf,
+                          const bdlm_smooth_out *sm, int32_t *status) {
+  int rc = validate(c, A_FILTER_SMOOTH, p);
+  if (rc) return rc;
+  if (!sm) return fail(c, BDLM_E_ARG, "null smoother output struct");
+  DevCall d{}; d.op = A_FILTER_SMOOTH; d.pr = *p; if (kf) d.kf = *kf; d.sm = *sm;
+  d.status = status;
+  return dispatch(c, d);
+}
+
+int bdlm_loglik(bdlm_ctx *c, const bdlm_problem *p, double *transition, double *innovations,
+                int32_t *status) {
+  int rc = validate(c, A_LOGLIK, p);
+  if (rc) return rc;
+  if (!transition && !innovations) return fail(c, BDLM_E_ARG, "no log-likelihood requested");
+  DevCall d{}; d.op = A_LOGLIK; d.pr = *p; d.pr.keep_init = 1;
+  d.ll_tr = transition; d.ll_in = innovations; d.status = status;
+  return dispatch(c, d);
+}
+
+int bdlm_ffbs(bdlm_ctx *c, const bdlm_problem *p, const double *z, double *theta,
+              const bdlm_kf_out *kf, const bdlm_gibbs_stats *stats, int32_t *status) {
+  int rc = validate(c, A_FFBS, p);
+  if (rc) return rc;
+  if (!z || !theta) return fail(c, BDLM_E_ARG, "null z or theta");
+  DevCall d{}; d.op = A_FFBS; d.pr = *p; d.z = z; d.theta = theta;
+  if (kf) d.kf = *kf;
+  if (stats) d.stats = *stats;
+  d.status = status;
+  return dispatch(c, d);
+}
+
+int bdlm_svd_filter(bdlm_ctx *c, const bdlm_problem *p, const bdlm_svd_out *out,
+                    int32_t *status) {
+  int rc = validate(c, A_SVD_FILTER, p);
+  if (rc) return rc;
+  if (!out) return fail(c, BDLM_E_ARG, "null output struct");
+  DevCall d{}; d.op = A_SVD_FILTER; d.pr = *p; d.svd = *out; d.status = status;
+  return dispatch(c, d);
+}
+
+int bdlm_svd_ffbs(bdlm_ctx *c, const bdlm_problem *p, const double *z, double *theta,
+                  const bdlm_svd_out *filt, const bdlm_gibbs_stats *stats, int32_t *status) {
+  int rc = validate(c, A_SVD_FFBS, p);
+  if (rc) return rc;
+  if (!z || !theta) return fail(c, BDLM_E_ARG, "null z or theta");
+  DevCall d{}; d.op = A_SVD_FFBS; d.pr = *p; d.z = z; d.theta = theta;
+  if (filt) d.svd = *filt;
+  if (stats) d.stats = *stats;
+  d.status = status;
+  return dispatch(c, d);
+}
+
+int bdlm_gibbs_suffstats(bdlm_ctx *c, const bdlm_problem *p, const double *theta,
+                         const bdlm_gibbs_stats *stats) {
+  int rc = validate(c, A_STATS, p);
+  if (rc) return rc;
+  if (!theta || !stats) return fail(c, BDLM_E_ARG, "null theta or stats");
+  DevCall d{}; d.op = A_STATS; d.pr = *p; d.theta = const_cast<double *>(theta);
+  d.stats = *stats;
+  return dispatch(c, d);
+}
+
+}  // extern "C"

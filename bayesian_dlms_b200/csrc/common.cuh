@@ -1,0 +1,67 @@
+// common.cuh -- shared device/host definitions for libbdlm.so (sm_100a only).
+//
+// Arithmetic contract (DESIGN.md "Parity"): every kernel performs the reference's fp64
+// operations in the reference's order with NO fused multiply-add (the JVM never fuses),
+// so results are bit-identical to oracle/bdlm_oracle.c.  This translation unit set is
+// therefore compiled with -fmad=false; do not introduce fma()/__fma_rn() calls.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/bdlm.h"
+
+namespace bdlm {
+
+// Strided view of a per-step array: element (series b, row r, component k) lives at
+// ptr[b * sb + r * sr + k * sk].  ptr == nullptr means "not wanted".
+struct View {
+  double *ptr;
+  int64_t sb, sr, sk;
+};
+struct CView {
+  const double *ptr;
+  int64_t sb, sr, sk;
+};
+
+// Per-series parameter view: element (b, k) at ptr[b * sb + k * sk]; sb = 0 when the
+// parameter is shared by the batch.
+struct PView {
+  const double *ptr;
+  int64_t sb, sk;
+};
+
+struct KfViews {
+  View m, C, a, R, f, Q;
+};
+
+// Launch description shared by all kernels.
+struct Batch {
+  int64_t B;       // series in this launch
+  int T;           // observations
+  int n, p;
+  int keep_init;   // rows = T + keep_init
+  int compat;      // BDLM_TEXTBOOK_* | BDLM_SVD_*
+  const double *F; // device [n*p] or [T][n*p]
+  const double *G; // device [n*n] or [T][n*n]
+  const double *dt;// device [T] (dt into observation t) or nullptr = all 1.0
+  int f_tv, g_tv;
+  PView V, W, m0, C0;
+  CView y;         // T rows
+  int32_t *status; // [B] or nullptr
+};
+
+__host__ __device__ inline int64_t vidx(int64_t sb, int64_t sr, int64_t sk, int64_t b,
+                                        int64_t r, int64_t k) {
+  return b * sb + r * sr + k * sk;
+}
+
+// Streaming (evict-first) store: outputs are written once and never re-read by the
+// same kernel except the (m, C) spill, which is stored with default policy.
+__device__ __forceinline__ void st_stream(double *p, double v) { __stcs(p, v); }
+__device__ __forceinline__ double ld_stream(const double *p) { return __ldcs(p); }
+
+constexpr double kJacobiThr2 = 1e-30; // rotate iff a_pq^2 > (1e-15)^2 |a_pp a_qq|
+constexpr int kJacobiMaxSweeps = 30;
+
+}  // namespace bdlm

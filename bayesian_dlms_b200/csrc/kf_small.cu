@@ -1,0 +1,412 @@
+// kf_small.cu -- register-resident Kalman filter + RTS smoother for small state
+// dimension (n <= 4, p = 1): ONE THREAD PER SERIES.
+//
+// This is the HBM-bound headline kernel (BASELINE.json config 2: polynomial(2), 1e6
+// series x T = 1000).  Per series-step it moves 8*(p + 2n + 2n^2 + p + p^2) bytes in the
+// forward pass and 8*(2n + 2n^2) in the backward pass (216 B for n = 2, p = 1) against
+// ~130 flops, so everything is organised around HBM:
+//   * device-native layout is time-major SoA [rows][k][B]: the 32 threads of a warp read
+//     or write 256 contiguous bytes per scalar field per step (two full 128 B lines),
+//   * the whole state (m, C, a, R, W, s, S) lives in registers, the shared model (F, G)
+//     in the kernel-parameter constant bank,
+//   * y is prefetched one 4-step chunk ahead and the backward pass's (m_t, C_t) one row
+//     ahead, so every thread always has independent loads in flight while it walks its
+//     strictly sequential recursion,
+//   * outputs are written once with streaming stores (evict-first) and a_{t+1}, R_{t+1}
+//     are recomputed in the backward pass (bit-identical to the forward values) instead
+//     of being re-read.
+//
+// Arithmetic mirrors oracle/bdlm_oracle.c operation for operation (see common.cuh);
+// reference citations: KalmanFilter.scala:64-107,273-321 and Smoothing.scala:31-64.
+#include "common.cuh"
+#include "launch.h"
+
+namespace bdlm {
+
+namespace {
+
+// out(AR x BC) = A(AR x AC) * B(AC x BC), column-major, TA/TB = operand stored
+// transposed.  Products summed in increasing inner index, first product initialises.
+template <int AR, int AC, int BC, bool TA, bool TB>
+__device__ __forceinline__ void smm(const double *A, const double *B, double *out) {
+#pragma unroll
+  for (int j = 0; j < BC; ++j)
+#pragma unroll
+    for (int i = 0; i < AR; ++i) {
+      double acc = 0.0;
+#pragma unroll
+      for (int k = 0; k < AC; ++k) {
+        const double a = TA ? A[k + i * AC] : A[i + k * AR];
+        const double b = TB ? B[j + k * BC] : B[k + j * AC];
+        const double prod = a * b;
+        acc = (k == 0) ? prod : acc + prod;
+      }
+      out[i + j * AR] = acc;
+    }
+}
+
+// dgesv restatement (see oracle lu_solve): A is N x N (destroyed), Bm is N x NR.
+template <int N, int NR>
+__device__ __forceinline__ int lu_solve(double (&A)[N * N], double (&Bm)[N * NR]) {
+  int st = 0;
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    int jp = j;
+    double best = fabs(A[j + j * N]);
+#pragma unroll
+    for (int i = j + 1; i < N; ++i) {
+      const double v = fabs(A[i + j * N]);
+      if (v > best) { best = v; jp = i; }
+    }
+    double pv = A[j + j * N];
+#pragma unroll
+    for (int i = j + 1; i < N; ++i)
+      if (jp == i) pv = A[i + j * N];
+    if (pv != 0.0) {
+#pragma unroll
+      for (int i = j + 1; i < N; ++i)
+        if (jp == i) {
+#pragma unroll
+          for (int c = 0; c < N; ++c) {
+            const double t = A[j + c * N]; A[j + c * N] = A[i + c * N]; A[i + c * N] = t;
+          }
+#pragma unroll
+          for (int c = 0; c < NR; ++c) {
+            const double t = Bm[j + c * N]; Bm[j + c * N] = Bm[i + c * N]; Bm[i + c * N] = t;
+          }
+        }
+      const double r = 1.0 / A[j + j * N];
+#pragma unroll
+      for (int i = j + 1; i < N; ++i) A[i + j * N] = A[i + j * N] * r;
+    } else {
+      st = BDLM_ST_SINGULAR;
+    }
+#pragma unroll
+    for (int c = j + 1; c < N; ++c)
+#pragma unroll
+      for (int i = j + 1; i < N; ++i)
+        A[i + c * N] = A[i + c * N] - A[i + j * N] * A[j + c * N];
+  }
+#pragma unroll
+  for (int c = 0; c < NR; ++c) {
+#pragma unroll
+    for (int k = 0; k < N; ++k)
+#pragma unroll
+      for (int i = k + 1; i < N; ++i)
+        Bm[i + c * N] = Bm[i + c * N] - Bm[k + c * N] * A[i + k * N];
+#pragma unroll
+    for (int k = N - 1; k >= 0; --k) {
+      Bm[k + c * N] = Bm[k + c * N] / A[k + k * N];
+#pragma unroll
+      for (int i = 0; i < k; ++i)
+        Bm[i + c * N] = Bm[i + c * N] - Bm[k + c * N] * A[i + k * N];
+    }
+  }
+  return st;
+}
+
+// KalmanFilter.advState (KalmanFilter.scala:273-286)
+template <int N, bool REG>
+__device__ __forceinline__ void advance(const double *G, const double (&W)[N * N],
+                                        double dt, const double (&m)[N],
+                                        const double (&C)[N * N], double (&a)[N],
+                                        double (&R)[N * N]) {
+  if (!REG && dt == 0.0) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) a[i] = m[i];
+#pragma unroll
+    for (int k = 0; k < N * N; ++k) R[k] = C[k];
+    return;
+  }
+  double t1[N * N];
+  smm<N, N, 1, false, false>(G, m, a);
+  smm<N, N, N, false, false>(G, C, t1);
+  smm<N, N, N, false, true>(t1, G, R);
+#pragma unroll
+  for (int k = 0; k < N * N; ++k) R[k] = R[k] + (REG ? W[k] : W[k] * dt);  // W * 1.0 == W
+}
+
+// oneStepPrediction (:311-321) + updateState (:64-94) for p = 1.
+template <int N>
+__device__ __forceinline__ void update(const double *F, double V, double y,
+                                       const double (&a)[N], const double (&R)[N * N],
+                                       double &f, double &Q, double (&m)[N],
+                                       double (&C)[N * N], int &st) {
+  double fr[N];
+  smm<1, N, 1, true, false>(F, a, &f);
+  smm<1, N, N, true, false>(F, R, fr);
+  smm<1, N, 1, false, false>(fr, F, &Q);
+  Q = Q + V;
+  if (isnan(y)) {  // all missing (:74-75)
+#pragma unroll
+    for (int i = 0; i < N; ++i) m[i] = a[i];
+#pragma unroll
+    for (int k = 0; k < N * N; ++k) C[k] = R[k];
+    return;
+  }
+  // oneStepMissing (:44-53) on the full F, V repeats the same operations: reuse f, Q.
+  const double e = y - f;
+  double rhs[N], K[N], D[N * N], t1[N * N], t2[N], C2[N * N];
+  smm<1, N, N, true, true>(F, R, rhs);  // F^T R^T
+  if (Q == 0.0) st |= BDLM_ST_SINGULAR;
+#pragma unroll
+  for (int i = 0; i < N; ++i) K[i] = rhs[i] / Q;  // (Q^T \ (F^T R^T))^T  (:83)
+#pragma unroll
+  for (int i = 0; i < N; ++i) m[i] = a[i] + K[i] * e;
+  smm<N, 1, N, false, true>(K, F, D);  // K F^T
+#pragma unroll
+  for (int j = 0; j < N; ++j)
+#pragma unroll
+    for (int i = 0; i < N; ++i) D[i + j * N] = ((i == j) ? 1.0 : 0.0) - D[i + j * N];
+  smm<N, N, N, false, false>(D, R, t1);
+  smm<N, N, N, false, true>(t1, D, C);
+#pragma unroll
+  for (int i = 0; i < N; ++i) t2[i] = K[i] * V;
+  smm<N, 1, N, false, true>(t2, K, C2);
+#pragma unroll
+  for (int k = 0; k < N * N; ++k) C[k] = C[k] + C2[k];
+}
+
+// Smoothing.smoothStep (Smoothing.scala:31-47)
+template <int N>
+__device__ __forceinline__ void rts_step(const double *G, const double (&m)[N],
+                                         const double (&C)[N * N], const double (&a1)[N],
+                                         const double (&R1)[N * N], bool textbook,
+                                         double (&s)[N], double (&S)[N * N], int &st) {
+  double rhs[N * N], At[N * N], Bg[N * N], d[N], t[N], Dm[N * N], t1[N * N], t2[N * N];
+  smm<N, N, N, false, true>(G, C, rhs);  // G C^T
+#pragma unroll
+  for (int j = 0; j < N; ++j)
+#pragma unroll
+    for (int i = 0; i < N; ++i) At[i + j * N] = R1[j + i * N];
+  st |= lu_solve<N, N>(At, rhs);
+#pragma unroll
+  for (int j = 0; j < N; ++j)
+#pragma unroll
+    for (int i = 0; i < N; ++i) Bg[i + j * N] = rhs[j + i * N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) d[i] = s[i] - a1[i];
+  smm<N, N, 1, false, false>(Bg, d, t);
+#pragma unroll
+  for (int k = 0; k < N * N; ++k) Dm[k] = R1[k] - S[k];
+  smm<N, N, N, false, false>(Bg, Dm, t1);
+  if (textbook) smm<N, N, N, false, true>(t1, Bg, t2);
+  else smm<N, N, N, false, false>(t1, Bg, t2);  // Smoothing.scala:44 (no transpose)
+#pragma unroll
+  for (int i = 0; i < N; ++i) s[i] = m[i] + t[i];
+#pragma unroll
+  for (int k = 0; k < N * N; ++k) S[k] = C[k] - t2[k];
+}
+
+template <int K>
+__device__ __forceinline__ void store_vec(const View &v, int64_t b, int64_t row,
+                                          const double *x) {
+  if (v.ptr == nullptr) return;
+  double *p = v.ptr + b * v.sb + row * v.sr;
+#pragma unroll
+  for (int k = 0; k < K; ++k) st_stream(p + k * v.sk, x[k]);
+}
+
+template <int K>
+__device__ __forceinline__ void load_vec(const View &v, int64_t b, int64_t row, double *x) {
+  const double *p = v.ptr + b * v.sb + row * v.sr;
+#pragma unroll
+  for (int k = 0; k < K; ++k) x[k] = ld_stream(p + k * v.sk);
+}
+
+template <int K>
+__device__ __forceinline__ void load_param(const PView &v, int64_t b, double *x) {
+  const double *p = v.ptr + b * v.sb;
+#pragma unroll
+  for (int k = 0; k < K; ++k) x[k] = p[k * v.sk];
+}
+
+template <int N>
+struct SmallModel {
+  double G[N * N];
+  double F[N];
+};
+
+// Model matrices for observation t: kernel-parameter constant bank when time-invariant
+// (static indices, no address taken), uniform global loads when they vary with t.
+template <int N, bool REG>
+__device__ __forceinline__ void load_model(const Batch &bt, const SmallModel<N> &mdl, int t,
+                                           double (&G)[N * N], double (&F)[N]) {
+  if (!REG && bt.g_tv) {
+    const double *g = bt.G + (int64_t)t * N * N;
+#pragma unroll
+    for (int k = 0; k < N * N; ++k) G[k] = __ldg(g + k);
+  } else {
+#pragma unroll
+    for (int k = 0; k < N * N; ++k) G[k] = mdl.G[k];
+  }
+  if (!REG && bt.f_tv) {
+    const double *f = bt.F + (int64_t)t * N;
+#pragma unroll
+    for (int k = 0; k < N; ++k) F[k] = __ldg(f + k);
+  } else {
+#pragma unroll
+    for (int k = 0; k < N; ++k) F[k] = mdl.F[k];
+  }
+}
+
+constexpr int kChunk = 4;  // y prefetch distance (steps)
+
+// mode bits
+constexpr int kDoFilter = 1, kDoSmooth = 2;
+
+template <int N, bool REG>
+__global__ void __launch_bounds__(128)
+kf_small_kernel(const Batch bt, const SmallModel<N> mdl, const KfViews kf, const View sv,
+                const View Sv, const int mode) {
+  const int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (b >= bt.B) return;
+  const int T = bt.T, ki = bt.keep_init, rows = T + ki;
+  int st = 0;
+
+  double W[N * N], m[N], C[N * N];
+  double V;
+  load_param<N * N>(bt.W, b, W);
+  load_param<1>(bt.V, b, &V);
+
+  if (mode & kDoFilter) {
+    load_param<N>(bt.m0, b, m);
+    load_param<N * N>(bt.C0, b, C);
+    if (ki) {  // initialiseState (KalmanFilter.scala:112-118): f, Q = None -> NaN
+      const double nanv = __longlong_as_double(0x7ff8000000000000LL);
+      store_vec<N>(kf.m, b, 0, m);
+      store_vec<N * N>(kf.C, b, 0, C);
+      store_vec<N>(kf.a, b, 0, m);
+      store_vec<N * N>(kf.R, b, 0, C);
+      store_vec<1>(kf.f, b, 0, &nanv);
+      store_vec<1>(kf.Q, b, 0, &nanv);
+    }
+    const double *yp = bt.y.ptr + b * bt.y.sb;
+    double ycur[kChunk], ynxt[kChunk];
+#pragma unroll
+    for (int u = 0; u < kChunk; ++u) ycur[u] = (u < T) ? ld_stream(yp + u * bt.y.sr) : 0.0;
+    for (int t0 = 0; t0 < T; t0 += kChunk) {
+#pragma unroll
+      for (int u = 0; u < kChunk; ++u) {
+        const int t = t0 + kChunk + u;
+        ynxt[u] = (t < T) ? ld_stream(yp + (int64_t)t * bt.y.sr) : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < kChunk; ++u) {
+        const int t = t0 + u;
+        if (t < T) {
+          double a[N], R[N * N], f, Q;
+          const double dt = REG ? 1.0 : (bt.dt ? bt.dt[t] : 1.0);
+          double G[N * N], F[N];
+          load_model<N, REG>(bt, mdl, t, G, F);
+          advance<N, REG>(G, W, dt, m, C, a, R);
+          update<N>(F, V, ycur[u], a, R, f, Q, m, C, st);
+          const int64_t row = t + ki;
+          store_vec<N>(kf.a, b, row, a);
+          store_vec<N * N>(kf.R, b, row, R);
+          store_vec<1>(kf.f, b, row, &f);
+          store_vec<1>(kf.Q, b, row, &Q);
+          store_vec<N>(kf.m, b, row, m);
+          store_vec<N * N>(kf.C, b, row, C);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kChunk; ++u) ycur[u] = ynxt[u];
+    }
+  } else {
+    load_vec<N>(kf.m, b, rows - 1, m);
+    load_vec<N * N>(kf.C, b, rows - 1, C);
+  }
+
+  if (mode & kDoSmooth) {
+    // backwardsSmoother (Smoothing.scala:57-64): s_T = m_T, S_T = C_T
+    double s[N], S[N * N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) s[i] = m[i];
+#pragma unroll
+    for (int k = 0; k < N * N; ++k) S[k] = C[k];
+    store_vec<N>(sv, b, rows - 1, s);
+    store_vec<N * N>(Sv, b, rows - 1, S);
+    const bool textbook = (bt.compat & BDLM_TEXTBOOK_SMOOTHER) != 0;
+    const bool reload_ar = !(mode & kDoFilter) && kf.a.ptr != nullptr && kf.R.ptr != nullptr;
+    double mn[N], Cn[N * N];
+    if (rows >= 2) {
+      load_vec<N>(kf.m, b, rows - 2, mn);
+      load_vec<N * N>(kf.C, b, rows - 2, Cn);
+    }
+    for (int r = rows - 2; r >= 0; --r) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) m[i] = mn[i];
+#pragma unroll
+      for (int k = 0; k < N * N; ++k) C[k] = Cn[k];
+      if (r > 0) {  // prefetch the next row of the spill while this one is processed
+        load_vec<N>(kf.m, b, r - 1, mn);
+        load_vec<N * N>(kf.C, b, r - 1, Cn);
+      }
+      const int tobs = r + 1 - ki;  // observation index of row r + 1
+      const double dt = REG ? 1.0 : (bt.dt ? bt.dt[tobs] : 1.0);
+      double G[N * N], F[N];
+      load_model<N, REG>(bt, mdl, tobs, G, F);
+      double a1[N], R1[N * N];
+      if (reload_ar) {
+        load_vec<N>(kf.a, b, r + 1, a1);
+        load_vec<N * N>(kf.R, b, r + 1, R1);
+      } else {
+        advance<N, REG>(G, W, dt, m, C, a1, R1);  // bit-identical to the forward a, R
+      }
+      rts_step<N>(G, m, C, a1, R1, textbook, s, S, st);
+      store_vec<N>(sv, b, r, s);
+      store_vec<N * N>(Sv, b, r, S);
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) m[i] = s[i];
+#pragma unroll
+    for (int k = 0; k < N * N; ++k) C[k] = S[k];
+  }
+
+  if (bt.status) {
+    bool finite = true;
+#pragma unroll
+    for (int i = 0; i < N; ++i) finite = finite && isfinite(m[i]);
+#pragma unroll
+    for (int k = 0; k < N * N; ++k) finite = finite && isfinite(C[k]);
+    if (!finite) st |= BDLM_ST_NONFINITE;
+    bt.status[b] = st;
+  }
+}
+
+template <int N>
+cudaError_t launch_n(const Batch &bt, const double *hG, const double *hF, const KfViews &kf,
+                     const View &sv, const View &Sv, int mode, cudaStream_t stream) {
+  SmallModel<N> mdl;
+  for (int k = 0; k < N * N; ++k) mdl.G[k] = hG[k];
+  for (int k = 0; k < N; ++k) mdl.F[k] = hF[k];
+  const bool reg = bt.dt == nullptr && !bt.g_tv && !bt.f_tv;
+  const int threads = 128;
+  const int64_t blocks = (bt.B + threads - 1) / threads;
+  if (blocks <= 0) return cudaSuccess;
+  if (reg)
+    kf_small_kernel<N, true><<<(unsigned)blocks, threads, 0, stream>>>(bt, mdl, kf, sv, Sv, mode);
+  else
+    kf_small_kernel<N, false><<<(unsigned)blocks, threads, 0, stream>>>(bt, mdl, kf, sv, Sv, mode);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+bool small_supported(int n, int p) { return p == 1 && n >= 1 && n <= 4; }
+
+cudaError_t launch_kf_small(const Batch &bt, const double *hG, const double *hF,
+                            const KfViews &kf, const View &sv, const View &Sv,
+                            bool do_filter, bool do_smooth, cudaStream_t stream) {
+  const int mode = (do_filter ? kDoFilter : 0) | (do_smooth ? kDoSmooth : 0);
+  switch (bt.n) {
+    case 1: return launch_n<1>(bt, hG, hF, kf, sv, Sv, mode, stream);
+    case 2: return launch_n<2>(bt, hG, hF, kf, sv, Sv, mode, stream);
+    case 3: return launch_n<3>(bt, hG, hF, kf, sv, Sv, mode, stream);
+    case 4: return launch_n<4>(bt, hG, hF, kf, sv, Sv, mode, stream);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+}  // namespace bdlm

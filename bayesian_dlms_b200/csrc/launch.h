@@ -1,0 +1,49 @@
+// launch.h -- host-callable launchers implemented in the .cu files.
+#pragma once
+#include "common.cuh"
+
+namespace bdlm {
+
+// kf_small.cu: thread-per-series register kernels (n <= 4, p = 1).
+bool small_supported(int n, int p);
+cudaError_t launch_kf_small(const Batch &bt, const double *hG, const double *hF,
+                            const KfViews &kf, const View &sv, const View &Sv,
+                            bool do_filter, bool do_smooth, cudaStream_t stream);
+
+// kf_warp.cu: warp-per-series shared-memory kernels (any n, p <= 32).
+struct SvdViews {
+  View m, dc, uc, a, dr, ur, f;
+};
+struct StatViews {  // one row per chain: element (b, k) at ptr[b*sb + k*sk]
+  View ssy, ny, ssw, scatter;
+};
+enum WarpOp {
+  kOpFilter = 0,       // forward Kalman filter
+  kOpSmooth = 1,       // RTS smoother from stored (m, C[, a, R])
+  kOpFilterSmooth = 2, // fused
+  kOpFfbs = 3,         // filter + backward sampling (+ Gibbs statistics)
+  kOpLoglik = 4,       // filter + both log-likelihoods
+  kOpSvdFilter = 5,
+  kOpSvdFfbs = 6,
+  kOpStats = 7         // Gibbs statistics of a given theta
+};
+struct WarpArgs {
+  Batch bt;
+  KfViews kf;          // user-visible KfState outputs (any may be null)
+  View s, S;           // smoother outputs
+  CView z;             // injected normals, rows x n
+  View theta;          // sampled path, rows x n (input for kOpStats)
+  SvdViews svd;
+  StatViews stats;
+  double *ll_transition, *ll_innov;  // [B]
+  double *spill;       // series-major workspace [B][rows][spill_k] or nullptr
+  int64_t spill_k;
+};
+size_t warp_spill_doubles_per_row(int op, int n, int p);
+cudaError_t launch_warp(int op, const WarpArgs &wa, cudaStream_t stream);
+
+// transpose.cu: [R][C] -> [C][R] for doubles (layout conversion of staged slabs).
+cudaError_t launch_transpose(const double *in, double *out, int64_t rows, int64_t cols,
+                             cudaStream_t stream);
+
+}  // namespace bdlm

@@ -168,9 +168,12 @@ def materialise(mod: Dlm, times: np.ndarray):
     (KalmanFilter.initialiseState, KalmanFilter.scala:112-118).
     """
     times = np.asarray(times, dtype=np.float64)
-    T = times.size
     prev = np.concatenate([[times.min() - 1.0], times[:-1]])
-    dts = times - prev
+    return materialise_dts(mod, times, times - prev)
+
+
+def materialise_dts(mod: Dlm, times: np.ndarray, dts: np.ndarray):
+    """As ``materialise`` with the time increments given explicitly (``G[t] = g(dts[t])``)."""
     Fs = [np.asarray(mod.f(float(t)), dtype=np.float64) for t in times]
     Gs = [np.asarray(mod.g(float(dt)), dtype=np.float64) for dt in dts]
     n, p = Fs[0].shape

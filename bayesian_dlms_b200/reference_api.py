@@ -1,0 +1,269 @@
+"""Drop-in mirror of the reference's operator API for the Kalman hot path.
+
+Same names, argument meaning, result types and error behaviour as the Scala objects
+``KalmanFilter``, ``Smoothing``, ``SvdFilter``, ``SvdSampler`` and the Gibbs sufficient
+statistics, so the parity tests read like the reference's own tests.  Every call runs
+on the GPU through libbdlm.so (batch of one series, host buffers); there is no CPU
+implementation behind this module.  The Scala facade that binds the same C ABI from
+the JVM is described in INTEGRATION.md.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _capi as capi
+from . import dlm as _dlm
+from .batch import Model, SERIES_MAJOR, default_engine
+from .dlm import Data, Dlm, DlmParameters
+
+
+class MatrixSingularException(ArithmeticError):
+    """Breeze's exception for a zero pivot in ``\\`` (status bit BDLM_ST_SINGULAR)."""
+
+
+class NotConvergedException(ArithmeticError):
+    """Breeze's exception for eigSym/svd non-convergence (BDLM_ST_NOTCONVERGED)."""
+
+
+def _raise_status(st: int):
+    if st & capi.ST_SINGULAR:
+        raise MatrixSingularException("singular matrix in solve")
+    if st & capi.ST_NOTCONVERGED:
+        raise NotConvergedException("Jacobi iteration did not converge")
+
+
+@dataclass
+class KfState:
+    """``KfState`` (KalmanFilter.scala:22-30); ft/qt are None at the initial state."""
+    time: float
+    mt: np.ndarray
+    ct: np.ndarray
+    at: np.ndarray
+    rt: np.ndarray
+    ft: Optional[np.ndarray]
+    qt: Optional[np.ndarray]
+
+
+@dataclass
+class SmoothingState:
+    """``Smoothing.SmoothingState`` (Smoothing.scala:18-22)."""
+    time: float
+    mean: np.ndarray
+    covariance: np.ndarray
+    at1: np.ndarray
+    rt1: np.ndarray
+
+
+@dataclass
+class SamplingState:
+    """``SamplingState`` (Smoothing.scala:10-15)."""
+    time: float
+    sample: np.ndarray
+    mean: np.ndarray
+    cov: np.ndarray
+    at1: np.ndarray
+    rt1: np.ndarray
+
+
+@dataclass
+class SvdState:
+    """``SvdState`` (SvdFilter.scala:7-14)."""
+    time: float
+    mt: np.ndarray
+    dc: np.ndarray
+    uc: np.ndarray
+    at: np.ndarray
+    dr: np.ndarray
+    ur: np.ndarray
+    ft: np.ndarray
+
+
+def _prep(mod: Dlm, ys: Sequence[Data], p: DlmParameters):
+    times, y = _dlm.flatten_data(ys)  # raises on empty data like t0.get
+    model = Model.build(mod, times)
+    params = dict(V=p.v, W=p.w, m0=p.m0, C0=p.c0)
+    return model, params, times, np.ascontiguousarray(y.reshape(1, model.T, model.p))
+
+
+def _row_times(times: np.ndarray, keep_init: bool):
+    return np.concatenate([[times.min() - 1.0], times]) if keep_init else times
+
+
+def _kf_states(model, out, tm, keep_init):
+    n, p = model.n, model.p
+    res = []
+    for r in range(len(tm)):
+        init = keep_init and r == 0
+        res.append(KfState(
+            float(tm[r]), out["m"][0, r].copy(), _dlm.from_cm(out["C"][0, r], n, n).copy(),
+            out["a"][0, r].copy(), _dlm.from_cm(out["R"][0, r], n, n).copy(),
+            None if init else out["f"][0, r].copy(),
+            None if init else _dlm.from_cm(out["Q"][0, r], p, p).copy()))
+    return res
+
+
+def _pack_filtered(filtered: Sequence[KfState]):
+    m = np.stack([s.mt for s in filtered])[None]
+    C = np.stack([_dlm.cm(s.ct) for s in filtered])[None]
+    a = np.stack([s.at for s in filtered])[None]
+    R = np.stack([_dlm.cm(s.rt) for s in filtered])[None]
+    return dict(m=np.ascontiguousarray(m), C=np.ascontiguousarray(C),
+                a=np.ascontiguousarray(a), R=np.ascontiguousarray(R))
+
+
+def _model_for_states(mod: Dlm, state_times: np.ndarray):
+    """Model for a vector of filtered states whose first element may be the initial state:
+    G between consecutive states is g(time[r+1] - time[r])."""
+    # states[1:] play the role of the observations; state 0 supplies the previous time.
+    # The smoother only needs G between consecutive states (a, R come with the KfStates).
+    st = np.asarray(state_times, dtype=np.float64)
+    F, f_tv, G, g_tv, n, p = _dlm.materialise_dts(mod, st[1:], np.diff(st))
+    return Model(np.ascontiguousarray(F.ravel()), np.ascontiguousarray(G.ravel()), bool(f_tv),
+                 bool(g_tv), n, p, int(st.size - 1), None)
+
+
+class KalmanFilter:
+    """``KalmanFilter`` companion-object entry points (KalmanFilter.scala)."""
+
+    @staticmethod
+    def filterDlm(mod: Dlm, ys: Sequence[Data], p: DlmParameters) -> List[KfState]:
+        """``KalmanFilter.filterDlm`` (:291-294): T states, initial state dropped."""
+        return KalmanFilter._run(mod, ys, p, keep_init=False)
+
+    @staticmethod
+    def filter(mod: Dlm, ys: Sequence[Data], p: DlmParameters) -> List[KfState]:
+        """``KalmanFilter(advanceState(p, mod.g)).filter`` (Filter.scala:41-45): T+1 states."""
+        return KalmanFilter._run(mod, ys, p, keep_init=True)
+
+    @staticmethod
+    def _run(mod, ys, p, keep_init):
+        model, params, times, y = _prep(mod, ys, p)
+        out = default_engine().filter(model, params, y, layout=SERIES_MAJOR, keep_init=keep_init)
+        _raise_status(int(out["status"][0]))
+        return _kf_states(model, out, _row_times(times, keep_init), keep_init)
+
+    @staticmethod
+    def likelihood(mod: Dlm, ys: Sequence[Data]):
+        """``KalmanFilter.likelihood(mod, ys)(p)`` (:299-306), curried like the reference."""
+        def at(p: DlmParameters) -> float:
+            model, params, times, y = _prep(mod, ys, p)
+            out = default_engine().loglik(model, params, y, layout=SERIES_MAJOR)
+            return float(out["transition"][0])
+        return at
+
+    @staticmethod
+    def innovationsLikelihood(mod: Dlm, ys: Sequence[Data]):
+        """Sum over t of ``KalmanFilter.conditionalLikelihood`` (:138-153)."""
+        def at(p: DlmParameters) -> float:
+            model, params, times, y = _prep(mod, ys, p)
+            out = default_engine().loglik(model, params, y, layout=SERIES_MAJOR)
+            return float(out["innovations"][0])
+        return at
+
+
+class Smoothing:
+    """``Smoothing`` object entry points (Smoothing.scala)."""
+
+    @staticmethod
+    def backwardsSmoother(mod: Dlm, w: Optional[np.ndarray] = None):
+        """``Smoothing.backwardsSmoother(mod)(kfState)`` (:57-64).  The smoother recursion
+        never reads W; it is only needed when a_{t+1}, R_{t+1} must be recomputed, which
+        does not happen here because the KfStates carry them."""
+        def run(filtered: Sequence[KfState]) -> List[SmoothingState]:
+            tm = np.array([s.time for s in filtered])
+            n = filtered[0].mt.size
+            model = _model_for_states(mod, tm) if len(filtered) > 1 else None
+            if model is None:
+                s = filtered[0]
+                return [SmoothingState(s.time, s.mt, s.ct, s.at, s.rt)]
+            packed = _pack_filtered(filtered)
+            params = dict(V=np.eye(model.p), W=np.eye(n) if w is None else w)
+            out = default_engine().smooth(model, params, packed, layout=SERIES_MAJOR,
+                                          keep_init=True)
+            _raise_status(int(out["status"][0]))
+            return [SmoothingState(float(tm[r]), out["s"][0, r].copy(),
+                                   _dlm.from_cm(out["S"][0, r], n, n).copy(),
+                                   filtered[r].at, filtered[r].rt) for r in range(len(tm))]
+        return run
+
+    @staticmethod
+    def ffbsDlm(mod: Dlm, ys: Sequence[Data], p: DlmParameters, *, z: Optional[np.ndarray] = None,
+                rng: Optional[np.random.Generator] = None) -> List[SamplingState]:
+        """``Smoothing.ffbsDlm`` (:173-180).  The N(0,1) draws are injected: ``z[row]`` are the
+        n values used for theta[row]; with ``rng`` they are generated in the reference's
+        draw order (last row first, MultivariateGaussianSvd.scala:19-22)."""
+        model, params, times, y = _prep(mod, ys, p)
+        rows, n = model.T + 1, model.n
+        if z is None:
+            rng = rng or np.random.default_rng()
+            z = rng.standard_normal((rows, n))[::-1]
+        z = np.ascontiguousarray(np.asarray(z, dtype=np.float64).reshape(1, rows, n))
+        out = default_engine().ffbs(model, params, y, z, layout=SERIES_MAJOR,
+                                    want_kf=("m", "C", "a", "R"))
+        _raise_status(int(out["status"][0]))
+        tm = _row_times(times, True)
+        return [SamplingState(float(tm[r]), out["theta"][0, r].copy(), out["m"][0, r].copy(),
+                              _dlm.from_cm(out["C"][0, r], n, n).copy(), out["a"][0, r].copy(),
+                              _dlm.from_cm(out["R"][0, r], n, n).copy()) for r in range(rows)]
+
+
+class SvdFilter:
+    """``SvdFilter`` entry points (SvdFilter.scala)."""
+
+    @staticmethod
+    def filterDlm(mod: Dlm, ys: Sequence[Data], p: DlmParameters) -> List[SvdState]:
+        """``SvdFilter.filterDlm`` (:158-161): T states; advance closure holds the raw W."""
+        return SvdFilter._run(mod, ys, p, keep_init=False)
+
+    @staticmethod
+    def filter(mod: Dlm, ys: Sequence[Data], p: DlmParameters) -> List[SvdState]:
+        """``SvdFilter(advanceState(p, mod.g)).filter`` (:112-119): T+1 states."""
+        return SvdFilter._run(mod, ys, p, keep_init=True)
+
+    @staticmethod
+    def _run(mod, ys, p, keep_init):
+        model, params, times, y = _prep(mod, ys, p)
+        out = default_engine().svd_filter(model, params, y, layout=SERIES_MAJOR,
+                                          keep_init=keep_init)
+        _raise_status(int(out["status"][0]))
+        n = model.n
+        tm = _row_times(times, keep_init)
+        return [SvdState(float(tm[r]), out["m"][0, r].copy(), out["dc"][0, r].copy(),
+                         _dlm.from_cm(out["uc"][0, r], n, n).copy(), out["a"][0, r].copy(),
+                         out["dr"][0, r].copy(), _dlm.from_cm(out["ur"][0, r], n, n).copy(),
+                         out["f"][0, r].copy()) for r in range(len(tm))]
+
+
+class SvdSampler:
+    """``SvdSampler`` entry points (SvdSampler.scala)."""
+
+    @staticmethod
+    def ffbsDlm(mod: Dlm, ys: Sequence[Data], p: DlmParameters, *, z: Optional[np.ndarray] = None,
+                rng: Optional[np.random.Generator] = None):
+        """``SvdSampler.ffbsDlm`` (:79-82); returns (time, sample) per row."""
+        model, params, times, y = _prep(mod, ys, p)
+        rows, n = model.T + 1, model.n
+        if z is None:
+            rng = rng or np.random.default_rng()
+            z = rng.standard_normal((rows, n))[::-1]
+        z = np.ascontiguousarray(np.asarray(z, dtype=np.float64).reshape(1, rows, n))
+        out = default_engine().ffbs(model, params, y, z, layout=SERIES_MAJOR, svd=True)
+        _raise_status(int(out["status"][0]))
+        tm = _row_times(times, True)
+        return [(float(tm[r]), out["theta"][0, r].copy()) for r in range(rows)]
+
+
+class GibbsSampling:
+    """Sufficient statistics of ``GibbsSampling`` / ``GibbsWishart`` (Gibbs.scala:29-43,63-73)."""
+
+    @staticmethod
+    def sufficientStatistics(mod: Dlm, ys: Sequence[Data], theta: np.ndarray):
+        times, y = _dlm.flatten_data(ys)
+        model = Model.build(mod, times)
+        yb = np.ascontiguousarray(y.reshape(1, model.T, model.p))
+        th = np.ascontiguousarray(np.asarray(theta, dtype=np.float64).reshape(1, model.T + 1, model.n))
+        out = default_engine().gibbs_stats(model, yb, th, layout=SERIES_MAJOR)
+        return {k: v[0] for k, v in out.items()}

@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the Kalman hot path (BASELINE.json config 2).
+
+Workload: second-order (linear trend) DLM, polynomial(2), n = 2, p = 1; 1e6 independent
+synthetic series x T = 1000 per GPU; fused Kalman filter + RTS smoother in fp64 writing the
+full KfState (m, C, a, R, f, Q) and SmoothingState (s, S) of every step.
+Metric: filter+smoother series-steps/s (whole job, all ranks).
+
+A "step" = one pass over the rank's 1e6 series, issued as `--chunks` launches over resident
+inputs; outputs go to one reused device buffer set (1e9 steps x 160 B does not fit next to
+anything else in 180 GB).  Every launch reads/writes >> 126 MB (L2), so no explicit flush.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--series S] [--T T]
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_STATE, N_OBS = 2, 1
+ALGO_BYTES_PER_STEP = 8 * (N_OBS + (2 * N_STATE + 2 * N_STATE ** 2 + N_OBS + N_OBS ** 2)
+                           + (N_STATE + N_STATE ** 2) + (N_STATE + N_STATE ** 2))  # 216
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--series", type=int, default=1_000_000, help="series per GPU")
+    ap.add_argument("--T", type=int, default=1000)
+    ap.add_argument("--chunks", type=int, default=4)
+    ap.add_argument("--e2e-series", type=int, default=0,
+                    help="series per e2e step (0 = same as --series)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_ev = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_ev.is_set():
+            try:
+                r = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                    "-i", str(self.index)], capture_output=True, text=True, timeout=5)
+                if r.returncode == 0 and r.stdout.strip():
+                    self.rows.append([c.strip() for c in r.stdout.strip().split(",")])
+            except Exception:
+                pass
+            self._stop_ev.wait(0.2)
+
+    def stop(self):
+        self._stop_ev.set()
+        self.join(timeout=6)
+        sm, reasons, smax = [], set(), None
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); smax = float(r[1])
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def synth_params(B, seed, xp):
+    """Per-series parameters: base x logU(0.5, 2) so nothing constant-folds."""
+    rng = np.random.default_rng(seed + 1)
+    sc = np.exp(rng.uniform(np.log(0.5), np.log(2.0), size=(2, B)))
+    Vs = (3.0 * sc[0])[None, :]                                   # [1][B]
+    Ws = np.array([2.0, 0.0, 0.0, 1.0])[:, None] * sc[1][None, :]  # [4][B] column-major diag(2,1)
+    return np.ascontiguousarray(Vs), np.ascontiguousarray(Ws)
+
+
+def cpu_reference_leg(series, T, seconds_target=15.0, threads=None, warm_passes=1):
+    """Time the CPU restatement of the reference (oracle, all host cores) on a bounded sample of
+    the same workload.  The JVM reference itself cannot run here (no JDK): kind = "port"."""
+    import oracle
+    from bayesian_dlms_b200 import dlm
+    oracle.build()
+    threads = threads or os.cpu_count()
+    mod = dlm.polynomial(2)
+    times = np.arange(1, T + 1.0)
+    F, _, G, _, n, p = dlm.materialise(mod, times)
+    rng = np.random.default_rng(20260101)
+
+    # bounded sample: Bs series (<= 16384: 160 KB of outputs each), repeated into the same
+    # output arrays until ~seconds_target of CPU work has been timed
+    Bs = int(min(series, 16384))
+    y = rng.standard_normal((Bs, T, 1)).cumsum(axis=1)
+    Vs, Ws = synth_params(Bs, 20260101, np)
+    Vt, Wt = np.ascontiguousarray(Vs.T), np.ascontiguousarray(Ws.T)
+    m0, C0 = np.zeros(n), dlm.cm(100 * np.eye(n))
+
+    def run(out=None):
+        t0 = time.perf_counter()
+        out = oracle.batch_filter_smooth(Bs, n, p, T, F, G, Vt, Wt, m0, C0, times, y,
+                                         keep_init=True, nthreads=threads, out=out)
+        return time.perf_counter() - t0, out
+
+    _, out = run()          # warm: page-faults the output arrays, spins up the OpenMP team
+    for _ in range(max(0, warm_passes - 1)):
+        run(out)
+    dt1, out = run(out)
+    reps = int(max(1, min(200, round(seconds_target / max(dt1, 1e-6)))))
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        run(out)
+    dt = time.perf_counter() - t0
+    return {"value": reps * Bs * T / dt, "unit": "series-steps/s", "cores": threads, "kind": "port",
+            "sample": f"{Bs} series x T={T} x {reps} passes (config-2 model, full "
+                      f"KfState+SmoothingState outputs into reused arrays), {dt:.2f} s wall, "
+                      f"oracle/bdlm_oracle.c gcc -O2 OpenMP"}, reps * Bs, dt
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    T, B = args.T, args.series
+    config = {"workload": "config2: polynomial(2) n=2 p=1, %d series/GPU x T=%d, fused Kalman filter + "
+                          "RTS smoother, full KfState+SmoothingState outputs" % (B, T),
+              "series_per_gpu": B, "T": T, "chunks_per_step": args.chunks,
+              "device_layout": "time-major SoA [rows][k][B]",
+              "l2": "inputs+outputs per launch >> 126 MB L2 (no flush needed)"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        # K timed steps, each one pass over the bounded sample (W untimed passes first)
+        base, nser, dt = cpu_reference_leg(B, T, seconds_target=3.0 * max(1, args.steps),
+                                           warm_passes=max(1, args.warmup))
+        v = base["value"]
+        print(json.dumps({
+            "impl": "reference", "metric": "filter+smoother series-steps/s", "value": v,
+            "unit": "series-steps/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup,
+            "ms_per_step": 1e3 * dt / max(1, args.steps), "higher_is_better": True,
+            "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+            "cpu_baseline": base,
+            "e2e": {"value": v, "unit": "series-steps/s", "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 0},
+            "note": "JVM/Scala toolchain absent: CPU restatement of the reference (oracle port), "
+                    "all host cores, bounded sample"}))
+        return
+
+    import torch
+    import torch.distributed as dist
+    from bayesian_dlms_b200 import Engine, Model, TIME_MAJOR, dlm
+
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    eng = Engine(local)
+    eng.use_torch_stream()
+
+    # ---- synthetic inputs, resident in HBM (Dlm.simStep generative model, Dlm.scala:245-282)
+    nch = args.chunks
+    bounds = [(i * B) // nch for i in range(nch + 1)]
+    Bc_max = max(bounds[i + 1] - bounds[i] for i in range(nch))
+    rows = T + 1
+    g = torch.Generator(device=dev).manual_seed(20260101 + rank)
+    ys, pars = [], []
+    Vs_all, Ws_all = synth_params(B, 20260101 + 1000 * rank, np)
+    for i in range(nch):
+        b0, b1 = bounds[i], bounds[i + 1]
+        Bc = b1 - b0
+        Vs = torch.from_numpy(Vs_all[:, b0:b1].copy()).to(dev)
+        Ws = torch.from_numpy(Ws_all[:, b0:b1].copy()).to(dev)
+        x0 = 10.0 * torch.randn((Bc,), generator=g, device=dev, dtype=torch.float64)
+        x1 = 10.0 * torch.randn((Bc,), generator=g, device=dev, dtype=torch.float64)
+        y = torch.empty((T, 1, Bc), device=dev, dtype=torch.float64)
+        sw0, sw1, sv = Ws[0].sqrt(), Ws[3].sqrt(), Vs[0].sqrt()
+        for t in range(T):
+            x0 = x0 + x1 + sw0 * torch.randn((Bc,), generator=g, device=dev, dtype=torch.float64)
+            x1 = x1 + sw1 * torch.randn((Bc,), generator=g, device=dev, dtype=torch.float64)
+            y[t, 0] = x0 + sv * torch.randn((Bc,), generator=g, device=dev, dtype=torch.float64)
+        ys.append(y)
+        pars.append(dict(V=Vs, W=Ws, m0=np.zeros(2), C0=100.0 * np.eye(2), per_series=("V", "W")))
+    model = Model.build(dlm.polynomial(2), T=T)
+    dims = dict(m=2, C=4, a=2, R=4, f=1, Q=1, s=2, S=4)
+    outbuf = {k: torch.empty((rows, d, Bc_max), device=dev, dtype=torch.float64)
+              for k, d in dims.items()}
+    outbuf["status"] = torch.empty((Bc_max,), device=dev, dtype=torch.int32)
+
+    def views(Bc):
+        if Bc == Bc_max:
+            return outbuf
+        o = {k: outbuf[k].view(-1)[: rows * dims[k] * Bc].view(rows, dims[k], Bc) for k in dims}
+        o["status"] = outbuf["status"][:Bc]
+        return o
+
+    chk = torch.zeros(4, device=dev, dtype=torch.float64)
+
+    def step(timers=None):
+        for i in range(nch):
+            Bc = bounds[i + 1] - bounds[i]
+            if timers is not None:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+            o = eng.filter_smooth(model, pars[i], ys[i], out=views(Bc))
+            if timers is not None:
+                e1.record()
+                timers.append((e0, e1, Bc))
+        chk[0] = o["s"][0, 0, 0]; chk[1] = o["S"][0, 0, 0]; chk[2] = o["m"][-1, 0, 0]
+        chk[3] = o["status"].max().double()
+        if world > 1:
+            dist.all_reduce(chk)  # the only inter-GPU traffic: a 4-double checksum reduce
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    timers = []
+    launches0 = eng.ctx.launch_count()
+    barrier()
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(args.steps):
+        step(timers)
+    t1.record()
+    barrier()
+    ms = t0.elapsed_time(t1)
+    launches = eng.ctx.launch_count() - launches0
+    clocks = sampler.stop() if sampler else None
+    tt = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms = float(tt.item())
+    status_max = float(chk[3].item())
+    kern_ms = [a.elapsed_time(b) for a, b, _ in timers]
+    kern_steps = [bc * T for _, _, bc in timers]
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = sum(kern_steps) * ALGO_BYTES_PER_STEP / (sum(kern_ms) * 1e-3) / 1e9
+    value = world * B * T * args.steps / (ms * 1e-3)
+
+    # ---- e2e: same metric through the C ABI with pinned HOST buffers (H2D + D2H timed)
+    e2e = None
+    if not args.no_e2e:
+        Be = args.e2e_series or B
+        slab = min(Be, 50_000)
+        hy = torch.empty((slab, T, 1), dtype=torch.float64).pin_memory()
+        hy.copy_(torch.randn((slab, T, 1), dtype=torch.float64).cumsum(1))
+        hV = torch.from_numpy(np.ascontiguousarray(Vs_all[:, :slab].T.copy())).pin_memory()
+        hW = torch.from_numpy(np.ascontiguousarray(Ws_all[:, :slab].T.copy())).pin_memory()
+        hout = {k: torch.empty((slab, rows, d), dtype=torch.float64).pin_memory() for k, d in dims.items()}
+        hout["status"] = torch.empty((slab,), dtype=torch.int32).pin_memory()
+        hp = dict(V=hV, W=hW, m0=np.zeros(2), C0=100.0 * np.eye(2), per_series=("V", "W"))
+        from bayesian_dlms_b200 import SERIES_MAJOR
+        ncall = (Be + slab - 1) // slab
+
+        def e2e_step():
+            for _ in range(ncall):
+                eng.filter_smooth(model, hp, hy, layout=SERIES_MAJOR, out=hout)
+
+        e2e_step()  # warm-up (arena allocation, page faults)
+        barrier()
+        w0 = time.perf_counter()
+        ksteps = max(1, min(args.steps, 3))
+        for _ in range(ksteps):
+            e2e_step()
+        barrier()
+        wall = time.perf_counter() - w0
+        wt = torch.tensor([wall], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(wt, op=dist.ReduceOp.MAX)
+        wall = float(wt.item())
+        h2d = ncall * slab * (T * 8 + 5 * 8)
+        d2h = ncall * slab * (rows * sum(dims.values()) * 8 + 4)
+        e2e = {"value": world * ncall * slab * T * ksteps / wall, "unit": "series-steps/s",
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": ksteps,
+               "host_layout": "series-major [B][T+1][k], pinned", "series_per_call": slab,
+               "calls_per_step": ncall}
+
+    if rank == 0:
+        line = {
+            "metric": "filter+smoother series-steps/s", "value": value, "unit": "series-steps/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+            "gpu_launches": int(launches), "clocks": clocks, "status_max": status_max,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None,
+                         "kernel": "kf_small_kernel<2,true> (fused filter+smoother)",
+                         "algorithmic_bytes_per_series_step": ALGO_BYTES_PER_STEP,
+                         "launch_ms_avg": float(np.mean(kern_ms)),
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650"},
+        }
+        if e2e:
+            line["e2e"] = e2e
+        if not args.no_cpu and world >= 1:
+            try:
+                base, _, _ = cpu_reference_leg(B, T)
+                line["cpu_baseline"] = base
+            except Exception as ex:  # the baseline leg must never take the bench line down
+                line["cpu_baseline"] = {"error": repr(ex)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

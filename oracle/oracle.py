@@ -242,8 +242,9 @@ def _stride(x, k, B):
 
 
 def batch_filter_smooth(B, n, p, T, F, G, V, W, m0, C0, times, y, keep_init=True,
-                        nthreads=None):
-    """[B][rows][k] outputs; V/W/m0/C0 either shared (k values) or per series (B*k)."""
+                        nthreads=None, out=None):
+    """[B][rows][k] outputs; V/W/m0/C0 either shared (k values) or per series (B*k).
+    `out` lets a timing loop reuse the output arrays of a previous call."""
     nthreads = nthreads or os.cpu_count()
     rows = T + int(keep_init)
     V, vs = _stride(V, p * p, B)
@@ -251,8 +252,9 @@ def batch_filter_smooth(B, n, p, T, F, G, V, W, m0, C0, times, y, keep_init=True
     m0, ms = _stride(m0, n, B)
     C0, cs = _stride(C0, n * n, B)
     y = _a(y, (B, T, p))
-    out = {k: np.empty((B, rows, d)) for k, d in
-           dict(m=n, C=n * n, a=n, R=n * n, f=p, Q=p * p, s=n, S=n * n).items()}
+    if out is None:
+        out = {k: np.empty((B, rows, d)) for k, d in
+               dict(m=n, C=n * n, a=n, R=n * n, f=p, Q=p * p, s=n, S=n * n).items()}
     L = lib()
     L.oracle_batch_filter_smooth.argtypes = (
         [C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp] +

@@ -1,0 +1,84 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol
+include/bdlm.h declares, and refuses to run without a GPU (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from bayesian_dlms_b200 import _capi as capi
+from bayesian_dlms_b200 import dlm
+from bayesian_dlms_b200.batch import Model
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "bdlm.h")).read()
+    return sorted(set(re.findall(r"BDLM_API[^;(]*?\b(bdlm_[a-z_]+)\s*\(", hdr)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = capi.load()
+    names = _declared_symbols()
+    assert len(names) >= 16
+    for name in names:
+        assert hasattr(lib, name), f"{name} declared in include/bdlm.h but not exported"
+    assert lib.bdlm_version() == 100
+
+
+def test_binding_covers_every_declared_symbol():
+    assert set(_declared_symbols()) == set(capi.SYMBOLS)
+
+
+def test_struct_layout_matches_header():
+    # bdlm_problem: int64 + 10 x int32 + 8 pointers (no padding needed)
+    assert C.sizeof(capi.Problem) == 8 + 10 * 4 + 8 * 8
+    assert C.sizeof(capi.KfOut) == 6 * 8 and C.sizeof(capi.SmoothOut) == 2 * 8
+    assert C.sizeof(capi.SvdOut) == 7 * 8 and C.sizeof(capi.GibbsStats) == 4 * 8
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(capi.BdlmError) as ei:
+        capi.Context(0)
+    assert ei.value.code == capi.E_NODEVICE
+    assert "no CPU fallback" in str(ei.value)
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "bayesian_dlms_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                src = open(os.path.join(dirpath, fn)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), fn
+                assert "liboracle" not in src, fn
+
+
+def test_model_materialisation_flags():
+    m = Model.build(dlm.polynomial(2), T=10)
+    assert (m.n, m.p, m.f_tv, m.g_tv, m.times) == (2, 1, False, False, None)
+    assert np.array_equal(m.G, [1, 0, 1, 1])  # column-major [[1,1],[0,1]]
+    seas = dlm.polynomial(1) + dlm.seasonal(24, 6)
+    m = Model.build(seas, T=5)
+    assert (m.n, m.p, m.g_tv) == (13, 1, False)  # regular grid: one rotation matrix
+    m = Model.build(seas, times=[1.0, 2.0, 3.5, 7.0])
+    assert m.g_tv and m.G.size == 4 * 169 and m.times is not None
+    x = [np.array([0.5]), np.array([1.5]), np.array([2.5])]
+    m = Model.build(dlm.regression(x), T=3)
+    assert m.f_tv and m.F.size == 3 * 2
+    with pytest.raises(ValueError):
+        Model.build(dlm.polynomial(1), times=[])
+
+
+def test_outer_sum_and_compose_shapes():
+    a = dlm.polynomial(1) * dlm.polynomial(1)
+    assert a.f(1.0).shape == (2, 2) and a.g(1.0).shape == (2, 2)
+    b = dlm.polynomial(1) + dlm.seasonal(24, 3)
+    assert b.f(1.0).shape == (7, 1) and b.g(1.0).shape == (7, 7)
+    p = dlm.DlmParameters(3.0, 1.0, 0.0, 1.0) * dlm.DlmParameters(2.0, 1.0, 0.0, 1.0)
+    assert p.v.shape == (2, 2) and p.m0.shape == (2,)

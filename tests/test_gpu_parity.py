@@ -1,0 +1,361 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle.
+
+Bars (north_star): filter / smoother moments and log-likelihood within relative 1e-9 of the
+reference; FFBS bit-for-bit given identical injected N(0,1) draws.  The kernels mirror the
+oracle operation for operation (no FMA), so the moments are in fact compared BIT-EXACTLY
+(``np.array_equal``); only quantities that go through log() carry the 1e-9 tolerance.
+"""
+import numpy as np
+import pytest
+
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import torch
+    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+    from bayesian_dlms_b200 import default_engine
+    return default_engine(0)
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    import oracle as o
+    o.build()
+    return o
+
+
+def _dlm():
+    from bayesian_dlms_b200 import dlm
+    return dlm
+
+
+def _exact(a, b, what=""):
+    a, b = np.asarray(a), np.asarray(b)
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    ok = (a == b) | (np.isnan(a) & np.isnan(b))
+    assert ok.all(), f"{what}: {np.sum(~ok)} of {a.size} differ, max rel {H.rel_err(a[~ok], b[~ok])}"
+
+
+def _cuda(x):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+# ---------------------------------------------------------------- golden CSV, via the mirror API
+
+def test_golden_first_order_through_reference_api(eng):
+    from bayesian_dlms_b200 import Data, DlmParameters, KalmanFilter, Smoothing, polynomial
+    times, y, g = H.first_order_golden()
+    data = [Data(t, [v]) for t, v in zip(times, y[:, 0])]
+    mod = polynomial(1)
+    p = DlmParameters(v=2.0, w=3.0, m0=0.0, c0=10.0)
+    filtered = KalmanFilter.filter(mod, data, p)          # FirstOrderDlm.scala:58-59
+    assert len(filtered) == len(data) + 1 and filtered[0].ft is None
+    _exact([s.time for s in filtered], g["time"], "time")
+    _exact([s.mt[0] for s in filtered], g["m"], "m")
+    _exact([s.ct[0, 0] for s in filtered], g["C"], "C")
+    _exact([s.ft[0] for s in filtered[1:]], g["f"], "f")
+    _exact([s.qt[0, 0] for s in filtered[1:]], g["Q"], "Q")
+    smoothed = Smoothing.backwardsSmoother(mod)(filtered)  # FirstOrderDlm.scala:245-246
+    _exact([s.mean[0] for s in smoothed], g["s"], "s")
+    _exact([s.covariance[0, 0] for s in smoothed], g["S"], "S")
+    dropped = KalmanFilter.filterDlm(mod, data, p)
+    assert len(dropped) == len(data)
+    _exact([s.mt[0] for s in dropped], g["m"][1:], "filterDlm m")
+
+
+def test_kalman_filter_test_known_answers_on_gpu(eng):
+    """KalmanFilterTest (core/src/test/scala/KalmanFilter.scala:79-188) through the mirror."""
+    from bayesian_dlms_b200 import Data, DlmParameters, KalmanFilter, polynomial
+    k = H.kat()["kalman_filter_test"]
+    mod = polynomial(1) * polynomial(1)
+    p = DlmParameters(np.diag(k["v_diag"]), np.diag(k["w_diag"]), k["m0"], np.diag(k["c0_diag"]))
+    data = [Data(t, o) for t, o in zip(k["times"], k["obs"])]
+    out = KalmanFilter.filterDlm(mod, data, p)
+    tol = k["tol"]
+    for idx, exp in k["expected"].items():
+        s = out[int(idx)]
+        for name, got in (("a", s.at), ("f", s.ft), ("m", s.mt)):
+            if name in exp:
+                assert np.allclose(got, exp[name], atol=tol, rtol=0), (idx, name)
+        for name, got in (("R", s.rt), ("Q", s.qt), ("C", s.ct)):
+            if name in exp:
+                assert np.allclose(got, np.diag(exp[name]), atol=tol, rtol=0), (idx, name)
+        if "m0_commented" in exp:
+            assert abs(s.mt[0] - exp["m0_commented"]) < tol
+            assert abs(s.ct[0, 0] - exp["C00_commented"]) < tol
+
+
+def test_empty_data_raises(eng):
+    from bayesian_dlms_b200 import DlmParameters, KalmanFilter, polynomial
+    with pytest.raises(ValueError):
+        KalmanFilter.filterDlm(polynomial(1), [], DlmParameters(1.0, 1.0, 0.0, 1.0))
+
+
+# ---------------------------------------------------------------- batched, both layouts / memory spaces
+
+CASES = {
+    # name: (model factory, T, missing, irregular, B)
+    "first_order": (lambda: (_dlm().polynomial(1), np.array([[2.0]]), np.array([[3.0]]),
+                             np.zeros(1), np.array([[10.0]])), 97, 0.1, False, 70),
+    "second_order": (H.second_order, 64, 0.0, False, 300),
+    "second_order_irregular": (H.second_order, 41, 0.15, True, 65),
+    "third_order": (lambda: (_dlm().polynomial(3), np.array([[1.5]]), np.diag([1.0, 0.5, 0.1]),
+                             np.zeros(3), 10 * np.eye(3)), 33, 0.1, True, 40),
+    "fourth_order": (lambda: (_dlm().polynomial(4), np.array([[1.5]]),
+                              np.diag([1.0, 0.5, 0.1, 0.05]), np.zeros(4), 10 * np.eye(4)),
+                     25, 0.1, False, 33),
+    "kat_bivariate": (lambda: (_dlm().polynomial(1) * _dlm().polynomial(1), 3 * np.eye(2),
+                               np.eye(2), np.zeros(2), np.eye(2)), 30, 0.3, True, 37),
+    "seasonal13": (H.seasonal13, 30, 0.1, False, 9),
+    "seasonal13_irregular": (H.seasonal13, 21, 0.1, True, 5),
+    "correlated8": (H.correlated8, 20, 0.2, True, 7),
+}
+
+
+def _make_case(name, seed=3):
+    make, T, missing, irregular, B = CASES[name]
+    mod, V, W, m0, C0 = make()
+    rng = np.random.default_rng(seed)
+    times = (np.cumsum(rng.choice([0.5, 1.0, 1.0, 2.0, 3.25], size=T)) if irregular
+             else np.arange(1, T + 1, dtype=float))
+    n, p = len(m0), V.shape[0]
+    ys = np.stack([H.simulate(mod, V, W, m0, C0, times, rng, missing) for _ in range(B)])
+    scale = np.exp(rng.uniform(np.log(0.5), np.log(2.0), size=(B, 2)))
+    Vs = np.stack([V * s[0] for s in scale])
+    Ws = np.stack([W * s[1] for s in scale])
+    m0s = rng.standard_normal((B, n))
+    return dict(mod=mod, V=V, W=W, m0=m0, C0=C0, times=times, y=ys, Vs=Vs, Ws=Ws, m0s=m0s,
+                n=n, p=p, T=T, B=B, irregular=irregular)
+
+
+def _oracle_batch(oracle, c, per_series, keep_init=True, textbook=False):
+    dlm = _dlm()
+    F, _, G, _, n, p = dlm.materialise(c["mod"], c["times"])
+    res = []
+    for b in range(c["B"]):
+        V = c["Vs"][b] if per_series else c["V"]
+        W = c["Ws"][b] if per_series else c["W"]
+        m0 = c["m0s"][b] if per_series else c["m0"]
+        o = oracle.kf_filter(n, p, F, G, dlm.cm(V), dlm.cm(W), m0, dlm.cm(c["C0"]), c["times"],
+                             c["y"][b], keep_init=keep_init)
+        s = oracle.rts_smooth(n, G, o, keep_init=keep_init, textbook=textbook)
+        o.update(s=s["s"], S=s["S"])
+        res.append(o)
+    return {k: np.stack([r[k] for r in res]) for k in ("m", "C", "a", "R", "f", "Q", "s", "S")}
+
+
+def _params(c, per_series, layout, to):
+    dlm = _dlm()
+    from bayesian_dlms_b200 import TIME_MAJOR
+    if not per_series:
+        return dict(V=c["V"], W=c["W"], m0=c["m0"], C0=c["C0"])
+    Vs = np.stack([dlm.cm(v) for v in c["Vs"]])
+    Ws = np.stack([dlm.cm(w) for w in c["Ws"]])
+    m0s = c["m0s"]
+    if layout == TIME_MAJOR:
+        Vs, Ws, m0s = Vs.T, Ws.T, m0s.T
+    return dict(V=to(Vs), W=to(Ws), m0=to(m0s), C0=c["C0"], per_series=("V", "W", "m0"))
+
+
+def _to_layout(x_bm, layout):
+    """[B][rows][k] -> requested layout."""
+    from bayesian_dlms_b200 import TIME_MAJOR
+    return np.ascontiguousarray(np.transpose(x_bm, (1, 2, 0))) if layout == TIME_MAJOR else x_bm
+
+
+def _from_layout(x, layout):
+    from bayesian_dlms_b200 import TIME_MAJOR
+    x = x.cpu().numpy() if hasattr(x, "cpu") else np.asarray(x)
+    return np.transpose(x, (2, 0, 1)) if layout == TIME_MAJOR else x
+
+
+@pytest.mark.parametrize("name", list(CASES))
+@pytest.mark.parametrize("layout_name", ["time_major", "series_major"])
+@pytest.mark.parametrize("mem", ["device", "host"])
+def test_filter_smooth_bit_exact(eng, oracle, name, layout_name, mem):
+    from bayesian_dlms_b200 import Model, SERIES_MAJOR, TIME_MAJOR
+    layout = TIME_MAJOR if layout_name == "time_major" else SERIES_MAJOR
+    c = _make_case(name)
+    per_series = name != "kat_bivariate"
+    to = _cuda if mem == "device" else np.ascontiguousarray
+    model = Model.build(c["mod"], c["times"] if c["irregular"] else None, T=c["T"])
+    y = to(_to_layout(c["y"], layout))
+    params = _params(c, per_series, layout, to)
+    exp = _oracle_batch(oracle, c, per_series)
+    out = eng.filter_smooth(model, params, y, layout=layout, keep_init=True)
+    eng.sync()
+    for k in ("m", "C", "a", "R", "f", "Q", "s", "S"):
+        _exact(_from_layout(out[k], layout), exp[k], f"{name}/{k}")
+    st = out["status"].cpu().numpy() if hasattr(out["status"], "cpu") else out["status"]
+    assert (st == 0).all()
+    # separate filter then smoother calls give the same bits as the fused call
+    f = eng.filter(model, params, y, layout=layout, keep_init=True)
+    s = eng.smooth(model, params, f, layout=layout, keep_init=True)
+    eng.sync()
+    for k in ("m", "C", "a", "R"):
+        _exact(_from_layout(f[k], layout), exp[k], f"{name}/filter/{k}")
+    for k in ("s", "S"):
+        _exact(_from_layout(s[k], layout), exp[k], f"{name}/smooth/{k}")
+
+
+@pytest.mark.parametrize("name", ["second_order", "kat_bivariate", "seasonal13"])
+def test_filter_dlm_drops_initial_state_and_textbook_mode(eng, oracle, name):
+    from bayesian_dlms_b200 import Model, TIME_MAJOR
+    c = _make_case(name)
+    model = Model.build(c["mod"], c["times"] if c["irregular"] else None, T=c["T"])
+    y = _cuda(_to_layout(c["y"], TIME_MAJOR))
+    params = _params(c, False, TIME_MAJOR, _cuda)
+    exp = _oracle_batch(oracle, c, False, keep_init=False, textbook=True)
+    out = eng.filter_smooth(model, params, y, keep_init=False, textbook=True)
+    eng.sync()
+    for k in ("m", "C", "a", "R", "f", "Q", "s", "S"):
+        got = _from_layout(out[k], TIME_MAJOR)
+        assert got.shape[1] == c["T"]
+        _exact(got, exp[k], f"{name}/{k}")
+    # lean outputs: only the smoother result requested, spill goes to workspace
+    lean = eng.filter_smooth(model, params, y, keep_init=False, textbook=True, want=("s", "S"))
+    eng.sync()
+    assert set(lean) == {"s", "S", "status"}
+    _exact(_from_layout(lean["S"], TIME_MAJOR), exp["S"], f"{name}/lean S")
+
+
+@pytest.mark.parametrize("name", ["first_order", "second_order_irregular", "kat_bivariate",
+                                  "seasonal13", "correlated8"])
+def test_loglik_matches_oracle(eng, oracle, name):
+    from bayesian_dlms_b200 import Model, SERIES_MAJOR
+    dlm = _dlm()
+    c = _make_case(name)
+    model = Model.build(c["mod"], c["times"] if c["irregular"] else None, T=c["T"])
+    out = eng.loglik(model, _params(c, False, SERIES_MAJOR, _cuda), _cuda(c["y"]),
+                     layout=SERIES_MAJOR)
+    eng.sync()
+    F, _, G, _, n, p = dlm.materialise(c["mod"], c["times"])
+    tr, inn = out["transition"].cpu().numpy(), out["innovations"].cpu().numpy()
+    for b in range(c["B"]):
+        o = oracle.loglik(n, p, F, G, dlm.cm(c["V"]), dlm.cm(c["W"]), c["m0"], dlm.cm(c["C0"]),
+                          c["times"], c["y"][b])
+        assert abs(tr[b] - o["transition"]) <= TOL * abs(o["transition"]), (b, tr[b], o)
+        assert abs(inn[b] - o["innovations"]) <= TOL * abs(o["innovations"]), (b, inn[b], o)
+
+
+@pytest.mark.parametrize("name", ["first_order", "second_order", "second_order_irregular",
+                                  "kat_bivariate", "seasonal13", "seasonal13_irregular",
+                                  "correlated8"])
+@pytest.mark.parametrize("svd", [False, True])
+def test_ffbs_bit_for_bit_with_injected_normals(eng, oracle, name, svd):
+    from bayesian_dlms_b200 import Model, SERIES_MAJOR, TIME_MAJOR
+    dlm = _dlm()
+    c = _make_case(name)
+    if svd and name == "correlated8":
+        c["V"] = np.diag([1.0, 4.0, 1.5, 4.5, 2.0, 5.0, 2.5, 5.5])  # see oracle test (Q6)
+    n, p, T, B = c["n"], c["p"], c["T"], c["B"]
+    rng = np.random.default_rng(17)
+    z = rng.standard_normal((B, T + 1, n))
+    model = Model.build(c["mod"], c["times"] if c["irregular"] else None, T=T)
+    F, _, G, _, _, _ = dlm.materialise(c["mod"], c["times"])
+    tr = np.concatenate([[c["times"].min() - 1.0], c["times"]])
+    for layout in (SERIES_MAJOR, TIME_MAJOR):
+        out = eng.ffbs(model, _params(c, False, layout, _cuda), _cuda(_to_layout(c["y"], layout)),
+                       _cuda(_to_layout(z, layout)), layout=layout, stats=True, svd=svd)
+        eng.sync()
+        theta = _from_layout(out["theta"], layout)
+        st = out["status"].cpu().numpy()
+        assert (st == 0).all(), st
+        for b in range(B):
+            fn = oracle.svd_ffbs if svd else oracle.ffbs
+            o = fn(n, p, F, G, dlm.cm(c["V"]), dlm.cm(c["W"]), c["m0"], dlm.cm(c["C0"]),
+                   c["times"], c["y"][b], z[b])
+            assert o["status"] == 0
+            _exact(theta[b], o["theta"], f"{name}/theta[{b}]")
+            gs = oracle.gibbs_stats(n, p, F, G, tr, c["y"][b], o["theta"])
+            for key in ("ssy", "ny", "ssw", "scatter"):
+                got = out[key].cpu().numpy()
+                got = got[:, b] if layout == TIME_MAJOR else got[b]
+                _exact(got, gs[key], f"{name}/{key}[{b}]")
+
+
+@pytest.mark.parametrize("name", ["second_order", "kat_bivariate", "seasonal13", "correlated8"])
+@pytest.mark.parametrize("consistent", [False, True])
+def test_svd_filter_bit_exact(eng, oracle, name, consistent):
+    from bayesian_dlms_b200 import Model, SERIES_MAJOR
+    dlm = _dlm()
+    c = _make_case(name)
+    if name == "correlated8":
+        c["V"] = np.diag([1.0, 4.0, 1.5, 4.5, 2.0, 5.0, 2.5, 5.5])
+    n, p = c["n"], c["p"]
+    model = Model.build(c["mod"], c["times"] if c["irregular"] else None, T=c["T"])
+    out = eng.svd_filter(model, _params(c, False, SERIES_MAJOR, _cuda), _cuda(c["y"]),
+                         layout=SERIES_MAJOR, keep_init=True, consistent_w=consistent)
+    eng.sync()
+    F, _, G, _, _, _ = dlm.materialise(c["mod"], c["times"])
+    sqrtW = oracle.sqrt_svd(dlm.cm(c["W"]))
+    for b in range(c["B"]):
+        o = oracle.svd_filter(n, p, F, G, dlm.cm(c["V"]), sqrtW if consistent else dlm.cm(c["W"]),
+                              c["m0"], dlm.cm(c["C0"]), c["times"], c["y"][b])
+        for k in ("m", "dc", "uc", "a", "dr", "ur", "f"):
+            _exact(out[k][b].cpu().numpy(), o[k], f"{name}/svd {k}[{b}]")
+
+
+def test_singular_and_nonfinite_are_flagged_not_fatal(eng):
+    """A series whose Q is exactly zero is reported in status[b]; the rest of the batch is fine."""
+    from bayesian_dlms_b200 import Model, SERIES_MAJOR, _capi as capi
+    dlm = _dlm()
+    model = Model.build(dlm.polynomial(1), T=5)
+    y = np.ones((3, 5, 1))
+    V = np.array([[1.0], [0.0], [1.0]])       # series 1: V = W = C0 = 0 -> Q = 0
+    W = np.array([[1.0], [0.0], [1.0]])
+    C0 = np.array([[1.0], [0.0], [1.0]])
+    params = dict(V=V, W=W, m0=np.zeros(1), C0=C0, per_series=("V", "W", "C0"))
+    out = eng.filter(model, params, np.ascontiguousarray(y), layout=SERIES_MAJOR)
+    st = out["status"]
+    assert st[0] == 0 and st[2] == 0
+    assert st[1] & capi.ST_SINGULAR and st[1] & capi.ST_NONFINITE
+    assert np.isfinite(out["m"][0]).all() and np.isfinite(out["m"][2]).all()
+
+
+def test_large_batch_properties_config2_shape(eng, oracle):
+    """Config-2-shaped run (polynomial(2), T = 1000) at a batch too large for the oracle:
+    size-independent properties + oracle spot checks on a few series."""
+    import torch
+    from bayesian_dlms_b200 import Model, TIME_MAJOR
+    dlm = _dlm()
+    mod, V, W, m0, C0 = H.second_order()
+    T, B = 1000, 20000
+    g = torch.Generator(device="cuda").manual_seed(20260101)
+    y = torch.randn((T, 1, B), generator=g, device="cuda", dtype=torch.float64).cumsum(0)
+    scale = torch.exp(torch.rand((2, B), generator=g, device="cuda", dtype=torch.float64) * 1.386 - 0.693)
+    Vs = (3.0 * scale[0:1]).contiguous()
+    Ws = (torch.tensor([2.0, 0.0, 0.0, 1.0], device="cuda", dtype=torch.float64)[:, None] * scale[1:2]).contiguous()
+    params = dict(V=Vs, W=Ws, m0=m0, C0=C0, per_series=("V", "W"))
+    model = Model.build(mod, T=T)
+    out = eng.filter_smooth(model, params, y)
+    eng.sync()
+    assert int(out["status"].abs().max()) == 0
+    m, C, a, R, s, S = (out[k] for k in ("m", "C", "a", "R", "s", "S"))
+    # last smoothed state equals last filtered state; row 0 is the prior
+    assert torch.equal(s[-1], m[-1]) and torch.equal(S[-1], C[-1])
+    assert torch.equal(m[0], torch.zeros_like(m[0])) and torch.equal(C[0, 0], torch.full_like(C[0, 0], 100.0))
+    # a_t = G m_{t-1} exactly (G = [[1,1],[0,1]]): a0 = m0 + m1, a1 = m1
+    assert torch.equal(a[1:, 0], m[:-1, 0] + m[:-1, 1]) and torch.equal(a[1:, 1], m[:-1, 1])
+    # f = F^T a = a0 ; Q = R00 + V ; covariances stay symmetric positive
+    assert torch.equal(out["f"][1:, 0], a[1:, 0])
+    assert torch.equal(out["Q"][1:, 0], R[1:, 0] + Vs)
+    assert (C[:, 0] > 0).all() and (C[:, 3] > 0).all()
+    assert torch.allclose(C[:, 1], C[:, 2], rtol=1e-9, atol=1e-12)
+    # spot-check series against the oracle, bit for bit
+    F, _, G, _, n, p = dlm.materialise(mod, np.arange(1, T + 1.0))
+    for b in (0, 1, 777, B - 1):
+        o = oracle.kf_filter(2, 1, F, G, [float(Vs[0, b])], Ws[:, b].cpu().numpy(), m0, dlm.cm(C0),
+                             np.arange(1, T + 1.0), y[:, :, b].cpu().numpy())
+        sm = oracle.rts_smooth(2, G, o)
+        _exact(m[:, :, b].cpu().numpy(), o["m"], "m")
+        _exact(C[:, :, b].cpu().numpy(), o["C"], "C")
+        _exact(s[:, :, b].cpu().numpy(), sm["s"], "s")
+        _exact(S[:, :, b].cpu().numpy(), sm["S"], "S")
