@@ -81,7 +81,7 @@ def load():
     lib.bdlm_destroy.restype = None
     lib.bdlm_last_error.argtypes = [C.c_void_p]
     lib.bdlm_last_error.restype = C.c_char_p
-    lib.bdlm_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+    lib.bdlm_set_stream.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     lib.bdlm_sync.argtypes = [C.c_void_p]
     lib.bdlm_launch_count.argtypes = [C.c_void_p]
     lib.bdlm_launch_count.restype = C.c_int64
@@ -136,7 +136,11 @@ class Context:
         return rc
 
     def set_stream(self, cuda_stream_handle):
-        self.check(load().bdlm_set_stream(self._h, C.c_void_p(cuda_stream_handle or 0)))
+        """Adopt a cudaStream_t handle (0 = legacy default stream); None = own stream."""
+        if cuda_stream_handle is None:
+            self.check(load().bdlm_set_stream(self._h, None, 1))
+        else:
+            self.check(load().bdlm_set_stream(self._h, C.c_void_p(int(cuda_stream_handle)), 0))
 
     def sync(self):
         self.check(load().bdlm_sync(self._h))

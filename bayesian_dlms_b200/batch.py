@@ -55,6 +55,18 @@ class Model:
                      None if regular else tgrid)
 
 
+_engines_by_device = {}
+
+
+def _adopt_torch_stream(x):
+    """Device-mode calls are enqueued on torch's CURRENT stream of the tensor's device, so they
+    are ordered with the torch ops that produced the inputs and consume the outputs."""
+    import torch
+    eng = _engines_by_device.get(x.device.index)
+    if eng is not None:
+        eng.ctx.set_stream(torch.cuda.current_stream(x.device).cuda_stream)
+
+
 def _is_torch(x):
     return type(x).__module__.startswith("torch")
 
@@ -63,6 +75,8 @@ def _mem_and_ptr(x):
     if x is None:
         return None, None
     if _is_torch(x):
+        if x.is_cuda:
+            _adopt_torch_stream(x)
         assert x.is_contiguous() and str(x.dtype) in ("torch.float64", "torch.int32"), \
             "contiguous fp64 tensors only"
         return (capi.DEVICE if x.is_cuda else capi.HOST), x.data_ptr()
@@ -86,6 +100,7 @@ class Engine:
     def __init__(self, device: int = 0):
         self.ctx = capi.Context(device)
         self.device = device
+        _engines_by_device[device] = self  # latest engine of a device adopts torch's stream
 
     # ------------------------------------------------------------------ helpers
     def use_torch_stream(self):

@@ -549,9 +549,9 @@ void bdlm_destroy(bdlm_ctx *c) {
 
 const char *bdlm_last_error(bdlm_ctx *c) { return c ? c->err.c_str() : g_create_err.c_str(); }
 
-int bdlm_set_stream(bdlm_ctx *c, void *s) {
+int bdlm_set_stream(bdlm_ctx *c, void *s, int use_own) {
   if (!c) return BDLM_E_ARG;
-  c->stream = s ? reinterpret_cast<cudaStream_t>(s) : c->own_stream;
+  c->stream = use_own ? c->own_stream : reinterpret_cast<cudaStream_t>(s);
   return 0;
 }
 

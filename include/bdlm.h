@@ -150,9 +150,10 @@ BDLM_API int bdlm_create(int device, bdlm_ctx **out);
 BDLM_API void bdlm_destroy(bdlm_ctx *ctx);
 BDLM_API const char *bdlm_last_error(bdlm_ctx *ctx); /* ctx may be NULL: last create error */
 BDLM_API int bdlm_version(void);
-/* Adopt a caller-owned cudaStream_t (e.g. torch's current stream); NULL restores the
- * context's own stream. */
-BDLM_API int bdlm_set_stream(bdlm_ctx *ctx, void *cuda_stream);
+/* Adopt a caller-owned cudaStream_t (e.g. torch's current stream).  The handle is used
+ * as given: NULL is the legacy default stream.  use_own != 0 ignores the handle and
+ * restores the context's own (non-blocking) stream. */
+BDLM_API int bdlm_set_stream(bdlm_ctx *ctx, void *cuda_stream, int use_own);
 BDLM_API int bdlm_sync(bdlm_ctx *ctx);
 /* Kernel launches issued by this context since creation (bench.py's gpu_launches). */
 BDLM_API int64_t bdlm_launch_count(bdlm_ctx *ctx);
