@@ -27,7 +27,7 @@ SYMBOLS = [
     "bdlm_create", "bdlm_destroy", "bdlm_last_error", "bdlm_version", "bdlm_set_stream",
     "bdlm_sync", "bdlm_launch_count", "bdlm_set_staging_bytes", "bdlm_kf_filter",
     "bdlm_rts_smooth", "bdlm_kf_filter_smooth", "bdlm_loglik", "bdlm_ffbs",
-    "bdlm_svd_filter", "bdlm_svd_ffbs", "bdlm_gibbs_suffstats",
+    "bdlm_svd_filter", "bdlm_svd_ffbs", "bdlm_gibbs_suffstats", "bdlm_wave_series",
 ]
 
 
@@ -86,6 +86,8 @@ def load():
     lib.bdlm_launch_count.argtypes = [C.c_void_p]
     lib.bdlm_launch_count.restype = C.c_int64
     lib.bdlm_set_staging_bytes.argtypes = [C.c_void_p, C.c_int64]
+    lib.bdlm_wave_series.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
+    lib.bdlm_wave_series.restype = C.c_int64
     PP = C.POINTER(Problem)
     lib.bdlm_kf_filter.argtypes = [C.c_void_p, PP, C.POINTER(KfOut), C.c_void_p]
     lib.bdlm_rts_smooth.argtypes = [C.c_void_p, PP, C.POINTER(KfOut), C.POINTER(SmoothOut),
@@ -147,6 +149,10 @@ class Context:
 
     def launch_count(self) -> int:
         return int(load().bdlm_launch_count(self._h))
+
+    def wave_series(self, n: int, p: int) -> int:
+        """Series per full wave of the fused filter+smoother register kernel."""
+        return int(self.check(load().bdlm_wave_series(self._h, int(n), int(p))))
 
     def set_staging_bytes(self, nbytes: int):
         self.check(load().bdlm_set_staging_bytes(self._h, int(nbytes)))

@@ -564,6 +564,19 @@ int bdlm_sync(bdlm_ctx *c) {
 
 int64_t bdlm_launch_count(bdlm_ctx *c) { return c ? c->launches : 0; }
 
+int64_t bdlm_wave_series(bdlm_ctx *c, int32_t n, int32_t p) {
+  if (!c) return BDLM_E_ARG;
+  if (!small_supported(n, p)) return fail(c, BDLM_E_ARG, "wave query: warp-kernel dimensions");
+  CU(cudaSetDevice(c->device));
+  Batch bt{};
+  bt.n = n; bt.p = p;
+  KfViews kv{};
+  View v{nullptr, 0, 0, 0};
+  int wave = 0;
+  CU(launch_kf_small(bt, nullptr, nullptr, kv, v, v, true, true, c->stream, &wave));
+  return wave;
+}
+
 int bdlm_set_staging_bytes(bdlm_ctx *c, int64_t bytes) {
   if (!c || bytes < ((int64_t)1 << 20)) return BDLM_E_ARG;
   c->staging_cap = (size_t)bytes;

@@ -252,13 +252,21 @@ __device__ __forceinline__ void load_model(const Batch &bt, const SmallModel<N> 
 
 constexpr int kChunk = 4;  // y prefetch distance (steps)
 
-// mode bits
+// mode bits (compile-time: a runtime branch between "recompute a,R" and "reload a,R" made
+// ptxas put the prefetch loads and the reload loads on one scoreboard slot and wait for it
+// at the merge point, which serialised the (m, C) prefetch with the recursion)
 constexpr int kDoFilter = 1, kDoSmooth = 2;
 
-template <int N, bool REG>
-__global__ void __launch_bounds__(128)
+// Minimum resident blocks per SM asked of ptxas (register cap = 65536 / (128 * blocks)).
+template <int N> struct Occ { static constexpr int kMinBlocks = 1; };
+template <> struct Occ<1> { static constexpr int kMinBlocks = 6; };
+template <> struct Occ<2> { static constexpr int kMinBlocks = 5; };
+template <> struct Occ<3> { static constexpr int kMinBlocks = 2; };
+
+template <int N, bool REG, int MODE, bool RELOAD>
+__global__ void __launch_bounds__(128, Occ<N>::kMinBlocks)
 kf_small_kernel(const Batch bt, const SmallModel<N> mdl, const KfViews kf, const View sv,
-                const View Sv, const int mode) {
+                const View Sv) {
   const int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (b >= bt.B) return;
   const int T = bt.T, ki = bt.keep_init, rows = T + ki;
@@ -269,7 +277,7 @@ kf_small_kernel(const Batch bt, const SmallModel<N> mdl, const KfViews kf, const
   load_param<N * N>(bt.W, b, W);
   load_param<1>(bt.V, b, &V);
 
-  if (mode & kDoFilter) {
+  if (MODE & kDoFilter) {
     load_param<N>(bt.m0, b, m);
     load_param<N * N>(bt.C0, b, C);
     if (ki) {  // initialiseState (KalmanFilter.scala:112-118): f, Q = None -> NaN
@@ -318,7 +326,7 @@ kf_small_kernel(const Batch bt, const SmallModel<N> mdl, const KfViews kf, const
     load_vec<N * N>(kf.C, b, rows - 1, C);
   }
 
-  if (mode & kDoSmooth) {
+  if (MODE & kDoSmooth) {
     // backwardsSmoother (Smoothing.scala:57-64): s_T = m_T, S_T = C_T
     double s[N], S[N * N];
 #pragma unroll
@@ -328,32 +336,40 @@ kf_small_kernel(const Batch bt, const SmallModel<N> mdl, const KfViews kf, const
     store_vec<N>(sv, b, rows - 1, s);
     store_vec<N * N>(Sv, b, rows - 1, S);
     const bool textbook = (bt.compat & BDLM_TEXTBOOK_SMOOTHER) != 0;
-    const bool reload_ar = !(mode & kDoFilter) && kf.a.ptr != nullptr && kf.R.ptr != nullptr;
-    double mn[N], Cn[N * N];
+    double mn[N], Cn[N * N], an[N], Rn[N * N];
     if (rows >= 2) {
       load_vec<N>(kf.m, b, rows - 2, mn);
       load_vec<N * N>(kf.C, b, rows - 2, Cn);
+      if (RELOAD) {
+        load_vec<N>(kf.a, b, rows - 1, an);
+        load_vec<N * N>(kf.R, b, rows - 1, Rn);
+      }
     }
     for (int r = rows - 2; r >= 0; --r) {
+      double a1[N], R1[N * N];
 #pragma unroll
       for (int i = 0; i < N; ++i) m[i] = mn[i];
 #pragma unroll
       for (int k = 0; k < N * N; ++k) C[k] = Cn[k];
+      if (RELOAD) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) a1[i] = an[i];
+#pragma unroll
+        for (int k = 0; k < N * N; ++k) R1[k] = Rn[k];
+      }
       if (r > 0) {  // prefetch the next row of the spill while this one is processed
         load_vec<N>(kf.m, b, r - 1, mn);
         load_vec<N * N>(kf.C, b, r - 1, Cn);
+        if (RELOAD) {
+          load_vec<N>(kf.a, b, r, an);
+          load_vec<N * N>(kf.R, b, r, Rn);
+        }
       }
       const int tobs = r + 1 - ki;  // observation index of row r + 1
       const double dt = REG ? 1.0 : (bt.dt ? bt.dt[tobs] : 1.0);
       double G[N * N], F[N];
       load_model<N, REG>(bt, mdl, tobs, G, F);
-      double a1[N], R1[N * N];
-      if (reload_ar) {
-        load_vec<N>(kf.a, b, r + 1, a1);
-        load_vec<N * N>(kf.R, b, r + 1, R1);
-      } else {
-        advance<N, REG>(G, W, dt, m, C, a1, R1);  // bit-identical to the forward a, R
-      }
+      if (!RELOAD) advance<N, REG>(G, W, dt, m, C, a1, R1);  // bit-identical to the forward a, R
       rts_step<N>(G, m, C, a1, R1, textbook, s, S, st);
       store_vec<N>(sv, b, r, s);
       store_vec<N * N>(Sv, b, r, S);
@@ -375,21 +391,45 @@ kf_small_kernel(const Batch bt, const SmallModel<N> mdl, const KfViews kf, const
   }
 }
 
+constexpr int kThreads = 128;
+
+template <int N, bool REG, int MODE, bool RELOAD>
+cudaError_t launch_t(const Batch &bt, const SmallModel<N> &mdl, const KfViews &kf, const View &sv,
+                     const View &Sv, cudaStream_t stream, int *wave_series) {
+  if (wave_series) {  // occupancy query only
+    int blocks = 0, dev = 0, sms = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+        &blocks, kf_small_kernel<N, REG, MODE, RELOAD>, kThreads, 0);
+    if (e != cudaSuccess) return e;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    *wave_series = blocks * sms * kThreads;
+    return cudaSuccess;
+  }
+  const int64_t blocks = (bt.B + kThreads - 1) / kThreads;
+  if (blocks <= 0) return cudaSuccess;
+  kf_small_kernel<N, REG, MODE, RELOAD><<<(unsigned)blocks, kThreads, 0, stream>>>(bt, mdl, kf, sv, Sv);
+  return cudaGetLastError();
+}
+
 template <int N>
 cudaError_t launch_n(const Batch &bt, const double *hG, const double *hF, const KfViews &kf,
-                     const View &sv, const View &Sv, int mode, cudaStream_t stream) {
+                     const View &sv, const View &Sv, int mode, cudaStream_t stream,
+                     int *wave_series) {
   SmallModel<N> mdl;
-  for (int k = 0; k < N * N; ++k) mdl.G[k] = hG[k];
-  for (int k = 0; k < N; ++k) mdl.F[k] = hF[k];
+  for (int k = 0; k < N * N; ++k) mdl.G[k] = hG ? hG[k] : 0.0;
+  for (int k = 0; k < N; ++k) mdl.F[k] = hF ? hF[k] : 0.0;
   const bool reg = bt.dt == nullptr && !bt.g_tv && !bt.f_tv;
-  const int threads = 128;
-  const int64_t blocks = (bt.B + threads - 1) / threads;
-  if (blocks <= 0) return cudaSuccess;
-  if (reg)
-    kf_small_kernel<N, true><<<(unsigned)blocks, threads, 0, stream>>>(bt, mdl, kf, sv, Sv, mode);
-  else
-    kf_small_kernel<N, false><<<(unsigned)blocks, threads, 0, stream>>>(bt, mdl, kf, sv, Sv, mode);
-  return cudaGetLastError();
+  const bool reload = mode == kDoSmooth && kf.a.ptr != nullptr && kf.R.ptr != nullptr;
+#define BDLM_GO(REG_, MODE_, RELOAD_) \
+  return launch_t<N, REG_, MODE_, RELOAD_>(bt, mdl, kf, sv, Sv, stream, wave_series)
+  if (mode == kDoFilter) { if (reg) BDLM_GO(true, kDoFilter, false); else BDLM_GO(false, kDoFilter, false); }
+  if (mode == (kDoFilter | kDoSmooth)) {
+    if (reg) BDLM_GO(true, kDoFilter | kDoSmooth, false); else BDLM_GO(false, kDoFilter | kDoSmooth, false);
+  }
+  if (reload) { if (reg) BDLM_GO(true, kDoSmooth, true); else BDLM_GO(false, kDoSmooth, true); }
+  if (reg) BDLM_GO(true, kDoSmooth, false); else BDLM_GO(false, kDoSmooth, false);
+#undef BDLM_GO
 }
 
 }  // namespace
@@ -398,13 +438,14 @@ bool small_supported(int n, int p) { return p == 1 && n >= 1 && n <= 4; }
 
 cudaError_t launch_kf_small(const Batch &bt, const double *hG, const double *hF,
                             const KfViews &kf, const View &sv, const View &Sv,
-                            bool do_filter, bool do_smooth, cudaStream_t stream) {
+                            bool do_filter, bool do_smooth, cudaStream_t stream,
+                            int *wave_series) {
   const int mode = (do_filter ? kDoFilter : 0) | (do_smooth ? kDoSmooth : 0);
   switch (bt.n) {
-    case 1: return launch_n<1>(bt, hG, hF, kf, sv, Sv, mode, stream);
-    case 2: return launch_n<2>(bt, hG, hF, kf, sv, Sv, mode, stream);
-    case 3: return launch_n<3>(bt, hG, hF, kf, sv, Sv, mode, stream);
-    case 4: return launch_n<4>(bt, hG, hF, kf, sv, Sv, mode, stream);
+    case 1: return launch_n<1>(bt, hG, hF, kf, sv, Sv, mode, stream, wave_series);
+    case 2: return launch_n<2>(bt, hG, hF, kf, sv, Sv, mode, stream, wave_series);
+    case 3: return launch_n<3>(bt, hG, hF, kf, sv, Sv, mode, stream, wave_series);
+    case 4: return launch_n<4>(bt, hG, hF, kf, sv, Sv, mode, stream, wave_series);
     default: return cudaErrorInvalidValue;
   }
 }

@@ -8,7 +8,8 @@ namespace bdlm {
 bool small_supported(int n, int p);
 cudaError_t launch_kf_small(const Batch &bt, const double *hG, const double *hF,
                             const KfViews &kf, const View &sv, const View &Sv,
-                            bool do_filter, bool do_smooth, cudaStream_t stream);
+                            bool do_filter, bool do_smooth, cudaStream_t stream,
+                            int *wave_series = nullptr);  // non-null: occupancy query only
 
 // kf_warp.cu: warp-per-series shared-memory kernels (any n, p <= 32).
 struct SvdViews {

@@ -40,7 +40,9 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--series", type=int, default=1_000_000, help="series per GPU")
     ap.add_argument("--T", type=int, default=1000)
-    ap.add_argument("--chunks", type=int, default=4)
+    ap.add_argument("--chunks", type=int, default=0,
+                    help="launches per step; 0 = launches of --waves full waves each")
+    ap.add_argument("--waves", type=int, default=3, help="full GPU waves per launch")
     ap.add_argument("--e2e-series", type=int, default=0,
                     help="series per e2e step (0 = same as --series)")
     ap.add_argument("--no-e2e", action="store_true")
@@ -182,8 +184,17 @@ def main():
     eng.use_torch_stream()
 
     # ---- synthetic inputs, resident in HBM (Dlm.simStep generative model, Dlm.scala:245-282)
-    nch = args.chunks
-    bounds = [(i * B) // nch for i in range(nch + 1)]
+    if args.chunks > 0:
+        nch = args.chunks
+        bounds = [(i * B) // nch for i in range(nch + 1)]
+    else:
+        # every series of a launch takes the same time: launches that are whole waves
+        # (resident blocks x SMs x 128 series) leave no partially filled last wave
+        per = args.waves * eng.ctx.wave_series(N_STATE, N_OBS)
+        bounds = list(range(0, B, per)) + [B]
+        nch = len(bounds) - 1
+    config["chunks_per_step"] = nch
+    config["series_per_launch"] = bounds[1] - bounds[0]
     Bc_max = max(bounds[i + 1] - bounds[i] for i in range(nch))
     rows = T + 1
     g = torch.Generator(device=dev).manual_seed(20260101 + rank)

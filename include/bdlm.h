@@ -159,6 +159,12 @@ BDLM_API int bdlm_sync(bdlm_ctx *ctx);
 BDLM_API int64_t bdlm_launch_count(bdlm_ctx *ctx);
 /* Cap on the device bytes a mem = BDLM_HOST call may use for staging (default 8 GiB). */
 BDLM_API int bdlm_set_staging_bytes(bdlm_ctx *ctx, int64_t bytes);
+/* Series that exactly fill the GPU once ("one wave") for the fused filter+smoother kernel
+ * of a model with these dimensions on a regular grid: resident blocks per SM x SM count x
+ * threads per block.  Every series of a launch takes the same time, so batches (or slabs)
+ * that are a multiple of this number leave no partially filled last wave.  Returns
+ * BDLM_E_ARG for dimensions served by the warp-per-series kernels (wave = resident warps). */
+BDLM_API int64_t bdlm_wave_series(bdlm_ctx *ctx, int32_t n, int32_t p);
 
 /* ---- forward filter ----------------------------------------------------------------
  * KalmanFilter.filterDlm (KalmanFilter.scala:291-294) / KalmanFilter(adv).filter
