@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libbdlm.so")
+LIB_PATH = os.environ.get("BDLM_LIB_PATH") or os.path.join(HERE, "libbdlm.so")
 
 TIME_MAJOR, SERIES_MAJOR = 0, 1
 DEVICE, HOST = 0, 1

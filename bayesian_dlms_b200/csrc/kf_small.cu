@@ -214,6 +214,21 @@ __device__ __forceinline__ void load_vec(const View &v, int64_t b, int64_t row, 
   for (int k = 0; k < K; ++k) x[k] = ld_stream(p + k * v.sk);
 }
 
+// L2 prefetch (no destination register, no scoreboard slot): DRAM latency under the
+// write-heavy load of this kernel is several thousand cycles, more than one backward
+// iteration, so rows are pulled into L2 a few iterations before the register prefetch.
+template <int K>
+__device__ __forceinline__ void prefetch_vec(const View &v, int64_t b, int64_t row) {
+  const double *p = v.ptr + b * v.sb + row * v.sr;
+#pragma unroll
+  for (int k = 0; k < K; ++k) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + k * v.sk));
+}
+
+#ifndef BDLM_L2_AHEAD
+#define BDLM_L2_AHEAD 1000000 /* measured on B200: L2 prefetch 3/6 rows ahead is 5% SLOWER (profiles/r1_tuning.txt) */
+#endif
+constexpr int kL2Ahead = BDLM_L2_AHEAD;
+
 template <int K>
 __device__ __forceinline__ void load_param(const PView &v, int64_t b, double *x) {
   const double *p = v.ptr + b * v.sb;
@@ -260,7 +275,10 @@ constexpr int kDoFilter = 1, kDoSmooth = 2;
 // Minimum resident blocks per SM asked of ptxas (register cap = 65536 / (128 * blocks)).
 template <int N> struct Occ { static constexpr int kMinBlocks = 1; };
 template <> struct Occ<1> { static constexpr int kMinBlocks = 6; };
-template <> struct Occ<2> { static constexpr int kMinBlocks = 5; };
+#ifndef BDLM_OCC2
+#define BDLM_OCC2 5
+#endif
+template <> struct Occ<2> { static constexpr int kMinBlocks = BDLM_OCC2; };
 template <> struct Occ<3> { static constexpr int kMinBlocks = 2; };
 
 template <int N, bool REG, int MODE, bool RELOAD>
@@ -356,6 +374,14 @@ kf_small_kernel(const Batch bt, const SmallModel<N> mdl, const KfViews kf, const
         for (int i = 0; i < N; ++i) a1[i] = an[i];
 #pragma unroll
         for (int k = 0; k < N * N; ++k) R1[k] = Rn[k];
+      }
+      if (r > kL2Ahead) {  // pull the row needed kL2Ahead iterations from now into L2
+        prefetch_vec<N>(kf.m, b, r - 1 - kL2Ahead);
+        prefetch_vec<N * N>(kf.C, b, r - 1 - kL2Ahead);
+        if (RELOAD) {
+          prefetch_vec<N>(kf.a, b, r - kL2Ahead);
+          prefetch_vec<N * N>(kf.R, b, r - kL2Ahead);
+        }
       }
       if (r > 0) {  // prefetch the next row of the spill while this one is processed
         load_vec<N>(kf.m, b, r - 1, mn);

@@ -42,7 +42,7 @@ def parse():
     ap.add_argument("--T", type=int, default=1000)
     ap.add_argument("--chunks", type=int, default=0,
                     help="launches per step; 0 = launches of --waves full waves each")
-    ap.add_argument("--waves", type=int, default=3, help="full GPU waves per launch")
+    ap.add_argument("--waves", type=int, default=5, help="full GPU waves per launch")
     ap.add_argument("--e2e-series", type=int, default=0,
                     help="series per e2e step (0 = same as --series)")
     ap.add_argument("--no-e2e", action="store_true")
