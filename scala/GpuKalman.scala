@@ -1,0 +1,154 @@
+// GpuKalman.scala -- reference-side facade over libbdlm.so (include/bdlm.h).
+//
+// SOURCE ONLY: this build image has no JVM / sbt, so this file is neither compiled nor tested
+// here (see INTEGRATION.md).  It lives in the reference's package so that switching a call
+// site is a one-word change (KalmanFilter.filterDlm -> GpuKalman.filterDlm).  The marshalling
+// below is the same as bayesian_dlms_b200/reference_api.py, which IS tested against the oracle.
+package com.github.jonnylaw.dlm
+
+import breeze.linalg.{DenseMatrix, DenseVector}
+import breeze.stats.distributions.{Rand, RandBasis}
+import java.lang.foreign._
+import java.lang.foreign.ValueLayout._
+
+object GpuKalman {
+  import BdlmNative._ // downcall handles + struct layout, INTEGRATION.md section 3
+
+  private lazy val ctx: MemorySegment = {
+    val out = Arena.global().allocate(ADDRESS)
+    val rc = create.invoke(0, out).asInstanceOf[Int]
+    if (rc != 0) throw new IllegalStateException(s"bdlm_create failed ($rc): no CUDA device, no CPU fallback")
+    out.get(ADDRESS, 0)
+  }
+
+  // ---- flattening ------------------------------------------------------------------------
+  private def cm(m: DenseMatrix[Double]): Array[Double] = m.toDenseMatrix.copy.data // column-major
+
+  private case class Flat(n: Int, p: Int, times: Array[Double], y: Array[Double],
+                          f: Array[Double], fTv: Boolean, g: Array[Double], gTv: Boolean)
+
+  private def flatten(mod: Dlm, ys: Vector[Data]): Flat = {
+    if (ys.isEmpty) throw new NoSuchElementException("None.get") // KalmanFilter.scala:116-117
+    val times = ys.map(_.time).toArray
+    val t0 = times.min - 1.0
+    val dts = times.zip(t0 +: times.init).map { case (t, prev) => t - prev }
+    val fs = times.map(t => cm(mod.f(t)))
+    val gs = dts.map(dt => cm(mod.g(dt)))
+    val fTv = fs.exists(!_.sameElements(fs.head))
+    val gTv = gs.exists(!_.sameElements(gs.head))
+    val f0 = mod.f(times.head)
+    val y = ys.flatMap(_.observation.data.map(_.getOrElse(Double.NaN))).toArray
+    Flat(f0.rows, f0.cols, times, y, if (fTv) fs.flatten else fs.head, fTv,
+         if (gTv) gs.flatten else gs.head, gTv)
+  }
+
+  private def seg(a: Arena, xs: Array[Double]): MemorySegment = {
+    val s = a.allocate(JAVA_DOUBLE, xs.length.toLong.max(1L))
+    MemorySegment.copy(xs, 0, s, JAVA_DOUBLE, 0, xs.length)
+    s
+  }
+
+  private def problem(a: Arena, fl: Flat, p: DlmParameters, keepInit: Boolean): MemorySegment = {
+    val pr = a.allocate(BdlmNative.problem)
+    def setL(name: String, v: Long) = pr.set(JAVA_LONG, BdlmNative.problem.byteOffset(MemoryLayout.PathElement.groupElement(name)), v)
+    def setI(name: String, v: Int) = pr.set(JAVA_INT, BdlmNative.problem.byteOffset(MemoryLayout.PathElement.groupElement(name)), v)
+    def setP(name: String, s: MemorySegment) = pr.set(ADDRESS, BdlmNative.problem.byteOffset(MemoryLayout.PathElement.groupElement(name)), s)
+    val regular = fl.times.zipWithIndex.forall { case (t, i) => t == (i + 1).toDouble }
+    setL("B", 1L); setI("T", fl.times.length); setI("n", fl.n); setI("p", fl.p)
+    setI("layout", 1 /* SERIES_MAJOR */); setI("mem", 1 /* HOST */)
+    setI("keep_init", if (keepInit) 1 else 0)
+    setI("f_tv", if (fl.fTv) 1 else 0); setI("g_tv", if (fl.gTv) 1 else 0)
+    setI("per_series", 0); setI("compat", 0)
+    setP("F", seg(a, fl.f)); setP("G", seg(a, fl.g))
+    setP("times", if (regular) MemorySegment.NULL else seg(a, fl.times))
+    setP("V", seg(a, cm(p.v))); setP("W", seg(a, cm(p.w)))
+    setP("m0", seg(a, p.m0.toArray)); setP("C0", seg(a, cm(p.c0)))
+    setP("y", seg(a, fl.y))
+    pr
+  }
+
+  private def check(rc: Int, status: Int): Unit = {
+    if (rc == -2) throw new NoSuchElementException("None.get")
+    if (rc < 0) throw new IllegalArgumentException(lastErr.invoke(ctx).asInstanceOf[MemorySegment].reinterpret(1024).getString(0))
+    if ((status & 1) != 0) throw new breeze.linalg.MatrixSingularException("")
+    if ((status & 2) != 0) throw new breeze.linalg.NotConvergedException(breeze.linalg.NotConvergedException.Iterations)
+  }
+
+  private def rowsOf(s: MemorySegment, rows: Int, k: Int): Array[Array[Double]] =
+    Array.tabulate(rows)(r => Array.tabulate(k)(j => s.getAtIndex(JAVA_DOUBLE, r.toLong * k + j)))
+
+  // ---- KalmanFilter ------------------------------------------------------------------------
+
+  /** KalmanFilter(advanceState(p, mod.g)).filter (Filter.scala:41-45): T+1 states. */
+  def filter(mod: Dlm, ys: Vector[Data], p: DlmParameters): Vector[KfState] = run(mod, ys, p, keepInit = true)
+
+  /** KalmanFilter.filterDlm (KalmanFilter.scala:291-294): T states. */
+  def filterDlm(mod: Dlm, ys: Vector[Data], p: DlmParameters): Vector[KfState] = run(mod, ys, p, keepInit = false)
+
+  private def run(mod: Dlm, ys: Vector[Data], p: DlmParameters, keepInit: Boolean): Vector[KfState] = {
+    val fl = flatten(mod, ys)
+    val a = Arena.ofConfined()
+    try {
+      val rows = fl.times.length + (if (keepInit) 1 else 0)
+      val (n, q) = (fl.n, fl.p)
+      val out = a.allocate(ADDRESS, 6)
+      val sizes = Array(n, n * n, n, n * n, q, q * q)
+      val bufs = sizes.map(k => a.allocate(JAVA_DOUBLE, rows.toLong * k))
+      bufs.zipWithIndex.foreach { case (b, i) => out.setAtIndex(ADDRESS, i, b) }
+      val status = a.allocate(JAVA_INT)
+      check(kfFilter.invoke(ctx, problem(a, fl, p, keepInit), out, status).asInstanceOf[Int], status.get(JAVA_INT, 0))
+      val Array(m, c, at, rt, f, qq) = bufs.zip(sizes).map { case (b, k) => rowsOf(b, rows, k) }
+      val tm = if (keepInit) (fl.times.min - 1.0) +: fl.times else fl.times
+      Vector.tabulate(rows) { r =>
+        val init = keepInit && r == 0
+        KfState(tm(r), DenseVector(m(r)), new DenseMatrix(n, n, c(r)), DenseVector(at(r)),
+                new DenseMatrix(n, n, rt(r)),
+                if (init) None else Some(DenseVector(f(r))),
+                if (init) None else Some(new DenseMatrix(q, q, qq(r))))
+      }
+    } finally a.close()
+  }
+
+  /** KalmanFilter.likelihood(mod, ys)(p) (KalmanFilter.scala:299-306). */
+  def likelihood(mod: Dlm, ys: Vector[Data])(p: DlmParameters): Double = {
+    val fl = flatten(mod, ys)
+    val a = Arena.ofConfined()
+    try {
+      val tr = a.allocate(JAVA_DOUBLE); val st = a.allocate(JAVA_INT)
+      check(loglik.invoke(ctx, problem(a, fl, p, true), tr, MemorySegment.NULL, st).asInstanceOf[Int], 0)
+      tr.get(JAVA_DOUBLE, 0)
+    } finally a.close()
+  }
+
+  // ---- Smoothing ----------------------------------------------------------------------------
+
+  /** Smoothing.ffbsDlm (Smoothing.scala:173-180); consumes the same N(0,1) stream as the reference:
+    * (T+1)*n draws, last row first. */
+  def ffbsDlm(mod: Dlm, ys: Vector[Data], p: DlmParameters)(implicit rand: RandBasis = Rand): Rand[Vector[SamplingState]] = {
+    val fl = flatten(mod, ys)
+    val rows = fl.times.length + 1
+    val n = fl.n
+    val draws = Array.fill(rows)(Array.fill(n)(rand.gaussian(0, 1).draw)) // draw order: last row first
+    val z = draws.reverse.flatten
+    val a = Arena.ofConfined()
+    try {
+      val theta = a.allocate(JAVA_DOUBLE, rows.toLong * n)
+      val kf = a.allocate(ADDRESS, 6)
+      val sizes = Array(n, n * n, n, n * n)
+      val bufs = sizes.map(k => a.allocate(JAVA_DOUBLE, rows.toLong * k))
+      bufs.zipWithIndex.foreach { case (b, i) => kf.setAtIndex(ADDRESS, i, b) }
+      kf.setAtIndex(ADDRESS, 4, MemorySegment.NULL); kf.setAtIndex(ADDRESS, 5, MemorySegment.NULL)
+      val st = a.allocate(JAVA_INT)
+      check(ffbs.invoke(ctx, problem(a, fl, p, true), seg(a, z), theta, kf, MemorySegment.NULL, st).asInstanceOf[Int], st.get(JAVA_INT, 0))
+      val th = rowsOf(theta, rows, n)
+      val Array(m, c, at, rt) = bufs.zip(sizes).map { case (b, k) => rowsOf(b, rows, k) }
+      val tm = (fl.times.min - 1.0) +: fl.times
+      Rand.always(Vector.tabulate(rows)(r =>
+        SamplingState(tm(r), DenseVector(th(r)), DenseVector(m(r)), new DenseMatrix(n, n, c(r)),
+                      DenseVector(at(r)), new DenseMatrix(n, n, rt(r)))))
+    } finally a.close()
+  }
+
+  // backwardsSmoother, svdFilterDlm, svdFfbsDlm and the batched overloads follow the same
+  // pattern over bdlm_rts_smooth, bdlm_svd_filter and bdlm_svd_ffbs (B > 1, per_series mask).
+}
