@@ -190,9 +190,13 @@ def main():
     else:
         # every series of a launch takes the same time: launches that are whole waves
         # (resident blocks x SMs x 128 series) leave no partially filled last wave
-        per = args.waves * eng.ctx.wave_series(N_STATE, N_OBS)
-        bounds = list(range(0, B, per)) + [B]
+        from bayesian_dlms_b200.sharding import shard_range, wave_aligned_slabs
+        glo, ghi = shard_range(world * B, rank, world)  # this rank's block of the global batch
+        assert ghi - glo == B
+        slabs = wave_aligned_slabs(0, B, eng.ctx.wave_series(N_STATE, N_OBS), args.waves)
+        bounds = [s[0] for s in slabs] + [B]
         nch = len(bounds) - 1
+        config["global_series"] = world * B
     config["chunks_per_step"] = nch
     config["series_per_launch"] = bounds[1] - bounds[0]
     Bc_max = max(bounds[i + 1] - bounds[i] for i in range(nch))
