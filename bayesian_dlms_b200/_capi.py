@@ -28,6 +28,7 @@ SYMBOLS = [
     "bdlm_sync", "bdlm_launch_count", "bdlm_set_staging_bytes", "bdlm_kf_filter",
     "bdlm_rts_smooth", "bdlm_kf_filter_smooth", "bdlm_loglik", "bdlm_ffbs",
     "bdlm_svd_filter", "bdlm_svd_ffbs", "bdlm_gibbs_suffstats", "bdlm_wave_series",
+    "bdlm_fp64_peak_tflops",
 ]
 
 
@@ -88,6 +89,7 @@ def load():
     lib.bdlm_set_staging_bytes.argtypes = [C.c_void_p, C.c_int64]
     lib.bdlm_wave_series.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
     lib.bdlm_wave_series.restype = C.c_int64
+    lib.bdlm_fp64_peak_tflops.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     PP = C.POINTER(Problem)
     lib.bdlm_kf_filter.argtypes = [C.c_void_p, PP, C.POINTER(KfOut), C.c_void_p]
     lib.bdlm_rts_smooth.argtypes = [C.c_void_p, PP, C.POINTER(KfOut), C.POINTER(SmoothOut),
@@ -153,6 +155,12 @@ class Context:
     def wave_series(self, n: int, p: int) -> int:
         """Series per full wave of the fused filter+smoother register kernel."""
         return int(self.check(load().bdlm_wave_series(self._h, int(n), int(p))))
+
+    def fp64_peak_tflops(self) -> float:
+        """Measured DFMA peak (TFLOP/s) of this context's GPU."""
+        v = C.c_double()
+        self.check(load().bdlm_fp64_peak_tflops(self._h, C.byref(v)))
+        return float(v.value)
 
     def set_staging_bytes(self, nbytes: int):
         self.check(load().bdlm_set_staging_bytes(self._h, int(nbytes)))

@@ -577,6 +577,16 @@ int64_t bdlm_wave_series(bdlm_ctx *c, int32_t n, int32_t p) {
   return wave;
 }
 
+int bdlm_fp64_peak_tflops(bdlm_ctx *c, double *tflops) {
+  if (!c || !tflops) return BDLM_E_ARG;
+  CU(cudaSetDevice(c->device));
+  int rc = ensure_arena(c, 4096);
+  if (rc) return rc;
+  CU(measure_fp64_peak(c->stream, reinterpret_cast<double *>(c->arena), tflops));
+  c->launches += 4;
+  return 0;
+}
+
 int bdlm_set_staging_bytes(bdlm_ctx *c, int64_t bytes) {
   if (!c || bytes < ((int64_t)1 << 20)) return BDLM_E_ARG;
   c->staging_cap = (size_t)bytes;

@@ -394,7 +394,7 @@ __device__ __forceinline__ void gibbs_stats(int lane, const Batch &bt, const Ws 
     }
 }
 
-template <int OP>
+template <int OP, int NT, int PT>
 __global__ void __launch_bounds__(64)
 warp_kernel(const WarpArgs wa, const int ws_doubles) {
   extern __shared__ double smem[];
@@ -402,7 +402,9 @@ warp_kernel(const WarpArgs wa, const int ws_doubles) {
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
   if (b >= bt.B) return;
-  const int n = bt.n, p = bt.p, nn = n * n, T = bt.T, ki = bt.keep_init, rows = T + ki;
+  // NT, PT > 0: dimensions known at compile time (hot shapes; loops unroll, index math folds)
+  const int n = NT > 0 ? NT : bt.n, p = PT > 0 ? PT : bt.p;
+  const int nn = n * n, T = bt.T, ki = bt.keep_init, rows = T + ki;
   Ws ws(smem + (size_t)wib * ws_doubles, n, p, OP);
   int st = 0;
 
@@ -703,19 +705,30 @@ warp_kernel(const WarpArgs wa, const int ws_doubles) {
   }
 }
 
-template <int OP>
-cudaError_t launch_op(const WarpArgs &wa, cudaStream_t stream) {
+template <int OP, int NT, int PT>
+cudaError_t launch_dims(const WarpArgs &wa, cudaStream_t stream) {
   Ws sz(nullptr, wa.bt.n, wa.bt.p, OP);
   const int ws_doubles = (int)((sz.total + 1) & ~(size_t)1);
   const int wpb = 2;
   const size_t smem = (size_t)wpb * ws_doubles * sizeof(double);
-  cudaError_t e = cudaFuncSetAttribute(warp_kernel<OP>,
+  cudaError_t e = cudaFuncSetAttribute(warp_kernel<OP, NT, PT>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const int64_t blocks = (wa.bt.B + wpb - 1) / wpb;
   if (blocks <= 0) return cudaSuccess;
-  warp_kernel<OP><<<(unsigned)blocks, wpb * 32, smem, stream>>>(wa, ws_doubles);
+  warp_kernel<OP, NT, PT><<<(unsigned)blocks, wpb * 32, smem, stream>>>(wa, ws_doubles);
   return cudaGetLastError();
+}
+
+// Hot shapes get compile-time dimensions: (13, 1) = polynomial(1) |+| seasonal(24, 6)
+// (BASELINE config 3) and (8, 8) = 8-fold outer sum of polynomial(1) (config 4).
+template <int OP>
+cudaError_t launch_op(const WarpArgs &wa, cudaStream_t stream) {
+  constexpr bool kHot = (OP == kOpFilter || OP == kOpFilterSmooth || OP == kOpFfbs ||
+                         OP == kOpSvdFilter || OP == kOpSvdFfbs);
+  if (kHot && wa.bt.n == 13 && wa.bt.p == 1) return launch_dims<OP, kHot ? 13 : 0, kHot ? 1 : 0>(wa, stream);
+  if (kHot && wa.bt.n == 8 && wa.bt.p == 8) return launch_dims<OP, kHot ? 8 : 0, kHot ? 8 : 0>(wa, stream);
+  return launch_dims<OP, 0, 0>(wa, stream);
 }
 
 }  // namespace

@@ -47,4 +47,7 @@ cudaError_t launch_warp(int op, const WarpArgs &wa, cudaStream_t stream);
 cudaError_t launch_transpose(const double *in, double *out, int64_t rows, int64_t cols,
                              cudaStream_t stream);
 
+// peak.cu: DFMA throughput microbenchmark (TFLOP/s at 2 flops per DFMA).
+cudaError_t measure_fp64_peak(cudaStream_t stream, double *scratch, double *tflops);
+
 }  // namespace bdlm

@@ -47,6 +47,7 @@ def parse():
                     help="series per e2e step (0 = same as --series)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-ffbs", action="store_true")
     return ap.parse_args()
 
 
@@ -137,6 +138,63 @@ def cpu_reference_leg(series, T, seconds_target=15.0, threads=None, warm_passes=
             "sample": f"{Bs} series x T={T} x {reps} passes (config-2 model, full "
                       f"KfState+SmoothingState outputs into reused arrays), {dt:.2f} s wall, "
                       f"oracle/bdlm_oracle.c gcc -O2 OpenMP"}, reps * Bs, dt
+
+
+def ffbs_leg(eng, dev, with_cpu=True, B=4096, T=2000):
+    """Secondary metric (BASELINE.json config 3): FFBS draws/s for the seasonal DLM
+    (polynomial(1) |+| seasonal(24, 6), n = 13, p = 1), 4096 chains x T = 2000 with 10 %
+    missing observations, injected normals, Gibbs sufficient statistics fused.  FP64-bound:
+    the roofline is the measured DFMA peak (halved: the parity contract forbids FMA)."""
+    import torch
+    from bayesian_dlms_b200 import Model, SERIES_MAJOR, dlm
+    mod = dlm.polynomial(1) + dlm.seasonal(24, 6)
+    n = 13
+    W = np.diag([0.01] + [0.2, 0.4, 0.5, 0.2, 0.1, 0.4] * 2)
+    params = dict(V=np.array([[1.0]]), W=W, m0=np.zeros(n), C0=np.eye(n))
+    g = torch.Generator(device=dev).manual_seed(20260103)
+    y = torch.randn((B, T, 1), generator=g, device=dev, dtype=torch.float64) * 2.0
+    y[torch.rand((B, T, 1), generator=g, device=dev) < 0.1] = float("nan")
+    z = torch.randn((B, T + 1, n), generator=g, device=dev, dtype=torch.float64)
+    model = Model.build(mod, T=T)
+    eng.ffbs(model, params, y, z, layout=SERIES_MAJOR, stats=True)  # warm-up
+    torch.cuda.synchronize()
+    ms = []
+    for _ in range(2):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = eng.ffbs(model, params, y, z, layout=SERIES_MAJOR, stats=True)
+        e1.record()
+        torch.cuda.synchronize()
+        ms.append(e0.elapsed_time(e1))
+    t = min(ms) * 1e-3
+    # dense algorithmic flops per step: filter 8n^3 + sampler 15n^3 + Jacobi eig ~ 60 n^3
+    flops_step = 83.0 * n ** 3
+    peak = eng.ctx.fp64_peak_tflops()
+    res = {"config": "config3: seasonal n=13 p=1, %d chains x T=%d, 10%% missing, FFBS + Gibbs stats" % (B, T),
+           "draws_per_s": B / t, "steps_per_s": B * (T + 1) / t, "ms_per_sweep": t * 1e3,
+           "status_max": int(out["status"].max()),
+           "roofline": {"bound": "fp64", "achieved": B * (T + 1) * flops_step / t / 1e12,
+                        "peak": peak / 2.0, "unit": "TFLOP/s",
+                        "frac": B * (T + 1) * flops_step / t / 1e12 / (peak / 2.0),
+                        "flops_per_step": flops_step,
+                        "peak_source": "bdlm_fp64_peak_tflops (DFMA microbenchmark) / 2: "
+                                       "mul and add issue separately under the no-FMA parity contract"}}
+    if with_cpu:
+        import oracle
+        F, _, G, _, _, p = dlm.materialise(mod, np.arange(1, T + 1.0))
+        threads = os.cpu_count()
+        Bs = threads
+        rng = np.random.default_rng(3)
+        yc = rng.standard_normal((Bs, T, 1)) * 2.0
+        yc[rng.random(yc.shape) < 0.1] = np.nan
+        zc = rng.standard_normal((Bs, T + 1, n))
+        t0 = time.perf_counter()
+        oracle.batch_ffbs(Bs, n, p, T, F, G, [1.0], dlm.cm(W), np.zeros(n), dlm.cm(np.eye(n)),
+                          np.arange(1, T + 1.0), yc, zc, nthreads=threads)
+        dt = time.perf_counter() - t0
+        res["cpu_baseline"] = {"value": Bs / dt, "unit": "draws/s", "cores": threads, "kind": "port",
+                               "sample": f"{Bs} chains x T={T}, {dt:.2f} s wall, oracle port OpenMP"}
+    return res
 
 
 def main():
@@ -342,6 +400,11 @@ def main():
         }
         if e2e:
             line["e2e"] = e2e
+        if not args.no_ffbs and world == 1:
+            try:
+                line["ffbs"] = ffbs_leg(eng, dev, with_cpu=not args.no_cpu)
+            except Exception as ex:  # secondary metric: never take the headline down
+                line["ffbs"] = {"error": repr(ex)}
         if not args.no_cpu and world >= 1:
             try:
                 base, _, _ = cpu_reference_leg(B, T)

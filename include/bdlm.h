@@ -165,6 +165,10 @@ BDLM_API int bdlm_set_staging_bytes(bdlm_ctx *ctx, int64_t bytes);
  * that are a multiple of this number leave no partially filled last wave.  Returns
  * BDLM_E_ARG for dimensions served by the warp-per-series kernels (wave = resident warps). */
 BDLM_API int64_t bdlm_wave_series(bdlm_ctx *ctx, int32_t n, int32_t p);
+/* Measured FP64 pipe peak of the context's GPU in TFLOP/s (DFMA microbenchmark, 2 flops per
+ * DFMA): the roofline denominator for the FP64-bound kernels (FFBS, SVD).  The numerical
+ * kernels never fuse multiply-add (parity contract), so their attainable rate is half of it. */
+BDLM_API int bdlm_fp64_peak_tflops(bdlm_ctx *ctx, double *tflops);
 
 /* ---- forward filter ----------------------------------------------------------------
  * KalmanFilter.filterDlm (KalmanFilter.scala:291-294) / KalmanFilter(adv).filter

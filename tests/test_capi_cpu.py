@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def _declared_symbols():
     hdr = open(os.path.join(ROOT, "include", "bdlm.h")).read()
-    return sorted(set(re.findall(r"BDLM_API[^;(]*?\b(bdlm_[a-z_]+)\s*\(", hdr)))
+    return sorted(set(re.findall(r"BDLM_API[^;(]*?\b(bdlm_[a-z0-9_]+)\s*\(", hdr)))
 
 
 def test_library_exports_every_declared_symbol():
