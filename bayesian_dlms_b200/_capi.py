@@ -28,7 +28,9 @@ SYMBOLS = [
     "bdlm_sync", "bdlm_launch_count", "bdlm_set_staging_bytes", "bdlm_kf_filter",
     "bdlm_rts_smooth", "bdlm_kf_filter_smooth", "bdlm_loglik", "bdlm_ffbs",
     "bdlm_svd_filter", "bdlm_svd_ffbs", "bdlm_gibbs_suffstats", "bdlm_wave_series",
-    "bdlm_fp64_peak_tflops",
+    "bdlm_fp64_peak_tflops", "bdlm_scan_filter_smooth", "bdlm_scan_elem_doubles",
+    "bdlm_scan_forward_reduce", "bdlm_scan_forward_apply", "bdlm_scan_backward_reduce",
+    "bdlm_scan_backward_apply", "bdlm_scan_combine",
 ]
 
 
@@ -103,9 +105,17 @@ def load():
     lib.bdlm_svd_ffbs.argtypes = [C.c_void_p, PP, C.c_void_p, C.c_void_p, C.POINTER(SvdOut),
                                   C.POINTER(GibbsStats), C.c_void_p]
     lib.bdlm_gibbs_suffstats.argtypes = [C.c_void_p, PP, C.c_void_p, C.POINTER(GibbsStats)]
-    if hasattr(lib, "bdlm_scan_filter_smooth"):
-        lib.bdlm_scan_filter_smooth.argtypes = [C.c_void_p, PP, C.POINTER(KfOut),
-                                                C.POINTER(SmoothOut), C.c_void_p, C.c_void_p]
+    lib.bdlm_scan_filter_smooth.argtypes = [C.c_void_p, PP, C.POINTER(KfOut),
+                                            C.POINTER(SmoothOut), C.c_void_p]
+    lib.bdlm_scan_elem_doubles.argtypes = [C.c_int32, C.c_int32]
+    lib.bdlm_scan_forward_reduce.argtypes = [C.c_void_p, PP, C.c_void_p]
+    lib.bdlm_scan_forward_apply.argtypes = [C.c_void_p, PP, C.c_void_p, C.POINTER(KfOut),
+                                            C.c_void_p]
+    lib.bdlm_scan_backward_reduce.argtypes = [C.c_void_p, PP, C.POINTER(KfOut), C.c_int32,
+                                              C.c_void_p]
+    lib.bdlm_scan_backward_apply.argtypes = [C.c_void_p, PP, C.POINTER(KfOut), C.c_void_p,
+                                             C.POINTER(SmoothOut), C.c_void_p]
+    lib.bdlm_scan_combine.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     _lib = lib
     return lib
 

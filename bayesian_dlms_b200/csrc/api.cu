@@ -668,6 +668,145 @@ int bdlm_svd_ffbs(bdlm_ctx *c, const bdlm_problem *p, const double *z, double *t
   return dispatch(c, d);
 }
 
+// ---- parallel-in-time scan (scan.cu) ----------------------------------------------------
+
+static int scan_validate(bdlm_ctx *c, const bdlm_problem *p) {
+  int rc = validate(c, A_FILTER, p);
+  if (rc) return rc;
+  if (p->B != 1 || p->p != 1 || p->n > 4 || p->times || p->f_tv || p->g_tv || p->per_series ||
+      p->mem != BDLM_DEVICE)
+    return fail(c, BDLM_E_ARG,
+                "scan path: B = 1, p = 1, n <= 4, regular grid, time-invariant model, shared "
+                "parameters, device memory");
+  return 0;
+}
+
+static void scan_fill(const bdlm_problem *p, ScanArgs &a) {
+  a = ScanArgs{};
+  a.n = p->n; a.T = p->T; a.keep_init = p->keep_init ? 1 : 0;
+  a.G = p->G; a.F = p->F; a.W = p->W; a.V = p->V[0]; a.y = p->y;
+}
+
+static KfViews scan_kf_views(const bdlm_problem *p, const bdlm_kf_out *kf) {
+  const int64_t n = p->n, R = rows_of(*p);
+  KfViews v{};
+  if (!kf) return v;
+  v.m = mk_view(kf->m, p->layout, 0, 1, R, n); v.C = mk_view(kf->C, p->layout, 0, 1, R, n * n);
+  v.a = mk_view(kf->a, p->layout, 0, 1, R, n); v.R = mk_view(kf->R, p->layout, 0, 1, R, n * n);
+  v.f = mk_view(kf->f, p->layout, 0, 1, R, 1); v.Q = mk_view(kf->Q, p->layout, 0, 1, R, 1);
+  return v;
+}
+
+int bdlm_scan_elem_doubles(int32_t n, int32_t backward) {
+  if (n < 1 || n > 4) return BDLM_E_ARG;
+  return backward ? scan_backward_elem_doubles(n) : scan_forward_elem_doubles(n);
+}
+
+int bdlm_scan_combine(int32_t n, int32_t backward, const double *earlier, const double *later,
+                      double *out) {
+  if (n < 1 || n > 4 || !earlier || !later || !out) return BDLM_E_ARG;
+  scan_combine_host(n, backward != 0, earlier, later, out);
+  return 0;
+}
+
+int bdlm_scan_forward_reduce(bdlm_ctx *c, const bdlm_problem *p, double *agg_host) {
+  int rc = scan_validate(c, p);
+  if (rc) return rc;
+  if (!agg_host) return fail(c, BDLM_E_ARG, "null aggregate pointer");
+  CU(cudaSetDevice(c->device));
+  rc = ensure_arena(c, scan_workspace_bytes(p->n, p->T) + 4096);
+  if (rc) return rc;
+  ScanArgs a;
+  scan_fill(p, a);
+  a.phase = kScanReduce; a.agg_out = agg_host; a.workspace = c->arena;
+  CU(launch_scan(a, c->stream, &c->launches));
+  return 0;
+}
+
+int bdlm_scan_forward_apply(bdlm_ctx *c, const bdlm_problem *p, const double *start_mC_host,
+                            const bdlm_kf_out *kf, int32_t *status) {
+  int rc = scan_validate(c, p);
+  if (rc) return rc;
+  if (!kf) return fail(c, BDLM_E_ARG, "null output struct");
+  CU(cudaSetDevice(c->device));
+  rc = ensure_arena(c, scan_workspace_bytes(p->n, p->T) + 4096);
+  if (rc) return rc;
+  std::vector<double> prior((size_t)p->n + p->n * p->n);
+  if (!start_mC_host) {
+    std::copy(p->m0, p->m0 + p->n, prior.begin());
+    std::copy(p->C0, p->C0 + p->n * p->n, prior.begin() + p->n);
+  }
+  ScanArgs a;
+  scan_fill(p, a);
+  a.phase = kScanApply; a.start = start_mC_host ? start_mC_host : prior.data();
+  a.kf = scan_kf_views(p, kf); a.status = status; a.workspace = c->arena;
+  if (status) CU(cudaMemsetAsync(status, 0, sizeof(int32_t), c->stream));
+  CU(launch_scan(a, c->stream, &c->launches));
+  CU(cudaStreamSynchronize(c->stream));  // `prior` / start are host buffers read by an async copy
+  return 0;
+}
+
+int bdlm_scan_backward_reduce(bdlm_ctx *c, const bdlm_problem *p, const bdlm_kf_out *filt,
+                              int32_t has_successor, double *agg_host) {
+  int rc = scan_validate(c, p);
+  if (rc) return rc;
+  if (!filt || !filt->m || !filt->C || !agg_host)
+    return fail(c, BDLM_E_ARG, "backward scan needs filtered m, C and an aggregate pointer");
+  CU(cudaSetDevice(c->device));
+  rc = ensure_arena(c, scan_workspace_bytes(p->n, p->T) + 4096);
+  if (rc) return rc;
+  ScanArgs a;
+  scan_fill(p, a);
+  a.backward = 1; a.phase = kScanReduce; a.has_successor = has_successor ? 1 : 0;
+  a.agg_out = agg_host; a.kf = scan_kf_views(p, filt); a.workspace = c->arena;
+  CU(launch_scan(a, c->stream, &c->launches));
+  return 0;
+}
+
+int bdlm_scan_backward_apply(bdlm_ctx *c, const bdlm_problem *p, const bdlm_kf_out *filt,
+                             const double *next_sS_host, const bdlm_smooth_out *sm,
+                             int32_t *status) {
+  int rc = scan_validate(c, p);
+  if (rc) return rc;
+  if (!filt || !filt->m || !filt->C || !sm)
+    return fail(c, BDLM_E_ARG, "backward scan needs filtered m, C and an output struct");
+  CU(cudaSetDevice(c->device));
+  rc = ensure_arena(c, scan_workspace_bytes(p->n, p->T) + 4096);
+  if (rc) return rc;
+  const int64_t n = p->n, R = rows_of(*p);
+  ScanArgs a;
+  scan_fill(p, a);
+  a.backward = 1; a.phase = kScanApply; a.has_successor = next_sS_host ? 1 : 0;
+  a.start = next_sS_host; a.kf = scan_kf_views(p, filt);
+  a.s = mk_view(sm->s, p->layout, 0, 1, R, n); a.S = mk_view(sm->S, p->layout, 0, 1, R, n * n);
+  a.status = status; a.workspace = c->arena;
+  CU(launch_scan(a, c->stream, &c->launches));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int bdlm_scan_filter_smooth(bdlm_ctx *c, const bdlm_problem *p, const bdlm_kf_out *kf,
+                            const bdlm_smooth_out *sm, int32_t *status) {
+  int rc = scan_validate(c, p);
+  if (rc) return rc;
+  if (!sm) return fail(c, BDLM_E_ARG, "null smoother output struct");
+  CU(cudaSetDevice(c->device));
+  const int64_t n = p->n, R = rows_of(*p);
+  bdlm_kf_out k{};
+  if (kf) k = *kf;
+  const size_t ws = align_up(scan_workspace_bytes(p->n, p->T) + 4096);
+  const size_t need = ws + (k.m ? 0 : align_up(sizeof(double) * R * n)) +
+                      (k.C ? 0 : align_up(sizeof(double) * R * n * n)) + 4096;
+  rc = ensure_arena(c, need);
+  if (rc) return rc;
+  Bump bump{c->arena, ws, c->arena_bytes};
+  if (!k.m) k.m = bump.take<double>((size_t)R * n);
+  if (!k.C) k.C = bump.take<double>((size_t)R * n * n);
+  rc = bdlm_scan_forward_apply(c, p, nullptr, &k, status);
+  if (rc) return rc;
+  return bdlm_scan_backward_apply(c, p, &k, nullptr, sm, status);
+}
+
 int bdlm_gibbs_suffstats(bdlm_ctx *c, const bdlm_problem *p, const double *theta,
                          const bdlm_gibbs_stats *stats) {
   int rc = validate(c, A_STATS, p);

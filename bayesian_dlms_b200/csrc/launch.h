@@ -47,6 +47,33 @@ cudaError_t launch_warp(int op, const WarpArgs &wa, cudaStream_t stream);
 cudaError_t launch_transpose(const double *in, double *out, int64_t rows, int64_t cols,
                              cudaStream_t stream);
 
+// scan.cu: parallel-in-time filter / smoother for one long series (n <= 4, p = 1, regular
+// grid, time-invariant model).
+enum { kScanReduce = 0, kScanApply = 1 };
+struct ScanArgs {
+  int n;
+  int64_t T;           // observations in this chunk
+  int keep_init;       // rows = T + keep_init
+  int backward;        // 0 = filter pass, 1 = smoother pass
+  int phase;           // kScanReduce: chunk aggregate only; kScanApply: write outputs
+  int has_successor;   // backward: another chunk follows this one in time
+  const double *G, *F, *W;  // host, column-major
+  double V;
+  const double *y;     // device [T]
+  const double *start; // host [n + n*n]: (m, C) before the chunk (forward apply) or (s, S)
+                       // of the first row of the next chunk (backward apply, has_successor)
+  double *agg_out;     // host: chunk aggregate (reduce phase)
+  KfViews kf;          // forward: outputs; backward: filtered (m, C) inputs
+  View s, S;           // backward outputs
+  int32_t *status;     // device, one int, OR-ed
+  void *workspace;     // device, scan_workspace_bytes(n, T)
+};
+size_t scan_workspace_bytes(int n, int64_t T);
+int scan_forward_elem_doubles(int n);
+int scan_backward_elem_doubles(int n);
+cudaError_t launch_scan(const ScanArgs &a, cudaStream_t stream, int64_t *launches);
+void scan_combine_host(int n, bool backward, const double *ei, const double *ej, double *out);
+
 // peak.cu: DFMA throughput microbenchmark (TFLOP/s at 2 flops per DFMA).
 cudaError_t measure_fp64_peak(cudaStream_t stream, double *scratch, double *tflops);
 

@@ -236,6 +236,43 @@ BDLM_API int bdlm_svd_ffbs(bdlm_ctx *ctx, const bdlm_problem *prob, const double
 BDLM_API int bdlm_gibbs_suffstats(bdlm_ctx *ctx, const bdlm_problem *prob, const double *theta,
                          const bdlm_gibbs_stats *stats);
 
+/* ---- parallel-in-time filter + smoother for ONE long series ---------------------------
+ * Not in the reference (its recursion is strictly sequential, Filter.scala:41-62; BASELINE
+ * config 5).  Temporal parallelisation by associative scan (Sarkka & Garcia-Fernandez 2021).
+ * Restrictions: B = 1, p = 1, n <= 4, regular grid (times = NULL), time-invariant F and G,
+ * shared parameters, mem = BDLM_DEVICE.  Results equal bdlm_kf_filter_smooth with
+ * BDLM_TEXTBOOK_SMOOTHER to 1e-9 relative (for n = 1 that is the reference itself).
+ *
+ * Single GPU: bdlm_scan_filter_smooth.  Several GPUs, each owning a contiguous time chunk
+ * (prob describes the chunk; keep_init = 1 only on the first rank):
+ *   1. every rank: bdlm_scan_forward_reduce  -> agg (bdlm_scan_elem_doubles(n, 0) doubles)
+ *   2. all-gather agg; rank r folds start = (prior state) (x) agg_0 (x) ... (x) agg_{r-1} with
+ *      bdlm_scan_combine and reads (m, C) before its chunk from it (bdlm_scan_state_*)
+ *   3. every rank: bdlm_scan_forward_apply(start_mC)           -> KfState rows of its chunk
+ *   4. every rank: bdlm_scan_backward_reduce(has_successor)    -> agg (.. (n, 1) doubles)
+ *   5. all-gather; rank r folds agg_{r+1} (x) ... (x) agg_last; its (g, L) part is (s, S) of
+ *      the first row after its chunk
+ *   6. every rank: bdlm_scan_backward_apply(next_sS)           -> (s, S) rows of its chunk
+ * Elements are laid out [A | b | C | eta | J] (forward) and [E | g | L] (backward), matrices
+ * column-major. */
+BDLM_API int bdlm_scan_filter_smooth(bdlm_ctx *ctx, const bdlm_problem *prob,
+                                     const bdlm_kf_out *kf, const bdlm_smooth_out *sm,
+                                     int32_t *status);
+BDLM_API int bdlm_scan_elem_doubles(int32_t n, int32_t backward);
+BDLM_API int bdlm_scan_forward_reduce(bdlm_ctx *ctx, const bdlm_problem *prob, double *agg_host);
+BDLM_API int bdlm_scan_forward_apply(bdlm_ctx *ctx, const bdlm_problem *prob,
+                                     const double *start_mC_host, const bdlm_kf_out *kf,
+                                     int32_t *status);
+BDLM_API int bdlm_scan_backward_reduce(bdlm_ctx *ctx, const bdlm_problem *prob,
+                                       const bdlm_kf_out *filt, int32_t has_successor,
+                                       double *agg_host);
+BDLM_API int bdlm_scan_backward_apply(bdlm_ctx *ctx, const bdlm_problem *prob,
+                                      const bdlm_kf_out *filt, const double *next_sS_host,
+                                      const bdlm_smooth_out *sm, int32_t *status);
+/* out = earlier (x) later on the host (carry folding between ranks; a few dozen flops). */
+BDLM_API int bdlm_scan_combine(int32_t n, int32_t backward, const double *earlier,
+                               const double *later, double *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,123 @@
+"""GPU parity of the parallel-in-time (associative scan) filter / smoother, BASELINE config 5.
+
+The reference has no parallel-in-time path, so the bar is: equal to the
+sequential kernel in textbook-smoother mode to 1e-9 relative, which for n = 1 is the reference
+itself (checked against the committed golden CSVs)."""
+import numpy as np
+import pytest
+
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import torch
+    assert torch.cuda.is_available()
+    from bayesian_dlms_b200 import default_engine
+    return default_engine(0)
+
+
+def _models():
+    from bayesian_dlms_b200 import dlm
+    return {
+        1: (dlm.polynomial(1), np.array([[2.0]]), np.array([[3.0]]), np.zeros(1), np.array([[10.0]])),
+        2: H.second_order(),
+        3: (dlm.polynomial(3), np.array([[1.5]]), np.diag([1.0, 0.5, 0.1]), np.zeros(3), 10 * np.eye(3)),
+    }
+
+
+def _sequential(eng, model, params, y):
+    from bayesian_dlms_b200 import TIME_MAJOR
+    out = eng.filter_smooth(model, params, y.reshape(-1, 1, 1).contiguous(), layout=TIME_MAJOR,
+                            keep_init=True, textbook=True)
+    eng.sync()
+    return {k: v[:, :, 0] for k, v in out.items() if k != "status"}
+
+
+@pytest.mark.parametrize("n", [1, 2, 3])
+@pytest.mark.parametrize("T", [1, 63, 64, 65, 1000, 40_001])
+def test_scan_equals_sequential(eng, n, T):
+    import torch
+    from bayesian_dlms_b200 import Model
+    from bayesian_dlms_b200.scan import scan_filter_smooth
+    mod, V, W, m0, C0 = _models()[n]
+    rng = np.random.default_rng(100 * n + T % 97)
+    y = H.simulate(mod, V, W, m0, C0, np.arange(1, T + 1.0), rng, missing=0.05)[:, 0]
+    yd = torch.from_numpy(y).cuda()
+    model = Model.build(mod, T=T)
+    params = dict(V=V, W=W, m0=m0, C0=C0)
+    seq = _sequential(eng, model, params, yd)
+    out = scan_filter_smooth(eng, model, params, yd)
+    torch.cuda.synchronize()
+    assert int(out["status"][0]) == 0
+    for k in ("m", "C", "a", "R", "f", "Q", "s", "S"):
+        a, b = out[k].cpu().numpy(), seq[k].cpu().numpy()
+        if k in ("f", "Q"):
+            a, b = a[1:], b[1:]
+        assert H.rel_err(a, b) < TOL, (k, n, T, H.rel_err(a, b))
+
+
+def test_scan_reproduces_golden_csv(eng):
+    import torch
+    from bayesian_dlms_b200 import Model, dlm
+    from bayesian_dlms_b200.scan import scan_filter_smooth
+    times, y, g = H.first_order_golden()
+    model = Model.build(dlm.polynomial(1), T=len(times))
+    out = scan_filter_smooth(eng, model, dict(V=[[2.0]], W=[[3.0]], m0=[0.0], C0=[[10.0]]),
+                             torch.from_numpy(y[:, 0].copy()).cuda())
+    torch.cuda.synchronize()
+    for key, ref in (("m", g["m"]), ("C", g["C"]), ("s", g["s"]), ("S", g["S"])):
+        assert H.rel_err(out[key][:, 0].cpu().numpy(), ref) < TOL, key
+    assert H.rel_err(out["f"][1:, 0].cpu().numpy(), g["f"]) < TOL
+    assert H.rel_err(out["Q"][1:, 0].cpu().numpy(), g["Q"]) < TOL
+
+
+@pytest.mark.parametrize("n", [1, 2])
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_time_sharded_ranks_compose(eng, n, world):
+    """The multi-GPU protocol (reduce -> all-gather -> fold -> apply), ranks emulated one after
+    the other on one GPU: chunk aggregates are the only thing exchanged."""
+    import torch
+    from bayesian_dlms_b200 import Model
+    from bayesian_dlms_b200.scan import (ScanChunk, fold_backward_next, fold_forward_start)
+    from bayesian_dlms_b200.sharding import shard_range
+    mod, V, W, m0, C0 = _models()[n]
+    T = 5003
+    rng = np.random.default_rng(9)
+    y = H.simulate(mod, V, W, m0, C0, np.arange(1, T + 1.0), rng, missing=0.03)[:, 0]
+    yd = torch.from_numpy(y).cuda()
+    params = dict(V=V, W=W, m0=m0, C0=C0)
+    seq = _sequential(eng, Model.build(mod, T=T), params, yd)
+    chunks = []
+    for r in range(world):
+        lo, hi = shard_range(T, r, world)
+        chunks.append(ScanChunk(eng, Model.build(mod, T=hi - lo), params, yd[lo:hi].contiguous(),
+                                keep_init=(r == 0)))
+    aggs = [c.forward_reduce() for c in chunks]                       # phase 1 (+ all-gather)
+    for r, c in enumerate(chunks):                                    # phase 2-3
+        c.forward_apply(None if r == 0 else fold_forward_start(n, m0, C0, aggs, r))
+    sagg = [c.backward_reduce(True) if r < world - 1 else None for r, c in enumerate(chunks)]
+    chunks[-1].backward_apply(None)                                   # last rank: terminal state
+    torch.cuda.synchronize()
+    last = chunks[-1].first_row_sS()
+    for r in range(world - 1):
+        chunks[r].backward_apply(fold_backward_next(n, sagg, r, last))
+    torch.cuda.synchronize()
+    for k in ("m", "C", "a", "R", "s", "S"):
+        got = torch.cat([c.out[k] for c in chunks]).cpu().numpy()
+        assert got.shape == tuple(seq[k].shape)
+        assert H.rel_err(got, seq[k].cpu().numpy()) < TOL, (k, world)
+
+
+def test_scan_rejects_unsupported_shapes(eng):
+    import torch
+    from bayesian_dlms_b200 import Model, _capi as capi
+    from bayesian_dlms_b200.scan import scan_filter_smooth
+    mod, V, W, m0, C0 = H.seasonal13()
+    model = Model.build(mod, T=10)
+    model.times = None
+    with pytest.raises((capi.BdlmError, AssertionError)):
+        scan_filter_smooth(eng, model, dict(V=V, W=W, m0=m0, C0=C0), torch.zeros(10, dtype=torch.float64).cuda())
