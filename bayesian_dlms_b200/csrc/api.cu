@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -32,6 +33,7 @@ struct bdlm_ctx {
   size_t arena_bytes = 0;
   size_t staging_cap = (size_t)8 << 30;
   size_t workspace_cap = (size_t)48 << 30;  // device-mode spill/transposes per launch
+  bool use_group = std::getenv("BDLM_NO_GROUP_KERNEL") == nullptr;  // A/B switch for profiling
 };
 
 static std::string g_create_err;
@@ -351,6 +353,11 @@ int run_dev(bdlm_ctx *c, DevCall d, Bump bump) {
   const int wop = warp_op(d.op);
   wa.spill_k = (int64_t)warp_spill_doubles_per_row(wop, p.n, p.p);
   wa.spill = wa.spill_k ? bump.take<double>((size_t)wa.spill_k * R * d.Bc) : nullptr;
+  if (c->use_group && group_supported(wop, p.n, p.p, p.keep_init ? 1 : 0)) {
+    CU(launch_group(wop, wa, c->stream));  // two series per warp, compile-time n (kf_group.cu)
+    ++c->launches;
+    return 0;
+  }
   CU(launch_warp(wop, wa, c->stream));
   ++c->launches;
   return 0;

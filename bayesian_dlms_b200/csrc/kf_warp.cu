@@ -550,6 +550,7 @@ warp_kernel(const WarpArgs wa, const int ws_doubles) {
   if (OP == kOpSmooth || OP == kOpFilterSmooth) {
     // Smoothing.backwardsSmoother (Smoothing.scala:57-64)
     if (OP == kOpSmooth) {
+      load_model(lane, bt, ws, 0, true);  // no forward pass ran: G, F are not in smem yet
       load_view(lane, wa.kf.m, b, rows - 1, n, ws.m);
       load_view(lane, wa.kf.C, b, rows - 1, nn, ws.C);
       __syncwarp();

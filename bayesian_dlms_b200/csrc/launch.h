@@ -43,6 +43,10 @@ struct WarpArgs {
 size_t warp_spill_doubles_per_row(int op, int n, int p);
 cudaError_t launch_warp(int op, const WarpArgs &wa, cudaStream_t stream);
 
+// kf_group.cu: two series per warp, compile-time n, p = 1 (FFBS / filter, n in {7, 13}).
+bool group_supported(int op, int n, int p, int keep_init);
+cudaError_t launch_group(int op, const WarpArgs &wa, cudaStream_t stream);
+
 // transpose.cu: [R][C] -> [C][R] for doubles (layout conversion of staged slabs).
 cudaError_t launch_transpose(const double *in, double *out, int64_t rows, int64_t cols,
                              cudaStream_t stream);

@@ -114,6 +114,13 @@ CASES = {
     "kat_bivariate": (lambda: (_dlm().polynomial(1) * _dlm().polynomial(1), 3 * np.eye(2),
                                np.eye(2), np.zeros(2), np.eye(2)), 30, 0.3, True, 37),
     "seasonal13": (H.seasonal13, 30, 0.1, False, 9),
+    # polynomial(1) |+| seasonal(24, 3), n = 7 (SeasonalModel.scala:14)
+    "seasonal7": (lambda: (_dlm().polynomial(1) + _dlm().seasonal(24, 3), np.array([[1.0]]),
+                           np.diag([0.01, 0.2, 0.4, 0.5, 0.2, 0.1, 0.4]), np.zeros(7), np.eye(7)),
+                  45, 0.15, False, 11),
+    "seasonal7_irregular": (lambda: (_dlm().polynomial(1) + _dlm().seasonal(24, 3), np.array([[1.0]]),
+                                     np.diag([0.01, 0.2, 0.4, 0.5, 0.2, 0.1, 0.4]), np.zeros(7),
+                                     np.eye(7)), 26, 0.1, True, 4),
     "seasonal13_irregular": (H.seasonal13, 21, 0.1, True, 5),
     "correlated8": (H.correlated8, 20, 0.2, True, 7),
 }
@@ -203,6 +210,16 @@ def test_filter_smooth_bit_exact(eng, oracle, name, layout_name, mem):
         _exact(_from_layout(f[k], layout), exp[k], f"{name}/filter/{k}")
     for k in ("s", "S"):
         _exact(_from_layout(s[k], layout), exp[k], f"{name}/smooth/{k}")
+    # the stand-alone smoother must not depend on what a previous kernel left in shared
+    # memory (regression: G was only loaded by the forward pass): run something unrelated,
+    # then smooth again
+    eng.loglik(Model.build(_dlm().polynomial(1) * _dlm().polynomial(1), T=7),
+               dict(V=np.eye(2), W=np.eye(2), m0=np.zeros(2), C0=np.eye(2)),
+               to(np.ones((3, 7, 2))), layout=SERIES_MAJOR)
+    s2 = eng.smooth(model, params, f, layout=layout, keep_init=True)
+    eng.sync()
+    for k in ("s", "S"):
+        _exact(_from_layout(s2[k], layout), exp[k], f"{name}/smooth again/{k}")
 
 
 @pytest.mark.parametrize("name", ["second_order", "kat_bivariate", "seasonal13"])
@@ -247,6 +264,7 @@ def test_loglik_matches_oracle(eng, oracle, name):
 
 @pytest.mark.parametrize("name", ["first_order", "second_order", "second_order_irregular",
                                   "kat_bivariate", "seasonal13", "seasonal13_irregular",
+                                  "seasonal7", "seasonal7_irregular",
                                   "correlated8"])
 @pytest.mark.parametrize("svd", [False, True])
 def test_ffbs_bit_for_bit_with_injected_normals(eng, oracle, name, svd):
