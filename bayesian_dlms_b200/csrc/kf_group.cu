@@ -9,17 +9,16 @@
 //   * gives lane j COLUMN j of every matrix in registers, with all loops unrolled at compile
 //     time (static register indexing, no index arithmetic); products are always
 //     (matrix in shared memory, read by broadcast) x (column in registers),
-//   * unrolls the round-robin Jacobi schedule so pair partners are compile-time constants;
-//     per round a lane exchanges one column of A and V with its partner through shared
-//     memory and applies the fused two-sided rotation to its own column.
+//   * runs the round-robin Jacobi schedule with lane j owning column j of A and V: per round a
+//     lane reads its partner's column from shared memory and applies the fused two-sided
+//     rotation to its own column (rounds are a run-time loop: unrolling them made the kernel
+//     466 KB of code and ncu showed 87 % "no instruction" stalls, see profiles/).
 // Every output element is still produced by one lane with the oracle's operation order, so
 // results stay bit-identical to oracle/bdlm_oracle.c (asserted by tests/test_gpu_parity.py).
 //
 // Reference: Smoothing.ffbs / sample / step (Smoothing.scala:74-159), KalmanFilter.step
 // (KalmanFilter.scala:64-107,273-321), MultivariateGaussianSvd.draw (:13-22), Gibbs
 // sufficient statistics (Gibbs.scala:29-43,63-73; GibbsWishart.scala:22-29).
-#include <type_traits>
-
 #include "common.cuh"
 #include "launch.h"
 #include "warp_linalg.cuh"
@@ -55,29 +54,6 @@ __device__ __forceinline__ void mm_sx(const double *X, const double (&y)[N], dou
   }
 }
 
-// compile-time loop: f(std::integral_constant<int, I>) for I in [I0, I1)
-template <int I0, int I1, class F>
-__device__ __forceinline__ void static_for(F &&f) {
-  if constexpr (I0 < I1) {
-    f(std::integral_constant<int, I0>{});
-    static_for<I0 + 1, I1>(f);
-  }
-}
-
-// compile-time round-robin partner (oracle rr_partners)
-__host__ __device__ constexpr int rr_partner_c(int n, int round, int i) {
-  const int m = (n + 1) & ~1, mm1 = m - 1, r = round % mm1;
-  int q = 0;
-  if (i == mm1) q = r;
-  else {
-    int d = i - r;
-    if (d < 0) d += mm1;
-    if (d == 0) q = mm1;
-    else { q = r - d; if (q < 0) q += mm1; }
-  }
-  return (q < n) ? q : -1;
-}
-
 template <int N>
 struct Ctx {
   int lane, gl, grp;       // lane in warp, lane in group, group in warp
@@ -88,13 +64,17 @@ struct Ctx {
   int *IP;
 };
 
-template <int N, int ROUND>
-__device__ __forceinline__ void jacobi_round(const Ctx<N> &cx, double (&Acol)[N], double (&Vcol)[N],
-                                             bool &rot_any_grp) {
+// One round of the round-robin Jacobi schedule for both series of the warp.  `round` is a
+// run-time value on purpose: unrolling the rounds made the kernel 29 k instructions (466 KB)
+// and ncu showed 87 % of all stall samples as "no instruction" (I-cache misses).  Own-column
+// elements at run-time row indices come from the shared-memory copy of A instead.
+template <int N>
+__device__ __forceinline__ void jacobi_round(const Ctx<N> &cx, int round, double (&Acol)[N],
+                                             double (&Vcol)[N], bool &rot_any_grp) {
   constexpr int LD = GSmem<N>::LD;
   const int j = cx.jj;
   // --- rotation parameters of my pair (both members compute the same c, s)
-  const int q = rr_partner(N, ROUND, j);
+  const int q = rr_partner(N, round, j);
   double c = 1.0, s = 0.0;
   bool rot = false;
   if (cx.act && q >= 0) {
@@ -109,71 +89,51 @@ __device__ __forceinline__ void jacobi_round(const Ctx<N> &cx, double (&Acol)[N]
     }
   }
   const int pj = (q < 0) ? j : q;
-  if (cx.act) { cx.VC[j] = c; cx.VS[j] = s; }
+  if (cx.act) { cx.VC[j] = c; cx.VS[j] = s; cx.IP[j] = pj; }
   const unsigned bal = __ballot_sync(FULL, rot);
   const bool any = ((bal >> (cx.grp * GW)) & 0xffffu) != 0;
   __syncwarp();
+  double nA[N];
   if (any) {
     rot_any_grp = true;
     const double cj = c, sj = s;
-    // new (i, j) element of J^T A J from the old values x1 = A[i,j], x2 = A[pi,j],
-    // x3 = A[i,pj], x4 = A[pi,pj]:
-    //   i >= j: v = cj*(ci*x1 + si*x2) + sj*(ci*x3 + si*x4)     (element (i, j), lower triangle)
-    //   i <  j: v = ci*(cj*x1 + sj*x3) + si*(cj*x2 + sj*x4)     (mirror of element (j, i))
-    auto elem = [&](int i, double ci, double si, double x1, double x2, double x3, double x4) {
+    const double *Aj = cx.S1 + j * LD, *Ap = cx.S1 + pj * LD, *Vp = cx.S2 + pj * LD;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      // new (i, j) element of J^T A J from the old x1 = A[i,j], x2 = A[pi,j], x3 = A[i,pj],
+      // x4 = A[pi,pj]:
+      //   i >= j: v = cj*(ci*x1 + si*x2) + sj*(ci*x3 + si*x4)   (element (i, j), lower triangle)
+      //   i <  j: v = ci*(cj*x1 + sj*x3) + si*(cj*x2 + sj*x4)   (mirror of element (j, i))
+      const int pi = cx.IP[i];
+      const double ci = cx.VC[i], si = cx.VS[i];
+      const double x1 = Acol[i], x2 = Aj[pi], x3 = Ap[i], x4 = Ap[pi];
       const bool low = i >= j;
       const double co = low ? cj : ci, so = low ? sj : si;
       const double cn = low ? ci : cj, sn = low ? si : sj;
       const double y2 = low ? x2 : x3, y3 = low ? x3 : x2;
       const double t1 = cn * x1 + sn * y2;
       const double t2 = cn * y3 + sn * x4;
-      return co * t1 + so * t2;
-    };
-    // rows are updated pair by pair, in place: both members of a pair only need the OLD
-    // values of the two rows (own column in registers, partner column from shared memory)
-    static_for<0, N>([&](auto I) {
-      constexpr int i = decltype(I)::value;
-      constexpr int pi_raw = rr_partner_c(N, ROUND, i);
-      constexpr int pi = pi_raw < 0 ? i : pi_raw;  // compile-time: static register index
-      if constexpr (pi >= i) {
-        const double a_i = Acol[i], b_i = cx.S1[i + pj * LD];
-        if constexpr (pi == i) {
-          Acol[i] = elem(i, cx.VC[i], cx.VS[i], a_i, a_i, b_i, b_i);
-        } else {
-          const double a_p = Acol[pi], b_p = cx.S1[pi + pj * LD];
-          Acol[i] = elem(i, cx.VC[i], cx.VS[i], a_i, a_p, b_i, b_p);
-          Acol[pi] = elem(pi, cx.VC[pi], cx.VS[pi], a_p, a_i, b_p, b_i);
-        }
-      }
-      Vcol[i] = cj * Vcol[i] + sj * cx.S2[i + pj * LD];
-    });
+      nA[i] = co * t1 + so * t2;
+      Vcol[i] = cj * Vcol[i] + sj * Vp[i];
+    }
   }
-  __syncwarp();  // all partner-column reads done before anyone publishes
-  if (any && cx.act) {
+  __syncwarp();  // all shared-memory reads of the old columns done before anyone publishes
+  if (any) {
 #pragma unroll
-    for (int i = 0; i < N; ++i) { cx.S1[i + j * LD] = Acol[i]; cx.S2[i + j * LD] = Vcol[i]; }
+    for (int i = 0; i < N; ++i) Acol[i] = nA[i];
+    if (cx.act) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) { cx.S1[i + j * LD] = Acol[i]; cx.S2[i + j * LD] = Vcol[i]; }
+    }
   }
   __syncwarp();
 }
-
-template <int N, int ROUND, int NROUNDS>
-struct Rounds {
-  __device__ __forceinline__ static void run(const Ctx<N> &cx, double (&A)[N], double (&V)[N],
-                                             bool &rot) {
-    jacobi_round<N, ROUND>(cx, A, V, rot);
-    Rounds<N, ROUND + 1, NROUNDS>::run(cx, A, V, rot);
-  }
-};
-template <int N, int NROUNDS>
-struct Rounds<N, NROUNDS, NROUNDS> {
-  __device__ __forceinline__ static void run(const Ctx<N> &, double (&)[N], double (&)[N], bool &) {}
-};
 
 // MultivariateGaussianSvd(mu, cov).draw with injected normals.  Input: the symmetric matrix
 // whose LOWER triangle is read sits in S0 (column-major, ld LD); mu_j, z_j per lane.
 // Uses S1 (A), S2 (V), S3 (M), VC, VS, VL, VZ.  Returns the draw element of lane j.
 template <int N>
-__device__ __forceinline__ double eig_draw(const Ctx<N> &cx, double mu_j, double z_j, int &st) {
+__device__ __noinline__ double eig_draw(const Ctx<N> &cx, double mu_j, double z_j, int &st) {
   constexpr int LD = GSmem<N>::LD;
   const int j = cx.jj;
   double Acol[N], Vcol[N];
@@ -193,7 +153,7 @@ __device__ __forceinline__ double eig_draw(const Ctx<N> &cx, double mu_j, double
   bool converged_grp = (N == 1);
   for (int sweep = 0; sweep < kJacobiMaxSweeps && N > 1; ++sweep) {
     bool rot = false;
-    Rounds<N, 0, M - 1>::run(cx, Acol, Vcol, rot);
+    for (int round = 0; round < M - 1; ++round) jacobi_round<N>(cx, round, Acol, Vcol, rot);
     if (!rot) converged_grp = true;
     // continue while either series of the warp still rotates (a converged series only
     // executes no-op rounds, exactly like the oracle's `continue`)
@@ -328,6 +288,7 @@ group_kernel(const WarpArgs wa) {
   cx.VA = v; cx.VB = v + VEC; cx.VC = v + 2 * VEC; cx.VS = v + 3 * VEC; cx.VD = v + 4 * VEC;
   cx.VK = v + 5 * VEC; cx.VL = v + 6 * VEC; cx.VZ = v + 7 * VEC; cx.VX = v + 8 * VEC;
   cx.VY = v + 9 * VEC;
+  cx.IP = reinterpret_cast<int *>(v + GSmem<N>::kVecs * VEC);
   const int j = cx.jj;
   const bool wr = cx.act && !ghost;  // lane may write global memory
   const int T = bt.T, rows = T + 1;

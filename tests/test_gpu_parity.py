@@ -377,3 +377,14 @@ def test_large_batch_properties_config2_shape(eng, oracle):
         _exact(C[:, :, b].cpu().numpy(), o["C"], "C")
         _exact(s[:, :, b].cpu().numpy(), sm["s"], "s")
         _exact(S[:, :, b].cpu().numpy(), sm["S"], "S")
+
+
+def test_wave_query_and_fp64_peak(eng):
+    from bayesian_dlms_b200 import _capi as capi
+    w2 = eng.ctx.wave_series(2, 1)
+    assert w2 > 0 and w2 % 128 == 0
+    with pytest.raises(capi.BdlmError):
+        eng.ctx.wave_series(13, 1)
+    peak = eng.ctx.fp64_peak_tflops()
+    assert 5.0 < peak < 100.0, peak
+    assert eng.ctx.launch_count() > 0
