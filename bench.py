@@ -382,7 +382,22 @@ def main():
         e2e = {"value": world * ncall * slab * T * ksteps / wall, "unit": "series-steps/s",
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": ksteps,
                "host_layout": "series-major [B][T+1][k], pinned", "series_per_call": slab,
-               "calls_per_step": ncall}
+               "calls_per_step": ncall,
+               "outputs": "full KfState (m,C,a,R,f,Q) + SmoothingState (s,S): 160 B/series-step over PCIe"}
+        # the same call asking only for what the reference's SmoothDlm app writes out
+        # (smoothed mean and covariance, FirstOrderDlm.scala:248-254): 48 B/series-step D2H
+        lean = {k: hout[k] for k in ("s", "S", "status")}
+        eng.filter_smooth(model, hp, hy, layout=SERIES_MAJOR, out=lean)
+        barrier()
+        w0 = time.perf_counter()
+        for _ in range(ncall):
+            eng.filter_smooth(model, hp, hy, layout=SERIES_MAJOR, out=lean)
+        barrier()
+        wl = torch.tensor([time.perf_counter() - w0], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(wl, op=dist.ReduceOp.MAX)
+        e2e["lean_outputs_value"] = world * ncall * slab * T / float(wl.item())
+        e2e["lean_outputs"] = "s, S only (what SmoothDlm writes): 48 B/series-step over PCIe"
 
     if rank == 0:
         line = {

@@ -1,0 +1,106 @@
+"""C-ABI contract on a GPU box: error codes mirror the reference's exceptions, host-buffer calls
+go through the slab pipeline for every entry point, nothing launches on API misuse."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import torch
+    assert torch.cuda.is_available()
+    from bayesian_dlms_b200 import default_engine
+    return default_engine(0)
+
+
+def _problem(capi, **kw):
+    F = np.array([1.0]); G = np.array([1.0]); one = np.array([1.0]); y = np.zeros(4)
+    base = dict(B=1, T=4, n=1, p=1, layout=capi.SERIES_MAJOR, mem=capi.HOST, keep_init=1, F=F, G=G,
+                times=None, V=one, W=one, m0=np.zeros(1), C0=one, y=y)
+    base.update(kw)
+    keep = [v for v in base.values() if isinstance(v, np.ndarray)]
+    return capi.make_problem(**base), keep
+
+
+def test_error_codes(eng):
+    from bayesian_dlms_b200 import _capi as capi
+    lib, h = capi.load(), eng.ctx.handle
+    out = np.zeros(8)
+    ko = capi.KfOut(); ko.m = out.ctypes.data
+    n0 = eng.ctx.launch_count()
+    pr, keep = _problem(capi, T=0)
+    assert lib.bdlm_kf_filter(h, pr, ko, None) == capi.E_EMPTY      # NoSuchElementException
+    pr, keep = _problem(capi, n=40)
+    assert lib.bdlm_kf_filter(h, pr, ko, None) == capi.E_ARG
+    pr, keep = _problem(capi, layout=7)
+    assert lib.bdlm_kf_filter(h, pr, ko, None) == capi.E_ARG
+    pr, keep = _problem(capi, y=None)
+    assert lib.bdlm_kf_filter(h, pr, ko, None) == capi.E_ARG
+    pr, keep = _problem(capi, keep_init=0)
+    z = np.zeros(8); th = np.zeros(8)
+    assert lib.bdlm_ffbs(h, pr, z.ctypes.data, th.ctypes.data, None, None, None) == capi.E_ARG
+    assert b"keep_init" in lib.bdlm_last_error(h)
+    assert lib.bdlm_kf_filter(None, pr, ko, None) == capi.E_ARG
+    assert eng.ctx.launch_count() == n0, "API misuse must not launch anything"
+
+
+def test_host_buffers_for_every_entry_point(eng):
+    """mem = HOST for FFBS / SVD / log-likelihood / statistics, small staging cap so that the
+    batch is really cut into several slabs."""
+    import oracle
+    from bayesian_dlms_b200 import Model, SERIES_MAJOR, dlm
+    oracle.build()
+    eng.ctx.set_staging_bytes(1 << 20)
+    try:
+        mod, V, W, m0, C0 = H.seasonal13()
+        B, T, n, p = 150, 12, 13, 1
+        rng = np.random.default_rng(4)
+        times = np.arange(1, T + 1.0)
+        y = np.stack([H.simulate(mod, V, W, m0, C0, times, rng, 0.1) for _ in range(B)])
+        z = rng.standard_normal((B, T + 1, n))
+        model = Model.build(mod, T=T)
+        params = dict(V=V, W=W, m0=m0, C0=C0)
+        F, _, G, _, _, _ = dlm.materialise(mod, times)
+        out = eng.ffbs(model, params, y, z, layout=SERIES_MAJOR, stats=True)
+        svd = eng.ffbs(model, params, y, z, layout=SERIES_MAJOR, svd=True)
+        ll = eng.loglik(model, params, y, layout=SERIES_MAJOR)
+        gs = eng.gibbs_stats(model, y, out["theta"], layout=SERIES_MAJOR)
+        assert isinstance(out["theta"], np.ndarray) and (out["status"] == 0).all()
+        for b in (0, 77, B - 1):
+            o = oracle.ffbs(n, p, F, G, dlm.cm(V), dlm.cm(W), m0, dlm.cm(C0), times, y[b], z[b])
+            assert np.array_equal(out["theta"][b], o["theta"])
+            s = oracle.svd_ffbs(n, p, F, G, dlm.cm(V), dlm.cm(W), m0, dlm.cm(C0), times, y[b], z[b])
+            assert np.array_equal(svd["theta"][b], s["theta"])
+            l = oracle.loglik(n, p, F, G, dlm.cm(V), dlm.cm(W), m0, dlm.cm(C0), times, y[b])
+            assert abs(ll["innovations"][b] - l["innovations"]) <= 1e-9 * abs(l["innovations"])
+            assert np.array_equal(gs["ssw"][b], out["ssw"][b])
+            assert np.array_equal(gs["scatter"][b], out["scatter"][b])
+    finally:
+        eng.ctx.set_staging_bytes(8 << 30)
+
+
+def test_time_major_host_buffers_use_strided_copies(eng):
+    import oracle
+    from bayesian_dlms_b200 import Model, TIME_MAJOR, dlm
+    oracle.build()
+    eng.ctx.set_staging_bytes(1 << 20)
+    try:
+        mod, V, W, m0, C0 = H.second_order()
+        B, T = 3000, 20
+        rng = np.random.default_rng(5)
+        y = rng.standard_normal((T, 1, B)).cumsum(axis=0)
+        out = eng.filter_smooth(Model.build(mod, T=T), dict(V=V, W=W, m0=m0, C0=C0),
+                                np.ascontiguousarray(y), layout=TIME_MAJOR)
+        F, _, G, _, n, p = dlm.materialise(mod, np.arange(1, T + 1.0))
+        for b in (0, 1500, B - 1):
+            o = oracle.kf_filter(n, p, F, G, dlm.cm(V), dlm.cm(W), m0, dlm.cm(C0), np.arange(1, T + 1.0),
+                                 y[:, :, b])
+            s = oracle.rts_smooth(n, G, o)
+            assert np.array_equal(out["m"][:, :, b], o["m"]) and np.array_equal(out["S"][:, :, b], s["S"])
+    finally:
+        eng.ctx.set_staging_bytes(8 << 30)
