@@ -35,7 +35,7 @@ ALGO_BYTES_PER_STEP = 8 * (N_OBS + (2 * N_STATE + 2 * N_STATE ** 2 + N_OBS + N_O
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--series", type=int, default=1_000_000, help="series per GPU")
@@ -52,42 +52,72 @@ def parse():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md): NVML in-process
+    every 10 ms (the timed region of a few steps is only a fraction of a second), nvidia-smi as
+    the fallback."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    BITS = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40,
+            "sw_power_cap": 0x4}
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.rows, self._stop_ev = index, [], threading.Event()
+        self.reasons, self.smax, self.how = set(), None, "nvidia-smi"
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+            self._nvml, self.how = pynvml, "nvml"
+        except Exception:
+            self._nvml = None
+
+    def _sample_nvml(self):
+        nv = self._nvml
+        self.rows.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+        try:
+            mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+        except Exception:
+            mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+        for name, bit in self.BITS.items():
+            if mask & bit:
+                self.reasons.add(name)
+
+    def _sample_smi(self):
+        r = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                            "-i", str(self.index)], capture_output=True, text=True, timeout=5)
+        if r.returncode == 0 and r.stdout.strip():
+            c = [x.strip() for x in r.stdout.strip().split(",")]
+            self.rows.append(float(c[0]))
+            self.smax = float(c[1])
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                "sw_power_cap"), c[3:7]):
+                if v.lower().startswith("active"):
+                    self.reasons.add(name)
 
     def run(self):
         while not self._stop_ev.is_set():
             try:
-                r = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                    "-i", str(self.index)], capture_output=True, text=True, timeout=5)
-                if r.returncode == 0 and r.stdout.strip():
-                    self.rows.append([c.strip() for c in r.stdout.strip().split(",")])
+                if self._nvml:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            self._stop_ev.wait(0.2)
+            self._stop_ev.wait(0.01 if self._nvml else 0.2)
 
     def stop(self):
         self._stop_ev.set()
         self.join(timeout=6)
-        sm, reasons, smax = [], set(), None
-        for r in self.rows:
-            try:
-                sm.append(float(r[0])); smax = float(r[1])
-            except Exception:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
-                                "sw_power_cap"), r[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(self.rows)) if self.rows else None,
+                "sm_max_mhz": self.smax, "reasons": sorted(self.reasons),
+                "samples": len(self.rows), "how": self.how}
 
 
 def synth_params(B, seed, xp):
@@ -213,7 +243,7 @@ def main():
         if rank != 0:
             return
         # K timed steps, each one pass over the bounded sample (W untimed passes first)
-        base, nser, dt = cpu_reference_leg(B, T, seconds_target=3.0 * max(1, args.steps),
+        base, nser, dt = cpu_reference_leg(B, T, seconds_target=min(30.0, 3.0 * max(1, args.steps)),
                                            warm_passes=max(1, args.warmup))
         v = base["value"]
         print(json.dumps({
