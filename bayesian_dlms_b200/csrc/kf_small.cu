@@ -44,20 +44,8 @@ __device__ __forceinline__ void load_vec(const View &v, int64_t b, int64_t row, 
   for (int k = 0; k < K; ++k) x[k] = ld_stream(p + k * v.sk);
 }
 
-// L2 prefetch (no destination register, no scoreboard slot): DRAM latency under the
-// write-heavy load of this kernel is several thousand cycles, more than one backward
-// iteration, so rows are pulled into L2 a few iterations before the register prefetch.
-template <int K>
-__device__ __forceinline__ void prefetch_vec(const View &v, int64_t b, int64_t row) {
-  const double *p = v.ptr + b * v.sb + row * v.sr;
-#pragma unroll
-  for (int k = 0; k < K; ++k) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + k * v.sk));
-}
-
-#ifndef BDLM_L2_AHEAD
-#define BDLM_L2_AHEAD 1000000 /* measured on B200: L2 prefetch 3/6 rows ahead is 5% SLOWER (profiles/r1_tuning.txt) */
-#endif
-constexpr int kL2Ahead = BDLM_L2_AHEAD;
+// (prefetch.global.L2 of the spill rows 3 or 6 iterations ahead was measured 5 % SLOWER on
+// B200 and removed -- profiles/r1_tuning.txt; the backward pass uses a cp.async ring instead.)
 
 template <int K>
 __device__ __forceinline__ void load_param(const PView &v, int64_t b, double *x) {
@@ -96,6 +84,15 @@ __device__ __forceinline__ void load_model(const Batch &bt, const SmallModel<N> 
 }
 
 constexpr int kChunk = 4;  // y prefetch distance (steps)
+constexpr int kRing = 4;   // backward-pass spill rows in flight per thread (power of two)
+
+__device__ __forceinline__ void cp_async8(double *smem_dst, const double *gmem_src) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int K>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(K) : "memory"); }
 
 // mode bits (compile-time: a runtime branch between "recompute a,R" and "reload a,R" made
 // ptxas put the prefetch loads and the reload loads on one scoreboard slot and wait for it
@@ -184,39 +181,47 @@ kf_small_kernel(const Batch bt, const SmallModel<N> mdl, const KfViews kf, const
     store_vec<N>(sv, b, rows - 1, s);
     store_vec<N * N>(Sv, b, rows - 1, S);
     const bool textbook = (bt.compat & BDLM_TEXTBOOK_SMOOTHER) != 0;
-    double mn[N], Cn[N * N], an[N], Rn[N * N];
-    if (rows >= 2) {
-      load_vec<N>(kf.m, b, rows - 2, mn);
-      load_vec<N * N>(kf.C, b, rows - 2, Cn);
-      if (RELOAD) {
-        load_vec<N>(kf.a, b, rows - 1, an);
-        load_vec<N * N>(kf.R, b, rows - 1, Rn);
+    // (m_t, C_t) spill rows are staged through a per-thread shared-memory ring by cp.async
+    // (LDGSTS), kRing rows deep: the loads bypass the register file and the scoreboard, so
+    // they stay in flight across several iterations of the recursion.  (One row of register
+    // prefetch was not enough: ncu showed 25 % of all stall samples on its first use; DRAM
+    // latency under this kernel's write-heavy load exceeds one backward iteration.)
+    extern __shared__ double ring[];
+    constexpr int kRow = N + N * N;
+    const int nthr = blockDim.x;
+    auto slot = [&](int r, int k) { return ring + ((size_t)(r & (kRing - 1)) * kRow + k) * nthr + threadIdx.x; };
+    auto issue = [&](int r) {
+      if (r >= 0) {
+        const double *pm = kf.m.ptr + b * kf.m.sb + (int64_t)r * kf.m.sr;
+        const double *pc = kf.C.ptr + b * kf.C.sb + (int64_t)r * kf.C.sr;
+#pragma unroll
+        for (int k = 0; k < N; ++k) cp_async8(slot(r, k), pm + k * kf.m.sk);
+#pragma unroll
+        for (int k = 0; k < N * N; ++k) cp_async8(slot(r, N + k), pc + k * kf.C.sk);
       }
+      cp_async_commit();
+    };
+    double an[N], Rn[N * N];
+#pragma unroll
+    for (int d = 0; d < kRing - 1; ++d) issue(rows - 2 - d);
+    if (RELOAD && rows >= 2) {
+      load_vec<N>(kf.a, b, rows - 1, an);
+      load_vec<N * N>(kf.R, b, rows - 1, Rn);
     }
     for (int r = rows - 2; r >= 0; --r) {
       double a1[N], R1[N * N];
+      issue(r - (kRing - 1));
+      cp_async_wait<kRing - 1>();  // the group of row r has landed
 #pragma unroll
-      for (int i = 0; i < N; ++i) m[i] = mn[i];
+      for (int i = 0; i < N; ++i) m[i] = *slot(r, i);
 #pragma unroll
-      for (int k = 0; k < N * N; ++k) C[k] = Cn[k];
+      for (int k = 0; k < N * N; ++k) C[k] = *slot(r, N + k);
       if (RELOAD) {
 #pragma unroll
         for (int i = 0; i < N; ++i) a1[i] = an[i];
 #pragma unroll
         for (int k = 0; k < N * N; ++k) R1[k] = Rn[k];
-      }
-      if (r > kL2Ahead) {  // pull the row needed kL2Ahead iterations from now into L2
-        prefetch_vec<N>(kf.m, b, r - 1 - kL2Ahead);
-        prefetch_vec<N * N>(kf.C, b, r - 1 - kL2Ahead);
-        if (RELOAD) {
-          prefetch_vec<N>(kf.a, b, r - kL2Ahead);
-          prefetch_vec<N * N>(kf.R, b, r - kL2Ahead);
-        }
-      }
-      if (r > 0) {  // prefetch the next row of the spill while this one is processed
-        load_vec<N>(kf.m, b, r - 1, mn);
-        load_vec<N * N>(kf.C, b, r - 1, Cn);
-        if (RELOAD) {
+        if (r > 0) {
           load_vec<N>(kf.a, b, r, an);
           load_vec<N * N>(kf.R, b, r, Rn);
         }
@@ -255,7 +260,8 @@ cudaError_t launch_t(const Batch &bt, const SmallModel<N> &mdl, const KfViews &k
   if (wave_series) {  // occupancy query only
     int blocks = 0, dev = 0, sms = 0;
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-        &blocks, kf_small_kernel<N, REG, MODE, RELOAD>, kThreads, 0);
+        &blocks, kf_small_kernel<N, REG, MODE, RELOAD>, kThreads,
+        (MODE & kDoSmooth) ? sizeof(double) * kRing * (N + N * N) * kThreads : 0);
     if (e != cudaSuccess) return e;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -264,7 +270,13 @@ cudaError_t launch_t(const Batch &bt, const SmallModel<N> &mdl, const KfViews &k
   }
   const int64_t blocks = (bt.B + kThreads - 1) / kThreads;
   if (blocks <= 0) return cudaSuccess;
-  kf_small_kernel<N, REG, MODE, RELOAD><<<(unsigned)blocks, kThreads, 0, stream>>>(bt, mdl, kf, sv, Sv);
+  const size_t smem = (MODE & kDoSmooth) ? sizeof(double) * kRing * (N + N * N) * kThreads : 0;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kf_small_kernel<N, REG, MODE, RELOAD>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  kf_small_kernel<N, REG, MODE, RELOAD><<<(unsigned)blocks, kThreads, smem, stream>>>(bt, mdl, kf, sv, Sv);
   return cudaGetLastError();
 }
 
