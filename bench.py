@@ -227,6 +227,108 @@ def ffbs_leg(eng, dev, with_cpu=True, B=4096, T=2000):
     return res
 
 
+def svd_leg(eng, dev, with_cpu=True, B=16384, T=1000):
+    """Secondary metric (BASELINE.json config 4): SVD-stabilised filter + sampler
+    (SvdSampler.ffbs as GibbsSampling.stepSvd calls it) for the correlated model, 8-fold outer
+    sum of polynomial(1), n = p = 8, full W; a quarter of the config's 65 536 series."""
+    import torch
+    from bayesian_dlms_b200 import Model, SERIES_MAJOR, dlm
+    mod = dlm.polynomial(1)
+    for _ in range(7):
+        mod = mod * dlm.polynomial(1)
+    n = 8
+    V = np.diag([1.0, 4.0] * 4)
+    W = np.diag([0.75, 1.25] * 4) + 0.5 * (np.eye(8, k=1) + np.eye(8, k=-1))
+    params = dict(V=V, W=W, m0=np.zeros(n), C0=np.eye(n))
+    g = torch.Generator(device=dev).manual_seed(20260104)
+    y = torch.randn((B, T, n), generator=g, device=dev, dtype=torch.float64) * 2.0
+    z = torch.randn((B, T + 1, n), generator=g, device=dev, dtype=torch.float64)
+    model = Model.build(mod, T=T)
+    eng.ffbs(model, params, y, z, layout=SERIES_MAJOR, svd=True)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    out = eng.ffbs(model, params, y, z, layout=SERIES_MAJOR, svd=True)
+    e1.record()
+    torch.cuda.synchronize()
+    t = e0.elapsed_time(e1) * 1e-3
+    # three thin Jacobi SVDs of 2n x n per step (~8 sweeps x n(n-1)/2 pairs x 6*3n flops) + products
+    flops_step = 3 * 8 * (n * (n - 1) / 2) * 18 * n + 20.0 * n ** 3
+    peak = eng.ctx.fp64_peak_tflops()
+    res = {"config": "config4: correlated n=p=8, %d series x T=%d, SVD filter + SVD sampler" % (B, T),
+           "draws_per_s": B / t, "steps_per_s": B * (T + 1) / t, "ms_per_sweep": t * 1e3,
+           "status_max": int(out["status"].max()),
+           "roofline": {"bound": "fp64", "achieved": B * (T + 1) * flops_step / t / 1e12,
+                        "peak": peak / 2.0, "unit": "TFLOP/s",
+                        "frac": B * (T + 1) * flops_step / t / 1e12 / (peak / 2.0),
+                        "flops_per_step": flops_step}}
+    if with_cpu:
+        import oracle
+        F, _, G, _, _, p = dlm.materialise(mod, np.arange(1, T + 1.0))
+        threads = os.cpu_count()
+        Bs = 4 * threads
+        rng = np.random.default_rng(4)
+        yc = rng.standard_normal((Bs, T, n)) * 2.0
+        zc = rng.standard_normal((Bs, T + 1, n))
+        t0 = time.perf_counter()
+        oracle.batch_ffbs(Bs, n, p, T, F, G, dlm.cm(V), dlm.cm(W), np.zeros(n), dlm.cm(np.eye(n)),
+                          np.arange(1, T + 1.0), yc, zc, svd=True, nthreads=threads)
+        dt = time.perf_counter() - t0
+        res["cpu_baseline"] = {"value": Bs / dt, "unit": "draws/s", "cores": threads, "kind": "port",
+                               "sample": f"{Bs} series x T={T}, {dt:.2f} s wall, oracle port OpenMP"}
+    return res
+
+
+def scan_leg(eng, dev, with_cpu=True, logT=24):
+    """Secondary metric (BASELINE.json config 5): ONE series, T = 2^24, polynomial(2),
+    parallel-in-time filter + smoother on one GPU (the 8-GPU run shards the time axis and
+    exchanges one aggregate per rank)."""
+    import torch
+    from bayesian_dlms_b200 import Model, dlm
+    from bayesian_dlms_b200.scan import scan_filter_smooth
+    n, T = 2, 1 << logT
+    params = dict(V=[[3.0]], W=np.diag([2.0, 1.0]), m0=np.zeros(2), C0=100.0 * np.eye(2))
+    g = torch.Generator(device=dev).manual_seed(20260105)
+    y = torch.randn(T, generator=g, device=dev, dtype=torch.float64).cumsum(0) * 0.1
+    model = Model.build(dlm.polynomial(2), T=T)
+    scan_filter_smooth(eng, model, params, y)
+    torch.cuda.synchronize()
+    ms = []
+    for _ in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = scan_filter_smooth(eng, model, params, y)
+        e1.record()
+        torch.cuda.synchronize()
+        ms.append(e0.elapsed_time(e1))
+    t = float(np.median(ms)) * 1e-3
+    byt = 8 * (2 + 14 + 6 + 6 + 6)  # y twice, KfState, (m,C) re-read twice, (s,S)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    res = {"config": "config5: one series, T=2^%d, polynomial(2), associative-scan filter+smoother" % logT,
+           "steps_per_s": T / t, "ms": t * 1e3, "status": int(out["status"][0]),
+           "roofline": {"bound": "hbm", "achieved": T * byt / t / 1e9, "peak": peak, "unit": "GB/s",
+                        "frac": T * byt / t / 1e9 / peak, "bytes_per_step": byt}}
+    if with_cpu:
+        import oracle
+        Tc = 1 << 20  # the reference recursion is sequential: one core, bounded sample
+        F, _, G, _, _, p = dlm.materialise(dlm.polynomial(2), np.arange(1, 9.0))
+        yc = y[:Tc].cpu().numpy()
+        t0 = time.perf_counter()
+        o = oracle.kf_filter(2, 1, F, G, [3.0], dlm.cm(np.diag([2.0, 1.0])), np.zeros(2),
+                             dlm.cm(100.0 * np.eye(2)), np.arange(1, Tc + 1.0), yc)
+        oracle.rts_smooth(2, G, o)
+        dt = time.perf_counter() - t0
+        res["cpu_baseline"] = {"value": Tc / dt, "unit": "series-steps/s", "cores": 1, "kind": "port",
+                               "sample": f"first 2^20 steps, sequential (the reference has no "
+                                         f"parallel-in-time path), {dt:.2f} s wall"}
+    return res
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -446,10 +548,17 @@ def main():
         if e2e:
             line["e2e"] = e2e
         if not args.no_ffbs and world == 1:
+            outbuf.clear(); ys.clear(); pars.clear()  # release the headline buffers (84 GB)
+            torch.cuda.empty_cache()
             try:
                 line["ffbs"] = ffbs_leg(eng, dev, with_cpu=not args.no_cpu)
             except Exception as ex:  # secondary metric: never take the headline down
                 line["ffbs"] = {"error": repr(ex)}
+            for key, fn in (("svd_ffbs", svd_leg), ("scan", scan_leg)):
+                try:
+                    line[key] = fn(eng, dev, with_cpu=not args.no_cpu)
+                except Exception as ex:
+                    line[key] = {"error": repr(ex)}
         if not args.no_cpu and world >= 1:
             try:
                 base, _, _ = cpu_reference_leg(B, T)
