@@ -33,6 +33,8 @@ struct bdlm_ctx {
   size_t arena_bytes = 0;
   size_t staging_cap = (size_t)8 << 30;
   size_t workspace_cap = (size_t)48 << 30;  // device-mode spill/transposes per launch
+  void *scan_table = nullptr;          // scan.cu forward table of the model in scan_key
+  std::vector<double> scan_key;
   bool use_group = std::getenv("BDLM_NO_GROUP_KERNEL") == nullptr;  // A/B switch for profiling
 };
 
@@ -543,6 +545,7 @@ void bdlm_destroy(bdlm_ctx *c) {
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->arena) cudaFree(c->arena);
+  if (c->scan_table) cudaFree(c->scan_table);
   for (int i = 0; i < 2; ++i) {
     if (c->ev_in[i]) cudaEventDestroy(c->ev_in[i]);
     if (c->ev_comp[i]) cudaEventDestroy(c->ev_comp[i]);
@@ -688,10 +691,25 @@ static int scan_validate(bdlm_ctx *c, const bdlm_problem *p) {
   return 0;
 }
 
-static void scan_fill(const bdlm_problem *p, ScanArgs &a) {
+static int scan_fill(bdlm_ctx *c, const bdlm_problem *p, ScanArgs &a, bool forward = false) {
   a = ScanArgs{};
   a.n = p->n; a.T = p->T; a.keep_init = p->keep_init ? 1 : 0;
   a.G = p->G; a.F = p->F; a.W = p->W; a.V = p->V[0]; a.y = p->y;
+  if (!forward) return 0;
+  // The forward level-1 table depends on the model only: rebuild it when (n, G, F, W, V) change.
+  if (!c->scan_table) CU(cudaMalloc(&c->scan_table, scan_table_bytes()));
+  const int n = p->n;
+  std::vector<double> key;
+  key.push_back(n);
+  key.insert(key.end(), p->G, p->G + n * n);
+  key.insert(key.end(), p->F, p->F + n);
+  key.insert(key.end(), p->W, p->W + n * n);
+  key.push_back(p->V[0]);
+  a.table = c->scan_table;
+  a.table_upload = (key.size() != c->scan_key.size() ||
+                    std::memcmp(key.data(), c->scan_key.data(), key.size() * sizeof(double)) != 0);
+  if (a.table_upload) c->scan_key = key;
+  return 0;
 }
 
 static KfViews scan_kf_views(const bdlm_problem *p, const bdlm_kf_out *kf) {
@@ -724,7 +742,8 @@ int bdlm_scan_forward_reduce(bdlm_ctx *c, const bdlm_problem *p, double *agg_hos
   rc = ensure_arena(c, scan_workspace_bytes(p->n, p->T) + 4096);
   if (rc) return rc;
   ScanArgs a;
-  scan_fill(p, a);
+  rc = scan_fill(c, p, a, true);
+  if (rc) return rc;
   a.phase = kScanReduce; a.agg_out = agg_host; a.workspace = c->arena;
   CU(launch_scan(a, c->stream, &c->launches));
   return 0;
@@ -744,12 +763,12 @@ int bdlm_scan_forward_apply(bdlm_ctx *c, const bdlm_problem *p, const double *st
     std::copy(p->C0, p->C0 + p->n * p->n, prior.begin() + p->n);
   }
   ScanArgs a;
-  scan_fill(p, a);
+  rc = scan_fill(c, p, a, true);
+  if (rc) return rc;
   a.phase = kScanApply; a.start = start_mC_host ? start_mC_host : prior.data();
   a.kf = scan_kf_views(p, kf); a.status = status; a.workspace = c->arena;
   if (status) CU(cudaMemsetAsync(status, 0, sizeof(int32_t), c->stream));
-  CU(launch_scan(a, c->stream, &c->launches));
-  CU(cudaStreamSynchronize(c->stream));  // `prior` / start are host buffers read by an async copy
+  CU(launch_scan(a, c->stream, &c->launches));  // start state travels by value: no sync needed
   return 0;
 }
 
@@ -763,7 +782,8 @@ int bdlm_scan_backward_reduce(bdlm_ctx *c, const bdlm_problem *p, const bdlm_kf_
   rc = ensure_arena(c, scan_workspace_bytes(p->n, p->T) + 4096);
   if (rc) return rc;
   ScanArgs a;
-  scan_fill(p, a);
+  rc = scan_fill(c, p, a);
+  if (rc) return rc;
   a.backward = 1; a.phase = kScanReduce; a.has_successor = has_successor ? 1 : 0;
   a.agg_out = agg_host; a.kf = scan_kf_views(p, filt); a.workspace = c->arena;
   CU(launch_scan(a, c->stream, &c->launches));
@@ -782,13 +802,13 @@ int bdlm_scan_backward_apply(bdlm_ctx *c, const bdlm_problem *p, const bdlm_kf_o
   if (rc) return rc;
   const int64_t n = p->n, R = rows_of(*p);
   ScanArgs a;
-  scan_fill(p, a);
+  rc = scan_fill(c, p, a);
+  if (rc) return rc;
   a.backward = 1; a.phase = kScanApply; a.has_successor = next_sS_host ? 1 : 0;
   a.start = next_sS_host; a.kf = scan_kf_views(p, filt);
   a.s = mk_view(sm->s, p->layout, 0, 1, R, n); a.S = mk_view(sm->S, p->layout, 0, 1, R, n * n);
   a.status = status; a.workspace = c->arena;
   CU(launch_scan(a, c->stream, &c->launches));
-  CU(cudaStreamSynchronize(c->stream));
   return 0;
 }
 
@@ -801,17 +821,36 @@ int bdlm_scan_filter_smooth(bdlm_ctx *c, const bdlm_problem *p, const bdlm_kf_ou
   const int64_t n = p->n, R = rows_of(*p);
   bdlm_kf_out k{};
   if (kf) k = *kf;
+  // arena: [forward scan workspace | backward scan workspace | (m, C) spill when not wanted]
   const size_t ws = align_up(scan_workspace_bytes(p->n, p->T) + 4096);
-  const size_t need = ws + (k.m ? 0 : align_up(sizeof(double) * R * n)) +
+  const size_t need = 2 * ws + (k.m ? 0 : align_up(sizeof(double) * R * n)) +
                       (k.C ? 0 : align_up(sizeof(double) * R * n * n)) + 4096;
   rc = ensure_arena(c, need);
   if (rc) return rc;
-  Bump bump{c->arena, ws, c->arena_bytes};
+  Bump bump{c->arena, 2 * ws, c->arena_bytes};
   if (!k.m) k.m = bump.take<double>((size_t)R * n);
   if (!k.C) k.C = bump.take<double>((size_t)R * n * n);
-  rc = bdlm_scan_forward_apply(c, p, nullptr, &k, status);
+  std::vector<double> prior((size_t)n + n * n);
+  std::copy(p->m0, p->m0 + n, prior.begin());
+  std::copy(p->C0, p->C0 + n * n, prior.begin() + n);
+  ScanArgs a;
+  rc = scan_fill(c, p, a, true);
   if (rc) return rc;
-  return bdlm_scan_backward_apply(c, p, &k, nullptr, sm, status);
+  // forward: filter outputs + the smoother's level-1 aggregates (fused into the apply sweep)
+  a.phase = kScanApply; a.start = prior.data();
+  a.kf = scan_kf_views(p, &k); a.status = status; a.workspace = c->arena;
+  a.fuse_sagg = R > 1 ? c->arena + ws : nullptr;
+  if (status) CU(cudaMemsetAsync(status, 0, sizeof(int32_t), c->stream));
+  CU(launch_scan(a, c->stream, &c->launches));
+  // backward: scan the aggregates, apply
+  rc = scan_fill(c, p, a);
+  if (rc) return rc;
+  a.backward = 1; a.phase = kScanApply; a.has_successor = 0; a.pre_reduced = R > 1 ? 1 : 0;
+  a.kf = scan_kf_views(p, &k);
+  a.s = mk_view(sm->s, p->layout, 0, 1, R, n); a.S = mk_view(sm->S, p->layout, 0, 1, R, n * n);
+  a.status = status; a.workspace = c->arena + ws;
+  CU(launch_scan(a, c->stream, &c->launches));
+  return 0;
 }
 
 int bdlm_gibbs_suffstats(bdlm_ctx *c, const bdlm_problem *p, const double *theta,

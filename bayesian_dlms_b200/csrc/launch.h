@@ -71,7 +71,13 @@ struct ScanArgs {
   View s, S;           // backward outputs
   int32_t *status;     // device, one int, OR-ed
   void *workspace;     // device, scan_workspace_bytes(n, T)
+  void *fuse_sagg;     // forward apply: also write the smoother's level-1 aggregates here (the
+                       // backward workspace of the call that follows), or nullptr
+  int pre_reduced;     // backward apply: workspace already holds those aggregates
+  void *table;         // device, scan_table_bytes(): y-independent parts of the level-1 aggregates
+  int table_upload;    // 1 = (re)build the table for this model before the forward pass
 };
+size_t scan_table_bytes();
 size_t scan_workspace_bytes(int n, int64_t T);
 int scan_forward_elem_doubles(int n);
 int scan_backward_elem_doubles(int n);

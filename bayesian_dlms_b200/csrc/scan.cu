@@ -23,6 +23,7 @@
 // Parity: equals the sequential kernel in textbook-smoother mode to 1e-9 relative (for n = 1
 // that is the reference itself); the apply phases reuse the sequential step code, so the
 // only difference is the rounding of the scanned start states.
+#include <cstdlib>
 #include <vector>
 
 #include "common.cuh"
@@ -178,14 +179,28 @@ __host__ __device__ __forceinline__ void s_combine(const SElem<N> &ei, const SEl
   for (int k = 0; k < N * N; ++k) out.L[k] = t2[k] + ei.L[k];
 }
 
+template <int N>
+__host__ __device__ __forceinline__ void s_element_pred(const double *G, const double (&m)[N],
+                                                        const double (&C)[N * N], const double (&a1)[N],
+                                                        const double (&R1)[N * N], SElem<N> &e);
+
 // Smoothing element of a filtered row that has a successor: E = C G^T R1^-1 (the RTS gain),
 // g = m - E a1, L = C - E R1 E^T, with (a1, R1) the prediction from (m, C).
 template <int N>
 __host__ __device__ __forceinline__ void s_element(const double *G, const double (&W)[N * N],
                                                    const double (&m)[N], const double (&C)[N * N],
                                                    SElem<N> &e) {
-  double a1[N], R1[N * N], rhs[N * N], At[N * N], t1[N * N], t2[N * N], v[N];
+  double a1[N], R1[N * N];
   advance<N, true>(G, W, 1.0, m, C, a1, R1);
+  s_element_pred<N>(G, m, C, a1, R1, e);
+}
+
+// Same, with the one-step prediction (a1, R1) from (m, C) already at hand.
+template <int N>
+__host__ __device__ __forceinline__ void s_element_pred(const double *G, const double (&m)[N],
+                                                        const double (&C)[N * N], const double (&a1)[N],
+                                                        const double (&R1)[N * N], SElem<N> &e) {
+  double rhs[N * N], At[N * N], t1[N * N], t2[N * N], v[N];
   smm<N, N, N, false, true>(G, C, rhs);
 #pragma unroll
   for (int j = 0; j < N; ++j)
@@ -207,26 +222,252 @@ __host__ __device__ __forceinline__ void s_element(const double *G, const double
 
 namespace {
 
-constexpr int kSub = 64;       // time points per thread (level 1)
+constexpr int kSub = 64;       // ROWS per thread (level 1); multiple of kGrp
+constexpr int kGrp = 4;        // rows per vector group: 4 rows x K doubles = K 32-byte sectors
 constexpr int kScanBlock = 256;
+constexpr size_t kScanTableBytes = 64 << 10;
 
 template <int N>
 struct ScanModel {
   double G[N * N], F[N], W[N * N], V;
 };
 
-// ---- level 1, forward: per-thread aggregate over observations [c*kSub, (c+1)*kSub)
+// Thread c owns OUTPUT ROWS [c*kSub, (c+1)*kSub) (row = t + keep_init), so that every group of
+// kGrp rows of every output field is a run of whole, 32-byte-aligned sectors that the owning
+// thread alone writes with 256-bit stores.  With one thread per 64 consecutive rows a store
+// instruction can never be coalesced ACROSS threads; what matters is that no sector is written
+// piecemeal: the partially written lines of all resident threads (6 fields x 128 B x 2.6e5
+// threads at T = 2^24) exceed L2, so 8-byte stores were evicted half-filled and cost a DRAM
+// read-fill plus a second write (ncu: 245 MB read, 596 MB written for 470 MB of output).
+__device__ __forceinline__ int64_t first_step(int64_t c, int keep_init) {
+  const int64_t t = c * kSub - keep_init;
+  return t < 0 ? 0 : t;
+}
+
+// BDLM_SCAN_ST=1 (environment, read per launch): default write-back policy instead of
+// evict-first, an A/B knob for profiles/r1_tuning.txt.
+__device__ int g_scan_st_default = 0;
+__device__ __forceinline__ void st_v4(double *p, double a, double b, double c, double d) {
+  if (g_scan_st_default)
+    asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d)
+                 : "memory");
+  else
+    asm volatile("st.global.cs.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d)
+                 : "memory");
+}
+__device__ __forceinline__ void ld_v4(const double *p, double *x) {
+  asm volatile("ld.global.v4.f64 {%0, %1, %2, %3}, [%4];"
+               : "=d"(x[0]), "=d"(x[1]), "=d"(x[2]), "=d"(x[3]) : "l"(p));
+}
+__device__ __forceinline__ void ld_v2(const double *p, double *x) {
+  asm volatile("ld.global.v2.f64 {%0, %1}, [%2];" : "=d"(x[0]), "=d"(x[1]) : "l"(p));
+}
+
+// One row of a dense field (K contiguous doubles), widest aligned loads available.
+template <int K, bool VEC>
+__device__ __forceinline__ void load_row(const View &v, int64_t row, double (&x)[K]) {
+  const double *p = v.ptr + row * v.sr;
+  if (VEC && K % 4 == 0) {
+#pragma unroll
+    for (int k = 0; k < K; k += 4) ld_v4(p + k, x + k);
+  } else if (VEC && K % 2 == 0) {
+#pragma unroll
+    for (int k = 0; k < K; k += 2) ld_v2(p + k, x + k);
+  } else {
+#pragma unroll
+    for (int k = 0; k < K; ++k) x[k] = ld_stream(p + k * v.sk);
+  }
+}
+
+// Observations behind a group of kGrp rows [r, r + kGrp): y[r - keep_init + i].  Thread-private
+// streams must be fetched a whole aligned 32-byte sector (better: line) at a time -- 8-byte loads
+// spread over four steps were re-fetched from DRAM up to 4x (the sector is evicted between the
+// steps; ncu: 675 MB read for 168 MB of input).  With keep_init the rows are one observation
+// ahead of the aligned sector, so the last element of each sector is carried to the next group.
+template <bool VEC>
+struct YGroup {
+  double carry;
+  __device__ __forceinline__ void start(const double *y, int64_t r0, int keep_init) {
+    carry = (VEC && keep_init && r0 > 0) ? y[r0 - 1] : 0.0;
+  }
+  // precondition: rows r .. r + kGrp - 1 all exist (r + kGrp <= T + keep_init)
+  __device__ __forceinline__ void load(const double *y, int64_t r, int64_t T, int keep_init,
+                                       double (&yv)[kGrp]) {
+    if (VEC) {
+      double v[kGrp];
+      if (r + kGrp <= T) ld_v4(y + r, v);
+      else {
+#pragma unroll
+        for (int i = 0; i < kGrp; ++i) v[i] = (r + i < T) ? y[r + i] : 0.0;
+      }
+      if (keep_init) {
+        yv[0] = carry;
+#pragma unroll
+        for (int i = 1; i < kGrp; ++i) yv[i] = v[i - 1];
+        carry = v[kGrp - 1];
+      } else {
+#pragma unroll
+        for (int i = 0; i < kGrp; ++i) yv[i] = v[i];
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < kGrp; ++i) {
+        const int64_t t = r + i - keep_init;
+        yv[i] = t >= 0 ? y[t] : 0.0;
+      }
+    }
+  }
+};
+
+// kGrp consecutive rows of a dense field in one go (whole lines for K >= 4).
+template <int K>
+__device__ __forceinline__ void load_group(const View &v, int64_t row, double (&x)[kGrp * K]) {
+  const double *p = v.ptr + row * K;
+#pragma unroll
+  for (int k = 0; k < kGrp * K; k += 4) ld_v4(p + k, x + k);
+}
+
+// Group buffer of one field: kGrp rows x K doubles in registers (all indices are compile-time
+// after unrolling, so only the not-yet-flushed tail stays live).  put<I>() deposits row I of
+// the group and flushes every 32-byte chunk that has just become complete; ASC = rows arrive in
+// increasing order (filter), otherwise decreasing (smoother).
+template <int K>
+struct GroupBuf {
+  double g[kGrp * K];
+  template <int I, bool ASC>
+  __device__ __forceinline__ void put(double *base, const double *x) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) g[I * K + k] = x[k];
+    constexpr int lo = ASC ? (I * K / 4) * 4 : ((I * K + 3) / 4) * 4;
+    constexpr int hi = ASC ? ((I + 1) * K / 4) * 4 : (((I + 1) * K + 3) / 4) * 4;
+#pragma unroll
+    for (int q = lo; q < hi && q < kGrp * K; q += 4) st_v4(base + q, g[q], g[q + 1], g[q + 2], g[q + 3]);
+  }
+};
+
+template <int K>
+__device__ __forceinline__ void store_row_scalar(const View &v, int64_t row, const double *x) {
+  if (!v.ptr) return;
+  double *p = v.ptr + row * v.sr;
+#pragma unroll
+  for (int k = 0; k < K; ++k) st_stream(p + k * v.sk, x[k]);
+}
+
+// ---- level 1, forward: per-thread aggregate over the observations behind its rows.
+//
+// Time-invariant model, regular grid, no missing value in the thread's range (the common case):
+// the element of an observed step is (A1, K y, C1, h y, J1) with y-independent A1, C1, J1, K, h,
+// so the (A, C, J) parts of the k-step aggregate acc_k = e(y_0) (x) ... (x) e(y_{k-1}) are the same
+// for every thread and only (b, eta) depend on the data -- linearly:
+//     b_{k+1}   = X_k b_k + u_k y_k            X_k = A1 (I + C_k J1)^-1,  u_k = X_k C_k h + K
+//     eta_{k+1} = eta_k + v_k y_k - Z_k b_k    Y_k = A_k^T (I + J1 C_k)^-1,  v_k = Y_k h,  Z_k = Y_k J1
+// The host composes acc_1..acc_kSub once (kSub generic combines) and uploads the table; a thread
+// then spends 2N^2 + 2N multiply-adds per step instead of a generic combine (two LU solves and
+// ten small products).  A thread that meets a NaN recomputes its range generically.
 template <int N>
+struct FwdTable {
+  struct Step { double X[N * N], u[N], v[N], Z[N * N]; } step[kSub];  // step[k]: acc_k -> acc_{k+1}
+  struct Agg { double A[N * N], C[N * N], J[N * N]; } agg[kSub + 1];  // agg[k]: parts of acc_k
+  double K[N], h[N];
+};
+
+template <int N>
+void build_fwd_table(const ScanModel<N> &md, FwdTable<N> &tb) {
+  FElem<N> e1, acc, nxt;
+  f_element<N>(md.G, md.F, md.W, md.V, 1.0, e1);  // y = 1: b = K, eta = h
+  for (int i = 0; i < N; ++i) { tb.K[i] = e1.b[i]; tb.h[i] = e1.eta[i]; }
+  acc = e1;
+  for (int k = 1; k <= kSub; ++k) {
+    for (int q = 0; q < N * N; ++q) { tb.agg[k].A[q] = acc.A[q]; tb.agg[k].C[q] = acc.C[q]; tb.agg[k].J[q] = acc.J[q]; }
+    if (k == kSub) break;
+    // X_k, Y_k exactly as f_combine forms them
+    double CJ[N * N], Mt[N * N], X[N * N], JC[N * N], Nt[N * N], Y[N * N], Xm[N * N], Ym[N * N], t[N];
+    smm<N, N, N, false, false>(acc.C, e1.J, CJ);
+    smm<N, N, N, false, false>(e1.J, acc.C, JC);
+    for (int j = 0; j < N; ++j)
+      for (int i = 0; i < N; ++i) {
+        Mt[i + j * N] = ((i == j) ? 1.0 : 0.0) + CJ[j + i * N];
+        X[i + j * N] = e1.A[j + i * N];
+        Nt[i + j * N] = ((i == j) ? 1.0 : 0.0) + JC[j + i * N];
+        Y[i + j * N] = acc.A[i + j * N];
+      }
+    lu_solve<N, N>(Mt, X);  // X = (A1 M)^T
+    lu_solve<N, N>(Nt, Y);  // Y = (A_k^T N)^T
+    for (int j = 0; j < N; ++j)
+      for (int i = 0; i < N; ++i) { Xm[i + j * N] = X[j + i * N]; Ym[i + j * N] = Y[j + i * N]; }
+    typename FwdTable<N>::Step &sp = tb.step[k];
+    for (int q = 0; q < N * N; ++q) sp.X[q] = Xm[q];
+    smm<N, N, 1, false, false>(acc.C, tb.h, t);
+    smm<N, N, 1, false, false>(Xm, t, sp.u);
+    for (int i = 0; i < N; ++i) sp.u[i] = sp.u[i] + tb.K[i];
+    smm<N, N, 1, false, false>(Ym, tb.h, sp.v);
+    smm<N, N, N, false, false>(Ym, e1.J, sp.Z);
+    f_combine<N>(acc, e1, nxt);
+    acc = nxt;
+  }
+}
+
+template <int N, bool VEC>
 __global__ void __launch_bounds__(128)
-fwd_reduce_kernel(const ScanModel<N> md, const double *__restrict__ y, int64_t T, int64_t M,
+fwd_reduce_kernel(const ScanModel<N> md, const FwdTable<N> *__restrict__ tb,
+                  const double *__restrict__ y, int64_t T, int64_t M, int keep_init,
                   FElem<N> *agg /* [M + 1], slot 0 reserved for the start element */) {
   const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (c >= M) return;
-  const int64_t t0 = c * kSub, t1 = (t0 + kSub < T) ? t0 + kSub : T;
+  const int64_t rows = T + keep_init;
+  const int64_t r0 = c * kSub, r1 = (r0 + kSub < rows) ? r0 + kSub : rows;
+  const int64_t t0 = first_step(c, keep_init), t1 = r1 - keep_init;
+  double b[N], eta[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) { b[i] = 0.0; eta[i] = 0.0; }
+  bool missing = false;
+  int k = 0;  // steps composed so far
+  auto step = [&](double yk) {
+    missing |= isnan(yk);
+    if (k == 0) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) { b[i] = tb->K[i] * yk; eta[i] = tb->h[i] * yk; }
+    } else {
+      const typename FwdTable<N>::Step &sp = tb->step[k];
+      double nb[N], ne[N];
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        double xb = 0.0, zb = 0.0;
+#pragma unroll
+        for (int j = 0; j < N; ++j) { xb += sp.X[i + j * N] * b[j]; zb += sp.Z[i + j * N] * b[j]; }
+        nb[i] = xb + sp.u[i] * yk;
+        ne[i] = eta[i] + sp.v[i] * yk - zb;
+      }
+#pragma unroll
+      for (int i = 0; i < N; ++i) { b[i] = nb[i]; eta[i] = ne[i]; }
+    }
+    ++k;
+  };
+  YGroup<VEC> yg;
+  yg.start(y, r0, keep_init);
+  int64_t r = r0;
+  for (; r + kGrp <= r1; r += kGrp) {
+    double yv[kGrp];
+    yg.load(y, r, T, keep_init, yv);
+#pragma unroll
+    for (int i = 0; i < kGrp; ++i)
+      if (r + i >= keep_init) step(yv[i]);  // row 0 of a keep_init run is the prior, not a step
+  }
+  for (; r < r1; ++r)
+    if (r >= keep_init) step(y[r - keep_init]);
+  if (!missing) {
+    FElem<N> &o = agg[c + 1];
+#pragma unroll
+    for (int q = 0; q < N * N; ++q) { o.A[q] = tb->agg[k].A[q]; o.C[q] = tb->agg[k].C[q]; o.J[q] = tb->agg[k].J[q]; }
+#pragma unroll
+    for (int i = 0; i < N; ++i) { o.b[i] = b[i]; o.eta[i] = eta[i]; }
+    return;
+  }
+  // generic path: a missing observation changes the element's (A, C, J)
   FElem<N> acc, e, tmp;
-  f_element<N>(md.G, md.F, md.W, md.V, ld_stream(y + t0), acc);
+  f_element<N>(md.G, md.F, md.W, md.V, y[t0], acc);
   for (int64_t t = t0 + 1; t < t1; ++t) {
-    f_element<N>(md.G, md.F, md.W, md.V, ld_stream(y + t), e);
+    f_element<N>(md.G, md.F, md.W, md.V, y[t], e);
     f_combine<N>(acc, e, tmp);
     acc = tmp;
   }
@@ -253,25 +494,43 @@ struct Op<SElem<N>> {
   }
 };
 
+// first (x) second in SCAN order
+template <class E, bool OPREV>
+__device__ __forceinline__ void scan_comb(const E &first, const E &second, E &o) {
+  if (OPREV) Op<E>::apply(second, first, o);
+  else Op<E>::apply(first, second, o);
+}
+
+// A block scans kScanBlock * kPer consecutive positions: every thread folds its kPer elements
+// serially (kPer - 1 combines), the thread totals go through a Hillis-Steele scan in shared
+// memory (log2(kScanBlock) combines per THREAD, i.e. 2 per element), and a second serial sweep
+// applies the exclusive prefix (kPer combines).  3.75 combines per element instead of 8 -- the
+// combine (two LU solves + ten products) is what this level costs.
+constexpr int kPer = 4;
+
 template <class E, bool IDXREV, bool OPREV>
 __global__ void __launch_bounds__(kScanBlock)
 block_scan_kernel(E *x, int64_t M, E *totals) {
   extern __shared__ unsigned char raw[];
   E *buf0 = reinterpret_cast<E *>(raw), *buf1 = buf0 + kScanBlock;
   const int tid = threadIdx.x;
-  const int64_t base = (int64_t)blockIdx.x * kScanBlock;
-  const int64_t p = base + tid;
-  const int64_t idx = IDXREV ? (M - 1 - p) : p;
-  const bool act = p < M;
-  if (act) buf0[tid] = x[idx];
+  const int64_t base = (int64_t)blockIdx.x * (kScanBlock * kPer);
+  const int64_t p0 = base + (int64_t)tid * kPer;
+  const int cnt = (p0 >= M) ? 0 : (int)((M - p0 < kPer) ? (M - p0) : kPer);
+  auto at = [&](int64_t p) -> E & { return x[IDXREV ? (M - 1 - p) : p]; };
+  const bool act = cnt > 0;
+  if (act) {
+    E run = at(p0), o;
+    for (int j = 1; j < cnt; ++j) { scan_comb<E, OPREV>(run, at(p0 + j), o); run = o; }
+    buf0[tid] = run;
+  }
   __syncthreads();
   E *src = buf0, *dst = buf1;
   for (int off = 1; off < kScanBlock; off <<= 1) {
     if (act) {
       if (tid >= off) {
         E o;
-        if (OPREV) Op<E>::apply(src[tid], src[tid - off], o);
-        else Op<E>::apply(src[tid - off], src[tid], o);
+        scan_comb<E, OPREV>(src[tid - off], src[tid], o);
         dst[tid] = o;
       } else {
         dst[tid] = src[tid];
@@ -280,8 +539,14 @@ block_scan_kernel(E *x, int64_t M, E *totals) {
     __syncthreads();
     E *t = src; src = dst; dst = t;
   }
-  if (act) x[idx] = src[tid];
-  const int64_t last = (base + kScanBlock <= M) ? kScanBlock - 1 : (M - 1 - base);
+  if (act) {
+    E run, o;
+    if (tid > 0) { scan_comb<E, OPREV>(src[tid - 1], at(p0), o); run = o; at(p0) = run; }
+    else run = at(p0);
+    for (int j = 1; j < cnt; ++j) { scan_comb<E, OPREV>(run, at(p0 + j), o); run = o; at(p0 + j) = run; }
+  }
+  const int64_t left = M - base;  // positions in this block
+  const int last = (int)(((left < kScanBlock * kPer ? left : kScanBlock * kPer) - 1) / kPer);
   if (totals && tid == last) totals[blockIdx.x] = src[tid];
 }
 
@@ -289,20 +554,24 @@ template <class E, bool IDXREV, bool OPREV>
 __global__ void __launch_bounds__(kScanBlock)
 add_prefix_kernel(E *x, int64_t M, const E *totals /* scanned, scan order */) {
   if (blockIdx.x == 0) return;
-  const int64_t p = (int64_t)blockIdx.x * kScanBlock + threadIdx.x;
-  if (p >= M) return;
-  const int64_t idx = IDXREV ? (M - 1 - p) : p;
-  const E pre = totals[blockIdx.x - 1], cur = x[idx];
-  E o;
-  if (OPREV) Op<E>::apply(cur, pre, o);
-  else Op<E>::apply(pre, cur, o);
-  x[idx] = o;
+  const E pre = totals[blockIdx.x - 1];
+#pragma unroll 1
+  for (int j = 0; j < kPer; ++j) {
+    const int64_t p = (int64_t)blockIdx.x * (kScanBlock * kPer) + j * kScanBlock + threadIdx.x;
+    if (p >= M) return;
+    const int64_t idx = IDXREV ? (M - 1 - p) : p;
+    const E cur = x[idx];
+    E o;
+    scan_comb<E, OPREV>(pre, cur, o);
+    x[idx] = o;
+  }
 }
 
 template <class E, bool IDXREV, bool OPREV>
 cudaError_t device_scan(E *x, int64_t M, E *scratch, cudaStream_t stream, int64_t *launches) {
   if (M <= 1) return cudaSuccess;
-  const int64_t nb = (M + kScanBlock - 1) / kScanBlock;
+  const int64_t per_block = kScanBlock * kPer;
+  const int64_t nb = (M + per_block - 1) / per_block;
   const size_t smem = 2 * kScanBlock * sizeof(E);
   cudaError_t e = cudaFuncSetAttribute(block_scan_kernel<E, IDXREV, OPREV>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -321,45 +590,106 @@ cudaError_t device_scan(E *x, int64_t M, E *scratch, cudaStream_t stream, int64_
 
 // ---- apply, forward: sequential Kalman recursion from the scanned start state
 template <int N>
+struct FwdRow {  // everything KfState holds for one row
+  double a[N], R[N * N], f, Q, m[N], C[N * N];
+};
+
+// One output row.  (an, Rn) is the prediction INTO this row, carried from the previous row
+// (it doubles as the (a1, R1) of the previous row's smoothing element); on return it is the
+// prediction into the next row.  FUSE: also fold this row's smoothing element into sacc when the
+// row has a successor (r < nrows), which saves the smoother's level-1 pass over (m, C).
+template <int N, bool FUSE>
+__device__ __forceinline__ void fwd_row(const ScanModel<N> &md, const double (&W)[N * N], bool init_row,
+                                        double yv, double (&m)[N], double (&C)[N * N],
+                                        double (&an)[N], double (&Rn)[N * N], FwdRow<N> &o, int &st,
+                                        bool has_succ, SElem<N> &sacc, bool &shave) {
+  if (init_row) {  // KalmanFilter.initialiseState: a = m = m0, R = C = C0, f, Q = None
+    const double nanv = __longlong_as_double(0x7ff8000000000000LL);
+#pragma unroll
+    for (int k = 0; k < N; ++k) o.a[k] = m[k];
+#pragma unroll
+    for (int k = 0; k < N * N; ++k) o.R[k] = C[k];
+    o.f = nanv; o.Q = nanv;
+  } else {
+#pragma unroll
+    for (int k = 0; k < N; ++k) o.a[k] = an[k];
+#pragma unroll
+    for (int k = 0; k < N * N; ++k) o.R[k] = Rn[k];
+    update<N>(md.F, md.V, yv, o.a, o.R, o.f, o.Q, m, C, st);
+  }
+#pragma unroll
+  for (int k = 0; k < N; ++k) o.m[k] = m[k];
+#pragma unroll
+  for (int k = 0; k < N * N; ++k) o.C[k] = C[k];
+  advance<N, true>(md.G, W, 1.0, m, C, an, Rn);
+  if (FUSE && has_succ) {
+    SElem<N> e, tmp;
+    s_element_pred<N>(md.G, m, C, an, Rn, e);
+    if (shave) { s_combine<N>(sacc, e, tmp); sacc = tmp; }
+    else { sacc = e; shave = true; }
+  }
+}
+
+template <int N, bool VEC, bool FUSE>
 __global__ void __launch_bounds__(128)
 fwd_apply_kernel(const ScanModel<N> md, const double *__restrict__ y, int64_t T, int64_t M,
                  const FElem<N> *pre /* [M+1] inclusive scan with slot 0 = start */,
-                 int keep_init, KfViews kf, int32_t *status) {
+                 int keep_init, KfViews kf, int32_t *status,
+                 SElem<N> *sagg /* FUSE: smoother level-1 aggregates */, int64_t nrows) {
   const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (c >= M) return;
-  const int64_t t0 = c * kSub, t1 = (t0 + kSub < T) ? t0 + kSub : T;
-  double m[N], C[N * N], W[N * N];
+  const int64_t rows = T + keep_init;
+  const int64_t r0 = c * kSub, r1 = (r0 + kSub < rows) ? r0 + kSub : rows;
+  double m[N], C[N * N], W[N * N], an[N], Rn[N * N];
   int st = 0;
 #pragma unroll
   for (int k = 0; k < N; ++k) m[k] = pre[c].b[k];
 #pragma unroll
   for (int k = 0; k < N * N; ++k) { C[k] = pre[c].C[k]; W[k] = md.W[k]; }
-  auto store = [&](const View &v, int64_t row, const double *x, int K) {
-    if (!v.ptr) return;
-    double *p = v.ptr + row * v.sr;
-    for (int k = 0; k < K; ++k) st_stream(p + k * v.sk, x[k]);
-  };
-  if (c == 0 && keep_init) {
-    const double nanv = __longlong_as_double(0x7ff8000000000000LL);
-    store(kf.m, 0, m, N); store(kf.C, 0, C, N * N);
-    store(kf.a, 0, m, N); store(kf.R, 0, C, N * N);
-    store(kf.f, 0, &nanv, 1); store(kf.Q, 0, &nanv, 1);
+  advance<N, true>(md.G, W, 1.0, m, C, an, Rn);
+  SElem<N> sacc;
+  bool shave = false;
+  int64_t r = r0;
+  if (VEC) {
+    YGroup<true> yg;
+    yg.start(y, r0, keep_init);
+    for (; r + kGrp <= r1; r += kGrp) {
+      double yv[kGrp];
+      yg.load(y, r, T, keep_init, yv);
+      GroupBuf<N> ga, gm;
+      GroupBuf<N * N> gR, gC;
+      GroupBuf<1> gf, gQ;
+#define BDLM_FWD_ROW(I)                                                          \
+  {                                                                              \
+    FwdRow<N> o;                                                                 \
+    fwd_row<N, FUSE>(md, W, keep_init && r + I == 0, yv[I], m, C, an, Rn, o, st, \
+                     r + I < nrows, sacc, shave);                                \
+    if (kf.a.ptr) ga.template put<I, true>(kf.a.ptr + r * N, o.a);               \
+    if (kf.R.ptr) gR.template put<I, true>(kf.R.ptr + r * (N * N), o.R);         \
+    if (kf.f.ptr) gf.template put<I, true>(kf.f.ptr + r, &o.f);                  \
+    if (kf.Q.ptr) gQ.template put<I, true>(kf.Q.ptr + r, &o.Q);                  \
+    if (kf.m.ptr) gm.template put<I, true>(kf.m.ptr + r * N, o.m);               \
+    if (kf.C.ptr) gC.template put<I, true>(kf.C.ptr + r * (N * N), o.C);         \
   }
-  for (int64_t t = t0; t < t1; ++t) {
-    double a[N], R[N * N], f, Q;
-    advance<N, true>(md.G, W, 1.0, m, C, a, R);
-    update<N>(md.F, md.V, ld_stream(y + t), a, R, f, Q, m, C, st);
-    const int64_t row = t + keep_init;
-    store(kf.a, row, a, N); store(kf.R, row, R, N * N);
-    store(kf.f, row, &f, 1); store(kf.Q, row, &Q, 1);
-    store(kf.m, row, m, N); store(kf.C, row, C, N * N);
+      BDLM_FWD_ROW(0) BDLM_FWD_ROW(1) BDLM_FWD_ROW(2) BDLM_FWD_ROW(3)
+#undef BDLM_FWD_ROW
+    }
   }
+  for (; r < r1; ++r) {  // ragged tail (or unaligned / strided outputs): scalar stores
+    const int64_t t = r - keep_init;
+    FwdRow<N> o;
+    fwd_row<N, FUSE>(md, W, t < 0, t >= 0 ? y[t] : 0.0, m, C, an, Rn, o, st, r < nrows, sacc, shave);
+    store_row_scalar<N>(kf.a, r, o.a); store_row_scalar<N * N>(kf.R, r, o.R);
+    store_row_scalar<1>(kf.f, r, &o.f); store_row_scalar<1>(kf.Q, r, &o.Q);
+    store_row_scalar<N>(kf.m, r, o.m); store_row_scalar<N * N>(kf.C, r, o.C);
+  }
+  if (FUSE && shave) sagg[c] = sacc;
   if (status && st) atomicOr(status, st);
 }
 
 // ---- level 1, backward: per-thread aggregate of smoothing elements over rows
 // [c*kSub, (c+1)*kSub) of the `nrows` rows that HAVE a successor.
-template <int N>
+template <int N, bool VEC>
 __global__ void __launch_bounds__(128)
 bwd_reduce_kernel(const ScanModel<N> md, View fm, View fC, int64_t nrows, int64_t M,
                   SElem<N> *agg /* [M + 1], slot M reserved for the terminal element */) {
@@ -370,21 +700,57 @@ bwd_reduce_kernel(const ScanModel<N> md, View fm, View fC, int64_t nrows, int64_
 #pragma unroll
   for (int k = 0; k < N * N; ++k) W[k] = md.W[k];
   SElem<N> acc, e, tmp;
-  for (int64_t r = r0; r < r1; ++r) {
-    double m[N], C[N * N];
-#pragma unroll
-    for (int k = 0; k < N; ++k) m[k] = ld_stream(fm.ptr + r * fm.sr + k * fm.sk);
-#pragma unroll
-    for (int k = 0; k < N * N; ++k) C[k] = ld_stream(fC.ptr + r * fC.sr + k * fC.sk);
+  auto row = [&](int64_t r, const double (&m)[N], const double (&C)[N * N]) {
     s_element<N>(md.G, W, m, C, e);
     if (r == r0) acc = e;
     else { s_combine<N>(acc, e, tmp); acc = tmp; }
+  };
+  int64_t r = r0;
+  if (VEC && N <= 2) {  // whole-line loads of kGrp rows (register budget allows it for n <= 2)
+    for (; r + kGrp <= r1; r += kGrp) {
+      double gm[kGrp * N], gC[kGrp * N * N];
+      load_group<N>(fm, r, gm);
+      load_group<N * N>(fC, r, gC);
+#pragma unroll
+      for (int i = 0; i < kGrp; ++i) {
+        double m[N], C[N * N];
+#pragma unroll
+        for (int k = 0; k < N; ++k) m[k] = gm[i * N + k];
+#pragma unroll
+        for (int k = 0; k < N * N; ++k) C[k] = gC[i * N * N + k];
+        row(r + i, m, C);
+      }
+    }
+  }
+  for (; r < r1; ++r) {
+    double m[N], C[N * N];
+    load_row<N, VEC>(fm, r, m);
+    load_row<N * N, VEC>(fC, r, C);
+    row(r, m, C);
   }
   agg[c] = acc;
 }
 
 // ---- apply, backward: sequential (textbook) RTS recursion from the scanned successor state
 template <int N>
+__device__ __forceinline__ void bwd_step(const ScanModel<N> &md, const double (&W)[N * N],
+                                         const double (&m)[N], const double (&C)[N * N],
+                                         double (&s)[N], double (&S)[N * N], int &st) {
+  double a1[N], R1[N * N];
+  advance<N, true>(md.G, W, 1.0, m, C, a1, R1);
+  rts_step<N>(md.G, m, C, a1, R1, /*textbook=*/true, s, S, st);
+}
+template <int N, bool VEC>
+__device__ __forceinline__ void bwd_row(const ScanModel<N> &md, const double (&W)[N * N], const View &fm,
+                                        const View &fC, int64_t r, double (&s)[N], double (&S)[N * N],
+                                        int &st) {
+  double m[N], C[N * N];
+  load_row<N, VEC>(fm, r, m);
+  load_row<N * N, VEC>(fC, r, C);
+  bwd_step<N>(md, W, m, C, s, S, st);
+}
+
+template <int N, bool VEC>
 __global__ void __launch_bounds__(128)
 bwd_apply_kernel(const ScanModel<N> md, View fm, View fC, int64_t nrows, int64_t M,
                  const SElem<N> *suf /* [M+1] suffix-inclusive scan, slot M = terminal */,
@@ -398,32 +764,71 @@ bwd_apply_kernel(const ScanModel<N> md, View fm, View fC, int64_t nrows, int64_t
   for (int k = 0; k < N * N; ++k) { W[k] = md.W[k]; S[k] = suf[c + 1].L[k]; }
 #pragma unroll
   for (int k = 0; k < N; ++k) s[k] = suf[c + 1].g[k];
-  for (int64_t r = r1 - 1; r >= r0; --r) {
-    double m[N], C[N * N], a1[N], R1[N * N];
-#pragma unroll
-    for (int k = 0; k < N; ++k) m[k] = ld_stream(fm.ptr + r * fm.sr + k * fm.sk);
-#pragma unroll
-    for (int k = 0; k < N * N; ++k) C[k] = ld_stream(fC.ptr + r * fC.sr + k * fC.sk);
-    advance<N, true>(md.G, W, 1.0, m, C, a1, R1);
-    rts_step<N>(md.G, m, C, a1, R1, /*textbook=*/true, s, S, st);
-    if (sv.ptr)
-      for (int k = 0; k < N; ++k) st_stream(sv.ptr + r * sv.sr + k * sv.sk, s[k]);
-    if (Sv.ptr)
-      for (int k = 0; k < N * N; ++k) st_stream(Sv.ptr + r * Sv.sr + k * Sv.sk, S[k]);
+  int64_t r = r1;  // one past the next row to produce
+  // ragged head of the descending sweep (rows above the last whole group), scalar stores
+  const int64_t aligned_top = VEC ? r0 + (r1 - r0) / kGrp * kGrp : r1;
+  auto scalar_row = [&](int64_t row) {
+    bwd_row<N, VEC>(md, W, fm, fC, row, s, S, st);
+    store_row_scalar<N>(sv, row, s);
+    store_row_scalar<N * N>(Sv, row, S);
+  };
+  if (VEC) {
+    for (; r > aligned_top; --r) scalar_row(r - 1);
+    for (; r - kGrp >= r0; r -= kGrp) {
+      const int64_t g0 = r - kGrp;
+      GroupBuf<N> gs;
+      GroupBuf<N * N> gS;
+      constexpr bool kGroupLoad = N <= 2;  // whole-line loads when the register budget allows
+      double gm[kGrp * N], gC[kGrp * N * N];  // dead (eliminated) when !kGroupLoad
+      if constexpr (kGroupLoad) {
+        load_group<N>(fm, g0, gm);
+        load_group<N * N>(fC, g0, gC);
+      }
+#define BDLM_BWD_ROW(I)                                                          \
+  {                                                                              \
+    if constexpr (kGroupLoad) {                                                  \
+      double m_[N], C_[N * N];                                                   \
+      for (int k = 0; k < N; ++k) m_[k] = gm[I * N + k];                         \
+      for (int k = 0; k < N * N; ++k) C_[k] = gC[I * N * N + k];                 \
+      bwd_step<N>(md, W, m_, C_, s, S, st);                                      \
+    } else {                                                                     \
+      bwd_row<N, VEC>(md, W, fm, fC, g0 + I, s, S, st);                          \
+    }                                                                            \
+    if (sv.ptr) gs.template put<I, false>(sv.ptr + g0 * N, s);                   \
+    if (Sv.ptr) gS.template put<I, false>(Sv.ptr + g0 * (N * N), S);             \
   }
+      BDLM_BWD_ROW(3) BDLM_BWD_ROW(2) BDLM_BWD_ROW(1) BDLM_BWD_ROW(0)
+#undef BDLM_BWD_ROW
+    }
+  }
+  for (; r > r0; --r) scalar_row(r - 1);
   if (status && st) atomicOr(status, st);
 }
 
+// (m, C) or (s, S) handed over by value: no host buffer outlives the call.
 template <int N>
-__global__ void set_f_start(FElem<N> *slot, const double *mC, bool identity) {
+struct StateArg {
+  double v[N + N * N];
+};
+template <int N>
+StateArg<N> state_arg(const double *host) {
+  StateArg<N> s;
+  for (int k = 0; k < N + N * N; ++k) s.v[k] = host ? host[k] : 0.0;
+  return s;
+}
+template <int N>
+__global__ void set_f_start(FElem<N> *slot, const StateArg<N> mC, bool identity) {
   FElem<N> e;
-  if (identity) f_identity<N>(e); else f_state<N>(e, mC, mC + N);
+  if (identity) f_identity<N>(e); else f_state<N>(e, mC.v, mC.v + N);
   *slot = e;
 }
 template <int N>
-__global__ void set_s_terminal(SElem<N> *slot, const double *sS, bool identity) {
+__global__ void set_s_terminal(SElem<N> *slot, const StateArg<N> sS, const double *sS_dev,
+                               bool identity) {
   SElem<N> e;
-  if (identity) s_identity<N>(e); else s_state<N>(e, sS, sS + N);
+  if (identity) s_identity<N>(e);
+  else if (sS_dev) s_state<N>(e, sS_dev, sS_dev + N);
+  else s_state<N>(e, sS.v, sS.v + N);
   *slot = e;
 }
 template <int N>
@@ -451,31 +856,57 @@ ScanModel<N> make_model(const ScanArgs &a) {
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return e_; } while (0)
 
+// 256-bit path: dense rows (sk = 1, sr = K) on a 32-byte aligned base.
+static bool dense_aligned(const View &v, int64_t K) {
+  return !v.ptr || (v.sk == 1 && v.sr == K && (reinterpret_cast<uintptr_t>(v.ptr) & 31) == 0);
+}
+
 template <int N>
 cudaError_t scan_forward(const ScanArgs &a, cudaStream_t stream, int64_t *launches) {
   const ScanModel<N> md = make_model<N>(a);
-  const int64_t T = a.T, M = (T + kSub - 1) / kSub;
+  const int64_t T = a.T, M = (T + a.keep_init + kSub - 1) / kSub;
   FElem<N> *X = reinterpret_cast<FElem<N> *>(a.workspace);       // [M + 1]
   FElem<N> *scratch = X + (M + 1);                                // block totals
-  double *start_dev = reinterpret_cast<double *>(scratch + (M + 1) / kScanBlock * 2 + 8);
   const unsigned blocks = (unsigned)((M + 127) / 128);
-  if (a.phase == kScanReduce) {
-    set_f_start<N><<<1, 1, 0, stream>>>(X, nullptr, true);
-    fwd_reduce_kernel<N><<<blocks, 128, 0, stream>>>(md, a.y, T, M, X);
-    *launches += 2;
-    CK(cudaGetLastError());
-    CK((device_scan<FElem<N>, false, false>(X, M + 1, scratch, stream, launches)));
-    CK(cudaMemcpyAsync(a.agg_out, X + M, sizeof(FElem<N>), cudaMemcpyDeviceToHost, stream));
-    return cudaStreamSynchronize(stream);
+  FwdTable<N> *tb = reinterpret_cast<FwdTable<N> *>(a.table);
+  if (a.table_upload) {  // model changed since the context last built it
+    static_assert(sizeof(FwdTable<N>) <= kScanTableBytes, "table buffer too small");
+    FwdTable<N> host;
+    build_fwd_table<N>(md, host);
+    // pageable source: staged by the driver before the call returns
+    CK(cudaMemcpyAsync(tb, &host, sizeof(host), cudaMemcpyHostToDevice, stream));
   }
-  // apply: prefix of (start (x) aggregates); a.start = host (m, C) of the state before t = 0
-  CK(cudaMemcpyAsync(start_dev, a.start, sizeof(double) * (N + N * N), cudaMemcpyHostToDevice, stream));
-  set_f_start<N><<<1, 1, 0, stream>>>(X, start_dev, false);
-  fwd_reduce_kernel<N><<<blocks, 128, 0, stream>>>(md, a.y, T, M, X);
+  const bool reduce = a.phase == kScanReduce;
+  // reduce: chunk aggregate only (identity start); apply: prefix of (start (x) aggregates),
+  // a.start = host (m, C) of the state before t = 0
+  set_f_start<N><<<1, 1, 0, stream>>>(X, state_arg<N>(reduce ? nullptr : a.start), reduce);
+  if ((reinterpret_cast<uintptr_t>(a.y) & 31) == 0)
+    fwd_reduce_kernel<N, true><<<blocks, 128, 0, stream>>>(md, tb, a.y, T, M, a.keep_init, X);
+  else
+    fwd_reduce_kernel<N, false><<<blocks, 128, 0, stream>>>(md, tb, a.y, T, M, a.keep_init, X);
   *launches += 2;
   CK(cudaGetLastError());
   CK((device_scan<FElem<N>, false, false>(X, M + 1, scratch, stream, launches)));
-  fwd_apply_kernel<N><<<blocks, 128, 0, stream>>>(md, a.y, T, M, X, a.keep_init, a.kf, a.status);
+  if (reduce) {
+    CK(cudaMemcpyAsync(a.agg_out, X + M, sizeof(FElem<N>), cudaMemcpyDeviceToHost, stream));
+    return cudaStreamSynchronize(stream);
+  }
+  const bool vec = dense_aligned(a.kf.m, N) && dense_aligned(a.kf.C, N * N) &&
+                   dense_aligned(a.kf.a, N) && dense_aligned(a.kf.R, N * N) &&
+                   dense_aligned(a.kf.f, 1) && dense_aligned(a.kf.Q, 1) &&
+                   (reinterpret_cast<uintptr_t>(a.y) & 31) == 0;
+  // a.fuse_sagg: the caller runs the smoother next on the same rows (single-GPU call): fold the
+  // smoothing elements here so the backward pass starts from ready level-1 aggregates.
+  SElem<N> *sagg = reinterpret_cast<SElem<N> *>(a.fuse_sagg);
+  const int64_t nrows = T + a.keep_init - 1;
+#define BDLM_FWD_APPLY(VEC_, FUSE_)                                                         \
+  fwd_apply_kernel<N, VEC_, FUSE_><<<blocks, 128, 0, stream>>>(md, a.y, T, M, X, a.keep_init, \
+                                                               a.kf, a.status, sagg, nrows)
+  if (vec && sagg) BDLM_FWD_APPLY(true, true);
+  else if (vec) BDLM_FWD_APPLY(true, false);
+  else if (sagg) BDLM_FWD_APPLY(false, true);
+  else BDLM_FWD_APPLY(false, false);
+#undef BDLM_FWD_APPLY
   ++*launches;
   return cudaGetLastError();
 }
@@ -493,19 +924,22 @@ cudaError_t scan_backward(const ScanArgs &a, cudaStream_t stream, int64_t *launc
   double *term_dev = reinterpret_cast<double *>(scratch + (M + 1) / kScanBlock * 2 + 8);
   const unsigned blocks = (unsigned)((M + 127) / 128);
   const bool reduce = a.phase == kScanReduce;
+  const StateArg<N> none = state_arg<N>(nullptr);
+  const bool vec = dense_aligned(a.kf.m, N) && dense_aligned(a.kf.C, N * N) &&
+                   dense_aligned(a.s, N) && dense_aligned(a.S, N * N);
   if (reduce) {
-    set_s_terminal<N><<<1, 1, 0, stream>>>(X + M, nullptr, true);
+    set_s_terminal<N><<<1, 1, 0, stream>>>(X + M, none, nullptr, true);
   } else if (a.has_successor) {
-    CK(cudaMemcpyAsync(term_dev, a.start, sizeof(double) * (N + N * N), cudaMemcpyHostToDevice, stream));
-    set_s_terminal<N><<<1, 1, 0, stream>>>(X + M, term_dev, false);
+    set_s_terminal<N><<<1, 1, 0, stream>>>(X + M, state_arg<N>(a.start), nullptr, false);
   } else {  // last chunk: s_T = m_T, S_T = C_T (Smoothing.scala:59-61)
     copy_last_row<N><<<1, 1, 0, stream>>>(a.kf.m, a.kf.C, rows - 1, a.s, a.S, term_dev);
-    set_s_terminal<N><<<1, 1, 0, stream>>>(X + M, term_dev, false);
+    set_s_terminal<N><<<1, 1, 0, stream>>>(X + M, none, term_dev, false);
     ++*launches;
   }
   ++*launches;
-  if (M > 0) {
-    bwd_reduce_kernel<N><<<blocks, 128, 0, stream>>>(md, a.kf.m, a.kf.C, nrows, M, X);
+  if (M > 0 && !a.pre_reduced) {
+    if (vec) bwd_reduce_kernel<N, true><<<blocks, 128, 0, stream>>>(md, a.kf.m, a.kf.C, nrows, M, X);
+    else bwd_reduce_kernel<N, false><<<blocks, 128, 0, stream>>>(md, a.kf.m, a.kf.C, nrows, M, X);
     ++*launches;
   }
   CK(cudaGetLastError());
@@ -515,7 +949,10 @@ cudaError_t scan_backward(const ScanArgs &a, cudaStream_t stream, int64_t *launc
     return cudaStreamSynchronize(stream);
   }
   if (M > 0) {
-    bwd_apply_kernel<N><<<blocks, 128, 0, stream>>>(md, a.kf.m, a.kf.C, nrows, M, X, a.s, a.S, a.status);
+    if (vec)
+      bwd_apply_kernel<N, true><<<blocks, 128, 0, stream>>>(md, a.kf.m, a.kf.C, nrows, M, X, a.s, a.S, a.status);
+    else
+      bwd_apply_kernel<N, false><<<blocks, 128, 0, stream>>>(md, a.kf.m, a.kf.C, nrows, M, X, a.s, a.S, a.status);
     ++*launches;
   }
   return cudaGetLastError();
@@ -529,10 +966,18 @@ size_t scan_workspace_bytes(int n, int64_t T) {
   return elem * (size_t)(M + 1 + (M + 1) / kScanBlock * 2 + 16) + 4096;
 }
 
+size_t scan_table_bytes() { return kScanTableBytes; }
 int scan_forward_elem_doubles(int n) { return 3 * n * n + 2 * n; }
 int scan_backward_elem_doubles(int n) { return 2 * n * n + n; }
 
 cudaError_t launch_scan(const ScanArgs &a, cudaStream_t stream, int64_t *launches) {
+  static int st_default = -1;
+  if (st_default < 0) {
+    const char *e = std::getenv("BDLM_SCAN_ST");
+    st_default = (e && e[0] == '1') ? 1 : 0;
+    cudaError_t err = cudaMemcpyToSymbol(g_scan_st_default, &st_default, sizeof(int));
+    if (err != cudaSuccess) return err;
+  }
   switch (a.n) {
 #define BDLM_SCAN_CASE(N_)                                                         \
   case N_:                                                                         \
