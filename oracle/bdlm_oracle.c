@@ -906,6 +906,183 @@ ORACLE_API void oracle_gibbs_stats(int n, int p, int T, const double *F, int f_t
   }
 }
 
+/* ------------------------------------------- conjugate parameter draws (f1)
+ * GibbsSampling.sampleObservationMatrix (Gibbs.scala:41-49) and sampleSystemMatrix
+ * (:72-77): posterior InverseGamma(shape, rate) per diagonal element and
+ * InverseGamma.draw (InverseGamma.scala:14) = 1.0 / Gamma(shape, 1.0 / rate).draw.
+ * Breeze's Gamma(shape, scale).draw is scale * g with g a standard Gamma(shape, 1)
+ * variate (Marsaglia-Tsang: g = d * v); g is INJECTED here, so
+ *     draw = 1.0 / ((1.0 / rate) * g).
+ * count[k] = number of observed y_i (sampleObservationMatrix) or NULL with
+ * count_all = theta.size - 1 = T (sampleSystemMatrix). */
+ORACLE_API void oracle_gibbs_invgamma(int k, double prior_shape, double prior_scale,
+                                      const double *count, double count_all,
+                                      const double *ss, const double *g,
+                                      double *shape, double *rate, double *draw) {
+  for (int i = 0; i < k; ++i) {
+    double c = count ? count[i] : count_all;
+    shape[i] = prior_shape + c * 0.5;
+    rate[i] = prior_scale + ss[i] * 0.5;
+    if (draw) draw[i] = 1.0 / ((1.0 / rate[i]) * g[i]);
+  }
+}
+
+/* dpotrf 'L' with the strict upper triangle zeroed (Breeze cholesky). */
+static int chol_lower(int n, const double *S, double *L) {
+  int st = ST_OK;
+  memcpy(L, S, sizeof(double) * n * n);
+  for (int j = 0; j < n; ++j) {
+    double d = L[j + j * n];
+    for (int k = 0; k < j; ++k) d = d - L[j + k * n] * L[j + k * n];
+    if (!(d > 0.0)) st = ST_NOTPD;
+    d = sqrt(d);
+    L[j + j * n] = d;
+    for (int i = j + 1; i < n; ++i) {
+      double v = L[i + j * n];
+      for (int k = 0; k < j; ++k) v = v - L[i + k * n] * L[j + k * n];
+      L[i + j * n] = v / d;
+    }
+    for (int i = 0; i < j; ++i) L[i + j * n] = 0.0;
+  }
+  return st;
+}
+
+/* Breeze inv(M) (dgetrf + dgetri) restated as dgesv against the identity. */
+static int inv_lu(int n, const double *M, double *out) {
+  double A[64 * 64];
+  memcpy(A, M, sizeof(double) * n * n);
+  for (int k = 0; k < n * n; ++k) out[k] = (k % (n + 1) == 0) ? 1.0 : 0.0;
+  return lu_solve(n, A, n, out);
+}
+
+/* GibbsWishart.sampleSystemMatrix (GibbsWishart.scala:16-35) followed by
+ * InverseWishart.draw (InverseWishart.scala:17-25): dof = nu + T,
+ * scale = psi + scatter; l = cholesky(inv(scale)); a = Bartlett factor of
+ * Wishart(dof, scale) (Wishart.scala:34-43: lower triangular, a_ii = sqrt(chi2(dof - i)),
+ * a_ij = N(0,1) for i > j) -- INJECTED as A; draw = inv(l)^T inv(a)^T inv(a) inv(l). */
+ORACLE_API int oracle_inverse_wishart(int n, const double *psi, const double *scatter,
+                                      const double *A, double *scale_out, double *W) {
+  double sc[64 * 64], isc[64 * 64], l[64 * 64], il[64 * 64], ia[64 * 64],
+      t1[64 * 64], t2[64 * 64];
+  int st = ST_OK;
+  for (int k = 0; k < n * n; ++k) sc[k] = psi[k] + (scatter ? scatter[k] : 0.0);
+  if (scale_out) memcpy(scale_out, sc, sizeof(double) * n * n);
+  st |= inv_lu(n, sc, isc);
+  st |= chol_lower(n, isc, l);
+  st |= inv_lu(n, l, il);
+  st |= inv_lu(n, A, ia);
+  mm(n, n, n, il, n, 1, ia, n, 1, t1, n);   /* invl.t * inva.t */
+  mm(n, n, n, t1, n, 0, ia, n, 0, t2, n);   /* ... * inva      */
+  mm(n, n, n, t2, n, 0, il, n, 0, W, n);    /* ... * invl      */
+  return st;
+}
+
+/* ---------------------------------- scalar AR(1) / OU filters and samplers (f3)
+ * FilterAr.stepUni / filterUnivariate (FilterAr.scala:15-47), FilterOu.stepUni /
+ * filterUnivariate (FilterOu.scala:7-45), backStepUni / univariateSample
+ * (FilterAr.scala:56-75, FilterOu.scala:47-71).  SvParameters(phi, mu, sigmaEta).
+ * ou = 0: AR(1) on a unit grid; ou = 1: Ornstein-Uhlenbeck on times[].
+ * v[T]: per-step observation variances.  Outputs have T + 1 rows (row 0 = prior).
+ * Math.pow(x, 2) is evaluated as x * x (HotSpot's pow intrinsic special-cases y == 2). */
+ORACLE_API void oracle_ar_filter(int ou, int T, double phi, double mu, double sigma,
+                                 const double *times, const double *v, const double *y,
+                                 double *tm, double *m, double *C, double *a, double *R) {
+  double m0 = mu;
+  double c0 = ou ? sigma * sigma / phi * phi : sigma * sigma / (1 - phi * phi);
+  tm[0] = ou ? times[0] : times[0] - 1.0;
+  m[0] = m0; C[0] = c0; a[0] = m0; R[0] = c0;
+  for (int t = 0; t < T; ++t) {
+    double at, rt;
+    if (ou) {
+      double dt = times[t] - tm[t];
+      double variance = ((sigma * sigma) * (1 - exp(-2 * phi * dt))) / (2 * phi);
+      at = mu + exp(-phi * dt) * (m[t] - mu);
+      rt = exp(-2 * phi * dt) * C[t] + variance;
+    } else {
+      at = mu + phi * (m[t] - mu);
+      rt = phi * phi * C[t] + sigma * sigma;
+    }
+    tm[t + 1] = times[t];
+    a[t + 1] = at; R[t + 1] = rt;
+    if (isnan(y[t])) {
+      m[t + 1] = at; C[t + 1] = rt;
+    } else {
+      double kt = rt / (rt + v[t]);
+      double et = y[t] - at;
+      m[t + 1] = at + kt * et;
+      C[t + 1] = kt * v[t];
+    }
+  }
+}
+
+/* z[T + 1]: injected N(0,1); Gaussian(mean, sd).draw = mean + sd * z (Breeze). */
+ORACLE_API void oracle_ar_backward_sample(int ou, int T, double phi, const double *tm,
+                                          const double *m, const double *C,
+                                          const double *a, const double *R,
+                                          const double *z, double *theta) {
+  theta[T] = m[T] + sqrt(C[T]) * z[T];
+  for (int t = T - 1; t >= 0; --t) {
+    double ph = ou ? exp(-phi * (tm[t + 1] - tm[t])) : phi;
+    double mean = m[t] + (C[t] * ph / R[t + 1]) * (theta[t + 1] - a[t + 1]);
+    double cov = C[t] - ((C[t] * C[t]) * (ph * ph)) / R[t + 1];
+    theta[t] = mean + sqrt(cov) * z[t];
+  }
+}
+
+/* ------------------------------------------------- conjugate filter (f4)
+ * ConjugateFilter.step / updateStats / initialiseState (ConjugateFilter.scala:23-94)
+ * for p = 1 (the reference's own use: FirstOrderDlm.scala:144-172): unknown observation
+ * variance with an InverseGamma(shape, scale) prior updated alongside the Kalman step.
+ * Note the reference's m = mt + k e (it adds the gain term to the PREVIOUS mean, :83).
+ * Outputs T + 1 rows: m[n], C[n*n], shape, scale of the variance posterior. */
+ORACLE_API int oracle_conjugate_filter(int n, int T, const double *F, int f_tv,
+                                       const double *G, int g_tv, const double *W,
+                                       const double *m0, const double *C0,
+                                       double prior_shape, double prior_scale,
+                                       const double *times, const double *y,
+                                       double *m, double *C, double *shape, double *scale) {
+  int nn = n * n, st = ST_OK;
+  double a[64], R[64 * 64], fr[64], rhs[64], K[64], D[64 * 64], t1[64 * 64],
+      C1[64 * 64], kv[64], C2[64 * 64];
+  double tprev = min_time(T, times) - 1.0;
+  memcpy(m, m0, sizeof(double) * n);
+  memcpy(C, C0, sizeof(double) * nn);
+  shape[0] = prior_shape; scale[0] = prior_scale;
+  for (int t = 0; t < T; ++t) {
+    const double *Ft = F + (f_tv ? (size_t)t * n : 0);
+    const double *Gt = G + (g_tv ? (size_t)t * nn : 0);
+    const double *mp = m + (size_t)t * n, *Cp = C + (size_t)t * nn;
+    double *mn = m + (size_t)(t + 1) * n, *Cn = C + (size_t)(t + 1) * nn;
+    double dt = times[t] - tprev;
+    kf_advance(n, Gt, W, dt, mp, Cp, a, R, t1);
+    double v = scale[t] / (shape[t] - 1);          /* meanVariance: InverseGamma.mean */
+    double ft, qt;
+    mv(1, n, Ft, n, 1, a, &ft);
+    mm(1, n, n, Ft, n, 1, R, n, 0, fr, 1);
+    mm(1, n, 1, fr, 1, 0, Ft, n, 0, &qt, 1);
+    qt = qt + v;
+    double e = y[t] - ft;
+    mm(1, n, n, Ft, n, 1, R, n, 1, rhs, 1);          /* f.t * rt.t */
+    if (qt == 0.0) st |= ST_SINGULAR;
+    for (int i = 0; i < n; ++i) K[i] = rhs[i] / qt;  /* (qt.t \ ...).t */
+    /* updateStats: shape + 1, scale + qt.t \ (v * (e * e.t)) */
+    shape[t + 1] = shape[t] + 1;
+    scale[t + 1] = scale[t] + (v * (e * e)) / qt;
+    for (int j = 0; j < n; ++j)
+      for (int i = 0; i < n; ++i)
+        D[i + j * n] = (i == j ? 1.0 : 0.0) - K[i] * Ft[j];
+    mm(n, n, n, D, n, 0, R, n, 0, t1, n);
+    mm(n, n, n, t1, n, 0, D, n, 1, C1, n);
+    for (int i = 0; i < n; ++i) kv[i] = K[i] * v;
+    for (int j = 0; j < n; ++j)
+      for (int i = 0; i < n; ++i) C2[i + j * n] = kv[i] * K[j];
+    for (int k = 0; k < nn; ++k) Cn[k] = C1[k] + C2[k];
+    for (int i = 0; i < n; ++i) mn[i] = mp[i] + K[i] * e;   /* sic: mt, not at (:83) */
+    tprev = times[t];
+  }
+  return st;
+}
+
 /* -------------------------------------------------- exposed small helpers */
 ORACLE_API int oracle_eigsym(int n, const double *A, double *lam, double *V) {
   return jacobi_eigsym(n, A, lam, V);

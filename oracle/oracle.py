@@ -285,3 +285,64 @@ def batch_ffbs(B, n, p, T, F, G, V, W, m0, C0, times, y, z, svd=False, nthreads=
                               _p(W), ws, _p(m0), ms, _p(C0), cs, _p(_a(times)), _p(y),
                               _p(z), int(svd), _p(theta))
     return dict(theta=theta, bad=bad)
+
+
+# ---- "next" rows: conjugate draws, AR(1)/OU scalar filters, conjugate filter
+
+def gibbs_invgamma(prior_shape, prior_scale, ss, g, count=None, count_all=0.0):
+    """Posterior InverseGamma(shape, rate) per diagonal element and its draw given a standard
+    Gamma(shape, 1) variate g (Gibbs.scala:41-49,72-77; InverseGamma.scala:14)."""
+    ss = _a(ss).ravel()
+    k = ss.size
+    g = _a(g).ravel()
+    shape, rate, draw = np.empty(k), np.empty(k), np.empty(k)
+    cnt = _a(count).ravel() if count is not None else None
+    lib().oracle_gibbs_invgamma(k, C.c_double(prior_shape), C.c_double(prior_scale),
+                                _p(cnt) if cnt is not None else None, C.c_double(count_all),
+                                _p(ss), _p(g), _p(shape), _p(rate), _p(draw))
+    return dict(shape=shape, rate=rate, draw=draw)
+
+
+def inverse_wishart(n, psi, scatter, A):
+    """InverseWishart(nu + T, psi + scatter).draw for an injected Bartlett factor A
+    (GibbsWishart.scala:16-35, InverseWishart.scala:17-25).  Column-major flats."""
+    W, sc = np.empty(n * n), np.empty(n * n)
+    st = lib().oracle_inverse_wishart(n, _p(_a(psi)), _p(_a(scatter)) if scatter is not None else None,
+                                      _p(_a(A)), _p(sc), _p(W))
+    return dict(W=W, scale=sc, status=st)
+
+
+def ar_filter(phi, mu, sigma, times, v, y, ou=False):
+    """FilterAr / FilterOu.filterUnivariate (FilterAr.scala:15-47, FilterOu.scala:7-45)."""
+    times, v, y = _a(times), _a(v), _a(y)
+    T = times.size
+    out = {k: np.empty(T + 1) for k in ("time", "m", "C", "a", "R")}
+    lib().oracle_ar_filter(int(ou), T, C.c_double(phi), C.c_double(mu), C.c_double(sigma),
+                           _p(times), _p(v), _p(y),
+                           *(_p(out[k]) for k in ("time", "m", "C", "a", "R")))
+    return out
+
+
+def ar_backward_sample(phi, filt, z, ou=False):
+    """FilterAr / FilterOu.univariateSample (FilterAr.scala:56-75, FilterOu.scala:47-71)."""
+    T = filt["m"].size - 1
+    theta = np.empty(T + 1)
+    lib().oracle_ar_backward_sample(int(ou), T, C.c_double(phi), _p(filt["time"]), _p(filt["m"]),
+                                    _p(filt["C"]), _p(filt["a"]), _p(filt["R"]), _p(_a(z)),
+                                    _p(theta))
+    return theta
+
+
+def conjugate_filter(n, F, G, W, m0, C0, prior_shape, prior_scale, times, y):
+    """ConjugateFilter(prior, advanceState).filter for p = 1 (ConjugateFilter.scala:23-94)."""
+    times = _a(times)
+    T = times.size
+    F, f_tv, G, g_tv = _model(F, G, n, 1, T)
+    out = dict(m=np.empty((T + 1, n)), C=np.empty((T + 1, n * n)), shape=np.empty(T + 1),
+               scale=np.empty(T + 1))
+    st = lib().oracle_conjugate_filter(n, T, _p(F), f_tv, _p(G), g_tv, _p(_a(W)), _p(_a(m0)),
+                                       _p(_a(C0)), C.c_double(prior_shape), C.c_double(prior_scale),
+                                       _p(times), _p(_a(y)), _p(out["m"]), _p(out["C"]),
+                                       _p(out["shape"]), _p(out["scale"]))
+    out["status"] = st
+    return out

@@ -19,7 +19,11 @@ import sys
 ref = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
 here = os.path.dirname(os.path.abspath(__file__))
 for name in ("first_order_dlm.csv", "first_order_dlm_filtered.csv",
-             "first_order_dlm_smoothed.csv"):
+             "first_order_dlm_smoothed.csv",
+             # "next" rows: FilterAr.filterUnivariate output of FilterArDlm
+             # (examples/src/main/scala/dlm/ar.scala:47-60) and ConjugateFilter output of
+             # ConjFilter (FirstOrderDlm.scala:144-172)
+             "ar_dlm.csv", "ar_dlm_filtered.csv", "first_order_dlm_conjugate_filtered.csv"):
     shutil.copyfile(os.path.join(ref, "examples", "data", name), os.path.join(here, name))
 
 N = None

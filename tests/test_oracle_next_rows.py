@@ -1,0 +1,138 @@
+"""Oracle pins for the "next" rows of SURVEY.md section 8(f) (CPU, no GPU needed).
+
+* AR(1) scalar filter: the reference's committed ``ar_dlm.csv -> ar_dlm_filtered.csv``
+  (``FilterArDlm``, examples/src/main/scala/dlm/ar.scala:47-60) -- bit exact.
+* Conjugate filter: ``first_order_dlm_conjugate_filtered.csv`` (``ConjFilter``,
+  FirstOrderDlm.scala:144-172) -- bit exact on (m, C, E[V], Var[V]).
+* Conjugate draws: closed-form checks of the posterior arithmetic (Gibbs.scala:41-49,72-77;
+  GibbsWishart.scala:16-35; InverseWishart.scala:17-25) against numpy/LAPACK.
+"""
+import numpy as np
+
+import helpers as H
+import oracle
+
+
+def _ar_golden():
+    rows = H.read_csv("ar_dlm.csv")
+    times = np.array([float(r[0]) for r in rows])
+    y = np.array([float(r[1]) for r in rows])
+    g = H.read_csv("ar_dlm_filtered.csv")
+    return times, y, np.array([[float(v) for v in r] for r in g])
+
+
+def test_ar_filter_reproduces_reference_csv_bit_exact():
+    times, y, gold = _ar_golden()
+    out = oracle.ar_filter(0.8, 1.0, 0.3, times, np.full(times.size, 0.5), y)
+    assert gold.shape == (times.size + 1, 3)
+    assert np.array_equal(out["time"], gold[:, 0])
+    assert np.array_equal(out["m"], gold[:, 1])
+    assert np.array_equal(out["C"], gold[:, 2])
+
+
+def test_ar_filter_is_the_dlm_filter_with_a_mean_shift():
+    """AR(1) around mu == the generic DLM filter on (y - mu) with G = phi, W = sigma^2."""
+    rng = np.random.default_rng(3)
+    T, phi, mu, sig = 200, 0.9, -0.7, 0.4
+    y = rng.standard_normal(T) + mu
+    y[rng.random(T) < 0.1] = np.nan
+    v = 0.5 + rng.random(T)
+    ar = oracle.ar_filter(phi, mu, sig, np.arange(1.0, T + 1), v, y)
+    # generic filter, one step at a time is awkward with varying v: use a numpy scalar recursion
+    m, C = mu, sig * sig / (1 - phi * phi)
+    for t in range(T):
+        a, R = mu + phi * (m - mu), phi * phi * C + sig * sig
+        if np.isnan(y[t]):
+            m, C = a, R
+        else:
+            k = R / (R + v[t])
+            m, C = a + k * (y[t] - a), k * v[t]
+        assert abs(ar["m"][t + 1] - m) <= 1e-14 * max(1, abs(m))
+        assert abs(ar["C"][t + 1] - C) <= 1e-14 * max(1, abs(C))
+
+
+def test_ou_filter_and_sampler_moments():
+    """OU transition moments (FilterOu.scala:12-18) and the backward sampler's conditional
+    moments (FilterOu.scala:47-60) against a direct numpy evaluation."""
+    rng = np.random.default_rng(5)
+    T, phi, mu, sig = 50, 0.3, 1.2, 0.8
+    times = np.cumsum(rng.uniform(0.2, 2.0, T))
+    y = rng.standard_normal(T)
+    v = np.full(T, 0.7)
+    f = oracle.ar_filter(phi, mu, sig, times, v, y, ou=True)
+    assert f["time"][0] == times[0] and f["m"][0] == mu        # t0 = head time, dt_1 = 0
+    assert f["C"][0] == sig * sig / phi * phi                  # sic (FilterOu.scala:36)
+    m, C, tp = f["m"][0], f["C"][0], f["time"][0]
+    for t in range(T):
+        dt = times[t] - tp
+        a = mu + np.exp(-phi * dt) * (m - mu)
+        R = np.exp(-2 * phi * dt) * C + sig ** 2 * (1 - np.exp(-2 * phi * dt)) / (2 * phi)
+        k = R / (R + v[t])
+        m, C, tp = a + k * (y[t] - a), k * v[t], times[t]
+        assert np.isclose(f["a"][t + 1], a, rtol=1e-13) and np.isclose(f["R"][t + 1], R, rtol=1e-13)
+        assert np.isclose(f["m"][t + 1], m, rtol=1e-13) and np.isclose(f["C"][t + 1], C, rtol=1e-13)
+    z = rng.standard_normal(T + 1)
+    th = oracle.ar_backward_sample(phi, f, z, ou=True)
+    assert th[T] == f["m"][T] + np.sqrt(f["C"][T]) * z[T]
+    for t in range(T - 1, -1, -1):
+        ph = np.exp(-phi * (f["time"][t + 1] - f["time"][t]))
+        mean = f["m"][t] + f["C"][t] * ph / f["R"][t + 1] * (th[t + 1] - f["a"][t + 1])
+        cov = f["C"][t] - f["C"][t] ** 2 * ph ** 2 / f["R"][t + 1]
+        assert np.isclose(th[t], mean + np.sqrt(cov) * z[t], rtol=1e-12, atol=1e-14)
+
+
+def test_ar_backward_sampler_with_zero_noise_is_the_conditional_mean():
+    times, y, _ = _ar_golden()
+    times, y = times[:300], y[:300]
+    f = oracle.ar_filter(0.8, 1.0, 0.3, times, np.full(300, 0.5), y)
+    th = oracle.ar_backward_sample(0.8, f, np.zeros(301))
+    assert th[300] == f["m"][300]
+    # with z = 0 the draw is the RTS-smoothed mean of the scalar model
+    s = f["m"][300]
+    for t in range(299, -1, -1):
+        s = f["m"][t] + f["C"][t] * 0.8 / f["R"][t + 1] * (s - f["a"][t + 1])
+        assert np.isclose(th[t], s, rtol=1e-13)
+
+
+def test_conjugate_filter_reproduces_reference_csv_bit_exact():
+    times, y, _ = H.first_order_golden()
+    gold = np.array([[float(v) for v in r] for r in H.read_csv("first_order_dlm_conjugate_filtered.csv")])
+    out = oracle.conjugate_filter(1, [1.0], [1.0], [3.0], [0.0], [100.0], 3.0, 4.0, times, y[:, 0])
+    assert out["status"] == 0
+    assert gold.shape == (times.size + 1, 5)
+    mean = out["scale"] / (out["shape"] - 1)
+    var = (out["scale"] * out["scale"]) / ((out["shape"] - 1) * (out["shape"] - 1) * (out["shape"] - 2))
+    assert np.array_equal(out["m"][:, 0], gold[:, 1])
+    assert np.array_equal(out["C"][:, 0], gold[:, 2])
+    assert np.array_equal(mean, gold[:, 3])
+    assert np.array_equal(var, gold[:, 4])
+
+
+def test_invgamma_posterior_arithmetic():
+    ss = np.array([3.5, 0.25, 11.0])
+    cnt = np.array([10.0, 7.0, 0.0])
+    g = np.array([2.0, 0.5, 4.0])
+    o = oracle.gibbs_invgamma(5.0, 4.0, ss, g, count=cnt)
+    assert np.array_equal(o["shape"], 5.0 + cnt * 0.5)
+    assert np.array_equal(o["rate"], 4.0 + ss * 0.5)
+    assert np.array_equal(o["draw"], 1.0 / ((1.0 / o["rate"]) * g))
+    o = oracle.gibbs_invgamma(17.0, 4.0, ss, g, count_all=2000.0)
+    assert np.array_equal(o["shape"], np.full(3, 17.0 + 1000.0))
+
+
+def test_inverse_wishart_matches_lapack():
+    rng = np.random.default_rng(11)
+    n = 5
+    psi, scatter = H.spd(rng, n), H.spd(rng, n, 3.0)
+    A = np.tril(rng.standard_normal((n, n)), -1) + np.diag(np.sqrt(rng.chisquare(12 - np.arange(n))))
+    o = oracle.inverse_wishart(n, oracle.oracle.cm(psi), oracle.oracle.cm(scatter), oracle.oracle.cm(A))
+    assert o["status"] == 0
+    sc = psi + scatter
+    l = np.linalg.cholesky(np.linalg.inv(sc))
+    il, ia = np.linalg.inv(l), np.linalg.inv(A)
+    want = il.T @ ia.T @ ia @ il
+    got = o["W"].reshape(n, n).T
+    assert H.rel_err(got, want) < 1e-10
+    assert np.allclose(got, got.T, rtol=1e-12)
+    assert np.all(np.linalg.eigvalsh(got) > 0)
+    assert np.array_equal(o["scale"].reshape(n, n).T, sc)
