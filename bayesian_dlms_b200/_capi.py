@@ -31,7 +31,10 @@ SYMBOLS = [
     "bdlm_fp64_peak_tflops", "bdlm_scan_filter_smooth", "bdlm_scan_elem_doubles",
     "bdlm_scan_forward_reduce", "bdlm_scan_forward_apply", "bdlm_scan_backward_reduce",
     "bdlm_scan_backward_apply", "bdlm_scan_combine",
+    "bdlm_ar_filter", "bdlm_ar_ffbs", "bdlm_conjugate_filter", "bdlm_gibbs_draw",
 ]
+AR1, OU = 0, 1
+V_SCALAR, V_PER_STEP, V_PER_SERIES_STEP = 0, 1, 2
 
 
 class Problem(C.Structure):
@@ -58,6 +61,27 @@ class SvdOut(C.Structure):
 
 class GibbsStats(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in ("ssy", "ny", "ssw", "scatter")]
+
+
+class ArProblem(C.Structure):
+    _fields_ = [("B", C.c_int64), ("T", C.c_int32), ("layout", C.c_int32), ("mem", C.c_int32),
+                ("process", C.c_int32), ("per_series", C.c_int32), ("v_mode", C.c_int32),
+                ("phi", C.c_void_p), ("mu", C.c_void_p), ("sigma_eta", C.c_void_p),
+                ("times", C.c_void_p), ("v", C.c_void_p), ("y", C.c_void_p)]
+
+
+class ArOut(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ("m", "C", "a", "R")]
+
+
+class GibbsPrior(C.Structure):
+    _fields_ = [("v_shape", C.c_double), ("v_scale", C.c_double), ("w_shape", C.c_double),
+                ("w_scale", C.c_double), ("w_nu", C.c_double), ("w_psi", C.c_void_p)]
+
+
+class GibbsRng(C.Structure):
+    _fields_ = [("seed", C.c_uint64), ("sweep", C.c_uint64), ("gamma_v", C.c_void_p),
+                ("gamma_w", C.c_void_p), ("bartlett", C.c_void_p)]
 
 
 class BdlmError(RuntimeError):
@@ -116,6 +140,14 @@ def load():
     lib.bdlm_scan_backward_apply.argtypes = [C.c_void_p, PP, C.POINTER(KfOut), C.c_void_p,
                                              C.POINTER(SmoothOut), C.c_void_p]
     lib.bdlm_scan_combine.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.bdlm_ar_filter.argtypes = [C.c_void_p, C.POINTER(ArProblem), C.POINTER(ArOut)]
+    lib.bdlm_ar_ffbs.argtypes = [C.c_void_p, C.POINTER(ArProblem), C.c_void_p, C.c_void_p,
+                                 C.POINTER(ArOut)]
+    lib.bdlm_conjugate_filter.argtypes = [C.c_void_p, PP, C.c_double, C.c_double,
+                                          C.POINTER(KfOut), C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.bdlm_gibbs_draw.argtypes = [C.c_void_p, PP, C.POINTER(GibbsStats), C.POINTER(GibbsPrior),
+                                    C.POINTER(GibbsRng), C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p]
     _lib = lib
     return lib
 

@@ -331,6 +331,134 @@ class Engine:
                                                         _mem_and_ptr(theta)[1], gs))
         return out
 
+    # ------------------------------------------------------------------ "next" rows (8f)
+    def _ar_problem(self, sv: Dict, y, v, times, layout, ou):
+        """sv: dict(phi, mu, sigma_eta) -- python floats (shared) or [B] arrays living with y."""
+        mem, yptr = _mem_and_ptr(y)
+        if layout == TIME_MAJOR:
+            T, B = int(y.shape[0]), int(y.shape[1])
+        else:
+            B, T = int(y.shape[0]), int(y.shape[1])
+        keep = []
+        pr = capi.ArProblem()
+        pr.B, pr.T, pr.layout, pr.mem = B, T, int(layout), int(mem)
+        pr.process = capi.OU if ou else capi.AR1
+        per = not np.isscalar(sv["phi"])
+        pr.per_series = int(per)
+        for name in ("phi", "mu", "sigma_eta"):
+            x = sv[name]
+            if per:
+                m_, ptr = _mem_and_ptr(x)
+                assert m_ == mem and tuple(x.shape) == (B,), name
+                setattr(pr, name, ptr)
+            else:
+                a = np.array([float(x)])
+                keep.append(a)
+                setattr(pr, name, a.ctypes.data)
+        if np.isscalar(v):
+            a = np.array([float(v)]); keep.append(a)
+            pr.v_mode, pr.v = capi.V_SCALAR, a.ctypes.data
+        elif isinstance(v, np.ndarray) and v.ndim == 1:  # y is always 2-D, so 1-D = per step
+            a = np.ascontiguousarray(v, dtype=np.float64); keep.append(a)
+            assert a.size == T
+            pr.v_mode, pr.v = capi.V_PER_STEP, a.ctypes.data
+        else:
+            m_, ptr = _mem_and_ptr(v)
+            assert m_ == mem and tuple(v.shape) == tuple(y.shape)
+            pr.v_mode, pr.v = capi.V_PER_SERIES_STEP, ptr
+        if times is not None:
+            a = np.ascontiguousarray(times, dtype=np.float64); keep.append(a)
+            assert a.size == T
+            pr.times = a.ctypes.data
+        pr.y = yptr
+        return pr, keep, B, T
+
+    def ar_filter(self, sv: Dict, y, v, *, times=None, ou=False, layout=TIME_MAJOR,
+                  want=("m", "C", "a", "R")):
+        """FilterAr / FilterOu.filterUnivariate batched (FilterAr.scala:37-47, FilterOu.scala:30-45).
+        y: (T, B) time-major or (B, T) series-major, NaN = missing.  Outputs have T + 1 rows."""
+        pr, keep, B, T = self._ar_problem(sv, y, v, times, layout, ou)
+        shape = (T + 1, B) if layout == TIME_MAJOR else (B, T + 1)
+        out, ao = {}, capi.ArOut()
+        for k in ("m", "C", "a", "R"):
+            if k in want:
+                out[k] = self._alloc(y, shape)
+                setattr(ao, k, _mem_and_ptr(out[k])[1])
+        self.ctx.check(capi.load().bdlm_ar_filter(self.ctx.handle, pr, ao))
+        return out
+
+    def ar_ffbs(self, sv: Dict, y, v, z, *, times=None, ou=False, layout=TIME_MAJOR, want=()):
+        """FilterAr / FilterOu.ffbs batched (FilterAr.scala:77-83, FilterOu.scala:73-79) with
+        injected normals z (T + 1 rows)."""
+        pr, keep, B, T = self._ar_problem(sv, y, v, times, layout, ou)
+        shape = (T + 1, B) if layout == TIME_MAJOR else (B, T + 1)
+        assert tuple(z.shape) == shape, (tuple(z.shape), shape)
+        out, ao = dict(theta=self._alloc(y, shape)), capi.ArOut()
+        for k in ("m", "C", "a", "R"):
+            if k in want:
+                out[k] = self._alloc(y, shape)
+                setattr(ao, k, _mem_and_ptr(out[k])[1])
+        self.ctx.check(capi.load().bdlm_ar_ffbs(self.ctx.handle, pr, _mem_and_ptr(z)[1],
+                                                _mem_and_ptr(out["theta"])[1], ao))
+        return out
+
+    def conjugate_filter(self, model: Model, params: Dict, prior_shape: float, prior_scale: float,
+                         y, *, layout=TIME_MAJOR, want=("m", "C"), status=True):
+        """ConjugateFilter(prior, advanceState).filter batched (ConjugateFilter.scala:17-112)."""
+        mem, _ = _mem_and_ptr(y)
+        B = self._batch_of(model, y, layout)
+        rows = model.T + 1
+        pr, keep = self._problem(model, params, y, layout, True, 0, B, mem)
+        out, ko = self._outs(capi.KfOut, KF_FIELDS, want, y, layout, B, rows, self._kf_dims(model), False)
+        out["shape"] = self._alloc(y, self._shape(layout, B, rows, 1))
+        out["scale"] = self._alloc(y, self._shape(layout, B, rows, 1))
+        st, stp = self._status(y, B, status)
+        self.ctx.check(capi.load().bdlm_conjugate_filter(
+            self.ctx.handle, pr, float(prior_shape), float(prior_scale), ko,
+            _mem_and_ptr(out["shape"])[1], _mem_and_ptr(out["scale"])[1], stp))
+        if st is not None:
+            out["status"] = st
+        return out
+
+    def gibbs_draw(self, n: int, p: int, T: int, stats: Dict, prior: Dict, *, layout=TIME_MAJOR,
+                   seed=0, sweep=0, inject: Optional[Dict] = None, want_shape_rate=False,
+                   out: Optional[Dict] = None):
+        """Conjugate draws of V (diagonal inverse gamma) and W (diagonal inverse gamma, or inverse
+        Wishart when prior has ``w_psi``) from Gibbs sufficient statistics, on the device
+        (Gibbs.scala:41-49,72-77; GibbsWishart.scala:16-35).  Returns per-chain ``V`` (p*p) and
+        ``W`` (n*n) arrays usable as per-series parameters of the next sweep."""
+        like = stats["ssy"]
+        mem, _ = _mem_and_ptr(like)
+        B = like.shape[1] if layout == TIME_MAJOR else like.shape[0]
+        pr = capi.Problem()
+        pr.B, pr.T, pr.n, pr.p, pr.layout, pr.mem, pr.keep_init = B, T, n, p, int(layout), int(mem), 1
+        gs = capi.GibbsStats()
+        for k in ("ssy", "ny", "ssw", "scatter"):
+            setattr(gs, k, _mem_and_ptr(stats[k])[1] if stats.get(k) is not None else None)
+        gp = capi.GibbsPrior()
+        gp.v_shape, gp.v_scale = prior["v_shape"], prior["v_scale"]
+        gp.w_shape, gp.w_scale = prior.get("w_shape", 0.0), prior.get("w_scale", 0.0)
+        keep = []
+        if prior.get("w_psi") is not None:
+            psi = _shared_param(prior["w_psi"], n, n); keep.append(psi)
+            gp.w_nu, gp.w_psi = float(prior["w_nu"]), psi.ctypes.data
+        rng = capi.GibbsRng()
+        rng.seed, rng.sweep = int(seed), int(sweep)
+        for k in ("gamma_v", "gamma_w", "bartlett"):
+            setattr(rng, k, _mem_and_ptr(inject[k])[1] if inject and inject.get(k) is not None else None)
+        row = (lambda k: (k, B)) if layout == TIME_MAJOR else (lambda k: (B, k))
+        res = out if out is not None else dict(V=self._alloc(like, row(p * p)), W=self._alloc(like, row(n * n)))
+        if want_shape_rate:
+            res["v_shape_rate"] = self._alloc(like, row(2 * p))
+            res["w_shape_rate"] = self._alloc(like, row(2 * n))
+        if "status" not in res:
+            res["status"] = self._alloc(like, (B,), dtype="int32")
+        ptr = lambda k: _mem_and_ptr(res[k])[1] if k in res else None  # noqa: E731
+        self.ctx.check(capi.load().bdlm_gibbs_draw(self.ctx.handle, pr, gs, gp, rng, ptr("V"), ptr("W"),
+                                                   ptr("v_shape_rate"), ptr("w_shape_rate"),
+                                                   ptr("status")))
+        return res
+
     def sync(self):
         self.ctx.sync()
 

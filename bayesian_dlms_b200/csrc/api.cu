@@ -43,7 +43,9 @@ static std::string g_create_err;
 namespace {
 
 enum ApiOp { A_FILTER, A_SMOOTH, A_FILTER_SMOOTH, A_LOGLIK, A_FFBS, A_SVD_FILTER, A_SVD_FFBS,
-             A_STATS };
+             A_STATS,
+             // "next" rows
+             A_AR_FILTER, A_AR_FFBS, A_CONJ_FILTER, A_GIBBS_DRAW };
 
 int fail(bdlm_ctx *c, int code, const std::string &msg) {
   if (c) c->err = msg; else g_create_err = msg;
@@ -95,6 +97,16 @@ struct DevCall {
   double *theta = nullptr;
   double *ll_tr = nullptr, *ll_in = nullptr;
   int32_t *status = nullptr;
+  // scalar AR(1) / OU calls: pr carries B, T, layout, mem, times, y with n = p = 1
+  bdlm_ar_problem ar{};
+  bdlm_ar_out ar_out{};
+  // conjugate filter
+  double cj_shape = 0, cj_scale = 0;
+  double *cj_shape_out = nullptr, *cj_scale_out = nullptr;
+  // conjugate draws
+  bdlm_gibbs_prior prior{};
+  bdlm_gibbs_rng rng{};
+  double *V_out = nullptr, *W_out = nullptr, *v_sr = nullptr, *w_sr = nullptr;
 };
 
 int rows_of(const bdlm_problem &p) { return p.T + (p.keep_init ? 1 : 0); }
@@ -145,6 +157,36 @@ void collect_fields(DevCall &d, std::vector<Field> &f) {
   auto add = [&](const double *const *slot, int64_t rows, int64_t k, bool in, bool out) {
     if (*slot) f.push_back(Field{const_cast<double **>(slot), rows, k, in, out});
   };
+  if (d.op == A_AR_FILTER || d.op == A_AR_FFBS) {
+    add(&d.pr.y, p.T, 1, true, false);
+    if (d.ar.v_mode == BDLM_V_PER_SERIES_STEP) add(&d.ar.v, p.T, 1, true, false);
+    if (d.ar.per_series) {
+      add(&d.ar.phi, 1, 1, true, false);
+      add(&d.ar.mu, 1, 1, true, false);
+      add(&d.ar.sigma_eta, 1, 1, true, false);
+    }
+    add((const double *const *)&d.ar_out.m, R, 1, false, true);
+    add((const double *const *)&d.ar_out.C, R, 1, false, true);
+    add((const double *const *)&d.ar_out.a, R, 1, false, true);
+    add((const double *const *)&d.ar_out.R, R, 1, false, true);
+    add(&d.z, R, 1, true, false);
+    add((const double *const *)&d.theta, R, 1, false, true);
+    return;
+  }
+  if (d.op == A_GIBBS_DRAW) {
+    add((const double *const *)&d.stats.ssy, 1, pp, true, false);
+    add((const double *const *)&d.stats.ny, 1, pp, true, false);
+    add((const double *const *)&d.stats.ssw, 1, n, true, false);
+    add((const double *const *)&d.stats.scatter, 1, n * n, true, false);
+    add(&d.rng.gamma_v, 1, pp, true, false);
+    add(&d.rng.gamma_w, 1, n, true, false);
+    add(&d.rng.bartlett, 1, n * n, true, false);
+    add((const double *const *)&d.V_out, 1, pp * pp, false, true);
+    add((const double *const *)&d.W_out, 1, n * n, false, true);
+    add((const double *const *)&d.v_sr, 1, 2 * pp, false, true);
+    add((const double *const *)&d.w_sr, 1, 2 * n, false, true);
+    return;
+  }
   const bool smooth_in = d.op == A_SMOOTH;
   if (d.op != A_SMOOTH) add(&d.pr.y, p.T, pp, true, false);
   if (p.per_series & BDLM_PS_V) add(&d.pr.V, 1, pp * pp, true, false);
@@ -174,6 +216,8 @@ void collect_fields(DevCall &d, std::vector<Field> &f) {
   add((const double *const *)&d.stats.scatter, 1, n * n, false, true);
   add((const double *const *)&d.ll_tr, 1, 1, false, true);
   add((const double *const *)&d.ll_in, 1, 1, false, true);
+  add((const double *const *)&d.cj_shape_out, R, 1, false, true);
+  add((const double *const *)&d.cj_scale_out, R, 1, false, true);
 }
 
 // Device workspace (bytes) one run_dev call over Bc series needs beyond user arrays.
@@ -184,6 +228,12 @@ size_t dev_workspace_bytes(const DevCall &d, int64_t Bc) {
   // model: F, G, dt + shared params
   bytes += align_up(sizeof(double) * ((size_t)p.T * (n * p.p + n * n + 1) + 2 * n * n +
                                       (size_t)p.p * p.p + n + 64)) + 4096;
+  if (d.op == A_AR_FILTER || d.op == A_AR_FFBS) {
+    bytes += align_up(sizeof(double) * 2 * (size_t)p.T);  // dt, shared v
+    if (d.op == A_AR_FFBS) bytes += 2 * align_up(sizeof(double) * (size_t)R * Bc);  // (m, C) spill
+    return bytes + 8192;
+  }
+  if (d.op == A_GIBBS_DRAW || d.op == A_CONJ_FILTER) return bytes + 8192;
   if (small_path(d.op, p)) {
     if (p.layout == BDLM_SERIES_MAJOR) {  // time-major mirrors of every field
       DevCall tmp = d;
@@ -268,6 +318,103 @@ int run_dev(bdlm_ctx *c, DevCall d, Bump bump) {
   const int64_t n = p.n, R = rows_of(p);
   Batch bt{};
   std::vector<double> hG0, hF0;
+
+  if (d.op == A_AR_FILTER || d.op == A_AR_FFBS) {
+    const bdlm_ar_problem &ap = d.ar;
+    const int T = p.T, L = p.layout;
+    ArArgs a{};
+    a.B = d.Bc; a.T = T; a.ou = ap.process == BDLM_OU; a.ffbs = d.op == A_AR_FFBS;
+    // host -> device: dt (OU; FilterOu.scala:35: t0 = head time, so dt[0] = 0) and shared v[T]
+    std::vector<double> host;
+    size_t oDt = (size_t)-1, oV = (size_t)-1;
+    if (a.ou) {
+      oDt = host.size();
+      for (int t = 0; t < T; ++t)
+        host.push_back(t == 0 ? 0.0 : (ap.times ? ap.times[t] - ap.times[t - 1] : 1.0));
+    }
+    if (ap.v_mode == BDLM_V_PER_STEP) { oV = host.size(); host.insert(host.end(), ap.v, ap.v + T); }
+    if (!host.empty()) {
+      double *dev = bump.take<double>(host.size());
+      CU(cudaMemcpyAsync(dev, host.data(), host.size() * sizeof(double), cudaMemcpyHostToDevice,
+                         c->stream));
+      if (oDt != (size_t)-1) a.dt = dev + oDt;
+      if (oV != (size_t)-1) a.v_shared = dev + oV;
+    }
+    auto row1 = [&](double *ptr, int64_t rows) {  // k = 1 view
+      View v = mk_view(ptr, L, d.b0, d.Bp, rows, 1);
+      return v;
+    };
+    auto par = [&](const double *ptr, double &scalar) {
+      PView v{nullptr, 0, 1};
+      if (ap.per_series) { v.ptr = ptr + d.b0; v.sb = 1; }
+      else scalar = ptr[0];
+      return v;
+    };
+    a.phi = par(ap.phi, a.phi_s); a.mu = par(ap.mu, a.mu_s); a.sigma = par(ap.sigma_eta, a.sigma_s);
+    if (ap.v_mode == BDLM_V_SCALAR) a.v_s = ap.v[0];
+    if (ap.v_mode == BDLM_V_PER_SERIES_STEP) a.v = row1(const_cast<double *>(ap.v), T);
+    a.y = row1(const_cast<double *>(p.y), T);
+    a.m = row1(d.ar_out.m, R); a.C = row1(d.ar_out.C, R);
+    a.a = row1(d.ar_out.a, R); a.R = row1(d.ar_out.R, R);
+    if (a.ffbs) {
+      a.z = row1(const_cast<double *>(d.z), R);
+      a.theta = row1(d.theta, R);
+      // dense [R][Bc] workspace when the caller does not want (m, C)
+      a.sm = d.ar_out.m ? a.m : mk_view(bump.take<double>((size_t)R * d.Bc), BDLM_TIME_MAJOR, 0, d.Bc, R, 1);
+      a.sC = d.ar_out.C ? a.C : mk_view(bump.take<double>((size_t)R * d.Bc), BDLM_TIME_MAJOR, 0, d.Bc, R, 1);
+    }
+    CU(launch_ar(a, c->stream));
+    ++c->launches;
+    return 0;
+  }
+
+  if (d.op == A_GIBBS_DRAW) {
+    const int L = p.layout;
+    GibbsDrawArgs a{};
+    a.B = d.Bc; a.n = p.n; a.p = p.p; a.T = p.T;
+    a.wishart = d.prior.w_psi != nullptr;
+    a.v_shape = d.prior.v_shape; a.v_scale = d.prior.v_scale;
+    a.w_shape = d.prior.w_shape; a.w_scale = d.prior.w_scale; a.w_nu = d.prior.w_nu;
+    if (a.wishart) {
+      double *dev = bump.take<double>((size_t)n * n);
+      CU(cudaMemcpyAsync(dev, d.prior.w_psi, sizeof(double) * n * n, cudaMemcpyHostToDevice, c->stream));
+      a.psi = dev;
+    }
+    a.stats.ssy = mk_rowview(d.stats.ssy, L, d.b0, d.Bp, p.p);
+    a.stats.ny = mk_rowview(d.stats.ny, L, d.b0, d.Bp, p.p);
+    a.stats.ssw = mk_rowview(d.stats.ssw, L, d.b0, d.Bp, n);
+    a.stats.scatter = mk_rowview(d.stats.scatter, L, d.b0, d.Bp, n * n);
+    a.gv = mk_rowview(const_cast<double *>(d.rng.gamma_v), L, d.b0, d.Bp, p.p);
+    a.gw = mk_rowview(const_cast<double *>(d.rng.gamma_w), L, d.b0, d.Bp, n);
+    a.bart = mk_rowview(const_cast<double *>(d.rng.bartlett), L, d.b0, d.Bp, n * n);
+    a.seed = d.rng.seed; a.sweep = d.rng.sweep;
+    a.V = mk_rowview(d.V_out, L, d.b0, d.Bp, (int64_t)p.p * p.p);
+    a.W = mk_rowview(d.W_out, L, d.b0, d.Bp, n * n);
+    a.v_shape_rate = mk_rowview(d.v_sr, L, d.b0, d.Bp, 2 * p.p);
+    a.w_shape_rate = mk_rowview(d.w_sr, L, d.b0, d.Bp, 2 * n);
+    a.status = d.status ? d.status + d.b0 : nullptr;
+    if (a.status) CU(cudaMemsetAsync(a.status, 0, sizeof(int32_t) * d.Bc, c->stream));
+    CU(launch_gibbs_draw(a, c->stream, &c->launches));
+    return 0;
+  }
+
+  if (d.op == A_CONJ_FILTER) {
+    int rc = upload_model(c, d, bump, bt, hG0, hF0);
+    if (rc) return rc;
+    const int L = p.layout;
+    ConjArgs a{};
+    a.bt = bt;
+    a.prior_shape = d.cj_shape; a.prior_scale = d.cj_scale;
+    a.kf.m = mk_view(d.kf.m, L, d.b0, d.Bp, R, n); a.kf.C = mk_view(d.kf.C, L, d.b0, d.Bp, R, n * n);
+    a.kf.a = mk_view(d.kf.a, L, d.b0, d.Bp, R, n); a.kf.R = mk_view(d.kf.R, L, d.b0, d.Bp, R, n * n);
+    a.kf.f = mk_view(d.kf.f, L, d.b0, d.Bp, R, 1); a.kf.Q = mk_view(d.kf.Q, L, d.b0, d.Bp, R, 1);
+    a.shape = mk_view(d.cj_shape_out, L, d.b0, d.Bp, R, 1);
+    a.scale = mk_view(d.cj_scale_out, L, d.b0, d.Bp, R, 1);
+    if (bt.status) CU(cudaMemsetAsync(bt.status, 0, sizeof(int32_t) * d.Bc, c->stream));
+    CU(launch_conjugate(a, hG0.data(), hF0.data(), c->stream));
+    ++c->launches;
+    return 0;
+  }
 
   if (small_path(d.op, p)) {
     int layout = p.layout;
@@ -375,7 +522,12 @@ int validate(bdlm_ctx *c, int op, const bdlm_problem *p) {
   if (p->layout != BDLM_TIME_MAJOR && p->layout != BDLM_SERIES_MAJOR)
     return fail(c, BDLM_E_ARG, "bad layout");
   if (p->mem != BDLM_DEVICE && p->mem != BDLM_HOST) return fail(c, BDLM_E_ARG, "bad mem");
-  if (!p->F || !p->G) return fail(c, BDLM_E_ARG, "null F or G");
+  if (op != A_GIBBS_DRAW && (!p->F || !p->G)) return fail(c, BDLM_E_ARG, "null F or G");
+  if (op == A_GIBBS_DRAW) return 0;
+  if (op == A_CONJ_FILTER) {
+    if (!p->W || !p->m0 || !p->C0 || !p->y) return fail(c, BDLM_E_ARG, "null W, m0, C0 or y");
+    return 0;
+  }
   if (op != A_STATS && (!p->V || !p->W)) return fail(c, BDLM_E_ARG, "null V or W");
   if (op != A_SMOOTH && op != A_STATS && (!p->m0 || !p->C0))
     return fail(c, BDLM_E_ARG, "null m0 or C0");
@@ -851,6 +1003,79 @@ int bdlm_scan_filter_smooth(bdlm_ctx *c, const bdlm_problem *p, const bdlm_kf_ou
   a.status = status; a.workspace = c->arena + ws;
   CU(launch_scan(a, c->stream, &c->launches));
   return 0;
+}
+
+// ---- "next" rows: scalar AR(1) / OU, conjugate filter, conjugate draws -------------------
+
+static int ar_call(bdlm_ctx *c, int op, const bdlm_ar_problem *ap, const bdlm_ar_out *out,
+                   const double *z, double *theta) {
+  static const double one = 1.0;
+  if (!c) return fail(nullptr, BDLM_E_ARG, "null context");
+  if (!ap) return fail(c, BDLM_E_ARG, "null problem");
+  if (ap->T == 0) return fail(c, BDLM_E_EMPTY, "T == 0: empty observation vector");
+  if (ap->process != BDLM_AR1 && ap->process != BDLM_OU) return fail(c, BDLM_E_ARG, "bad process");
+  if (ap->v_mode < BDLM_V_SCALAR || ap->v_mode > BDLM_V_PER_SERIES_STEP)
+    return fail(c, BDLM_E_ARG, "bad v_mode");
+  if (!ap->phi || !ap->mu || !ap->sigma_eta || !ap->v || !ap->y)
+    return fail(c, BDLM_E_ARG, "null phi, mu, sigma_eta, v or y");
+  if (op == A_AR_FFBS && (!z || !theta)) return fail(c, BDLM_E_ARG, "null z or theta");
+  if (op == A_AR_FILTER && !out) return fail(c, BDLM_E_ARG, "null output struct");
+  DevCall d{};
+  d.op = op;
+  d.pr.B = ap->B; d.pr.T = ap->T; d.pr.n = 1; d.pr.p = 1; d.pr.layout = ap->layout;
+  d.pr.mem = ap->mem; d.pr.keep_init = 1; d.pr.times = ap->times; d.pr.y = ap->y;
+  d.pr.F = d.pr.G = d.pr.V = d.pr.W = d.pr.m0 = d.pr.C0 = &one;
+  int rc = validate(c, A_FILTER, &d.pr);
+  if (rc) return rc;
+  d.ar = *ap;
+  if (out) d.ar_out = *out;
+  d.z = z; d.theta = theta;
+  return dispatch(c, d);
+}
+
+int bdlm_ar_filter(bdlm_ctx *c, const bdlm_ar_problem *ap, const bdlm_ar_out *out) {
+  return ar_call(c, A_AR_FILTER, ap, out, nullptr, nullptr);
+}
+
+int bdlm_ar_ffbs(bdlm_ctx *c, const bdlm_ar_problem *ap, const double *z, double *theta,
+                 const bdlm_ar_out *filt) {
+  return ar_call(c, A_AR_FFBS, ap, filt, z, theta);
+}
+
+int bdlm_conjugate_filter(bdlm_ctx *c, const bdlm_problem *p, double prior_shape,
+                          double prior_scale, const bdlm_kf_out *out, double *shape,
+                          double *scale, int32_t *status) {
+  int rc = validate(c, A_CONJ_FILTER, p);
+  if (rc) return rc;
+  if (!conjugate_supported(p->n, p->p) || p->f_tv || p->g_tv || !p->keep_init)
+    return fail(c, BDLM_E_ARG,
+                "conjugate filter: p = 1, n <= 4, time-invariant F and G, keep_init = 1");
+  DevCall d{}; d.op = A_CONJ_FILTER; d.pr = *p;
+  d.pr.per_series &= ~BDLM_PS_V;  // V is what the filter learns
+  d.pr.V = nullptr;
+  if (out) d.kf = *out;
+  d.cj_shape = prior_shape; d.cj_scale = prior_scale;
+  d.cj_shape_out = shape; d.cj_scale_out = scale;
+  d.status = status;
+  return dispatch(c, d);
+}
+
+int bdlm_gibbs_draw(bdlm_ctx *c, const bdlm_problem *p, const bdlm_gibbs_stats *stats,
+                    const bdlm_gibbs_prior *prior, const bdlm_gibbs_rng *rng, double *V_out,
+                    double *W_out, double *v_shape_rate, double *w_shape_rate, int32_t *status) {
+  int rc = validate(c, A_GIBBS_DRAW, p);
+  if (rc) return rc;
+  if (!stats || !prior || !rng) return fail(c, BDLM_E_ARG, "null stats, prior or rng");
+  if (V_out && (!stats->ssy || !stats->ny)) return fail(c, BDLM_E_ARG, "V draw needs ssy and ny");
+  if (W_out && !prior->w_psi && !stats->ssw) return fail(c, BDLM_E_ARG, "diagonal W draw needs ssw");
+  if (W_out && prior->w_psi && !stats->scatter)
+    return fail(c, BDLM_E_ARG, "inverse-Wishart W draw needs the scatter matrix");
+  if (!W_out && prior->w_psi) return fail(c, BDLM_E_ARG, "inverse-Wishart prior without W_out");
+  DevCall d{}; d.op = A_GIBBS_DRAW; d.pr = *p;
+  d.stats = *stats; d.prior = *prior; d.rng = *rng;
+  d.V_out = V_out; d.W_out = W_out; d.v_sr = v_shape_rate; d.w_sr = w_shape_rate;
+  d.status = status;
+  return dispatch(c, d);
 }
 
 int bdlm_gibbs_suffstats(bdlm_ctx *c, const bdlm_problem *p, const double *theta,

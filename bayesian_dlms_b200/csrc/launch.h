@@ -84,6 +84,53 @@ int scan_backward_elem_doubles(int n);
 cudaError_t launch_scan(const ScanArgs &a, cudaStream_t stream, int64_t *launches);
 void scan_combine_host(int n, bool backward, const double *ei, const double *ej, double *out);
 
+// scalar_filters.cu: scalar AR(1) / OU filter + backward sampler (FilterAr.scala, FilterOu.scala)
+// and the conjugate (unknown observation variance) filter (ConjugateFilter.scala), one thread
+// per series.  Views here address element (series b, row r) at ptr[b*sb + r*sr].
+struct ArArgs {
+  int64_t B;
+  int T;
+  int ou;                   // 0 = AR(1) on the unit grid, 1 = Ornstein-Uhlenbeck on dt[]
+  int ffbs;                 // 0 = filter only, 1 = filter + backward sample
+  PView phi, mu, sigma;     // per series (ptr != nullptr) ...
+  double phi_s, mu_s, sigma_s;  // ... or shared scalars
+  const double *dt;         // device [T] (OU): dt[0] = 0, dt[t] = times[t] - times[t-1]
+  View v;                   // per-series per-step variances (T rows) or ptr == nullptr
+  const double *v_shared;   // device [T] shared by the batch, or nullptr
+  double v_s;               // one variance for every step
+  View y;                   // T rows
+  View m, C, a, R;          // T + 1 rows, any may be null (filter mode)
+  View sm, sC;              // ffbs mode: where (m, C) are spilled (user m, C or workspace)
+  View z, theta;            // T + 1 rows
+};
+cudaError_t launch_ar(const ArArgs &a, cudaStream_t stream);
+
+struct ConjArgs {
+  Batch bt;                 // V unused; F, G time-invariant (passed on the host side)
+  double prior_shape, prior_scale;
+  KfViews kf;
+  View shape, scale;        // T + 1 rows, k = 1
+};
+bool conjugate_supported(int n, int p);
+cudaError_t launch_conjugate(const ConjArgs &a, const double *hG, const double *hF,
+                             cudaStream_t stream);
+
+// gibbs_draw.cu: conjugate draws of V and W from the Gibbs sufficient statistics.
+struct GibbsDrawArgs {
+  int64_t B;
+  int n, p, T;
+  int wishart;              // 0: diagonal W ~ d-inverse-gamma; 1: full W ~ inverse Wishart
+  double v_shape, v_scale, w_shape, w_scale, w_nu;
+  const double *psi;        // device n*n (wishart)
+  StatViews stats;          // inputs (sb, sk strides)
+  View gv, gw, bart;        // injected standard-gamma variates [p], [n] / Bartlett factor [n*n]
+  unsigned long long seed, sweep;
+  View V, W;                // outputs: per-chain p*p and n*n (column-major), either may be null
+  View v_shape_rate, w_shape_rate;  // optional outputs [2p], [2n]: posterior shapes | rates
+  int32_t *status;          // [B] or nullptr (OR-ed)
+};
+cudaError_t launch_gibbs_draw(const GibbsDrawArgs &a, cudaStream_t stream, int64_t *launches);
+
 // peak.cu: DFMA throughput microbenchmark (TFLOP/s at 2 flops per DFMA).
 cudaError_t measure_fp64_peak(cudaStream_t stream, double *scratch, double *tflops);
 

@@ -273,6 +273,78 @@ BDLM_API int bdlm_scan_backward_apply(bdlm_ctx *ctx, const bdlm_problem *prob,
 BDLM_API int bdlm_scan_combine(int32_t n, int32_t backward, const double *earlier,
                                const double *later, double *out);
 
+/* ======================================================================================
+ * "Next" rows: the callers and neighbours of the hot path.
+ * ==================================================================================== */
+
+/* ---- scalar AR(1) / Ornstein-Uhlenbeck state: filter and backward sampler ---------------
+ * FilterAr.filterUnivariate / univariateSample / ffbs (FilterAr.scala:15-83) and
+ * FilterOu.filterUnivariate / univariateSample / ffbs (FilterOu.scala:7-79): the inner loop of
+ * the reference's stochastic-volatility samplers.  SvParameters(phi, mu, sigmaEta) are host
+ * scalars ([1]) or, with per_series = 1, [B] arrays in the data's memory space.  v holds the
+ * observation variances (`vs: Vector[Double]`): one host scalar, a host [T] array shared by the
+ * batch, or one value per series and step laid out like y.  times: host [T] or NULL (1..T); only
+ * the OU process reads it.  All per-step arrays have k = 1; outputs, z and theta have T + 1 rows
+ * (row 0 = the stationary prior), z[row] is the N(0,1) value consumed when drawing theta[row]. */
+enum { BDLM_AR1 = 0, BDLM_OU = 1 };
+enum { BDLM_V_SCALAR = 0, BDLM_V_PER_STEP = 1, BDLM_V_PER_SERIES_STEP = 2 };
+typedef struct bdlm_ar_problem {
+  int64_t B;
+  int32_t T;
+  int32_t layout, mem;    /* as bdlm_problem */
+  int32_t process;        /* BDLM_AR1 | BDLM_OU */
+  int32_t per_series;     /* phi, mu, sigma_eta are [B] arrays */
+  int32_t v_mode;         /* BDLM_V_* */
+  const double *phi, *mu, *sigma_eta;
+  const double *times;
+  const double *v;
+  const double *y;        /* T rows, NaN = None */
+} bdlm_ar_problem;
+/* FilterAr.FilterState fields (FilterAr.scala:9-13); NULL = not wanted. */
+typedef struct bdlm_ar_out {
+  double *m, *C, *a, *R;
+} bdlm_ar_out;
+BDLM_API int bdlm_ar_filter(bdlm_ctx *ctx, const bdlm_ar_problem *prob, const bdlm_ar_out *out);
+BDLM_API int bdlm_ar_ffbs(bdlm_ctx *ctx, const bdlm_ar_problem *prob, const double *z,
+                          double *theta, const bdlm_ar_out *filt /* optional */);
+
+/* ---- conjugate filter: unknown observation variance ---------------------------------------
+ * ConjugateFilter(prior, ConjugateFilter.advanceState(p, g)).filter (ConjugateFilter.scala:
+ * 17-112): Kalman filter with V replaced by the running mean of an InverseGamma(shape, scale)
+ * posterior that is updated at every step.  p = 1, n <= 4, time-invariant F and G, keep_init = 1;
+ * prob->V is ignored.  shape / scale: T + 1 rows, k = 1 (row 0 = the prior). */
+BDLM_API int bdlm_conjugate_filter(bdlm_ctx *ctx, const bdlm_problem *prob, double prior_shape,
+                                   double prior_scale, const bdlm_kf_out *out, double *shape,
+                                   double *scale, int32_t *status);
+
+/* ---- conjugate draws of V and W from the Gibbs sufficient statistics ----------------------
+ * The second half of GibbsSampling.dinvGammaStep / stepSvd (Gibbs.scala:134-151,182-198) and of
+ * GibbsWishart.wishartStep (GibbsWishart.scala:40-53), on the device, so that a sweep
+ * (bdlm_ffbs / bdlm_svd_ffbs with `stats`, then this call, then the next sweep with
+ * per_series = BDLM_PS_V | BDLM_PS_W) never leaves the GPU.
+ *   V_out [p*p] per chain: diag(InverseGamma(v_shape + ny_i / 2, v_scale + ssy_i / 2).draw)
+ *   W_out [n*n] per chain: w_psi == NULL: diag(InverseGamma(w_shape + T / 2, w_scale + ssw_i / 2))
+ *                          w_psi != NULL (host n*n): InverseWishart(w_nu + T, w_psi + scatter).draw
+ * prob supplies B, T, n, p, layout, mem (stats and outputs are one row per chain: [k][B] or
+ * [B][k]).  Randomness: Philox4x32-10 keyed by (seed, chain, element), advanced by `sweep`;
+ * or injected variates for bit-exact checks: gamma_v [p] / gamma_w [n] standard Gamma(shape, 1)
+ * values per chain, bartlett [n*n] the lower-triangular Bartlett factor (Wishart.scala:34-43).
+ * v_shape_rate [2p] / w_shape_rate [2n] (optional) receive the posterior shapes then rates. */
+typedef struct bdlm_gibbs_prior {
+  double v_shape, v_scale; /* InverseGamma prior on diag(V) */
+  double w_shape, w_scale; /* InverseGamma prior on diag(W) */
+  double w_nu;             /* InverseWishart(w_nu, w_psi) prior on W */
+  const double *w_psi;
+} bdlm_gibbs_prior;
+typedef struct bdlm_gibbs_rng {
+  uint64_t seed, sweep;
+  const double *gamma_v, *gamma_w, *bartlett; /* NULL = generate on the device */
+} bdlm_gibbs_rng;
+BDLM_API int bdlm_gibbs_draw(bdlm_ctx *ctx, const bdlm_problem *prob, const bdlm_gibbs_stats *stats,
+                             const bdlm_gibbs_prior *prior, const bdlm_gibbs_rng *rng,
+                             double *V_out, double *W_out, double *v_shape_rate,
+                             double *w_shape_rate, int32_t *status);
+
 #ifdef __cplusplus
 }
 #endif
