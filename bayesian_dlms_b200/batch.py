@@ -124,6 +124,9 @@ class Engine:
         per = 0
         ptrs = {}
         keep = []
+        # params["v_tv"] = True: V varies with t (StudentTGibbs.filter): shared V is (T, p*p)
+        # column-major per row [or (T, p, p)]; per-series V is laid out like y with k = p*p
+        v_tv = bool(params.get("v_tv", False))
         for name, bit, r, c in (("V", capi.PS_V, p, p), ("W", capi.PS_W, n, n),
                                 ("m0", capi.PS_M0, n, 1), ("C0", capi.PS_C0, n, n)):
             x = params.get(name)
@@ -133,11 +136,20 @@ class Engine:
             # per-series parameters are named explicitly: params["per_series"] = ("V", "W")
             if name in params.get("per_series", ()):
                 expect = (r * c, B) if layout == TIME_MAJOR else (B, r * c)
+                if name == "V" and v_tv:
+                    expect = self._shape(layout, B, model.T, r * c)
                 assert tuple(x.shape) == expect, (name, tuple(x.shape), expect)
                 m_, ptr = _mem_and_ptr(x)
                 assert m_ == mem, f"{name} lives in a different memory space than y"
                 per |= bit
                 ptrs[name] = ptr
+            elif name == "V" and v_tv:
+                a = np.asarray(x, dtype=np.float64)
+                if a.ndim == 3:  # (T, p, p) -> column-major rows
+                    a = a.transpose(0, 2, 1)
+                a = np.ascontiguousarray(a.reshape(model.T, r * c))
+                keep.append(a)
+                ptrs[name] = a
             else:
                 a = _shared_param(x, r, c)
                 keep.append(a)
@@ -146,7 +158,8 @@ class Engine:
         pr = capi.make_problem(B=B, T=model.T, n=n, p=p, layout=layout, mem=mem,
                                keep_init=keep_init, F=model.F, G=model.G, times=model.times,
                                V=ptrs["V"], W=ptrs["W"], m0=ptrs["m0"], C0=ptrs["C0"], y=yptr,
-                               per_series=per, compat=compat, f_tv=model.f_tv, g_tv=model.g_tv)
+                               per_series=per, compat=compat, f_tv=model.f_tv, g_tv=model.g_tv,
+                               v_tv=v_tv)
         return pr, keep
 
     def _batch_of(self, model, y, layout):

@@ -127,7 +127,8 @@ View mk_rowview(double *ptr, int layout, int64_t b0, int64_t Bp, int64_t k) {
 }
 
 bool small_path(int op, const bdlm_problem &p) {
-  return (op == A_FILTER || op == A_SMOOTH || op == A_FILTER_SMOOTH) && small_supported(p.n, p.p);
+  return (op == A_FILTER || op == A_SMOOTH || op == A_FILTER_SMOOTH) && !p.v_tv &&
+         small_supported(p.n, p.p);
 }
 
 int warp_op(int op) {
@@ -189,7 +190,7 @@ void collect_fields(DevCall &d, std::vector<Field> &f) {
   }
   const bool smooth_in = d.op == A_SMOOTH;
   if (d.op != A_SMOOTH) add(&d.pr.y, p.T, pp, true, false);
-  if (p.per_series & BDLM_PS_V) add(&d.pr.V, 1, pp * pp, true, false);
+  if (p.per_series & BDLM_PS_V) add(&d.pr.V, p.v_tv ? p.T : 1, pp * pp, true, false);
   if (p.per_series & BDLM_PS_W) add(&d.pr.W, 1, n * n, true, false);
   if (p.per_series & BDLM_PS_M0) add(&d.pr.m0, 1, n, true, false);
   if (p.per_series & BDLM_PS_C0) add(&d.pr.C0, 1, n * n, true, false);
@@ -227,7 +228,7 @@ size_t dev_workspace_bytes(const DevCall &d, int64_t Bc) {
   size_t bytes = 0;
   // model: F, G, dt + shared params
   bytes += align_up(sizeof(double) * ((size_t)p.T * (n * p.p + n * n + 1) + 2 * n * n +
-                                      (size_t)p.p * p.p + n + 64)) + 4096;
+                                      (size_t)p.p * p.p * (p.v_tv ? p.T : 1) + n + 64)) + 4096;
   if (d.op == A_AR_FILTER || d.op == A_AR_FFBS) {
     bytes += align_up(sizeof(double) * 2 * (size_t)p.T);  // dt, shared v
     if (d.op == A_AR_FFBS) bytes += 2 * align_up(sizeof(double) * (size_t)R * Bc);  // (m, C) spill
@@ -284,7 +285,7 @@ int upload_model(bdlm_ctx *c, const DevCall &d, Bump &bump, Batch &bt,
   auto shared = [&](const double *src, int bit, size_t cnt) {
     return ((p.per_series & bit) || !src) ? (size_t)-1 : push(src, cnt);
   };
-  const size_t oV = shared(p.V, BDLM_PS_V, (size_t)pp * pp);
+  const size_t oV = shared(p.V, BDLM_PS_V, (size_t)pp * pp * (p.v_tv ? T : 1));
   const size_t oW = shared(p.W, BDLM_PS_W, (size_t)n * n);
   const size_t oM = shared(p.m0, BDLM_PS_M0, n);
   const size_t oC = shared(p.C0, BDLM_PS_C0, (size_t)n * n);
@@ -304,6 +305,17 @@ int upload_model(bdlm_ctx *c, const DevCall &d, Bump &bump, Batch &bt,
     return v;
   };
   bt.V = pv(p.V, oV, (int64_t)pp * pp);
+  bt.v_tv = p.v_tv ? 1 : 0;
+  bt.V_sr = 0;
+  if (p.v_tv) {
+    if (oV != (size_t)-1) bt.V_sr = (int64_t)pp * pp;  // shared: [T][p*p]
+    else if (p.layout == BDLM_TIME_MAJOR) bt.V_sr = (int64_t)pp * pp * d.Bp;  // [T][k][B]
+    else {  // [B][T][k]
+      bt.V.ptr = p.V + d.b0 * (int64_t)T * pp * pp;
+      bt.V.sb = (int64_t)T * pp * pp;
+      bt.V_sr = (int64_t)pp * pp;
+    }
+  }
   bt.W = pv(p.W, oW, (int64_t)n * n);
   bt.m0 = pv(p.m0, oM, n);
   bt.C0 = pv(p.C0, oC, (int64_t)n * n);
@@ -502,7 +514,7 @@ int run_dev(bdlm_ctx *c, DevCall d, Bump bump) {
   const int wop = warp_op(d.op);
   wa.spill_k = (int64_t)warp_spill_doubles_per_row(wop, p.n, p.p);
   wa.spill = wa.spill_k ? bump.take<double>((size_t)wa.spill_k * R * d.Bc) : nullptr;
-  if (c->use_group && group_supported(wop, p.n, p.p, p.keep_init ? 1 : 0)) {
+  if (c->use_group && !p.v_tv && group_supported(wop, p.n, p.p, p.keep_init ? 1 : 0)) {
     CU(launch_group(wop, wa, c->stream));  // two series per warp, compile-time n (kf_group.cu)
     ++c->launches;
     return 0;
@@ -532,6 +544,8 @@ int validate(bdlm_ctx *c, int op, const bdlm_problem *p) {
   if (op != A_SMOOTH && op != A_STATS && (!p->m0 || !p->C0))
     return fail(c, BDLM_E_ARG, "null m0 or C0");
   if (op != A_SMOOTH && !p->y) return fail(c, BDLM_E_ARG, "null y");
+  if (p->v_tv && op != A_FILTER && op != A_FILTER_SMOOTH && op != A_FFBS && op != A_LOGLIK)
+    return fail(c, BDLM_E_ARG, "v_tv: supported by filter, filter+smoother, log-likelihood and FFBS");
   if ((op == A_FFBS || op == A_SVD_FFBS || op == A_STATS) && !p->keep_init)
     return fail(c, BDLM_E_ARG, "FFBS keeps the initial state: keep_init must be 1");
   return 0;

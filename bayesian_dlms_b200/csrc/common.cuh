@@ -46,6 +46,8 @@ struct Batch {
   const double *G; // device [n*n] or [T][n*n]
   const double *dt;// device [T] (dt into observation t) or nullptr = all 1.0
   int f_tv, g_tv;
+  int v_tv;        // V varies with t (StudentTGibbs.filter): V holds T matrices, row stride V_sr
+  int64_t V_sr;
   PView V, W, m0, C0;
   CView y;         // T rows
   int32_t *status; // [B] or nullptr

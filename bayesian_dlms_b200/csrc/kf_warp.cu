@@ -474,6 +474,11 @@ warp_kernel(const WarpArgs wa, const int ws_doubles) {
       load_model(lane, bt, ws, t, false);
       load_cview(lane, bt.y, b, t, p, ws.yrow);
       const double dt = bt.dt ? bt.dt[t] : 1.0;
+      if (bt.v_tv) {  // V_t: params.copy(v = V_t) at every step (StudentTGibbs.scala:105-118)
+        PView vt = bt.V;
+        vt.ptr += (int64_t)t * bt.V_sr;
+        load_pview(lane, vt, b, p * p, ws.V);
+      }
       __syncwarp();
       if (kSvd) {
         st |= svd_advance(lane, n, ws, dt);

@@ -227,10 +227,10 @@ def ffbs_leg(eng, dev, with_cpu=True, B=4096, T=2000):
     return res
 
 
-def svd_leg(eng, dev, with_cpu=True, B=16384, T=1000):
+def svd_leg(eng, dev, with_cpu=True, B=65536, T=1000):
     """Secondary metric (BASELINE.json config 4): SVD-stabilised filter + sampler
     (SvdSampler.ffbs as GibbsSampling.stepSvd calls it) for the correlated model, 8-fold outer
-    sum of polynomial(1), n = p = 8, full W; a quarter of the config's 65 536 series."""
+    sum of polynomial(1), n = p = 8, full W; all 65 536 series of the config in one call."""
     import torch
     from bayesian_dlms_b200 import Model, SERIES_MAJOR, dlm
     mod = dlm.polynomial(1)
@@ -279,6 +279,89 @@ def svd_leg(eng, dev, with_cpu=True, B=16384, T=1000):
     return res
 
 
+def gibbs_leg(eng, dev, B=4096, T=2000, sweeps=3):
+    """BASELINE.json config 3 as the reference runs it: FFBS INSIDE the d-inverse-gamma Gibbs
+    sampler (GibbsSampling.sample, Gibbs.scala:153-180).  One sweep = normals for the sweep,
+    FFBS with fused sufficient statistics, on-device conjugate draws of diag(V), diag(W); the
+    drawn parameters feed the next sweep as per-chain arrays without leaving the GPU."""
+    import torch
+    from bayesian_dlms_b200 import Model, SERIES_MAJOR, dlm, gibbs
+    mod = dlm.polynomial(1) + dlm.seasonal(24, 6)
+    n = 13
+    W = np.diag([0.01] + [0.2, 0.4, 0.5, 0.2, 0.1, 0.4] * 2)
+    init = dict(V=np.array([[1.0]]), W=W, m0=np.zeros(n), C0=np.eye(n))
+    prior = dict(v_shape=5.0, v_scale=4.0, w_shape=17.0, w_scale=4.0)  # SeasonalModel.scala:127
+    g = torch.Generator(device=dev).manual_seed(20260103)
+    y = torch.randn((B, T, 1), generator=g, device=dev, dtype=torch.float64) * 2.0
+    y[torch.rand((B, T, 1), generator=g, device=dev) < 0.1] = float("nan")
+    model = Model.build(mod, T=T)
+    gibbs.sample(eng, model, y, prior, init, 1, seed=1, layout=SERIES_MAJOR)  # warm-up
+    torch.cuda.synchronize()
+    l0 = eng.ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    res = gibbs.sample(eng, model, y, prior, init, sweeps, seed=2, layout=SERIES_MAJOR)
+    e1.record()
+    torch.cuda.synchronize()
+    t = e0.elapsed_time(e1) * 1e-3
+    return {"config": "config3: %d chains x T=%d, %d Gibbs sweeps (normals + FFBS + stats + "
+                      "inverse-gamma draws of V, W), device-resident" % (B, T, sweeps),
+            "chain_sweeps_per_s": B * sweeps / t, "ms_per_sweep": t * 1e3 / sweeps,
+            "launches_per_sweep": (eng.ctx.launch_count() - l0) / sweeps,
+            "status_max": int(res["status"].max()),
+            "posterior_mean_V_last": float(res["V"][-1].mean())}
+
+
+def ar_leg(eng, dev, with_cpu=True, B=1_000_000, T=1000):
+    """Next row f3: scalar AR(1) FFBS (FilterAr.ffbs, FilterAr.scala:77-83), the inner loop of the
+    stochastic-volatility samplers, 1e6 series x T = 1000, per-series parameters and per-step
+    per-series observation variances.  HBM-bound: y, v in; (m, C) spilled and re-read; z in;
+    theta out = 8 * 8 B per series-step."""
+    import torch
+    from bayesian_dlms_b200 import TIME_MAJOR
+    g = torch.Generator(device=dev).manual_seed(20260106)
+    r = lambda *s: torch.rand(s, generator=g, device=dev, dtype=torch.float64)  # noqa: E731
+    sv = dict(phi=0.5 + 0.45 * r(B), mu=r(B) - 0.5, sigma_eta=0.1 + r(B))
+    y = torch.randn((T, B), generator=g, device=dev, dtype=torch.float64)
+    v = 0.5 + r(T, B)
+    z = torch.randn((T + 1, B), generator=g, device=dev, dtype=torch.float64)
+    eng.ar_ffbs(sv, y, v, z, layout=TIME_MAJOR)
+    torch.cuda.synchronize()
+    ms = []
+    for _ in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = eng.ar_ffbs(sv, y, v, z, layout=TIME_MAJOR)
+        e1.record()
+        torch.cuda.synchronize()
+        ms.append(e0.elapsed_time(e1))
+    t = float(np.median(ms)) * 1e-3
+    byt = 8 * 8
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    res = {"config": "f3: scalar AR(1) FFBS, %d series x T=%d, per-series phi/mu/sigma and v_t" % (B, T),
+           "steps_per_s": B * T / t, "draws_per_s": B / t, "ms": t * 1e3,
+           "finite": bool(torch.isfinite(out["theta"][:, :1000]).all()),
+           "roofline": {"bound": "hbm", "achieved": B * T * byt / t / 1e9, "peak": peak,
+                        "unit": "GB/s", "frac": B * T * byt / t / 1e9 / peak, "bytes_per_step": byt}}
+    if with_cpu:
+        import oracle
+        Tc, reps = T, 2000
+        yc, vc, zc = np.random.default_rng(6).standard_normal((3, Tc + 1))
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            f = oracle.ar_filter(0.8, 0.1, 0.3, np.arange(1.0, Tc + 1), np.abs(vc[:Tc]) + 0.5, yc[:Tc])
+            oracle.ar_backward_sample(0.8, f, zc)
+        dt = time.perf_counter() - t0
+        res["cpu_baseline"] = {"value": reps * Tc / dt, "unit": "series-steps/s", "cores": 1,
+                               "kind": "port", "sample": f"{reps} series x T={Tc}, one core, {dt:.2f} s wall"}
+    return res
+
+
 def scan_leg(eng, dev, with_cpu=True, logT=24):
     """Secondary metric (BASELINE.json config 5): ONE series, T = 2^24, polynomial(2),
     parallel-in-time filter + smoother on one GPU (the 8-GPU run shards the time axis and
@@ -302,7 +385,7 @@ def scan_leg(eng, dev, with_cpu=True, logT=24):
         torch.cuda.synchronize()
         ms.append(e0.elapsed_time(e1))
     t = float(np.median(ms)) * 1e-3
-    byt = 8 * (2 + 14 + 6 + 6 + 6)  # y twice, KfState, (m,C) re-read twice, (s,S)
+    byt = 8 * (1 + 14 + 6 + 6)  # y, KfState, (m, C) re-read, (s, S) = 216 B/step
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -539,7 +622,15 @@ def main():
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
             "gpu_launches": int(launches), "clocks": clocks, "status_max": status_max,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None,
+                         "frac": achieved / peak,
+                         # ncu --set full capture of this kernel (profiles/r1_kf_small_full.txt):
+                         # dram read + write = 61.298 GB for a 284 160-series launch whose
+                         # algorithmic bytes are 61.379 GB -> 0.9987 x algorithmic, scaled here
+                         # to this run's average launch
+                         "traffic": 0.9987 * ALGO_BYTES_PER_STEP * float(np.mean(kern_steps)) / 1e9,
+                         "traffic_unit": "GB per launch",
+                         "traffic_source": "profiles/r1_kf_small_full.txt (61.298 GB measured / "
+                                           "61.379 GB algorithmic for its 284160-series launch)",
                          "kernel": "kf_small_kernel<2,true> (fused filter+smoother)",
                          "algorithmic_bytes_per_series_step": ALGO_BYTES_PER_STEP,
                          "launch_ms_avg": float(np.mean(kern_ms)),
@@ -554,11 +645,16 @@ def main():
                 line["ffbs"] = ffbs_leg(eng, dev, with_cpu=not args.no_cpu)
             except Exception as ex:  # secondary metric: never take the headline down
                 line["ffbs"] = {"error": repr(ex)}
-            for key, fn in (("svd_ffbs", svd_leg), ("scan", scan_leg)):
+            for key, fn in (("svd_ffbs", svd_leg), ("scan", scan_leg), ("ar_ffbs", ar_leg)):
                 try:
                     line[key] = fn(eng, dev, with_cpu=not args.no_cpu)
                 except Exception as ex:
                     line[key] = {"error": repr(ex)}
+                torch.cuda.empty_cache()
+            try:
+                line["gibbs"] = gibbs_leg(eng, dev)
+            except Exception as ex:
+                line["gibbs"] = {"error": repr(ex)}
         if not args.no_cpu and world >= 1:
             try:
                 base, _, _ = cpu_reference_leg(B, T)

@@ -115,6 +115,11 @@ typedef struct bdlm_problem {
   const double *m0;   /* DlmParameters.m0                                   */
   const double *C0;   /* DlmParameters.c0                                   */
   const double *y;    /* observations, T rows, k = p                        */
+  int32_t v_tv;       /* next row f2 (StudentTGibbs.filter, StudentTGibbs.scala:100-119;
+                         DlmFsv.ffbsSvd, DlmFsv.scala:208-229): V varies with t.  V then
+                         holds T matrices: host [T][p*p] when shared, or, with BDLM_PS_V, a
+                         per-step array laid out like y with k = p*p.  Served by the
+                         warp-per-series kernels.                               */
 } bdlm_problem;
 
 /* KfState fields (KalmanFilter.scala:22-30), `rows` rows each; NULL = not wanted. */

@@ -444,13 +444,13 @@ static double min_time(int T, const double *times) {
  * = initialiseState :112-118 with f,Q = NaN standing for None).
  * F: n x p, or T of them when f_tv; G likewise (G[t] = g(dt_t) advances INTO
  * observation t).  times_out[rows] receives the state times. */
-ORACLE_API int oracle_kf_filter(int n, int p, int T, const double *F, int f_tv,
-                                const double *G, int g_tv, const double *V,
-                                const double *W, const double *m0,
-                                const double *C0, const double *times,
-                                const double *y, int keep_init, double *times_out,
-                                double *m, double *C, double *a, double *R,
-                                double *f, double *Q) {
+static int kf_filter_impl(int n, int p, int T, const double *F, int f_tv,
+                          const double *G, int g_tv, const double *V, int v_tv,
+                          const double *W, const double *m0,
+                          const double *C0, const double *times,
+                          const double *y, int keep_init, double *times_out,
+                          double *m, double *C, double *a, double *R,
+                          double *f, double *Q) {
   if (T <= 0) return -1; /* t0.get on empty data, KalmanFilter.scala:116-117 */
   int st = ST_OK, nn = n * n, pp = p * p;
   double mc[64], Cc[64 * 64], tmp[64 * 64];
@@ -473,14 +473,39 @@ ORACLE_API int oracle_kf_filter(int n, int p, int T, const double *F, int f_tv,
     double *ar = a + (size_t)row * n, *Rr = R + (size_t)row * nn;
     double *mr = m + (size_t)row * n, *Cr = C + (size_t)row * nn;
     kf_advance(n, Gt, W, dt, mc, Cc, ar, Rr, tmp);
-    st |= kf_update(n, p, Ft, V, ar, Rr, y + (size_t)t * p, f + (size_t)row * p,
-                    Q + (size_t)row * pp, mr, Cr);
+    st |= kf_update(n, p, Ft, V + (v_tv ? (size_t)t * pp : 0), ar, Rr, y + (size_t)t * p,
+                    f + (size_t)row * p, Q + (size_t)row * pp, mr, Cr);
     memcpy(mc, mr, sizeof(double) * n);
     memcpy(Cc, Cr, sizeof(double) * nn);
     tprev = times[t];
     times_out[row] = tprev;
   }
   return st;
+}
+
+ORACLE_API int oracle_kf_filter(int n, int p, int T, const double *F, int f_tv,
+                                const double *G, int g_tv, const double *V,
+                                const double *W, const double *m0,
+                                const double *C0, const double *times,
+                                const double *y, int keep_init, double *times_out,
+                                double *m, double *C, double *a, double *R,
+                                double *f, double *Q) {
+  return kf_filter_impl(n, p, T, F, f_tv, G, g_tv, V, 0, W, m0, C0, times, y, keep_init,
+                        times_out, m, C, a, R, f, Q);
+}
+
+/* Time-varying observation variance V_t (next row f2): StudentTGibbs.filter
+ * (StudentTGibbs.scala:100-119) runs KalmanFilter.step with params.copy(v = V_t) at step t.
+ * V: T matrices of p x p. */
+ORACLE_API int oracle_kf_filter_vt(int n, int p, int T, const double *F, int f_tv,
+                                   const double *G, int g_tv, const double *V,
+                                   const double *W, const double *m0,
+                                   const double *C0, const double *times,
+                                   const double *y, int keep_init, double *times_out,
+                                   double *m, double *C, double *a, double *R,
+                                   double *f, double *Q) {
+  return kf_filter_impl(n, p, T, F, f_tv, G, g_tv, V, 1, W, m0, C0, times, y, keep_init,
+                        times_out, m, C, a, R, f, Q);
 }
 
 /* B = (R1^T \ (G C^T))^T  -- Smoothing.scala:41 and :85 */
@@ -595,6 +620,25 @@ ORACLE_API int oracle_ffbs(int n, int p, int T, const double *F, int f_tv,
   double *Q = (double *)malloc(sizeof(double) * rows * p * p);
   int st = oracle_kf_filter(n, p, T, F, f_tv, G, g_tv, V, W, m0, C0, times, y, 1,
                             times_out, m, C, a, R, f, Q);
+  if (st >= 0)
+    st |= oracle_backward_sample(n, T, 1, G, g_tv, W, times_out, m, C, a, R, z, theta);
+  free(f); free(Q);
+  return st;
+}
+
+/* StudentTGibbs.sampleState (StudentTGibbs.scala:128-136): filter with V_t, then
+ * Smoothing.sampleDlm. */
+ORACLE_API int oracle_ffbs_vt(int n, int p, int T, const double *F, int f_tv,
+                              const double *G, int g_tv, const double *V,
+                              const double *W, const double *m0, const double *C0,
+                              const double *times, const double *y, const double *z,
+                              double *times_out, double *theta, double *m, double *C,
+                              double *a, double *R) {
+  int rows = T + 1;
+  double *f = (double *)malloc(sizeof(double) * rows * p);
+  double *Q = (double *)malloc(sizeof(double) * rows * p * p);
+  int st = oracle_kf_filter_vt(n, p, T, F, f_tv, G, g_tv, V, W, m0, C0, times, y, 1,
+                               times_out, m, C, a, R, f, Q);
   if (st >= 0)
     st |= oracle_backward_sample(n, T, 1, G, g_tv, W, times_out, m, C, a, R, z, theta);
   free(f); free(Q);

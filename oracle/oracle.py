@@ -64,16 +64,20 @@ def cm(M):
     return np.ascontiguousarray(np.asarray(M, dtype=np.float64).T).ravel()
 
 
-def kf_filter(n, p, F, G, V, W, m0, C0, times, y, keep_init=True):
+def kf_filter(n, p, F, G, V, W, m0, C0, times, y, keep_init=True, v_tv=False):
+    """v_tv: V holds T matrices (StudentTGibbs.filter, StudentTGibbs.scala:100-119)."""
     times = _a(times)
     T = times.size
+    if v_tv:
+        assert _a(V).size == T * p * p
     y = _a(y, (T, p))
     F, f_tv, G, g_tv = _model(F, G, n, p, T)
     rows = T + int(keep_init)
     out = {k: np.empty((rows, d)) for k, d in
            dict(m=n, C=n * n, a=n, R=n * n, f=p, Q=p * p).items()}
     tm = np.empty(rows)
-    st = lib().oracle_kf_filter(
+    fn = lib().oracle_kf_filter_vt if v_tv else lib().oracle_kf_filter
+    st = fn(
         n, p, T, _p(F), f_tv, _p(G), g_tv, _p(_a(V)), _p(_a(W)), _p(_a(m0)), _p(_a(C0)),
         _p(times), _p(y), int(keep_init), _p(tm),
         *(_p(out[k]) for k in ("m", "C", "a", "R", "f", "Q")))
@@ -108,7 +112,7 @@ def backward_sample(n, G, W, filt, z, keep_init=True):
     return dict(theta=theta, status=st)
 
 
-def ffbs(n, p, F, G, V, W, m0, C0, times, y, z):
+def ffbs(n, p, F, G, V, W, m0, C0, times, y, z, v_tv=False):
     times = _a(times)
     T = times.size
     rows = T + 1
@@ -118,7 +122,8 @@ def ffbs(n, p, F, G, V, W, m0, C0, times, y, z):
     out = {k: np.empty((rows, d)) for k, d in
            dict(theta=n, m=n, C=n * n, a=n, R=n * n).items()}
     tm = np.empty(rows)
-    st = lib().oracle_ffbs(n, p, T, _p(F), f_tv, _p(G), g_tv, _p(_a(V)), _p(_a(W)),
+    fn = lib().oracle_ffbs_vt if v_tv else lib().oracle_ffbs
+    st = fn(n, p, T, _p(F), f_tv, _p(G), g_tv, _p(_a(V)), _p(_a(W)),
                            _p(_a(m0)), _p(_a(C0)), _p(times), _p(y), _p(z), _p(tm),
                            *(_p(out[k]) for k in ("theta", "m", "C", "a", "R")))
     out["time"] = tm

@@ -32,11 +32,31 @@ def test_binding_covers_every_declared_symbol():
     assert set(_declared_symbols()) == set(capi.SYMBOLS)
 
 
-def test_struct_layout_matches_header():
-    # bdlm_problem: int64 + 10 x int32 + 8 pointers (no padding needed)
-    assert C.sizeof(capi.Problem) == 8 + 10 * 4 + 8 * 8
-    assert C.sizeof(capi.KfOut) == 6 * 8 and C.sizeof(capi.SmoothOut) == 2 * 8
-    assert C.sizeof(capi.SvdOut) == 7 * 8 and C.sizeof(capi.GibbsStats) == 4 * 8
+def test_struct_layout_matches_header(tmp_path):
+    """sizeof / offsetof of every struct as gcc sees include/bdlm.h == the ctypes mirrors."""
+    import subprocess
+    structs = {"bdlm_problem": capi.Problem, "bdlm_kf_out": capi.KfOut,
+               "bdlm_smooth_out": capi.SmoothOut, "bdlm_svd_out": capi.SvdOut,
+               "bdlm_gibbs_stats": capi.GibbsStats, "bdlm_ar_problem": capi.ArProblem,
+               "bdlm_ar_out": capi.ArOut, "bdlm_gibbs_prior": capi.GibbsPrior,
+               "bdlm_gibbs_rng": capi.GibbsRng}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "bdlm.h"', 'int main(void) {']
+    for cname, cls in structs.items():
+        lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['return 0; }']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    inc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include")
+    subprocess.run(["gcc", "-I", inc, str(src), "-o", str(exe)], check=True)
+    got = dict(l.split() for l in subprocess.run([str(exe)], capture_output=True, text=True,
+                                                 check=True).stdout.splitlines())
+    for cname, cls in structs.items():
+        assert int(got[cname]) == C.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(cls, fname).offset, (cname, fname)
 
 
 def test_no_cpu_fallback_without_gpu():

@@ -272,3 +272,46 @@ def test_device_resident_gibbs_recovers_parameters(eng):
     v = res["V"][100:, 0, :].mean().item()
     w = res["W"][100:, 0, :].mean().item()
     assert abs(v - 2.0) < 0.35 and abs(w - 3.0) < 0.5, (v, w)
+
+
+# ------------------------------------------------------------------ time-varying V_t (f2)
+
+@pytest.mark.parametrize("n,p", [(2, 1), (3, 2), (13, 1)])
+@pytest.mark.parametrize("shared", [True, False])
+def test_time_varying_V_filter_and_ffbs(eng, oracle, n, p, shared):
+    """StudentTGibbs.filter / sampleState (StudentTGibbs.scala:100-136): KalmanFilter.step with
+    params.copy(v = V_t) at step t, then Smoothing.sampleDlm.  Bit-exact against the oracle."""
+    from bayesian_dlms_b200 import Model, SERIES_MAJOR, dlm
+    rng = np.random.default_rng(100 * n + p + int(shared))
+    B, T = 5, 60
+    if n == 13:
+        mod, _, W, m0, C0 = H.seasonal13()
+    else:
+        mod = dlm.polynomial(n) if p == 1 else dlm.polynomial(1) * dlm.polynomial(2)
+        W, m0, C0 = H.spd(rng, n, 0.3), rng.standard_normal(n), H.spd(rng, n, 4.0)
+    times = np.arange(1.0, T + 1)
+    Vb = np.stack([np.stack([H.spd(rng, p, 2.0) for _ in range(T)]) for _ in range(1 if shared else B)])
+    y = np.stack([H.simulate(mod, np.eye(p), W, m0, C0, times, rng, missing=0.1) for _ in range(B)])
+    z = rng.standard_normal((B, T + 1, n))
+    model = Model.build(mod, T=T)
+    Vflat = np.ascontiguousarray(Vb.transpose(0, 1, 3, 2).reshape(Vb.shape[0], T, p * p))  # col-major rows
+    if shared:
+        params = dict(V=Vflat[0], W=W, m0=m0, C0=C0, v_tv=True)
+    else:
+        params = dict(V=_cuda(Vflat), W=W, m0=m0, C0=C0, v_tv=True, per_series=("V",))
+    f = eng.filter(model, params, _cuda(y), layout=SERIES_MAJOR)
+    s = eng.ffbs(model, params, _cuda(y), _cuda(z), layout=SERIES_MAJOR)
+    fs = eng.filter_smooth(model, params, _cuda(y), layout=SERIES_MAJOR)
+    assert int(f["status"].max()) == 0 and int(s["status"].max()) == 0
+    cm = oracle.oracle.cm
+    for b in range(B):
+        Vt = Vflat[0 if shared else b]
+        o = oracle.kf_filter(n, p, model.F, model.G, Vt, cm(W), m0, cm(C0), times, y[b], v_tv=True)
+        for k in ("m", "C", "a", "R", "f", "Q"):
+            _exact(f[k][b].cpu().numpy()[1:], o[k][1:], k)
+            _exact(fs[k][b].cpu().numpy()[1:], o[k][1:], "fused " + k)
+        sm = oracle.rts_smooth(n, model.G, o)
+        _exact(fs["s"][b].cpu().numpy(), sm["s"], "s")
+        _exact(fs["S"][b].cpu().numpy(), sm["S"], "S")
+        th = oracle.ffbs(n, p, model.F, model.G, Vt, cm(W), m0, cm(C0), times, y[b], z[b], v_tv=True)
+        _exact(s["theta"][b].cpu().numpy(), th["theta"], "theta")
