@@ -1019,6 +1019,106 @@ int bdlm_scan_filter_smooth(bdlm_ctx *c, const bdlm_problem *p, const bdlm_kf_ou
   return 0;
 }
 
+// ---- device-side multi-GPU protocol for the scan (no host round trip) --------------------
+// arena: [forward scan workspace | backward scan workspace]; it must survive from the local to
+// the finish phase, so all four calls size it identically.
+
+static int scan_dist_common(bdlm_ctx *c, const bdlm_problem *p, const bdlm_kf_out *kf, int rank,
+                            int world, size_t *ws_out) {
+  int rc = scan_validate(c, p);
+  if (rc) return rc;
+  if (world < 1 || rank < 0 || rank >= world) return fail(c, BDLM_E_ARG, "bad rank / world");
+  if ((p->keep_init != 0) != (rank == 0))
+    return fail(c, BDLM_E_ARG, "time-sharded scan: keep_init = 1 on rank 0 only");
+  if (kf && (!kf->m || !kf->C)) return fail(c, BDLM_E_ARG, "time-sharded scan needs kf->m and kf->C");
+  CU(cudaSetDevice(c->device));
+  const size_t ws = align_up(scan_workspace_bytes(p->n, p->T) + 4096);
+  rc = ensure_arena(c, 2 * ws + 4096);
+  if (rc) return rc;
+  *ws_out = ws;
+  return 0;
+}
+
+int bdlm_scan_dist_forward_local(bdlm_ctx *c, const bdlm_problem *p, int32_t rank, int32_t world,
+                                 double *agg_dev) {
+  size_t ws;
+  int rc = scan_dist_common(c, p, nullptr, rank, world, &ws);
+  if (rc) return rc;
+  if (!agg_dev) return fail(c, BDLM_E_ARG, "null aggregate pointer");
+  ScanArgs a;
+  rc = scan_fill(c, p, a, true);
+  if (rc) return rc;
+  a.phase = kScanDistLocal; a.agg_dev = agg_dev; a.workspace = c->arena;
+  a.rank = rank; a.world = world;
+  CU(launch_scan(a, c->stream, &c->launches));
+  return 0;
+}
+
+int bdlm_scan_dist_forward_finish(bdlm_ctx *c, const bdlm_problem *p, int32_t rank, int32_t world,
+                                  const double *aggs_dev, const bdlm_kf_out *kf, int32_t *status) {
+  size_t ws;
+  if (!kf) return fail(c, BDLM_E_ARG, "null output struct");
+  int rc = scan_dist_common(c, p, kf, rank, world, &ws);
+  if (rc) return rc;
+  if (!aggs_dev) return fail(c, BDLM_E_ARG, "null aggregates pointer");
+  std::vector<double> prior((size_t)p->n + p->n * p->n);
+  std::copy(p->m0, p->m0 + p->n, prior.begin());
+  std::copy(p->C0, p->C0 + p->n * p->n, prior.begin() + p->n);
+  ScanArgs a;
+  rc = scan_fill(c, p, a, true);
+  if (rc) return rc;
+  a.table_upload = 0;  // built by the local phase
+  a.phase = kScanDistFinish; a.aggs_dev = aggs_dev; a.rank = rank; a.world = world;
+  a.start = prior.data(); a.has_successor = rank < world - 1;
+  a.kf = scan_kf_views(p, kf); a.status = status; a.workspace = c->arena;
+  a.fuse_sagg = c->arena + ws;  // smoother level-1 aggregates for the backward phases
+  if (status) CU(cudaMemsetAsync(status, 0, sizeof(int32_t), c->stream));
+  CU(launch_scan(a, c->stream, &c->launches));
+  return 0;
+}
+
+int bdlm_scan_dist_backward_local(bdlm_ctx *c, const bdlm_problem *p, int32_t rank, int32_t world,
+                                  const bdlm_kf_out *filt, const bdlm_smooth_out *sm,
+                                  double *agg_dev) {
+  size_t ws;
+  if (!filt) return fail(c, BDLM_E_ARG, "null filtered-state struct");
+  int rc = scan_dist_common(c, p, filt, rank, world, &ws);
+  if (rc) return rc;
+  if (!agg_dev || !sm) return fail(c, BDLM_E_ARG, "null aggregate pointer or output struct");
+  const int64_t n = p->n, R = rows_of(*p);
+  ScanArgs a;
+  rc = scan_fill(c, p, a);
+  if (rc) return rc;
+  a.backward = 1; a.phase = kScanDistLocal; a.has_successor = rank < world - 1;
+  a.pre_reduced = 1;  // written by bdlm_scan_dist_forward_finish
+  a.kf = scan_kf_views(p, filt);
+  a.s = mk_view(sm->s, p->layout, 0, 1, R, n); a.S = mk_view(sm->S, p->layout, 0, 1, R, n * n);
+  a.agg_dev = agg_dev; a.rank = rank; a.world = world; a.workspace = c->arena + ws;
+  CU(launch_scan(a, c->stream, &c->launches));
+  return 0;
+}
+
+int bdlm_scan_dist_backward_finish(bdlm_ctx *c, const bdlm_problem *p, int32_t rank, int32_t world,
+                                   const double *aggs_dev, const bdlm_kf_out *filt,
+                                   const bdlm_smooth_out *sm, int32_t *status) {
+  size_t ws;
+  if (!filt) return fail(c, BDLM_E_ARG, "null filtered-state struct");
+  int rc = scan_dist_common(c, p, filt, rank, world, &ws);
+  if (rc) return rc;
+  if (!aggs_dev || !sm) return fail(c, BDLM_E_ARG, "null aggregates pointer or output struct");
+  const int64_t n = p->n, R = rows_of(*p);
+  ScanArgs a;
+  rc = scan_fill(c, p, a);
+  if (rc) return rc;
+  a.backward = 1; a.phase = kScanDistFinish; a.has_successor = rank < world - 1;
+  a.kf = scan_kf_views(p, filt);
+  a.s = mk_view(sm->s, p->layout, 0, 1, R, n); a.S = mk_view(sm->S, p->layout, 0, 1, R, n * n);
+  a.aggs_dev = aggs_dev; a.rank = rank; a.world = world; a.status = status;
+  a.workspace = c->arena + ws;
+  CU(launch_scan(a, c->stream, &c->launches));
+  return 0;
+}
+
 // ---- "next" rows: scalar AR(1) / OU, conjugate filter, conjugate draws -------------------
 
 static int ar_call(bdlm_ctx *c, int op, const bdlm_ar_problem *ap, const bdlm_ar_out *out,

@@ -53,7 +53,11 @@ cudaError_t launch_transpose(const double *in, double *out, int64_t rows, int64_
 
 // scan.cu: parallel-in-time filter / smoother for one long series (n <= 4, p = 1, regular
 // grid, time-invariant model).
-enum { kScanReduce = 0, kScanApply = 1 };
+enum { kScanReduce = 0, kScanApply = 1,
+       // device-side multi-GPU protocol (no host round trip): local = level-1 + scan with an
+       // identity carry, chunk aggregate left in DEVICE memory for the all-gather; finish = fold
+       // the gathered aggregates of the other ranks on the device and apply
+       kScanDistLocal = 2, kScanDistFinish = 3 };
 struct ScanArgs {
   int n;
   int64_t T;           // observations in this chunk
@@ -74,6 +78,9 @@ struct ScanArgs {
   void *fuse_sagg;     // forward apply: also write the smoother's level-1 aggregates here (the
                        // backward workspace of the call that follows), or nullptr
   int pre_reduced;     // backward apply: workspace already holds those aggregates
+  double *agg_dev;     // dist local: device [elem doubles], this rank's chunk aggregate (out)
+  const double *aggs_dev;  // dist finish: device [world][elem doubles], all ranks' aggregates
+  int rank, world;     // dist phases
   void *table;         // device, scan_table_bytes(): y-independent parts of the level-1 aggregates
   int table_upload;    // 1 = (re)build the table for this model before the forward pass
 };

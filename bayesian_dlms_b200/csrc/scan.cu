@@ -635,17 +635,29 @@ __global__ void __launch_bounds__(128)
 fwd_apply_kernel(const ScanModel<N> md, const double *__restrict__ y, int64_t T, int64_t M,
                  const FElem<N> *pre /* [M+1] inclusive scan with slot 0 = start */,
                  int keep_init, KfViews kf, int32_t *status,
-                 SElem<N> *sagg /* FUSE: smoother level-1 aggregates */, int64_t nrows) {
+                 SElem<N> *sagg /* FUSE: smoother level-1 aggregates */, int64_t nrows,
+                 const FElem<N> *carry /* multi-GPU: everything before this chunk, or nullptr */) {
   const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (c >= M) return;
   const int64_t rows = T + keep_init;
   const int64_t r0 = c * kSub, r1 = (r0 + kSub < rows) ? r0 + kSub : rows;
   double m[N], C[N * N], W[N * N], an[N], Rn[N * N];
   int st = 0;
+  if (carry) {  // the scan ran with an identity start: compose the carry on the fly
+    FElem<N> o;
+    f_combine<N>(*carry, pre[c], o);
 #pragma unroll
-  for (int k = 0; k < N; ++k) m[k] = pre[c].b[k];
+    for (int k = 0; k < N; ++k) m[k] = o.b[k];
 #pragma unroll
-  for (int k = 0; k < N * N; ++k) { C[k] = pre[c].C[k]; W[k] = md.W[k]; }
+    for (int k = 0; k < N * N; ++k) C[k] = o.C[k];
+  } else {
+#pragma unroll
+    for (int k = 0; k < N; ++k) m[k] = pre[c].b[k];
+#pragma unroll
+    for (int k = 0; k < N * N; ++k) C[k] = pre[c].C[k];
+  }
+#pragma unroll
+  for (int k = 0; k < N * N; ++k) W[k] = md.W[k];
   advance<N, true>(md.G, W, 1.0, m, C, an, Rn);
   SElem<N> sacc;
   bool shave = false;
@@ -754,16 +766,28 @@ template <int N, bool VEC>
 __global__ void __launch_bounds__(128)
 bwd_apply_kernel(const ScanModel<N> md, View fm, View fC, int64_t nrows, int64_t M,
                  const SElem<N> *suf /* [M+1] suffix-inclusive scan, slot M = terminal */,
-                 View sv, View Sv, int32_t *status) {
+                 View sv, View Sv, int32_t *status,
+                 const SElem<N> *carry /* multi-GPU: everything after this chunk, or nullptr */) {
   const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (c >= M) return;
   const int64_t r0 = c * kSub, r1 = (r0 + kSub < nrows) ? r0 + kSub : nrows;
   double W[N * N], s[N], S[N * N];
   int st = 0;
+  if (carry) {
+    SElem<N> o;
+    s_combine<N>(suf[c + 1], *carry, o);
 #pragma unroll
-  for (int k = 0; k < N * N; ++k) { W[k] = md.W[k]; S[k] = suf[c + 1].L[k]; }
+    for (int k = 0; k < N * N; ++k) S[k] = o.L[k];
 #pragma unroll
-  for (int k = 0; k < N; ++k) s[k] = suf[c + 1].g[k];
+    for (int k = 0; k < N; ++k) s[k] = o.g[k];
+  } else {
+#pragma unroll
+    for (int k = 0; k < N * N; ++k) S[k] = suf[c + 1].L[k];
+#pragma unroll
+    for (int k = 0; k < N; ++k) s[k] = suf[c + 1].g[k];
+  }
+#pragma unroll
+  for (int k = 0; k < N * N; ++k) W[k] = md.W[k];
   int64_t r = r1;  // one past the next row to produce
   // ragged head of the descending sweep (rows above the last whole group), scalar stores
   const int64_t aligned_top = VEC ? r0 + (r1 - r0) / kGrp * kGrp : r1;
@@ -845,6 +869,24 @@ __global__ void copy_last_row(View fm, View fC, int64_t row, View sv, View Sv, d
   }
 }
 
+// Carry folding on the device (multi-GPU): one thread, at most world - 1 combines.
+template <int N>
+__global__ void fold_forward_kernel(const FElem<N> *aggs, int rank, const StateArg<N> prior,
+                                    FElem<N> *carry) {
+  FElem<N> e, t;
+  f_state<N>(e, prior.v, prior.v + N);  // the state before the first observation of rank 0
+  for (int r = 0; r < rank; ++r) { f_combine<N>(e, aggs[r], t); e = t; }
+  *carry = e;
+}
+// carry of rank r = agg_{r+1} (x) ... (x) agg_{world-1}; the last rank's aggregate already ends in
+// its terminal state s_T = m_T, S_T = C_T.
+template <int N>
+__global__ void fold_backward_kernel(const SElem<N> *aggs, int rank, int world, SElem<N> *carry) {
+  SElem<N> e = aggs[world - 1], t;
+  for (int r = world - 2; r > rank; --r) { s_combine<N>(aggs[r], e, t); e = t; }
+  *carry = e;
+}
+
 template <int N>
 ScanModel<N> make_model(const ScanArgs &a) {
   ScanModel<N> md;
@@ -876,32 +918,45 @@ cudaError_t scan_forward(const ScanArgs &a, cudaStream_t stream, int64_t *launch
     // pageable source: staged by the driver before the call returns
     CK(cudaMemcpyAsync(tb, &host, sizeof(host), cudaMemcpyHostToDevice, stream));
   }
-  const bool reduce = a.phase == kScanReduce;
-  // reduce: chunk aggregate only (identity start); apply: prefix of (start (x) aggregates),
-  // a.start = host (m, C) of the state before t = 0
-  set_f_start<N><<<1, 1, 0, stream>>>(X, state_arg<N>(reduce ? nullptr : a.start), reduce);
-  if ((reinterpret_cast<uintptr_t>(a.y) & 31) == 0)
-    fwd_reduce_kernel<N, true><<<blocks, 128, 0, stream>>>(md, tb, a.y, T, M, a.keep_init, X);
-  else
-    fwd_reduce_kernel<N, false><<<blocks, 128, 0, stream>>>(md, tb, a.y, T, M, a.keep_init, X);
-  *launches += 2;
-  CK(cudaGetLastError());
-  CK((device_scan<FElem<N>, false, false>(X, M + 1, scratch, stream, launches)));
-  if (reduce) {
-    CK(cudaMemcpyAsync(a.agg_out, X + M, sizeof(FElem<N>), cudaMemcpyDeviceToHost, stream));
-    return cudaStreamSynchronize(stream);
+  const bool reduce = a.phase == kScanReduce, local = a.phase == kScanDistLocal,
+             finish = a.phase == kScanDistFinish;
+  FElem<N> *carry = reinterpret_cast<FElem<N> *>(scratch + (M + 1) / kScanBlock * 2 + 8);
+  if (!finish) {
+    // reduce / dist local: chunk aggregate only (identity start); apply: prefix of
+    // (start (x) aggregates), a.start = host (m, C) of the state before t = 0
+    const bool ident = reduce || local;
+    set_f_start<N><<<1, 1, 0, stream>>>(X, state_arg<N>(ident ? nullptr : a.start), ident);
+    if ((reinterpret_cast<uintptr_t>(a.y) & 31) == 0)
+      fwd_reduce_kernel<N, true><<<blocks, 128, 0, stream>>>(md, tb, a.y, T, M, a.keep_init, X);
+    else
+      fwd_reduce_kernel<N, false><<<blocks, 128, 0, stream>>>(md, tb, a.y, T, M, a.keep_init, X);
+    *launches += 2;
+    CK(cudaGetLastError());
+    CK((device_scan<FElem<N>, false, false>(X, M + 1, scratch, stream, launches)));
+    if (reduce) {
+      CK(cudaMemcpyAsync(a.agg_out, X + M, sizeof(FElem<N>), cudaMemcpyDeviceToHost, stream));
+      return cudaStreamSynchronize(stream);
+    }
+    if (local)  // stays on the device: the caller all-gathers it (NCCL) on the same stream
+      return cudaMemcpyAsync(a.agg_dev, X + M, sizeof(FElem<N>), cudaMemcpyDeviceToDevice, stream);
+  } else {
+    // X still holds this rank's scanned prefixes from the local phase
+    fold_forward_kernel<N><<<1, 1, 0, stream>>>(reinterpret_cast<const FElem<N> *>(a.aggs_dev),
+                                                a.rank, state_arg<N>(a.start), carry);
+    ++*launches;
   }
   const bool vec = dense_aligned(a.kf.m, N) && dense_aligned(a.kf.C, N * N) &&
                    dense_aligned(a.kf.a, N) && dense_aligned(a.kf.R, N * N) &&
                    dense_aligned(a.kf.f, 1) && dense_aligned(a.kf.Q, 1) &&
                    (reinterpret_cast<uintptr_t>(a.y) & 31) == 0;
-  // a.fuse_sagg: the caller runs the smoother next on the same rows (single-GPU call): fold the
-  // smoothing elements here so the backward pass starts from ready level-1 aggregates.
+  // a.fuse_sagg: the caller runs the smoother next on the same rows: fold the smoothing
+  // elements here so the backward pass starts from ready level-1 aggregates.
   SElem<N> *sagg = reinterpret_cast<SElem<N> *>(a.fuse_sagg);
-  const int64_t nrows = T + a.keep_init - 1;
+  const int64_t nrows = T + a.keep_init - (a.has_successor ? 0 : 1);
+  const FElem<N> *cr = finish ? carry : nullptr;
 #define BDLM_FWD_APPLY(VEC_, FUSE_)                                                         \
   fwd_apply_kernel<N, VEC_, FUSE_><<<blocks, 128, 0, stream>>>(md, a.y, T, M, X, a.keep_init, \
-                                                               a.kf, a.status, sagg, nrows)
+                                                               a.kf, a.status, sagg, nrows, cr)
   if (vec && sagg) BDLM_FWD_APPLY(true, true);
   else if (vec) BDLM_FWD_APPLY(true, false);
   else if (sagg) BDLM_FWD_APPLY(false, true);
@@ -923,36 +978,47 @@ cudaError_t scan_backward(const ScanArgs &a, cudaStream_t stream, int64_t *launc
   SElem<N> *scratch = X + (M + 1);
   double *term_dev = reinterpret_cast<double *>(scratch + (M + 1) / kScanBlock * 2 + 8);
   const unsigned blocks = (unsigned)((M + 127) / 128);
-  const bool reduce = a.phase == kScanReduce;
+  const bool reduce = a.phase == kScanReduce, local = a.phase == kScanDistLocal,
+             finish = a.phase == kScanDistFinish;
   const StateArg<N> none = state_arg<N>(nullptr);
   const bool vec = dense_aligned(a.kf.m, N) && dense_aligned(a.kf.C, N * N) &&
                    dense_aligned(a.s, N) && dense_aligned(a.S, N * N);
-  if (reduce) {
-    set_s_terminal<N><<<1, 1, 0, stream>>>(X + M, none, nullptr, true);
+  SElem<N> *carry = reinterpret_cast<SElem<N> *>(term_dev + 64);
+  if (!finish) {
+    if (reduce || (local && a.has_successor)) {
+      set_s_terminal<N><<<1, 1, 0, stream>>>(X + M, none, nullptr, true);
+    } else if (a.has_successor) {
+      set_s_terminal<N><<<1, 1, 0, stream>>>(X + M, state_arg<N>(a.start), nullptr, false);
+    } else {  // last chunk: s_T = m_T, S_T = C_T (Smoothing.scala:59-61)
+      copy_last_row<N><<<1, 1, 0, stream>>>(a.kf.m, a.kf.C, rows - 1, a.s, a.S, term_dev);
+      set_s_terminal<N><<<1, 1, 0, stream>>>(X + M, none, term_dev, false);
+      ++*launches;
+    }
+    ++*launches;
+    if (M > 0 && !a.pre_reduced) {
+      if (vec) bwd_reduce_kernel<N, true><<<blocks, 128, 0, stream>>>(md, a.kf.m, a.kf.C, nrows, M, X);
+      else bwd_reduce_kernel<N, false><<<blocks, 128, 0, stream>>>(md, a.kf.m, a.kf.C, nrows, M, X);
+      ++*launches;
+    }
+    CK(cudaGetLastError());
+    CK((device_scan<SElem<N>, true, true>(X, M + 1, scratch, stream, launches)));
+    if (reduce) {
+      CK(cudaMemcpyAsync(a.agg_out, X, sizeof(SElem<N>), cudaMemcpyDeviceToHost, stream));
+      return cudaStreamSynchronize(stream);
+    }
+    if (local)
+      return cudaMemcpyAsync(a.agg_dev, X, sizeof(SElem<N>), cudaMemcpyDeviceToDevice, stream);
   } else if (a.has_successor) {
-    set_s_terminal<N><<<1, 1, 0, stream>>>(X + M, state_arg<N>(a.start), nullptr, false);
-  } else {  // last chunk: s_T = m_T, S_T = C_T (Smoothing.scala:59-61)
-    copy_last_row<N><<<1, 1, 0, stream>>>(a.kf.m, a.kf.C, rows - 1, a.s, a.S, term_dev);
-    set_s_terminal<N><<<1, 1, 0, stream>>>(X + M, none, term_dev, false);
+    fold_backward_kernel<N><<<1, 1, 0, stream>>>(reinterpret_cast<const SElem<N> *>(a.aggs_dev),
+                                                 a.rank, a.world, carry);
     ++*launches;
   }
-  ++*launches;
-  if (M > 0 && !a.pre_reduced) {
-    if (vec) bwd_reduce_kernel<N, true><<<blocks, 128, 0, stream>>>(md, a.kf.m, a.kf.C, nrows, M, X);
-    else bwd_reduce_kernel<N, false><<<blocks, 128, 0, stream>>>(md, a.kf.m, a.kf.C, nrows, M, X);
-    ++*launches;
-  }
-  CK(cudaGetLastError());
-  CK((device_scan<SElem<N>, true, true>(X, M + 1, scratch, stream, launches)));
-  if (reduce) {
-    CK(cudaMemcpyAsync(a.agg_out, X, sizeof(SElem<N>), cudaMemcpyDeviceToHost, stream));
-    return cudaStreamSynchronize(stream);
-  }
+  const SElem<N> *cr = (finish && a.has_successor) ? carry : nullptr;
   if (M > 0) {
     if (vec)
-      bwd_apply_kernel<N, true><<<blocks, 128, 0, stream>>>(md, a.kf.m, a.kf.C, nrows, M, X, a.s, a.S, a.status);
+      bwd_apply_kernel<N, true><<<blocks, 128, 0, stream>>>(md, a.kf.m, a.kf.C, nrows, M, X, a.s, a.S, a.status, cr);
     else
-      bwd_apply_kernel<N, false><<<blocks, 128, 0, stream>>>(md, a.kf.m, a.kf.C, nrows, M, X, a.s, a.S, a.status);
+      bwd_apply_kernel<N, false><<<blocks, 128, 0, stream>>>(md, a.kf.m, a.kf.C, nrows, M, X, a.s, a.S, a.status, cr);
     ++*launches;
   }
   return cudaGetLastError();
@@ -963,7 +1029,7 @@ cudaError_t scan_backward(const ScanArgs &a, cudaStream_t stream, int64_t *launc
 size_t scan_workspace_bytes(int n, int64_t T) {
   const int64_t M = (T + 1 + kSub - 1) / kSub + 2;
   const size_t elem = sizeof(double) * (3 * n * n + 2 * n);
-  return elem * (size_t)(M + 1 + (M + 1) / kScanBlock * 2 + 16) + 4096;
+  return elem * (size_t)(M + 1 + (M + 1) / kScanBlock * 2 + 24) + 8192;
 }
 
 size_t scan_table_bytes() { return kScanTableBytes; }

@@ -29,16 +29,20 @@ class Dlm:
 
     f: Callable[[float], np.ndarray]
     g: Callable[[float], np.ndarray]
+    # Host-side hint, not part of the reference's type: the builder KNOWS f ignores its argument
+    # (polynomial, autoregressive, seasonal), so flattening a long grid evaluates it once
+    # instead of T times.  Hand-written closures leave it False and are probed at every t.
+    f_const: bool = False
 
     def outer_sum(self, y: "Dlm") -> "Dlm":
         """The reference's ``|*|`` (Dlm.scala:22-23, outerSumModel :117-122)."""
         return Dlm(lambda t: block_diagonal(self.f(t), y.f(t)),
-                   lambda dt: block_diagonal(self.g(dt), y.g(dt)))
+                   lambda dt: block_diagonal(self.g(dt), y.g(dt)), self.f_const and y.f_const)
 
     def compose(self, y: "Dlm") -> "Dlm":
         """The reference's ``|+|`` (Dlm.scala:29-30, composeModels :107-111)."""
         return Dlm(lambda t: np.vstack([self.f(t), y.f(t)]),
-                   lambda dt: block_diagonal(self.g(dt), y.g(dt)))
+                   lambda dt: block_diagonal(self.g(dt), y.g(dt)), self.f_const and y.f_const)
 
     __mul__ = outer_sum
     __add__ = compose
@@ -86,7 +90,7 @@ def polynomial(order: int) -> Dlm:
     def g(dt):
         return np.eye(order) + np.eye(order, k=1)
 
-    return Dlm(f, g)
+    return Dlm(f, g, True)
 
 
 def regression(x: Sequence[np.ndarray]) -> Dlm:
@@ -107,7 +111,7 @@ def autoregressive(*phi: float) -> Dlm:
         m[0, 0] = 1.0
         return m
 
-    return Dlm(f, lambda dt: np.asarray(phi, dtype=np.float64).reshape(k, 1))
+    return Dlm(f, lambda dt: np.asarray(phi, dtype=np.float64).reshape(k, 1), True)
 
 
 def rotation_matrix(theta: float) -> np.ndarray:
@@ -132,7 +136,7 @@ def seasonal(period: int, harmonics: int) -> Dlm:
             out = block_diagonal(out, rotation_matrix(h * angle(period, dt)))
         return out
 
-    return Dlm(f, g)
+    return Dlm(f, g, True)
 
 
 # ---------------------------------------------------------------- flattening
@@ -174,8 +178,13 @@ def materialise(mod: Dlm, times: np.ndarray):
 
 def materialise_dts(mod: Dlm, times: np.ndarray, dts: np.ndarray):
     """As ``materialise`` with the time increments given explicitly (``G[t] = g(dts[t])``)."""
-    Fs = [np.asarray(mod.f(float(t)), dtype=np.float64) for t in times]
-    Gs = [np.asarray(mod.g(float(dt)), dtype=np.float64) for dt in dts]
+    # g is a function of dt alone: evaluate it once per distinct increment (a regular grid has
+    # one); f is evaluated at every t unless the builder marked it constant
+    tsel = times[:1] if getattr(mod, "f_const", False) else times
+    Fs = [np.asarray(mod.f(float(t)), dtype=np.float64) for t in tsel]
+    udt, inv = np.unique(np.asarray(dts, dtype=np.float64), return_inverse=True)
+    Gu = [np.asarray(mod.g(float(dt)), dtype=np.float64) for dt in udt]
+    Gs = Gu if len(udt) == 1 else [Gu[i] for i in inv]
     n, p = Fs[0].shape
     if Gs[0].shape != (n, n):
         raise ValueError(f"g(dt) is {Gs[0].shape}, expected {(n, n)}")

@@ -140,19 +140,24 @@ class ScanChunk:
 
 def scan_filter_smooth_sharded(eng: Engine, mod, params: Dict, y_chunk, rank: int, world: int,
                                all_gather=None):
-    """One rank's part of a time-sharded run.  ``y_chunk``: this rank's CUDA slice of the series.
+    """One rank's part of a time-sharded run.  ``y_chunk``: this rank's CUDA slice of the series;
+    ``mod``: the ``Dlm`` or a prebuilt ``Model`` for the chunk length.
     ``all_gather(np.ndarray) -> List[np.ndarray]`` exchanges the per-rank aggregates (defaults
     to torch.distributed.all_gather_object).  Returns the rank's output dict."""
     if all_gather is None:
+        import torch
         import torch.distributed as dist
 
         def all_gather(x):
-            out = [None] * dist.get_world_size()
-            dist.all_gather_object(out, x)
-            return out
+            # a few dozen doubles per rank: one tensor all-gather (NCCL on GPUs, gloo on CPU)
+            dev = y_chunk.device if dist.get_backend() == "nccl" else "cpu"
+            t = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64)).to(dev)
+            out = [torch.empty_like(t) for _ in range(dist.get_world_size())]
+            dist.all_gather(out, t)
+            return [o.cpu().numpy() for o in out]
 
     n = len(np.asarray(params["m0"]).ravel())
-    model = Model.build(mod, T=int(y_chunk.shape[0]))
+    model = mod if isinstance(mod, Model) else Model.build(mod, T=int(y_chunk.shape[0]))
     ch = ScanChunk(eng, model, params, y_chunk, keep_init=(rank == 0))
     aggs = all_gather(ch.forward_reduce())
     ch.forward_apply(None if rank == 0 else fold_forward_start(n, params["m0"], params["C0"], aggs, rank))
@@ -166,3 +171,66 @@ def scan_filter_smooth_sharded(eng: Engine, mod, params: Dict, y_chunk, rank: in
     if has_succ:
         ch.backward_apply(fold_backward_next(n, sagg, rank, last))
     return ch.out
+
+
+class DistScan:
+    """Time-sharded scan of ONE series over ``world`` GPUs with no host round trip
+    (``bdlm_scan_dist_*``): per pass one all-gather of a 3n^2+2n (filter) / 2n^2+n (smoother)
+    double aggregate per rank, issued on the engine's stream between the local and the finish
+    kernels.  ``all_gather_into(out, x)`` defaults to ``torch.distributed.all_gather_into_tensor``
+    (NCCL); tests pass their own to emulate several ranks on one GPU."""
+
+    def __init__(self, eng: Engine, model: Model, params: Dict, y_chunk, rank: int, world: int):
+        import torch
+        self.eng, self.rank, self.world, self.n = eng, rank, world, model.n
+        self.model, self.y = model, y_chunk   # the problem struct points into model.F / model.G
+        self.keep_init = rank == 0
+        self.rows = model.T + int(self.keep_init)
+        self.pr, self._keep = _problem(model, params, y_chunk, self.keep_init)
+        n = self.n
+        self.out = {k: _alloc(y_chunk, self.rows, d) for k, d in
+                    dict(m=n, C=n * n, a=n, R=n * n, f=1, Q=1, s=n, S=n * n).items()}
+        self.ko, self.so = capi.KfOut(), capi.SmoothOut()
+        for k in ("m", "C", "a", "R", "f", "Q"):
+            setattr(self.ko, k, self.out[k].data_ptr())
+        for k in ("s", "S"):
+            setattr(self.so, k, self.out[k].data_ptr())
+        ef, eb = elem_doubles(n, False), elem_doubles(n, True)
+        z = lambda k: torch.zeros(k, dtype=torch.float64, device=y_chunk.device)  # noqa: E731
+        self.agg_f, self.aggs_f = z(ef), z(world * ef)
+        self.agg_b, self.aggs_b = z(eb), z(world * eb)
+        self.status = torch.zeros(1, dtype=torch.int32, device=y_chunk.device)
+
+    def _ck(self, rc):
+        self.eng.ctx.check(rc)
+
+    def forward_local(self):
+        self._ck(capi.load().bdlm_scan_dist_forward_local(self.eng.ctx.handle, self.pr, self.rank,
+                                                          self.world, self.agg_f.data_ptr()))
+
+    def forward_finish(self):
+        self._ck(capi.load().bdlm_scan_dist_forward_finish(
+            self.eng.ctx.handle, self.pr, self.rank, self.world, self.aggs_f.data_ptr(), self.ko,
+            self.status.data_ptr()))
+
+    def backward_local(self):
+        self._ck(capi.load().bdlm_scan_dist_backward_local(
+            self.eng.ctx.handle, self.pr, self.rank, self.world, self.ko, self.so,
+            self.agg_b.data_ptr()))
+
+    def backward_finish(self):
+        self._ck(capi.load().bdlm_scan_dist_backward_finish(
+            self.eng.ctx.handle, self.pr, self.rank, self.world, self.aggs_b.data_ptr(), self.ko,
+            self.so, self.status.data_ptr()))
+
+    def run(self, all_gather_into=None):
+        if all_gather_into is None:
+            import torch.distributed as dist
+            all_gather_into = dist.all_gather_into_tensor
+        self.forward_local()
+        all_gather_into(self.aggs_f, self.agg_f)
+        self.forward_finish()
+        self.backward_local()
+        all_gather_into(self.aggs_b, self.agg_b)
+        self.backward_finish()
+        return self.out

@@ -274,6 +274,25 @@ BDLM_API int bdlm_scan_backward_reduce(bdlm_ctx *ctx, const bdlm_problem *prob,
 BDLM_API int bdlm_scan_backward_apply(bdlm_ctx *ctx, const bdlm_problem *prob,
                                       const bdlm_kf_out *filt, const double *next_sS_host,
                                       const bdlm_smooth_out *sm, int32_t *status);
+/* The same protocol WITHOUT host round trips (what a multi-GPU run should use): the chunk
+ * aggregate stays in device memory, the caller all-gathers it with NCCL on the context's stream
+ * (aggs_dev = [world][bdlm_scan_elem_doubles] doubles), and the carry is folded by a one-thread
+ * kernel inside the finish call.  Per rank: forward_local -> all-gather -> forward_finish ->
+ * backward_local -> all-gather -> backward_finish; nothing synchronises with the host.  prob
+ * describes the rank's chunk (keep_init = 1 on rank 0 only); kf->m and kf->C are required; the
+ * context's workspace must not be used by other calls between a local and its finish phase. */
+BDLM_API int bdlm_scan_dist_forward_local(bdlm_ctx *ctx, const bdlm_problem *prob, int32_t rank,
+                                          int32_t world, double *agg_dev);
+BDLM_API int bdlm_scan_dist_forward_finish(bdlm_ctx *ctx, const bdlm_problem *prob, int32_t rank,
+                                           int32_t world, const double *aggs_dev,
+                                           const bdlm_kf_out *kf, int32_t *status);
+BDLM_API int bdlm_scan_dist_backward_local(bdlm_ctx *ctx, const bdlm_problem *prob, int32_t rank,
+                                           int32_t world, const bdlm_kf_out *filt,
+                                           const bdlm_smooth_out *sm, double *agg_dev);
+BDLM_API int bdlm_scan_dist_backward_finish(bdlm_ctx *ctx, const bdlm_problem *prob, int32_t rank,
+                                            int32_t world, const double *aggs_dev,
+                                            const bdlm_kf_out *filt, const bdlm_smooth_out *sm,
+                                            int32_t *status);
 /* out = earlier (x) later on the host (carry folding between ranks; a few dozen flops). */
 BDLM_API int bdlm_scan_combine(int32_t n, int32_t backward, const double *earlier,
                                const double *later, double *out);

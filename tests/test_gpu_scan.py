@@ -121,3 +121,48 @@ def test_scan_rejects_unsupported_shapes(eng):
     model.times = None
     with pytest.raises((capi.BdlmError, AssertionError)):
         scan_filter_smooth(eng, model, dict(V=V, W=W, m0=m0, C0=C0), torch.zeros(10, dtype=torch.float64).cuda())
+
+
+@pytest.mark.parametrize("n", [1, 2, 3])
+@pytest.mark.parametrize("world", [1, 2, 5])
+def test_device_side_protocol_emulated_ranks(n, world):
+    """bdlm_scan_dist_*: local -> all-gather (emulated by a device concat) -> finish, one context
+    per emulated rank, nothing copied to the host between the phases."""
+    import torch
+    from bayesian_dlms_b200 import Engine, Model, default_engine
+    from bayesian_dlms_b200.scan import DistScan
+    from bayesian_dlms_b200.sharding import shard_range
+    mod, V, W, m0, C0 = _models()[n]
+    T = 7001
+    rng = np.random.default_rng(31 + n)
+    y = H.simulate(mod, V, W, m0, C0, np.arange(1, T + 1.0), rng, missing=0.02)[:, 0]
+    yd = torch.from_numpy(y).cuda()
+    params = dict(V=V, W=W, m0=m0, C0=C0)
+    seq = _sequential(default_engine(0), Model.build(mod, T=T), params, yd)
+    ranks = []
+    for r in range(world):
+        lo, hi = shard_range(T, r, world)
+        e = Engine(0)
+        e.use_torch_stream()   # every emulated rank on torch's stream, like the copies below
+        ranks.append(DistScan(e, Model.build(mod, T=hi - lo), params, yd[lo:hi].contiguous(),
+                              r, world))
+    for d in ranks:
+        d.forward_local()
+    torch.cuda.synchronize()
+    gathered = torch.cat([d.agg_f for d in ranks])
+    for d in ranks:
+        d.aggs_f.copy_(gathered)
+        d.forward_finish()
+        d.backward_local()
+    torch.cuda.synchronize()
+    gathered = torch.cat([d.agg_b for d in ranks])
+    for d in ranks:
+        d.aggs_b.copy_(gathered)
+        d.backward_finish()
+    torch.cuda.synchronize()
+    for d in ranks:
+        assert int(d.status[0]) == 0
+    for k in ("m", "C", "a", "R", "s", "S"):
+        got = torch.cat([d.out[k] for d in ranks]).cpu().numpy()
+        assert got.shape == tuple(seq[k].shape)
+        assert H.rel_err(got, seq[k].cpu().numpy()) < TOL, (k, world, H.rel_err(got, seq[k].cpu().numpy()))
