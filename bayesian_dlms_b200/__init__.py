@@ -9,12 +9,15 @@ implementation, and nothing here imports ``oracle/``.
 from .dlm import (Data, Dlm, DlmParameters, autoregressive, polynomial, regression,  # noqa: F401
                   seasonal)
 from .batch import Engine, Model, SERIES_MAJOR, TIME_MAJOR, default_engine  # noqa: F401
-from .reference_api import (GibbsSampling, KalmanFilter, KfState, SamplingState,  # noqa: F401
-                            Smoothing, SmoothingState, SvdFilter, SvdSampler, SvdState)
+from .reference_api import (ConjugateFilter, FilterAr, FilterOu, GibbsSampling,  # noqa: F401
+                            InverseGamma, InverseWishart, KalmanFilter, KfState, SamplingState,
+                            Smoothing, SmoothingState, SvParameters, SvdFilter, SvdSampler,
+                            SvdState)
 
 __all__ = [
     "Data", "Dlm", "DlmParameters", "polynomial", "regression", "autoregressive", "seasonal",
     "Engine", "Model", "TIME_MAJOR", "SERIES_MAJOR", "default_engine",
     "KalmanFilter", "Smoothing", "SvdFilter", "SvdSampler", "GibbsSampling",
     "KfState", "SmoothingState", "SamplingState", "SvdState",
+    "FilterAr", "FilterOu", "SvParameters", "ConjugateFilter", "InverseGamma", "InverseWishart",
 ]

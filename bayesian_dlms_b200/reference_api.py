@@ -267,3 +267,167 @@ class GibbsSampling:
         th = np.ascontiguousarray(np.asarray(theta, dtype=np.float64).reshape(1, model.T + 1, model.n))
         out = default_engine().gibbs_stats(model, yb, th, layout=SERIES_MAJOR)
         return {k: v[0] for k, v in out.items()}
+
+    @staticmethod
+    def sample(mod: Dlm, priorV, priorW, initParams: DlmParameters, observations: Sequence[Data],
+               n_iters: int, *, chains: int = 1, seed: int = 0, svd: bool = False):
+        """``GibbsSampling.sample`` / ``sampleSvd`` (Gibbs.scala:153-217) -- or
+        ``GibbsWishart.sample`` (GibbsWishart.scala:64-80) when ``priorW`` is an
+        ``InverseWishart`` -- for ``chains`` independent chains on the same observations, every
+        sweep on the GPU (FFBS + sufficient statistics + conjugate draws).  Returns a list (one
+        entry per chain) of lists of ``DlmParameters`` (one per iteration)."""
+        import torch
+        from . import gibbs as _gibbs
+        times, y = _dlm.flatten_data(observations)
+        model = Model.build(mod, times)
+        yb = torch.from_numpy(np.ascontiguousarray(np.repeat(y[None], chains, axis=0))).cuda()
+        prior = dict(v_shape=priorV.shape, v_scale=priorV.scale)
+        if isinstance(priorW, InverseWishart):
+            prior.update(w_nu=priorW.nu, w_psi=np.asarray(priorW.psi, dtype=np.float64))
+        else:
+            prior.update(w_shape=priorW.shape, w_scale=priorW.scale)
+        init = dict(V=initParams.v, W=initParams.w, m0=initParams.m0, C0=initParams.c0)
+        res = _gibbs.sample(default_engine(), model, yb, prior, init, n_iters, seed=seed,
+                            layout=SERIES_MAJOR, svd=svd)
+        torch.cuda.synchronize()
+        st = int(res["status"].max())
+        _raise_status(st)
+        V, W = res["V"].cpu().numpy(), res["W"].cpu().numpy()   # (iters, k, chains)
+        n = model.n
+        out = []
+        for c in range(chains):
+            out.append([DlmParameters(np.diag(V[i, :, c]),
+                                      _dlm.from_cm(W[i, :, c], n, n) if W.shape[1] == n * n
+                                      else np.diag(W[i, :, c]),
+                                      initParams.m0, initParams.c0) for i in range(n_iters)])
+        return out
+
+
+@dataclass
+class InverseGamma:
+    """``InverseGamma(shape, scale)`` (InverseGamma.scala:6): prior on a variance."""
+    shape: float
+    scale: float
+
+    @property
+    def mean(self):
+        return self.scale / (self.shape - 1)
+
+    @property
+    def variance(self):
+        return (self.scale * self.scale) / ((self.shape - 1) * (self.shape - 1) * (self.shape - 2))
+
+
+@dataclass
+class InverseWishart:
+    """``InverseWishart(nu, psi)`` (InverseWishart.scala:6): prior on a covariance matrix."""
+    nu: float
+    psi: np.ndarray
+
+
+@dataclass
+class SvParameters:
+    """``SvParameters(phi, mu, sigmaEta)`` (StochasticVolatility.scala): AR(1) / OU state."""
+    phi: float
+    mu: float
+    sigmaEta: float
+
+
+@dataclass
+class FilterState:
+    """``FilterAr.FilterState`` (FilterAr.scala:9-13)."""
+    time: float
+    mt: float
+    ct: float
+    at: float
+    rt: float
+
+
+@dataclass
+class SampleState:
+    """``FilterAr.SampleState`` (FilterAr.scala:49-54)."""
+    time: float
+    sample: float
+    mean: float
+    cov: float
+    at1: float
+    rt1: float
+
+
+class _ScalarFilter:
+    ou = False
+
+    @classmethod
+    def _arrays(cls, ys, vs):
+        if len(ys) == 0:
+            raise ValueError("empty observation vector (ys.head on an empty Vector)")
+        times = np.array([t for t, _ in ys], dtype=np.float64)
+        y = np.array([[np.nan if o is None else float(o)] for _, o in ys], dtype=np.float64)
+        return times, np.ascontiguousarray(y), np.ascontiguousarray(np.asarray(vs, dtype=np.float64))
+
+    @classmethod
+    def _row_times(cls, times):
+        t0 = times[0] if cls.ou else times[0] - 1.0   # FilterOu.scala:37 / FilterAr.scala:42
+        return np.concatenate([[t0], times])
+
+    @classmethod
+    def filterUnivariate(cls, ys, vs, p: SvParameters) -> List[FilterState]:
+        """``filterUnivariate(ys: Vector[(Double, Option[Double])], vs, p)``."""
+        times, y, v = cls._arrays(ys, vs)
+        o = default_engine().ar_filter(dict(phi=p.phi, mu=p.mu, sigma_eta=p.sigmaEta), y, v,
+                                       times=times, ou=cls.ou)
+        tm = cls._row_times(times)
+        return [FilterState(float(tm[r]), *(float(o[k][r, 0]) for k in ("m", "C", "a", "R")))
+                for r in range(len(tm))]
+
+    @classmethod
+    def ffbs(cls, p: SvParameters, ys, vs, *, z: Optional[np.ndarray] = None, seed=None) -> List[SampleState]:
+        """``ffbs(p, ys, vs)``: filter, then ``univariateSample``.  ``z``: injected N(0,1) values,
+        one per row (row T is consumed first); drawn from ``seed`` when omitted."""
+        times, y, v = cls._arrays(ys, vs)
+        T = len(times)
+        if z is None:
+            z = np.random.default_rng(seed).standard_normal(T + 1)
+        z = np.ascontiguousarray(np.asarray(z, dtype=np.float64).reshape(T + 1, 1))
+        o = default_engine().ar_ffbs(dict(phi=p.phi, mu=p.mu, sigma_eta=p.sigmaEta), y, v, z,
+                                     times=times, ou=cls.ou, want=("m", "C", "a", "R"))
+        tm = cls._row_times(times)
+        return [SampleState(float(tm[r]), float(o["theta"][r, 0]),
+                            *(float(o[k][r, 0]) for k in ("m", "C", "a", "R"))) for r in range(T + 1)]
+
+
+class FilterAr(_ScalarFilter):
+    """``FilterAr`` (FilterAr.scala:8-83): scalar AR(1) state, unit time grid."""
+    ou = False
+
+
+class FilterOu(_ScalarFilter):
+    """``FilterOu`` (FilterOu.scala:6-79): Ornstein-Uhlenbeck state, irregular times."""
+    ou = True
+
+
+@dataclass
+class InverseGammaState:
+    """``InverseGammaState(kfState, variance)`` (ConjugateFilter.scala:12)."""
+    kfState: KfState
+    variance: List[InverseGamma]
+
+
+class ConjugateFilter:
+    """``ConjugateFilter(prior, advState)`` (ConjugateFilter.scala:17-112), p = 1."""
+
+    def __init__(self, prior: InverseGamma):
+        self.prior = prior
+
+    def filter(self, mod: Dlm, ys: Sequence[Data], p: DlmParameters) -> List[InverseGammaState]:
+        times, y = _dlm.flatten_data(ys)
+        model = Model.build(mod, times)
+        yb = np.ascontiguousarray(y.reshape(1, model.T, model.p))
+        o = default_engine().conjugate_filter(model, dict(W=p.w, m0=p.m0, C0=p.c0), self.prior.shape,
+                                              self.prior.scale, yb, layout=SERIES_MAJOR,
+                                              want=("m", "C", "a", "R", "f", "Q"))
+        _raise_status(int(o["status"][0]))
+        tm = _row_times(times, True)
+        states = _kf_states(model, o, tm, True)
+        return [InverseGammaState(s, [InverseGamma(float(o["shape"][0, r, 0]), float(o["scale"][0, r, 0]))])
+                for r, s in enumerate(states)]

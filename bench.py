@@ -412,6 +412,39 @@ def scan_leg(eng, dev, with_cpu=True, logT=24):
     return res
 
 
+def scan_dist_leg(eng, dev, rank, world, logT=24, reps=5):
+    """BASELINE.json config 5 on N GPUs: ONE series, T = 2^24, time-sharded across the ranks
+    (device-side protocol: two NCCL all-gathers of one <= 16-double aggregate per rank and pass,
+    no host synchronisation).  Strong scaling: total work is fixed.  Time = max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from bayesian_dlms_b200 import Model, dlm
+    from bayesian_dlms_b200.scan import DistScan
+    from bayesian_dlms_b200.sharding import shard_range
+    T = 1 << logT
+    params = dict(V=[[3.0]], W=np.diag([2.0, 1.0]), m0=np.zeros(2), C0=100.0 * np.eye(2))
+    lo, hi = shard_range(T, rank, world)
+    g = torch.Generator(device=dev).manual_seed(20260105 + rank)
+    yc = torch.randn(hi - lo, generator=g, device=dev, dtype=torch.float64).cumsum(0) * 0.1
+    ds = DistScan(eng, Model.build(dlm.polynomial(2), T=hi - lo), params, yc, rank, world)
+    ds.run(); ds.run()
+    ms = []
+    for _ in range(reps):
+        dist.barrier(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); ds.run(); e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms.append(float(t.item()))
+    st = ds.status.clone()
+    dist.all_reduce(st, op=dist.ReduceOp.MAX)
+    t = float(np.median(ms)) * 1e-3
+    return {"config": "config5: one series, T=2^%d, polynomial(2), time-sharded over %d GPUs" % (logT, world),
+            "scaling": "strong", "steps_per_s": T / t, "ms": t * 1e3, "status": int(st.item()),
+            "collectives": "2 NCCL all-gathers of <= 16 doubles per rank per call"}
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -614,6 +647,12 @@ def main():
         e2e["lean_outputs_value"] = world * ncall * slab * T / float(wl.item())
         e2e["lean_outputs"] = "s, S only (what SmoothDlm writes): 48 B/series-step over PCIe"
 
+    scan_dist = None
+    if world > 1 and not args.no_ffbs:  # collective: every rank takes part
+        outbuf.clear(); ys.clear(); pars.clear()
+        torch.cuda.empty_cache()
+        scan_dist = scan_dist_leg(eng, dev, rank, world)
+
     if rank == 0:
         line = {
             "metric": "filter+smoother series-steps/s", "value": value, "unit": "series-steps/s",
@@ -655,6 +694,8 @@ def main():
                 line["gibbs"] = gibbs_leg(eng, dev)
             except Exception as ex:
                 line["gibbs"] = {"error": repr(ex)}
+        if scan_dist is not None:
+            line["scan"] = scan_dist
         if not args.no_cpu and world >= 1:
             try:
                 base, _, _ = cpu_reference_leg(B, T)

@@ -152,3 +152,53 @@ object GpuKalman {
   // backwardsSmoother, svdFilterDlm, svdFfbsDlm and the batched overloads follow the same
   // pattern over bdlm_rts_smooth, bdlm_svd_filter and bdlm_svd_ffbs (B > 1, per_series mask).
 }
+
+/** FilterAr.filterUnivariate (FilterAr.scala:37-47) over bdlm_ar_filter.
+  * struct bdlm_ar_problem { int64 B; int32 T, layout, mem, process, per_series, v_mode;
+  *                          const double *phi, *mu, *sigma_eta, *times, *v, *y; }  (80 bytes) */
+object GpuFilterAr {
+  import BdlmNative._
+  import ValueLayout._
+  val arProblem: StructLayout = MemoryLayout.structLayout(
+    JAVA_LONG.withName("B"), JAVA_INT.withName("T"), JAVA_INT.withName("layout"),
+    JAVA_INT.withName("mem"), JAVA_INT.withName("process"), JAVA_INT.withName("per_series"),
+    JAVA_INT.withName("v_mode"),
+    ADDRESS.withName("phi"), ADDRESS.withName("mu"), ADDRESS.withName("sigma_eta"),
+    ADDRESS.withName("times"), ADDRESS.withName("v"), ADDRESS.withName("y"))
+
+  def filterUnivariate(ys: Vector[(Double, Option[Double])], vs: Vector[Double],
+                       p: SvParameters, ou: Boolean = false): Vector[FilterAr.FilterState] = {
+    val a = Arena.ofConfined()
+    try {
+      val T = ys.size
+      val rows = T + 1
+      val pr = a.allocate(arProblem)
+      pr.set(JAVA_LONG, 0, 1L); pr.set(JAVA_INT, 8, T); pr.set(JAVA_INT, 12, 1 /* SERIES_MAJOR */)
+      pr.set(JAVA_INT, 16, 1 /* HOST */); pr.set(JAVA_INT, 20, if (ou) 1 else 0)
+      pr.set(JAVA_INT, 24, 0); pr.set(JAVA_INT, 28, 1 /* BDLM_V_PER_STEP */)
+      pr.set(ADDRESS, 32, GpuKalman.seg(a, Array(p.phi))); pr.set(ADDRESS, 40, GpuKalman.seg(a, Array(p.mu)))
+      pr.set(ADDRESS, 48, GpuKalman.seg(a, Array(p.sigmaEta)))
+      pr.set(ADDRESS, 56, GpuKalman.seg(a, ys.map(_._1).toArray))
+      pr.set(ADDRESS, 64, GpuKalman.seg(a, vs.toArray))
+      pr.set(ADDRESS, 72, GpuKalman.seg(a, ys.map(_._2.getOrElse(Double.NaN)).toArray))
+      val out = a.allocate(ADDRESS, 4)
+      val bufs = Array.fill(4)(a.allocate(JAVA_DOUBLE, rows.toLong))
+      bufs.zipWithIndex.foreach { case (b, i) => out.setAtIndex(ADDRESS, i, b) }
+      GpuKalman.check(arFilter.invoke(GpuKalman.ctx, pr, out).asInstanceOf[Int], 0)
+      val t0 = if (ou) ys.head._1 else ys.head._1 - 1.0
+      val tm = t0 +: ys.map(_._1)
+      Vector.tabulate(rows)(r => FilterAr.FilterState(tm(r), bufs(0).getAtIndex(JAVA_DOUBLE, r),
+        bufs(1).getAtIndex(JAVA_DOUBLE, r), bufs(2).getAtIndex(JAVA_DOUBLE, r), bufs(3).getAtIndex(JAVA_DOUBLE, r)))
+    } finally a.close()
+  }
+  // ffbs(p, ys, vs): same problem struct + z (T + 1 normals drawn from the caller's RandBasis,
+  // last row first) over bdlm_ar_ffbs; GpuFilterOu = the same with ou = true.
+}
+
+/** The conjugate half of a Gibbs sweep on the device (Gibbs.scala:41-49,72-77;
+  * GibbsWishart.scala:16-35): GpuGibbs.sample keeps the per-chain V, W arrays in device memory and
+  * alternates bdlm_ffbs(stats) / bdlm_gibbs_draw, copying back only the recorded draws. */
+object GpuGibbs {
+  // struct bdlm_gibbs_prior { double v_shape, v_scale, w_shape, w_scale, w_nu; const double *w_psi; }
+  // struct bdlm_gibbs_rng   { uint64 seed, sweep; const double *gamma_v, *gamma_w, *bartlett; }
+}

@@ -315,3 +315,41 @@ def test_time_varying_V_filter_and_ffbs(eng, oracle, n, p, shared):
         _exact(fs["S"][b].cpu().numpy(), sm["S"], "S")
         th = oracle.ffbs(n, p, model.F, model.G, Vt, cm(W), m0, cm(C0), times, y[b], z[b], v_tv=True)
         _exact(s["theta"][b].cpu().numpy(), th["theta"], "theta")
+
+
+# ------------------------------------------------------------------ reference-API mirrors
+
+def test_reference_api_mirrors_of_the_next_rows(eng):
+    """The calls as the reference's own apps make them: FilterArDlm (ar.scala:47-60), ConjFilter
+    (FirstOrderDlm.scala:144-172), GibbsSampling.sample (Gibbs.scala:153-180)."""
+    from bayesian_dlms_b200 import (ConjugateFilter, Data, DlmParameters, FilterAr, GibbsSampling,
+                                    InverseGamma, SvParameters, polynomial)
+    rows = H.read_csv("ar_dlm.csv")[:500]
+    data = [(float(r[0]), float(r[1])) for r in rows]
+    gold = np.array([[float(v) for v in r] for r in H.read_csv("ar_dlm_filtered.csv")[:501]])
+    p = SvParameters(0.8, 1.0, 0.3)
+    filtered = FilterAr.filterUnivariate(data, [0.5] * len(data), p)
+    assert len(filtered) == len(data) + 1
+    _exact([s.time for s in filtered], gold[:, 0], "time")
+    _exact([s.mt for s in filtered], gold[:, 1], "mt")
+    _exact([s.ct for s in filtered], gold[:, 2], "ct")
+    sampled = FilterAr.ffbs(p, data, [0.5] * len(data), z=np.zeros(len(data) + 1))
+    assert sampled[-1].sample == filtered[-1].mt and len(sampled) == len(filtered)
+
+    times, y, _ = H.first_order_golden()
+    obs = [Data(t, [v]) for t, v in zip(times, y[:, 0])]
+    goldc = np.array([[float(v) for v in r] for r in H.read_csv("first_order_dlm_conjugate_filtered.csv")])
+    pc = DlmParameters(v=2.0, w=3.0, m0=0.0, c0=100.0)
+    out = ConjugateFilter(InverseGamma(3.0, 4.0)).filter(polynomial(1), obs, pc)
+    _exact([s.kfState.mt[0] for s in out], goldc[:, 1], "conj m")
+    _exact([s.kfState.ct[0, 0] for s in out], goldc[:, 2], "conj C")
+    _exact([s.variance[0].mean for s in out], goldc[:, 3], "E[V]")
+    _exact([s.variance[0].variance for s in out], goldc[:, 4], "Var[V]")
+    assert out[0].kfState.ft is None
+
+    chains = GibbsSampling.sample(polynomial(1), InverseGamma(3.0, 4.0), InverseGamma(3.0, 6.0),
+                                  DlmParameters(v=1.0, w=1.0, m0=0.0, c0=10.0), obs[:300], 50,
+                                  chains=4, seed=2)
+    assert len(chains) == 4 and len(chains[0]) == 50
+    assert all(c[-1].v[0, 0] > 0 and c[-1].w[0, 0] > 0 for c in chains)
+    assert chains[0][-1].v[0, 0] != chains[1][-1].v[0, 0]
