@@ -11,6 +11,8 @@
 // series) so every spill access of a warp is a run of full 128-byte lines.
 //
 // Arithmetic mirrors oracle/bdlm_oracle.c operation for operation; citations there.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "launch.h"
 #include "warp_linalg.cuh"
@@ -30,6 +32,43 @@ struct Ws {
   double *scr;
   int *iscr;
   size_t total;  // doubles
+
+  __host__ __device__ Ws() {}
+
+  // svd4_kernel layout: the temporaries and the (batch-shared) model matrices exist ONCE per
+  // warp, only what must survive from one phase to the next is kept per series.  Four full
+  // workspaces (41.7 KB) allow 5 warps per SM; this layout (23.6 KB) allows 9, which is what
+  // hides the serial rotation-parameter chain of the joint SVDs.
+  static __host__ __device__ size_t svd4_shared_doubles(int n, int p) {
+    const int L = imax(n, p), LL = L * L;
+    return (size_t)n * n + (size_t)n * p + 6 * (size_t)LL + 4 * (size_t)L + p + 96 + 32;
+  }
+  static __host__ __device__ size_t svd4_series_doubles(int n, int p) {
+    const int nn = n * n, L = imax(n, p);
+    return 2 * (size_t)nn + (size_t)p * p + 3 * (size_t)n + 2 * (size_t)nn + p + 2 * (size_t)n +
+           (size_t)imax((n + L) * n, L * L) + nn + n;
+  }
+  static __device__ Ws svd4(double *shared, double *series, int n, int p, double *&sV, double *&sS) {
+    Ws w;
+    const int nn = n * n, L = imax(n, p), LL = L * L;
+    double *o = shared;
+    auto take = [&](size_t cnt) { double *ptr = o; o += cnt; return ptr; };
+    w.G = take(nn); w.F = take((size_t)n * p);
+    w.t1 = take(LL); w.t2 = take(LL); w.t3 = take(LL); w.t4 = take(LL); w.t5 = take(LL); w.t6 = take(LL);
+    w.v1 = take(L); w.v2 = take(L); w.v3 = take(L); w.v4 = take(L); w.yrow = take(p);
+    w.scr = take(96);
+    w.iscr = reinterpret_cast<int *>(take(32));
+    o = series;
+    w.W = take(nn); w.Wsq = take(nn); w.V = take((size_t)p * p);
+    w.m = take(n); w.a = take(n); w.th = take(n);
+    w.C = take(nn); w.R = take(nn); w.f = take(p);
+    w.dcv = take(n); w.drv = take(n);
+    w.stk = take((size_t)imax((n + L) * n, LL));
+    sV = take(nn); sS = take(n);
+    w.Q = nullptr; w.Sm = nullptr;
+    w.total = 0;
+    return w;
+  }
 
   __host__ __device__ Ws(double *base, int n, int p, int op) {
     const int nn = n * n, L = imax(n, p), LL = L * L;
@@ -711,6 +750,436 @@ warp_kernel(const WarpArgs wa, const int ws_doubles) {
   }
 }
 
+// =====================================================================================
+// FOUR SERIES PER WARP for the SVD path with n, p <= 8 (BASELINE config 4: n = p = 8).
+//
+// ncu on warp_kernel<kOpSvdFfbs, 8, 8> (profiles/r1_warp_svd_ffbs_full.txt): 7.8 warps per
+// issue-active cycle wait on shared memory (short scoreboard), FP64 pipe 12 % busy.  The time
+// goes into the three one-sided Jacobi SVDs per step (stacks of <= 16 x 8): their dot products
+// are 16-long serial chains through shared memory on 12 of 32 lanes, with four __syncwarp per
+// round.  Here a warp owns FOUR series: everything around the SVDs still runs one series after
+// the other on all 32 lanes (the same code as above, so bit-identical), but the SVDs of the
+// four series run TOGETHER, one octet of lanes per series, lane j holding column j of U
+// (16 rows) and of V (8 rows) in registers; partners exchange columns with width-8 shuffles.
+// No shared-memory traffic and no barrier inside a sweep, all 32 lanes busy.
+
+constexpr int kQuad = 4;     // series per warp
+constexpr int kOctRows = 16; // max rows of a stacked matrix: (p + n) or 2n with n, p <= 8
+constexpr int kOctN = 8;
+
+// One-sided Jacobi SVD (oracle jacobi_svd) of this octet's r x n matrix U (column-major, leading
+// dimension r; nullptr = nothing to do for this series).  Results to shared memory: sv[n]
+// descending, Vout (n x n) ordered + sign-normalised right singular vectors.  All 32 lanes must
+// call it; returns the octet's status (uniform within the octet).  Rows r..15 are zero padding:
+// they add exact zeros to the sums, which leaves every partial sum bit-identical.
+__device__ __forceinline__ int oct_jacobi_svd(int lane, int n, int r, const double *U, double *sv,
+                                              double *Vout) {
+  const int j = lane & 7;
+  const bool col = U != nullptr && j < n;
+  double u[kOctRows], v[kOctN];
+#pragma unroll
+  for (int i = 0; i < kOctRows; ++i) u[i] = (col && i < r) ? U[i + j * r] : 0.0;
+#pragma unroll
+  for (int i = 0; i < kOctN; ++i) v[i] = (i == j) ? 1.0 : 0.0;
+  const unsigned octmask = 0xffu << (lane & 24);
+  const int m = (n + 1) & ~1;
+  bool conv = (n == 1) || U == nullptr;
+  for (int sweep = 0; sweep < kJacobiMaxSweeps && n > 1; ++sweep) {
+    bool rotated = false;
+    for (int round = 0; round < m - 1; ++round) {
+      const int q = col ? rr_partner(n, round, j) : -1;
+      const int src = q < 0 ? j : q;
+      const bool low = j < src;  // this lane holds column p (the smaller index) of the pair
+      double alpha = 0.0, beta = 0.0, gamma = 0.0;
+      double w[kOctRows], vw[kOctN];
+#pragma unroll
+      for (int i = 0; i < kOctRows; ++i) {
+        w[i] = __shfl_sync(FULL, u[i], src, 8);
+        const double up = low ? u[i] : w[i], uq = low ? w[i] : u[i];
+        const double pp = up * up, qq = uq * uq, pq = up * uq;
+        alpha = (i == 0) ? pp : alpha + pp;
+        beta = (i == 0) ? qq : beta + qq;
+        gamma = (i == 0) ? pq : gamma + pq;
+      }
+#pragma unroll
+      for (int i = 0; i < kOctN; ++i) vw[i] = __shfl_sync(FULL, v[i], src, 8);
+      const bool rot = q >= 0 && (gamma * gamma > kJacobiThr2 * (alpha * beta));
+      if (rot) {
+        double c, sn;
+        sym_rot(alpha, beta, gamma, c, sn);
+        if (low) {
+#pragma unroll
+          for (int i = 0; i < kOctRows; ++i) u[i] = c * u[i] - sn * w[i];
+#pragma unroll
+          for (int i = 0; i < kOctN; ++i) v[i] = c * v[i] - sn * vw[i];
+        } else {
+#pragma unroll
+          for (int i = 0; i < kOctRows; ++i) u[i] = sn * w[i] + c * u[i];
+#pragma unroll
+          for (int i = 0; i < kOctN; ++i) v[i] = sn * vw[i] + c * v[i];
+        }
+      }
+      rotated = rotated || rot;
+    }
+    const unsigned ball = __ballot_sync(FULL, rotated);
+    if ((ball & octmask) == 0) conv = true;  // this series saw a sweep without a rotation
+    if (ball == 0) break;                    // every series of the warp has converged
+  }
+  // singular values = column norms, stable descending order; sign rule of order_and_sign
+  double acc = 0.0;
+#pragma unroll
+  for (int i = 0; i < kOctRows; ++i) {
+    const double sq = u[i] * u[i];
+    acc = (i == 0) ? sq : acc + sq;
+  }
+  const double nrm = sqrt(acc);
+  int rank = 0;
+#pragma unroll
+  for (int k = 0; k < kOctN; ++k) {
+    const double nk = __shfl_sync(FULL, nrm, k, 8);
+    if (k < n) rank += ((nk > nrm) || (nk == nrm && k < j)) ? 1 : 0;
+  }
+  if (col) {
+    int im = 0;
+    double best = fabs(v[0]);
+#pragma unroll
+    for (int i = 1; i < kOctN; ++i) {
+      const double a = fabs(v[i]);
+      if (i < n && a > best) { best = a; im = i; }
+    }
+    double vim = v[0];
+#pragma unroll
+    for (int i = 1; i < kOctN; ++i) vim = (im == i) ? v[i] : vim;
+    const bool flip = vim < 0.0;
+    sv[rank] = nrm;
+#pragma unroll
+    for (int i = 0; i < kOctN; ++i)
+      if (i < n) Vout[i + rank * n] = flip ? -v[i] : v[i];
+  }
+  __syncwarp();
+  return conv ? 0 : BDLM_ST_NOTCONVERGED;
+}
+
+// svd_advance split around its SVD: pre builds the stack, the joint SVD writes (drv, R).
+__device__ __forceinline__ void svd_advance_pre(int lane, int n, const Ws &ws, double dt) {
+  if (dt == 0.0) {
+    for (int k = lane; k < n; k += 32) { ws.a[k] = ws.m[k]; ws.drv[k] = ws.dcv[k]; }
+    for (int k = lane; k < n * n; k += 32) ws.R[k] = ws.C[k];
+    __syncwarp();
+    return;
+  }
+  w_mv(lane, n, n, ws.G, n, false, ws.m, ws.a);
+  for (ElemIter it(lane, n, n); it.ok(); it.next())
+    ws.t1[it.i + it.j * n] = ws.dcv[it.i] * ws.C[it.j + it.i * n];
+  __syncwarp();
+  w_mm(lane, n, n, n, ws.t1, n, false, ws.G, n, true, ws.t2, n);
+  const double sq = sqrt(dt);
+  for (ElemIter it(lane, n, n); it.ok(); it.next()) {
+    ws.stk[it.i + it.j * 2 * n] = ws.t2[it.i + it.j * n];
+    ws.stk[n + it.i + it.j * 2 * n] = ws.W[it.i + it.j * n] * sq;
+  }
+  __syncwarp();
+}
+
+// svd_update split around its SVD.  pre returns po (0 = all missing: state copied, no SVD).
+__device__ __forceinline__ int svd_update_pre(int lane, int n, int p, const Ws &ws) {
+  int *obs = ws.iscr + 32;
+  const int po = observed(lane, p, ws.yrow, obs);
+  if (po == 0) {
+    for (int k = lane; k < n; k += 32) { ws.m[k] = ws.a[k]; ws.dcv[k] = ws.drv[k]; }
+    for (int k = lane; k < n * n; k += 32) ws.C[k] = ws.R[k];
+    __syncwarp();
+    return 0;
+  }
+  double *Fm = ws.t1, *Vm = ws.t2;
+  for (ElemIter it(lane, n, po); it.ok(); it.next()) Fm[it.i + it.j * n] = ws.F[it.i + obs[it.j] * n];
+  for (ElemIter it(lane, po, po); it.ok(); it.next())
+    Vm[it.i + it.j * po] = ws.V[obs[it.i] + obs[it.j] * p];
+  __syncwarp();
+  w_mv(lane, po, n, Fm, n, true, ws.a, ws.v1);  // fm
+  w_mm(lane, po, po, n, Vm, po, false, Fm, n, true, ws.t3, po);
+  w_mm(lane, po, n, n, ws.t3, po, false, ws.R, n, false, ws.t4, po);
+  const int r = po + n;
+  for (ElemIter it(lane, r, n); it.ok(); it.next()) {
+    const int i = it.i, j = it.j;
+    ws.stk[i + j * r] = (i < po) ? ws.t4[i + j * po]
+                                 : ((i - po == j) ? 1.0 / ws.drv[j] : 0.0);
+  }
+  if (lane < po) ws.v1[lane] = ws.yrow[obs[lane]] - ws.v1[lane];  // e
+  __syncwarp();
+  return po;
+}
+
+// Second half of svd_update.  The shared temporaries were overwritten by the other series'
+// phases in between, so the observed-component selection (Fm, Vm) and the innovation e are
+// rebuilt -- the same operations on the same inputs, hence the same bits.  sS / sV: singular
+// values and right vectors the joint SVD left for this series.
+__device__ __forceinline__ void svd_update_post(int lane, int n, int p, const Ws &ws,
+                                                const double *sS, const double *sV) {
+  int *obs = ws.iscr + 32;
+  const int po = observed(lane, p, ws.yrow, obs);
+  double *Fm = ws.t1, *Vm = ws.t2;
+  for (ElemIter it(lane, n, po); it.ok(); it.next()) Fm[it.i + it.j * n] = ws.F[it.i + obs[it.j] * n];
+  for (ElemIter it(lane, po, po); it.ok(); it.next())
+    Vm[it.i + it.j * po] = ws.V[obs[it.i] + obs[it.j] * p];
+  __syncwarp();
+  w_mv(lane, po, n, Fm, n, true, ws.a, ws.v1);  // fm
+  if (lane < po) ws.v1[lane] = ws.yrow[obs[lane]] - ws.v1[lane];  // e
+  __syncwarp();
+  w_mm(lane, n, n, n, ws.R, n, false, sV, n, false, ws.C, n);  // uc = ur * V
+  w_mm(lane, n, po, po, Fm, n, false, Vm, po, true, ws.t3, n);
+  w_mm(lane, n, po, po, ws.t3, n, false, Vm, po, false, ws.t4, n);  // fv
+  for (int k = lane; k < n; k += 32) ws.dcv[k] = 1.0 / sS[k];
+  __syncwarp();
+  for (ElemIter it(lane, n, n); it.ok(); it.next())
+    ws.t3[it.i + it.j * n] = ws.dcv[it.i] * ws.C[it.j + it.i * n];  // X = diag(dc) uc^T
+  __syncwarp();
+  w_mm(lane, n, n, n, ws.t3, n, true, ws.t3, n, false, ws.t5, n);
+  w_mm(lane, n, n, po, ws.t5, n, false, ws.t4, n, false, ws.t6, n);  // gain
+  w_mv(lane, n, po, ws.t6, n, false, ws.v1, ws.v3);
+  for (int k = lane; k < n; k += 32) ws.m[k] = ws.a[k] + ws.v3[k];
+  __syncwarp();
+}
+
+template <int OP>
+__global__ void __launch_bounds__(32)
+svd4_kernel(const WarpArgs wa, const int shared_doubles, const int series_doubles) {
+  extern __shared__ double smem[];
+  const Batch &bt = wa.bt;
+  const int lane = threadIdx.x;
+  const int64_t b0 = (int64_t)blockIdx.x * kQuad;
+  if (b0 >= bt.B) return;
+  const int n = bt.n, p = bt.p, nn = n * n, T = bt.T, ki = bt.keep_init, rows = T + ki;
+  const int oct = lane >> 3;
+  constexpr bool kSpill = OP == kOpSvdFfbs;
+  // series s of this warp: shared temporaries + its own state slice; series past the end of the
+  // batch are skipped
+  struct Slot { Ws ws; double *sV, *sS; };
+  auto slot = [&](int s) {
+    Slot q;
+    q.ws = Ws::svd4(smem, smem + shared_doubles + (size_t)s * series_doubles, n, p, q.sV, q.sS);
+    return q;
+  };
+  auto live = [&](int s) { return b0 + s < bt.B; };
+  const Slot mine = slot(oct);
+  const bool mine_live = live(oct);
+  int st[kQuad] = {0, 0, 0, 0};
+  auto fold_status = [&](int so) {
+#pragma unroll
+    for (int s = 0; s < kQuad; ++s) st[s] |= __shfl_sync(FULL, so, s * 8);
+  };
+  {  // the model is shared by the batch: one copy per warp
+    const Ws ws = mine.ws;
+    load_model(lane, bt, ws, 0, true);
+  }
+
+  // ---- initial state: transformParams (SvdFilter.scala:232-236) + initialiseState (:83-95);
+  // once per series, generic routines
+#pragma unroll
+  for (int s = 0; s < kQuad; ++s) {
+    if (!live(s)) continue;
+    const Ws ws = slot(s).ws;
+    const int64_t b = b0 + s;
+    load_pview(lane, bt.W, b, nn, ws.W);
+    load_pview(lane, bt.V, b, p * p, ws.V);
+    load_pview(lane, bt.m0, b, n, ws.m);
+    load_pview(lane, bt.C0, b, nn, ws.C);
+    __syncwarp();
+    st[s] |= w_sqrt_svd(lane, p, ws, ws.V, true, ws.t5);
+    w_copy(lane, p * p, ws.t5, ws.V);
+    st[s] |= w_sqrt_svd(lane, n, ws, ws.W, false, ws.Wsq);
+    if (bt.compat & BDLM_SVD_CONSISTENT_W) w_copy(lane, nn, ws.Wsq, ws.W);
+    w_copy(lane, nn, ws.C, ws.stk);
+    st[s] |= w_jacobi_svd(lane, n, n, ws.stk, ws.t3, ws.scr, ws.iscr, ws.v1, ws.t4);
+    for (int k = lane; k < n; k += 32) ws.dcv[k] = sqrt(ws.v1[k]);
+    w_copy(lane, nn, ws.t4, ws.C);
+    if (ki) {
+      w_mv(lane, p, n, ws.F, n, true, ws.m, ws.f);
+      store_view(lane, wa.svd.m, b, 0, n, ws.m);
+      store_view(lane, wa.svd.a, b, 0, n, ws.m);
+      store_view(lane, wa.svd.dc, b, 0, n, ws.dcv);
+      store_view(lane, wa.svd.dr, b, 0, n, ws.dcv);
+      store_view(lane, wa.svd.uc, b, 0, nn, ws.C);
+      store_view(lane, wa.svd.ur, b, 0, nn, ws.C);
+      store_view(lane, wa.svd.f, b, 0, p, ws.f);
+      if (kSpill) {  // [m, dc, uc, a]
+        double *spill = wa.spill + (size_t)b * rows * wa.spill_k;
+        for (int k = lane; k < n; k += 32) {
+          spill[k] = ws.m[k]; spill[n + k] = ws.dcv[k]; spill[2 * n + nn + k] = ws.m[k];
+        }
+        for (int k = lane; k < nn; k += 32) spill[2 * n + k] = ws.C[k];
+      }
+    }
+    __syncwarp();
+  }
+
+  // ---- forward filter
+  for (int t = 0; t < T; ++t) {
+    const int64_t row = t + ki;
+    const double dt = bt.dt ? bt.dt[t] : 1.0;
+    load_model(lane, bt, mine.ws, t, false);  // no-op unless F or G vary with t
+#pragma unroll
+    for (int s = 0; s < kQuad; ++s)
+      if (live(s)) svd_advance_pre(lane, n, slot(s).ws, dt);
+    if (dt != 0.0)  // the four time updates' SVDs together: stack (2n x n) -> (drv, R)
+      fold_status(oct_jacobi_svd(lane, n, 2 * n, mine_live ? mine.ws.stk : nullptr, mine.ws.drv,
+                                 mine.ws.R));
+    int po_mine = 0;
+#pragma unroll
+    for (int s = 0; s < kQuad; ++s) {
+      if (!live(s)) continue;
+      const Ws ws = slot(s).ws;
+      load_cview(lane, bt.y, b0 + s, t, p, ws.yrow);
+      __syncwarp();
+      w_mv(lane, p, n, ws.F, n, true, ws.a, ws.f);
+      const int po = svd_update_pre(lane, n, p, ws);
+      if (oct == s) po_mine = po;
+    }
+    // the four measurement updates' SVDs: stack ((po + n) x n) -> (sS, sV)
+    fold_status(oct_jacobi_svd(lane, n, po_mine + n, po_mine > 0 ? mine.ws.stk : nullptr, mine.sS,
+                               mine.sV));
+#pragma unroll
+    for (int s = 0; s < kQuad; ++s) {
+      if (!live(s)) continue;
+      const Slot q = slot(s);
+      const Ws &ws = q.ws;
+      const int64_t b = b0 + s;
+      const int po = __shfl_sync(FULL, po_mine, s * 8);
+      if (po > 0) {
+        load_cview(lane, bt.y, b, t, p, ws.yrow);
+        __syncwarp();
+        svd_update_post(lane, n, p, ws, q.sS, q.sV);
+      }
+      store_view(lane, wa.svd.m, b, row, n, ws.m);
+      store_view(lane, wa.svd.a, b, row, n, ws.a);
+      store_view(lane, wa.svd.dc, b, row, n, ws.dcv);
+      store_view(lane, wa.svd.dr, b, row, n, ws.drv);
+      store_view(lane, wa.svd.uc, b, row, nn, ws.C);
+      store_view(lane, wa.svd.ur, b, row, nn, ws.R);
+      store_view(lane, wa.svd.f, b, row, p, ws.f);
+      if (kSpill) {
+        double *sp = wa.spill + ((size_t)b * rows + row) * wa.spill_k;
+        for (int k = lane; k < n; k += 32) {
+          sp[k] = ws.m[k]; sp[n + k] = ws.dcv[k]; sp[2 * n + nn + k] = ws.a[k];
+        }
+        for (int k = lane; k < nn; k += 32) sp[2 * n + k] = ws.C[k];
+      }
+      __syncwarp();
+    }
+  }
+
+  // ---- backward sampler: SvdSampler.sample (SvdSampler.scala:54-60), initialise (:38-45),
+  // step (:15-36)
+  if (OP == kOpSvdFfbs) {
+#pragma unroll
+    for (int s = 0; s < kQuad; ++s) {
+      if (!live(s)) continue;
+      const Ws ws = slot(s).ws;
+      const int64_t b = b0 + s;
+      load_cview(lane, wa.z, b, rows - 1, n, ws.v3);
+      for (ElemIter it(lane, n, n); it.ok(); it.next())
+        ws.t1[it.i + it.j * n] = ws.C[it.i + it.j * n] * ws.dcv[it.j];
+      __syncwarp();
+      w_mv(lane, n, n, ws.t1, n, false, ws.v3, ws.v2);
+      for (int k = lane; k < n; k += 32) ws.th[k] = ws.m[k] + ws.v2[k];
+      __syncwarp();
+      store_view(lane, wa.theta, b, rows - 1, n, ws.th);
+      __syncwarp();
+    }
+    for (int r = rows - 2; r >= 0; --r) {
+      const int tobs = r + 1 - ki;
+      load_model(lane, bt, mine.ws, tobs, false);
+#pragma unroll
+      for (int s = 0; s < kQuad; ++s) {
+        if (!live(s)) continue;
+        const Ws ws = slot(s).ws;
+        const int64_t b = b0 + s;
+        const double *sp = wa.spill + ((size_t)b * rows + r) * wa.spill_k, *sp1 = sp + wa.spill_k;
+        for (int k = lane; k < n; k += 32) {
+          ws.m[k] = sp[k]; ws.dcv[k] = sp[n + k]; ws.a[k] = sp1[2 * n + nn + k];
+        }
+        for (int k = lane; k < nn; k += 32) ws.C[k] = sp[2 * n + k];
+        __syncwarp();
+        w_mm(lane, n, n, n, ws.Wsq, n, false, ws.G, n, false, ws.t1, n);
+        w_mm(lane, n, n, n, ws.t1, n, false, ws.C, n, false, ws.t2, n);
+        for (ElemIter it(lane, n, n); it.ok(); it.next()) {
+          ws.stk[it.i + it.j * 2 * n] = ws.t2[it.i + it.j * n];
+          ws.stk[n + it.i + it.j * 2 * n] = (it.i == it.j) ? 1.0 / ws.dcv[it.i] : 0.0;
+        }
+        __syncwarp();
+      }
+      fold_status(oct_jacobi_svd(lane, n, 2 * n, mine_live ? mine.ws.stk : nullptr, mine.sS, mine.sV));
+#pragma unroll
+      for (int s = 0; s < kQuad; ++s) {
+        if (!live(s)) continue;
+        const Slot q = slot(s);
+        const Ws &ws = q.ws;
+        load_cview(lane, wa.z, b0 + s, r, n, ws.v3);
+        w_mm(lane, n, n, n, ws.C, n, false, q.sV, n, false, ws.t5, n);  // uh
+        for (int k = lane; k < n; k += 32) ws.v1[k] = 1.0 / q.sS[k];    // dh
+        __syncwarp();
+        w_mm(lane, n, n, n, ws.G, n, true, ws.Wsq, n, true, ws.t1, n);
+        w_mm(lane, n, n, n, ws.t1, n, false, ws.Wsq, n, false, ws.t2, n);  // gWinv
+        for (ElemIter it(lane, n, n); it.ok(); it.next())
+          ws.t3[it.i + it.j * n] = ws.v1[it.i] * ws.t5[it.j + it.i * n];  // du
+        __syncwarp();
+        w_mm(lane, n, n, n, ws.t3, n, true, ws.t3, n, false, ws.t4, n);
+        w_mm(lane, n, n, n, ws.t4, n, false, ws.t2, n, false, ws.t6, n);
+        for (int k = lane; k < n; k += 32) ws.v2[k] = ws.th[k] - ws.a[k];
+        __syncwarp();
+        w_mv(lane, n, n, ws.t6, n, false, ws.v2, ws.v4);
+        for (int k = lane; k < n; k += 32) ws.v4[k] = ws.m[k] + ws.v4[k];  // h
+        for (ElemIter it(lane, n, n); it.ok(); it.next())
+          ws.t1[it.i + it.j * n] = ws.t5[it.i + it.j * n] * ws.v1[it.j];
+        __syncwarp();
+        w_mv(lane, n, n, ws.t1, n, false, ws.v3, ws.v2);
+        for (int k = lane; k < n; k += 32) ws.th[k] = ws.v4[k] + ws.v2[k];
+        __syncwarp();
+        store_view(lane, wa.theta, b0 + s, r, n, ws.th);
+        __syncwarp();
+      }
+    }
+    if (wa.stats.ssy.ptr || wa.stats.ny.ptr || wa.stats.ssw.ptr || wa.stats.scatter.ptr) {
+      __threadfence_block();
+      __syncwarp();
+#pragma unroll
+      for (int s = 0; s < kQuad; ++s)
+        if (live(s)) gibbs_stats(lane, bt, slot(s).ws, wa.theta, wa.stats, b0 + s);
+    }
+  }
+
+  if (bt.status) {
+#pragma unroll
+    for (int s = 0; s < kQuad; ++s) {
+      if (!live(s) || lane != 0) continue;
+      const Ws ws = slot(s).ws;
+      const double *chk = (OP == kOpSvdFilter) ? ws.m : ws.th;
+      bool finite = true;
+      for (int k = 0; k < n; ++k) finite = finite && isfinite(chk[k]);
+      bt.status[b0 + s] = st[s] | (finite ? 0 : BDLM_ST_NONFINITE);
+    }
+  }
+}
+
+bool svd4_supported(int op, const Batch &bt) {
+  return (op == kOpSvdFilter || op == kOpSvdFfbs) && bt.n <= kOctN && bt.p <= kOctN && !bt.v_tv;
+}
+
+template <int OP>
+cudaError_t launch_svd4(const WarpArgs &wa, cudaStream_t stream) {
+  const int n = wa.bt.n, p = wa.bt.p;
+  const int shared_doubles = (int)((Ws::svd4_shared_doubles(n, p) + 1) & ~(size_t)1);
+  const int series_doubles = (int)((Ws::svd4_series_doubles(n, p) + 1) & ~(size_t)1);
+  const size_t smem = ((size_t)shared_doubles + (size_t)kQuad * series_doubles) * sizeof(double);
+  cudaError_t e = cudaFuncSetAttribute(svd4_kernel<OP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem);
+  if (e != cudaSuccess) return e;
+  const int64_t blocks = (wa.bt.B + kQuad - 1) / kQuad;
+  if (blocks <= 0) return cudaSuccess;
+  svd4_kernel<OP><<<(unsigned)blocks, 32, smem, stream>>>(wa, shared_doubles, series_doubles);
+  return cudaGetLastError();
+}
+
 template <int OP, int NT, int PT>
 cudaError_t launch_dims(const WarpArgs &wa, cudaStream_t stream) {
   Ws sz(nullptr, wa.bt.n, wa.bt.p, OP);
@@ -747,6 +1216,11 @@ size_t warp_spill_doubles_per_row(int op, int n, int p) {
 }
 
 cudaError_t launch_warp(int op, const WarpArgs &wa, cudaStream_t stream) {
+  // BDLM_NO_SVD4=1: A/B switch back to one warp per series for the SVD path
+  static const bool use_svd4 = std::getenv("BDLM_NO_SVD4") == nullptr;
+  if (use_svd4 && svd4_supported(op, wa.bt))
+    return op == kOpSvdFilter ? launch_svd4<kOpSvdFilter>(wa, stream)
+                              : launch_svd4<kOpSvdFfbs>(wa, stream);
   switch (op) {
     case kOpFilter: return launch_op<kOpFilter>(wa, stream);
     case kOpSmooth: return launch_op<kOpSmooth>(wa, stream);
