@@ -790,17 +790,19 @@ __device__ __forceinline__ int oct_jacobi_svd(int lane, int n, int r, const doub
       const int q = col ? rr_partner(n, round, j) : -1;
       const int src = q < 0 ? j : q;
       const bool low = j < src;  // this lane holds column p (the smaller index) of the pair
-      double alpha = 0.0, beta = 0.0, gamma = 0.0;
+      // every lane: |own column|^2 and own . partner; the partner's norm arrives by shuffle
+      // (it sums the same squares in the same order, so alpha / beta are the oracle's bits)
+      double own = 0.0, gamma = 0.0;
       double w[kOctRows], vw[kOctN];
 #pragma unroll
       for (int i = 0; i < kOctRows; ++i) {
         w[i] = __shfl_sync(FULL, u[i], src, 8);
-        const double up = low ? u[i] : w[i], uq = low ? w[i] : u[i];
-        const double pp = up * up, qq = uq * uq, pq = up * uq;
-        alpha = (i == 0) ? pp : alpha + pp;
-        beta = (i == 0) ? qq : beta + qq;
+        const double sq = u[i] * u[i], pq = u[i] * w[i];
+        own = (i == 0) ? sq : own + sq;
         gamma = (i == 0) ? pq : gamma + pq;
       }
+      const double other = __shfl_sync(FULL, own, src, 8);
+      const double alpha = low ? own : other, beta = low ? other : own;
 #pragma unroll
       for (int i = 0; i < kOctN; ++i) vw[i] = __shfl_sync(FULL, v[i], src, 8);
       const bool rot = q >= 0 && (gamma * gamma > kJacobiThr2 * (alpha * beta));
@@ -942,7 +944,7 @@ __device__ __forceinline__ void svd_update_post(int lane, int n, int p, const Ws
 }
 
 template <int OP>
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(32)  // (32, 9) caps ptxas at 168 registers -> spills, 16 % slower
 svd4_kernel(const WarpArgs wa, const int shared_doubles, const int series_doubles) {
   extern __shared__ double smem[];
   const Batch &bt = wa.bt;
