@@ -38,9 +38,11 @@ class Model:
     p: int
     T: int
     times: Optional[np.ndarray]  # None = regular grid 1..T
+    t_init: Optional[np.ndarray] = None  # 1-element array: time of the saved state to resume from
 
     @staticmethod
-    def build(mod: _dlm.Dlm, times: Optional[Sequence[float]] = None, T: Optional[int] = None):
+    def build(mod: _dlm.Dlm, times: Optional[Sequence[float]] = None, T: Optional[int] = None,
+              t_init: Optional[float] = None):
         if times is None:
             assert T is not None and T > 0, "give times or T"
             tgrid = np.arange(1, T + 1, dtype=np.float64)
@@ -48,11 +50,13 @@ class Model:
             tgrid = np.ascontiguousarray(times, dtype=np.float64)
         if tgrid.size == 0:
             raise ValueError("empty observation vector (NoSuchElementException in the reference)")
-        F, f_tv, G, g_tv, n, p = _dlm.materialise(mod, tgrid)
-        regular = times is None or np.array_equal(tgrid, np.arange(1, tgrid.size + 1))
+        F, f_tv, G, g_tv, n, p = _dlm.materialise(mod, tgrid, t_init)
+        regular = t_init is None and (times is None or
+                                      np.array_equal(tgrid, np.arange(1, tgrid.size + 1)))
         return Model(np.ascontiguousarray(F.ravel()), np.ascontiguousarray(G.ravel()),
                      bool(f_tv), bool(g_tv), n, p, int(tgrid.size),
-                     None if regular else tgrid)
+                     None if regular else tgrid,
+                     None if t_init is None else np.array([float(t_init)]))
 
 
 _engines_by_device = {}
@@ -159,7 +163,7 @@ class Engine:
                                keep_init=keep_init, F=model.F, G=model.G, times=model.times,
                                V=ptrs["V"], W=ptrs["W"], m0=ptrs["m0"], C0=ptrs["C0"], y=yptr,
                                per_series=per, compat=compat, f_tv=model.f_tv, g_tv=model.g_tv,
-                               v_tv=v_tv)
+                               v_tv=v_tv, t_init=model.t_init)
         return pr, keep
 
     def _batch_of(self, model, y, layout):

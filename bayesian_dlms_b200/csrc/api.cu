@@ -272,7 +272,8 @@ int upload_model(bdlm_ctx *c, const DevCall &d, Bump &bump, Batch &bt,
   if (p.times) {
     double tmin = p.times[0];
     for (int t = 1; t < T; ++t) tmin = std::fmin(tmin, p.times[t]);
-    double prev = tmin - 1.0;  // KalmanFilter.initialiseState, KalmanFilter.scala:116-117
+    // KalmanFilter.initialiseState, KalmanFilter.scala:116-117 -- or the time of a saved state
+    double prev = p.t_init ? *p.t_init : tmin - 1.0;
     bool all_one = true;
     std::vector<double> dts(T);
     for (int t = 0; t < T; ++t) {

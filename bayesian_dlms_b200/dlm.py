@@ -164,15 +164,17 @@ def flatten_data(ys: Sequence[Data]):
     return times, y
 
 
-def materialise(mod: Dlm, times: np.ndarray):
+def materialise(mod: Dlm, times: np.ndarray, t_init: Optional[float] = None):
     """Evaluate the closures for a time grid.
 
     Returns (F, f_tv, G, g_tv, n, p): F is ``[n*p]`` or ``[T][n*p]``, G is ``[n*n]`` or
     ``[T][n*n]`` with ``G[t] = g(times[t] - times[t-1])`` and ``times[-1] := min(times) - 1``
-    (KalmanFilter.initialiseState, KalmanFilter.scala:112-118).
+    (KalmanFilter.initialiseState, KalmanFilter.scala:112-118), or ``t_init`` when the filter
+    resumes from a saved state at that time.
     """
     times = np.asarray(times, dtype=np.float64)
-    prev = np.concatenate([[times.min() - 1.0], times[:-1]])
+    t0 = times.min() - 1.0 if t_init is None else float(t_init)
+    prev = np.concatenate([[t0], times[:-1]])
     return materialise_dts(mod, times, times - prev)
 
 

@@ -146,6 +146,39 @@ class KalmanFilter:
         return _kf_states(model, out, _row_times(times, keep_init), keep_init)
 
     @staticmethod
+    def filterFrom(mod: Dlm, state: KfState, ys: Sequence[Data], p: DlmParameters) -> List[KfState]:
+        """``ys.foldLeft(state)(KalmanFilter(adv).step(mod, p))`` collected (KalmanFilter.scala:99-107,
+        the "carry on from the last filtered state" pattern of NoModel.scala:153-155): the states
+        after each new observation, starting from a saved ``KfState``."""
+        times, y = _dlm.flatten_data(ys)
+        model = Model.build(mod, times, t_init=state.time)
+        params = dict(V=p.v, W=p.w, m0=state.mt, C0=state.ct)
+        yb = np.ascontiguousarray(y.reshape(1, model.T, model.p))
+        out = default_engine().filter(model, params, yb, layout=SERIES_MAJOR, keep_init=False)
+        _raise_status(int(out["status"][0]))
+        return _kf_states(model, out, times, False)
+
+    @staticmethod
+    def forecast(mod: Dlm, mt: np.ndarray, ct: np.ndarray, time: float, p: DlmParameters,
+                 horizon: int):
+        """``Dlm.forecast(mod, mt, ct, time, p).take(horizon)`` (Dlm.scala:322-338): the forecast
+        mean and variance of the observation at ``time``, ``time + 1``, ...  A filter run without
+        observations from the state (mt, ct) at ``time``: the first step has dt = 0
+        (``oneStepPrediction`` on the state itself), the following ones are ``stepForecast``."""
+        if horizon <= 0:
+            return []
+        times = float(time) + np.arange(horizon, dtype=np.float64)
+        model = Model.build(mod, times, t_init=float(time))
+        params = dict(V=p.v, W=p.w, m0=np.asarray(mt, float), C0=np.asarray(ct, float))
+        yb = np.full((1, horizon, model.p), np.nan)
+        out = default_engine().filter(model, params, yb, layout=SERIES_MAJOR, keep_init=False,
+                                      want=("f", "Q"))
+        _raise_status(int(out["status"][0]))
+        pp = model.p
+        return [(float(times[r]), out["f"][0, r].copy(), _dlm.from_cm(out["Q"][0, r], pp, pp).copy())
+                for r in range(horizon)]
+
+    @staticmethod
     def likelihood(mod: Dlm, ys: Sequence[Data]):
         """``KalmanFilter.likelihood(mod, ys)(p)`` (:299-306), curried like the reference."""
         def at(p: DlmParameters) -> float:

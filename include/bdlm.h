@@ -120,6 +120,12 @@ typedef struct bdlm_problem {
                          holds T matrices: host [T][p*p] when shared, or, with BDLM_PS_V, a
                          per-step array laid out like y with k = p*p.  Served by the
                          warp-per-series kernels.                               */
+  const double *t_init; /* host scalar or NULL.  NULL: the state (m0, C0) sits at min(times) - 1
+                         (KalmanFilter.initialiseState).  Non-NULL: it sits at *t_init, i.e.
+                         the call RESUMES a filter from a saved state -- folding
+                         KalmanFilter.step over later data (NoModel.scala:153-155) or starting
+                         Dlm.forecast (Dlm.scala:322-338, first dt = 0).  Ignored when times is
+                         NULL (unit grid).                                        */
 } bdlm_problem;
 
 /* KfState fields (KalmanFilter.scala:22-30), `rows` rows each; NULL = not wanted. */

@@ -446,6 +446,7 @@ static double min_time(int T, const double *times) {
  * observation t).  times_out[rows] receives the state times. */
 static int kf_filter_impl(int n, int p, int T, const double *F, int f_tv,
                           const double *G, int g_tv, const double *V, int v_tv,
+                          const double *t_init,
                           const double *W, const double *m0,
                           const double *C0, const double *times,
                           const double *y, int keep_init, double *times_out,
@@ -454,7 +455,10 @@ static int kf_filter_impl(int n, int p, int T, const double *F, int f_tv,
   if (T <= 0) return -1; /* t0.get on empty data, KalmanFilter.scala:116-117 */
   int st = ST_OK, nn = n * n, pp = p * p;
   double mc[64], Cc[64 * 64], tmp[64 * 64];
-  double tprev = min_time(T, times) - 1.0;
+  /* t_init: resume from a saved state (m0, C0) at that time -- what folding KalmanFilter.step
+   * over later observations does (NoModel.scala:153-155), and Dlm.forecast's start
+   * (Dlm.scala:322-338); NULL = initialiseState's min(time) - 1. */
+  double tprev = t_init ? *t_init : min_time(T, times) - 1.0;
   memcpy(mc, m0, sizeof(double) * n);
   memcpy(Cc, C0, sizeof(double) * nn);
   int row = 0;
@@ -490,8 +494,20 @@ ORACLE_API int oracle_kf_filter(int n, int p, int T, const double *F, int f_tv,
                                 const double *y, int keep_init, double *times_out,
                                 double *m, double *C, double *a, double *R,
                                 double *f, double *Q) {
-  return kf_filter_impl(n, p, T, F, f_tv, G, g_tv, V, 0, W, m0, C0, times, y, keep_init,
+  return kf_filter_impl(n, p, T, F, f_tv, G, g_tv, V, 0, NULL, W, m0, C0, times, y, keep_init,
                         times_out, m, C, a, R, f, Q);
+}
+
+/* Filter resumed from the state (m0, C0) at time t_init (see kf_filter_impl). */
+ORACLE_API int oracle_kf_filter_from(int n, int p, int T, const double *F, int f_tv,
+                                     const double *G, int g_tv, const double *V,
+                                     const double *W, const double *m0,
+                                     const double *C0, double t_init, const double *times,
+                                     const double *y, int keep_init, double *times_out,
+                                     double *m, double *C, double *a, double *R,
+                                     double *f, double *Q) {
+  return kf_filter_impl(n, p, T, F, f_tv, G, g_tv, V, 0, &t_init, W, m0, C0, times, y,
+                        keep_init, times_out, m, C, a, R, f, Q);
 }
 
 /* Time-varying observation variance V_t (next row f2): StudentTGibbs.filter
@@ -504,7 +520,7 @@ ORACLE_API int oracle_kf_filter_vt(int n, int p, int T, const double *F, int f_t
                                    const double *y, int keep_init, double *times_out,
                                    double *m, double *C, double *a, double *R,
                                    double *f, double *Q) {
-  return kf_filter_impl(n, p, T, F, f_tv, G, g_tv, V, 1, W, m0, C0, times, y, keep_init,
+  return kf_filter_impl(n, p, T, F, f_tv, G, g_tv, V, 1, NULL, W, m0, C0, times, y, keep_init,
                         times_out, m, C, a, R, f, Q);
 }
 

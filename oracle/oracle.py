@@ -64,7 +64,7 @@ def cm(M):
     return np.ascontiguousarray(np.asarray(M, dtype=np.float64).T).ravel()
 
 
-def kf_filter(n, p, F, G, V, W, m0, C0, times, y, keep_init=True, v_tv=False):
+def kf_filter(n, p, F, G, V, W, m0, C0, times, y, keep_init=True, v_tv=False, t_init=None):
     """v_tv: V holds T matrices (StudentTGibbs.filter, StudentTGibbs.scala:100-119)."""
     times = _a(times)
     T = times.size
@@ -76,6 +76,15 @@ def kf_filter(n, p, F, G, V, W, m0, C0, times, y, keep_init=True, v_tv=False):
     out = {k: np.empty((rows, d)) for k, d in
            dict(m=n, C=n * n, a=n, R=n * n, f=p, Q=p * p).items()}
     tm = np.empty(rows)
+    if t_init is not None:
+        assert not v_tv
+        st = lib().oracle_kf_filter_from(
+            n, p, T, _p(F), f_tv, _p(G), g_tv, _p(_a(V)), _p(_a(W)), _p(_a(m0)), _p(_a(C0)),
+            C.c_double(float(t_init)), _p(times), _p(y), int(keep_init), _p(tm),
+            *(_p(out[k]) for k in ("m", "C", "a", "R", "f", "Q")))
+        out["time"] = tm
+        out["status"] = st
+        return out
     fn = lib().oracle_kf_filter_vt if v_tv else lib().oracle_kf_filter
     st = fn(
         n, p, T, _p(F), f_tv, _p(G), g_tv, _p(_a(V)), _p(_a(W)), _p(_a(m0)), _p(_a(C0)),

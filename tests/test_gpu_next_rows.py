@@ -353,3 +353,36 @@ def test_reference_api_mirrors_of_the_next_rows(eng):
     assert len(chains) == 4 and len(chains[0]) == 50
     assert all(c[-1].v[0, 0] > 0 and c[-1].w[0, 0] > 0 for c in chains)
     assert chains[0][-1].v[0, 0] != chains[1][-1].v[0, 0]
+
+
+# ------------------------------------------------------------------ resume / forecast (f4)
+
+def test_filter_from_saved_state_and_forecast(eng, oracle):
+    from bayesian_dlms_b200 import Data, DlmParameters, KalmanFilter, dlm
+    rng = np.random.default_rng(3)
+    mod = dlm.polynomial(1) + dlm.seasonal(24, 2)
+    n = 5
+    V, W, m0, C0 = np.array([[1.5]]), np.diag(rng.uniform(0.1, 1, n)), rng.standard_normal(n), np.eye(n)
+    times = np.cumsum(rng.choice([1.0, 2.0, 0.5], 60))
+    y = H.simulate(mod, V, W, m0, C0, times, rng, missing=0.1)
+    data = [Data(t, [None if np.isnan(v) else v for v in row]) for t, row in zip(times, y)]
+    p = DlmParameters(V, W, m0, C0)
+    full = KalmanFilter.filter(mod, data, p)              # T + 1 states
+    k = 25
+    rest = KalmanFilter.filterFrom(mod, full[k], data[k:], p)
+    assert len(rest) == len(data) - k
+    for a, b in zip(rest, full[k + 1:]):
+        assert a.time == b.time
+        _exact(a.mt, b.mt, "mt"); _exact(a.ct, b.ct, "ct"); _exact(a.at, b.at, "at")
+        _exact(a.rt, b.rt, "rt"); _exact(a.ft, b.ft, "ft"); _exact(a.qt, b.qt, "qt")
+    fc = KalmanFilter.forecast(mod, full[-1].mt, full[-1].ct, full[-1].time, p, 5)
+    cm = oracle.oracle.cm
+    ft = full[-1].time + np.arange(5.0)
+    Ff, _, Gf, _, _, _ = dlm.materialise(mod, ft, t_init=full[-1].time)
+    o = oracle.kf_filter(n, 1, Ff, Gf, cm(V), cm(W), full[-1].mt, cm(full[-1].ct), ft,
+                         np.full((5, 1), np.nan), keep_init=False, t_init=full[-1].time)
+    for h, (t, f, q) in enumerate(fc):
+        assert t == ft[h]
+        _exact(f, o["f"][h], "forecast mean"); _exact(q.ravel(), o["Q"][h], "forecast variance")
+    # first forecast step is oneStepPrediction on the state itself (dt = 0)
+    assert np.allclose(fc[0][1], mod.f(0.0).T @ full[-1].mt)

@@ -136,3 +136,39 @@ def test_inverse_wishart_matches_lapack():
     assert np.allclose(got, got.T, rtol=1e-12)
     assert np.all(np.linalg.eigvalsh(got) > 0)
     assert np.array_equal(o["scale"].reshape(n, n).T, sc)
+
+
+def test_resumed_filter_equals_one_shot_and_forecast_matches_numpy():
+    """t_init: folding KalmanFilter.step from a saved state (NoModel.scala:153-155) gives the same
+    bits as filtering everything at once; Dlm.forecast (Dlm.scala:322-338) = the filter without
+    observations, first dt = 0."""
+    from bayesian_dlms_b200 import dlm
+    rng = np.random.default_rng(12)
+    mod = dlm.polynomial(1) + dlm.seasonal(24, 2)
+    n, p = 5, 1
+    V, W, m0, C0 = np.array([[1.5]]), np.diag(rng.uniform(0.1, 1, n)), rng.standard_normal(n), np.eye(n)
+    times = np.cumsum(rng.choice([1.0, 2.0, 0.5], 80))
+    y = H.simulate(mod, V, W, m0, C0, times, rng, missing=0.1)
+    cm = oracle.oracle.cm
+    F, f_tv, G, g_tv, _, _ = dlm.materialise(mod, times)
+    full = oracle.kf_filter(n, p, F, G, cm(V), cm(W), m0, cm(C0), times, y)
+    k = 33
+    F2, _, G2, _, _, _ = dlm.materialise(mod, times[k:], t_init=times[k - 1])
+    rest = oracle.kf_filter(n, p, F2, G2, cm(V), cm(W), full["m"][k], full["C"][k], times[k:], y[k:],
+                            keep_init=False, t_init=times[k - 1])
+    for key in ("m", "C", "a", "R", "f", "Q"):
+        assert np.array_equal(rest[key], full[key][k + 1:]), key
+    # forecast from the last state
+    Hn = 6
+    ft = times[-1] + np.arange(Hn)
+    Ff, _, Gf, _, _, _ = dlm.materialise(mod, ft, t_init=times[-1])
+    fc = oracle.kf_filter(n, p, Ff, Gf, cm(V), cm(W), full["m"][-1], full["C"][-1], ft,
+                          np.full((Hn, 1), np.nan), keep_init=False, t_init=times[-1])
+    m, C = full["m"][-1], full["C"][-1].reshape(n, n).T
+    Fm = mod.f(0.0)
+    assert np.allclose(fc["f"][0], Fm.T @ m, rtol=1e-13) and np.allclose(fc["Q"][0], Fm.T @ C @ Fm + V, rtol=1e-13)
+    for h in range(1, Hn):
+        Gm = mod.g(1.0)
+        m, C = Gm @ m, Gm @ C @ Gm.T + W
+        assert np.allclose(fc["f"][h], Fm.T @ m, rtol=1e-12)
+        assert np.allclose(fc["Q"][h], Fm.T @ C @ Fm + V, rtol=1e-12)
