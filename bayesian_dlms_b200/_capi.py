@@ -46,7 +46,7 @@ class Problem(C.Structure):
                 ("compat", C.c_int32),
                 ("F", C.c_void_p), ("G", C.c_void_p), ("times", C.c_void_p),
                 ("V", C.c_void_p), ("W", C.c_void_p), ("m0", C.c_void_p), ("C0", C.c_void_p),
-                ("y", C.c_void_p), ("v_tv", C.c_int32), ("t_init", C.c_void_p)]
+                ("y", C.c_void_p), ("v_tv", C.c_int32), ("w_tv", C.c_int32), ("t_init", C.c_void_p)]
 
 
 class KfOut(C.Structure):
@@ -230,7 +230,7 @@ def host_ptr(a):
 
 
 def make_problem(*, B, T, n, p, layout, mem, keep_init, F, G, times, V, W, m0, C0, y,
-                 per_series=0, compat=0, f_tv=0, g_tv=0, v_tv=0, t_init=None):
+                 per_series=0, compat=0, f_tv=0, g_tv=0, v_tv=0, t_init=None, w_tv=0):
     """F, G, times: host numpy arrays (kept alive by the caller).  V, W, m0, C0, y: raw
     addresses (ints) in the memory space named by `mem`, or numpy arrays when shared."""
     pr = Problem()
@@ -246,5 +246,6 @@ def make_problem(*, B, T, n, p, layout, mem, keep_init, F, G, times, V, W, m0, C
     pr.F, pr.G, pr.times = addr(F), addr(G), addr(times)
     pr.V, pr.W, pr.m0, pr.C0, pr.y = addr(V), addr(W), addr(m0), addr(C0), addr(y)
     pr.v_tv = int(bool(v_tv))
+    pr.w_tv = int(bool(w_tv))
     pr.t_init = addr(t_init)   # 1-element host array (kept alive by the caller) or None
     return pr

@@ -131,6 +131,7 @@ class Engine:
         # params["v_tv"] = True: V varies with t (StudentTGibbs.filter): shared V is (T, p*p)
         # column-major per row [or (T, p, p)]; per-series V is laid out like y with k = p*p
         v_tv = bool(params.get("v_tv", False))
+        w_tv = bool(params.get("w_tv", False))  # same for W (DlmFsvSystem.ffbs), k = n*n
         for name, bit, r, c in (("V", capi.PS_V, p, p), ("W", capi.PS_W, n, n),
                                 ("m0", capi.PS_M0, n, 1), ("C0", capi.PS_C0, n, n)):
             x = params.get(name)
@@ -140,14 +141,14 @@ class Engine:
             # per-series parameters are named explicitly: params["per_series"] = ("V", "W")
             if name in params.get("per_series", ()):
                 expect = (r * c, B) if layout == TIME_MAJOR else (B, r * c)
-                if name == "V" and v_tv:
+                if (name == "V" and v_tv) or (name == "W" and w_tv):
                     expect = self._shape(layout, B, model.T, r * c)
                 assert tuple(x.shape) == expect, (name, tuple(x.shape), expect)
                 m_, ptr = _mem_and_ptr(x)
                 assert m_ == mem, f"{name} lives in a different memory space than y"
                 per |= bit
                 ptrs[name] = ptr
-            elif name == "V" and v_tv:
+            elif (name == "V" and v_tv) or (name == "W" and w_tv):
                 a = np.asarray(x, dtype=np.float64)
                 if a.ndim == 3:  # (T, p, p) -> column-major rows
                     a = a.transpose(0, 2, 1)
@@ -163,7 +164,7 @@ class Engine:
                                keep_init=keep_init, F=model.F, G=model.G, times=model.times,
                                V=ptrs["V"], W=ptrs["W"], m0=ptrs["m0"], C0=ptrs["C0"], y=yptr,
                                per_series=per, compat=compat, f_tv=model.f_tv, g_tv=model.g_tv,
-                               v_tv=v_tv, t_init=model.t_init)
+                               v_tv=v_tv, w_tv=w_tv, t_init=model.t_init)
         return pr, keep
 
     def _batch_of(self, model, y, layout):

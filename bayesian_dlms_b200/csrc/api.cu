@@ -127,7 +127,7 @@ View mk_rowview(double *ptr, int layout, int64_t b0, int64_t Bp, int64_t k) {
 }
 
 bool small_path(int op, const bdlm_problem &p) {
-  return (op == A_FILTER || op == A_SMOOTH || op == A_FILTER_SMOOTH) && !p.v_tv &&
+  return (op == A_FILTER || op == A_SMOOTH || op == A_FILTER_SMOOTH) && !p.v_tv && !p.w_tv &&
          small_supported(p.n, p.p);
 }
 
@@ -191,7 +191,7 @@ void collect_fields(DevCall &d, std::vector<Field> &f) {
   const bool smooth_in = d.op == A_SMOOTH;
   if (d.op != A_SMOOTH) add(&d.pr.y, p.T, pp, true, false);
   if (p.per_series & BDLM_PS_V) add(&d.pr.V, p.v_tv ? p.T : 1, pp * pp, true, false);
-  if (p.per_series & BDLM_PS_W) add(&d.pr.W, 1, n * n, true, false);
+  if (p.per_series & BDLM_PS_W) add(&d.pr.W, p.w_tv ? p.T : 1, n * n, true, false);
   if (p.per_series & BDLM_PS_M0) add(&d.pr.m0, 1, n, true, false);
   if (p.per_series & BDLM_PS_C0) add(&d.pr.C0, 1, n * n, true, false);
   add((const double *const *)&d.kf.m, R, n, smooth_in, !smooth_in);
@@ -228,7 +228,8 @@ size_t dev_workspace_bytes(const DevCall &d, int64_t Bc) {
   size_t bytes = 0;
   // model: F, G, dt + shared params
   bytes += align_up(sizeof(double) * ((size_t)p.T * (n * p.p + n * n + 1) + 2 * n * n +
-                                      (size_t)p.p * p.p * (p.v_tv ? p.T : 1) + n + 64)) + 4096;
+                                      (size_t)p.p * p.p * (p.v_tv ? p.T : 1) +
+                                      (size_t)n * n * (p.w_tv ? p.T : 1) + n + 64)) + 4096;
   if (d.op == A_AR_FILTER || d.op == A_AR_FFBS) {
     bytes += align_up(sizeof(double) * 2 * (size_t)p.T);  // dt, shared v
     if (d.op == A_AR_FFBS) bytes += 2 * align_up(sizeof(double) * (size_t)R * Bc);  // (m, C) spill
@@ -287,7 +288,7 @@ int upload_model(bdlm_ctx *c, const DevCall &d, Bump &bump, Batch &bt,
     return ((p.per_series & bit) || !src) ? (size_t)-1 : push(src, cnt);
   };
   const size_t oV = shared(p.V, BDLM_PS_V, (size_t)pp * pp * (p.v_tv ? T : 1));
-  const size_t oW = shared(p.W, BDLM_PS_W, (size_t)n * n);
+  const size_t oW = shared(p.W, BDLM_PS_W, (size_t)n * n * (p.w_tv ? T : 1));
   const size_t oM = shared(p.m0, BDLM_PS_M0, n);
   const size_t oC = shared(p.C0, BDLM_PS_C0, (size_t)n * n);
   double *dev = bump.take<double>(host.size());
@@ -318,6 +319,17 @@ int upload_model(bdlm_ctx *c, const DevCall &d, Bump &bump, Batch &bt,
     }
   }
   bt.W = pv(p.W, oW, (int64_t)n * n);
+  bt.w_tv = p.w_tv ? 1 : 0;
+  bt.W_sr = 0;
+  if (p.w_tv) {
+    if (oW != (size_t)-1) bt.W_sr = (int64_t)n * n;  // shared: [T][n*n]
+    else if (p.layout == BDLM_TIME_MAJOR) bt.W_sr = (int64_t)n * n * d.Bp;  // [T][k][B]
+    else {  // [B][T][k]
+      bt.W.ptr = p.W + d.b0 * (int64_t)T * n * n;
+      bt.W.sb = (int64_t)T * n * n;
+      bt.W_sr = (int64_t)n * n;
+    }
+  }
   bt.m0 = pv(p.m0, oM, n);
   bt.C0 = pv(p.C0, oC, (int64_t)n * n);
   bt.y = mk_cview(p.y, p.layout, d.b0, d.Bp, T, pp);
@@ -515,7 +527,7 @@ int run_dev(bdlm_ctx *c, DevCall d, Bump bump) {
   const int wop = warp_op(d.op);
   wa.spill_k = (int64_t)warp_spill_doubles_per_row(wop, p.n, p.p);
   wa.spill = wa.spill_k ? bump.take<double>((size_t)wa.spill_k * R * d.Bc) : nullptr;
-  if (c->use_group && !p.v_tv && group_supported(wop, p.n, p.p, p.keep_init ? 1 : 0)) {
+  if (c->use_group && !p.v_tv && !p.w_tv && group_supported(wop, p.n, p.p, p.keep_init ? 1 : 0)) {
     CU(launch_group(wop, wa, c->stream));  // two series per warp, compile-time n (kf_group.cu)
     ++c->launches;
     return 0;
@@ -547,6 +559,8 @@ int validate(bdlm_ctx *c, int op, const bdlm_problem *p) {
   if (op != A_SMOOTH && !p->y) return fail(c, BDLM_E_ARG, "null y");
   if (p->v_tv && op != A_FILTER && op != A_FILTER_SMOOTH && op != A_FFBS && op != A_LOGLIK)
     return fail(c, BDLM_E_ARG, "v_tv: supported by filter, filter+smoother, log-likelihood and FFBS");
+  if (p->w_tv && op != A_FILTER && op != A_FILTER_SMOOTH && op != A_FFBS)
+    return fail(c, BDLM_E_ARG, "w_tv: supported by filter, filter+smoother and FFBS");
   if ((op == A_FFBS || op == A_SVD_FFBS || op == A_STATS) && !p->keep_init)
     return fail(c, BDLM_E_ARG, "FFBS keeps the initial state: keep_init must be 1");
   return 0;

@@ -48,6 +48,8 @@ struct Batch {
   int f_tv, g_tv;
   int v_tv;        // V varies with t (StudentTGibbs.filter): V holds T matrices, row stride V_sr
   int64_t V_sr;
+  int w_tv;        // W varies with t (DlmFsvSystem.ffbs): W holds T matrices, row stride W_sr
+  int64_t W_sr;
   PView V, W, m0, C0;
   CView y;         // T rows
   int32_t *status; // [B] or nullptr

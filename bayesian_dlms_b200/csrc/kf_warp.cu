@@ -518,6 +518,11 @@ warp_kernel(const WarpArgs wa, const int ws_doubles) {
         vt.ptr += (int64_t)t * bt.V_sr;
         load_pview(lane, vt, b, p * p, ws.V);
       }
+      if (bt.w_tv) {  // W_t: params.copy(w = W_t) (DlmFsvSystem.scala:142-153)
+        PView wt = bt.W;
+        wt.ptr += (int64_t)t * bt.W_sr;
+        load_pview(lane, wt, b, nn, ws.W);
+      }
       __syncwarp();
       if (kSvd) {
         st |= svd_advance(lane, n, ws, dt);
@@ -654,6 +659,11 @@ warp_kernel(const WarpArgs wa, const int ws_doubles) {
       for (int k = lane; k < n; k += 32) { ws.m[k] = sp[k]; ws.a[k] = sp1[n + nn + k]; }
       for (int k = lane; k < nn; k += 32) { ws.C[k] = sp[n + k]; ws.R[k] = sp1[2 * n + nn + k]; }
       load_cview(lane, wa.z, b, r, n, ws.v3);
+      if (bt.w_tv) {  // W of the transition r -> r + 1 (DlmFsvSystem.scala:155-163)
+        PView wt = bt.W;
+        wt.ptr += (int64_t)tobs * bt.W_sr;
+        load_pview(lane, wt, b, nn, ws.W);
+      }
       __syncwarp();
       st |= smoothing_gain(lane, n, ws, ws.C, ws.R);  // B in t3
       for (int k = lane; k < n; k += 32) ws.v1[k] = ws.th[k] - ws.a[k];
@@ -772,8 +782,8 @@ constexpr int kOctN = 8;
 // descending, Vout (n x n) ordered + sign-normalised right singular vectors.  All 32 lanes must
 // call it; returns the octet's status (uniform within the octet).  Rows r..15 are zero padding:
 // they add exact zeros to the sums, which leaves every partial sum bit-identical.
-__device__ __forceinline__ int oct_jacobi_svd(int lane, int n, int r, const double *U, double *sv,
-                                              double *Vout) {
+__device__ __noinline__ int oct_jacobi_svd(int lane, int n, int r, const double *U, double *sv,
+                                           double *Vout) {
   const int j = lane & 7;
   const bool col = U != nullptr && j < n;
   double u[kOctRows], v[kOctN];
@@ -965,11 +975,13 @@ svd4_kernel(const WarpArgs wa, const int shared_doubles, const int series_double
   auto live = [&](int s) { return b0 + s < bt.B; };
   const Slot mine = slot(oct);
   const bool mine_live = live(oct);
-  int st[kQuad] = {0, 0, 0, 0};
-  auto fold_status = [&](int so) {
-#pragma unroll
-    for (int s = 0; s < kQuad; ++s) st[s] |= __shfl_sync(FULL, so, s * 8);
-  };
+  // The series loops are run-time loops on purpose: unrolled four times (with the SVD inlined at
+  // its three call sites) the kernel was 87.7 k SASS instructions and ncu showed 1.8 warps per
+  // issue-active cycle stalled on instruction fetch.  Status bits are kept per octet (st_mine =
+  // the status of this lane's own series).
+  int st_mine = 0;
+  auto fold_status = [&](int so) { st_mine |= so; };
+  auto add_status = [&](int s, int bits) { if (oct == s) st_mine |= bits; };
   {  // the model is shared by the batch: one copy per warp
     const Ws ws = mine.ws;
     load_model(lane, bt, ws, 0, true);
@@ -977,7 +989,7 @@ svd4_kernel(const WarpArgs wa, const int shared_doubles, const int series_double
 
   // ---- initial state: transformParams (SvdFilter.scala:232-236) + initialiseState (:83-95);
   // once per series, generic routines
-#pragma unroll
+#pragma unroll 1
   for (int s = 0; s < kQuad; ++s) {
     if (!live(s)) continue;
     const Ws ws = slot(s).ws;
@@ -987,12 +999,12 @@ svd4_kernel(const WarpArgs wa, const int shared_doubles, const int series_double
     load_pview(lane, bt.m0, b, n, ws.m);
     load_pview(lane, bt.C0, b, nn, ws.C);
     __syncwarp();
-    st[s] |= w_sqrt_svd(lane, p, ws, ws.V, true, ws.t5);
+    add_status(s, w_sqrt_svd(lane, p, ws, ws.V, true, ws.t5));
     w_copy(lane, p * p, ws.t5, ws.V);
-    st[s] |= w_sqrt_svd(lane, n, ws, ws.W, false, ws.Wsq);
+    add_status(s, w_sqrt_svd(lane, n, ws, ws.W, false, ws.Wsq));
     if (bt.compat & BDLM_SVD_CONSISTENT_W) w_copy(lane, nn, ws.Wsq, ws.W);
     w_copy(lane, nn, ws.C, ws.stk);
-    st[s] |= w_jacobi_svd(lane, n, n, ws.stk, ws.t3, ws.scr, ws.iscr, ws.v1, ws.t4);
+    add_status(s, w_jacobi_svd(lane, n, n, ws.stk, ws.t3, ws.scr, ws.iscr, ws.v1, ws.t4));
     for (int k = lane; k < n; k += 32) ws.dcv[k] = sqrt(ws.v1[k]);
     w_copy(lane, nn, ws.t4, ws.C);
     if (ki) {
@@ -1020,14 +1032,14 @@ svd4_kernel(const WarpArgs wa, const int shared_doubles, const int series_double
     const int64_t row = t + ki;
     const double dt = bt.dt ? bt.dt[t] : 1.0;
     load_model(lane, bt, mine.ws, t, false);  // no-op unless F or G vary with t
-#pragma unroll
+#pragma unroll 1
     for (int s = 0; s < kQuad; ++s)
       if (live(s)) svd_advance_pre(lane, n, slot(s).ws, dt);
     if (dt != 0.0)  // the four time updates' SVDs together: stack (2n x n) -> (drv, R)
       fold_status(oct_jacobi_svd(lane, n, 2 * n, mine_live ? mine.ws.stk : nullptr, mine.ws.drv,
                                  mine.ws.R));
     int po_mine = 0;
-#pragma unroll
+#pragma unroll 1
     for (int s = 0; s < kQuad; ++s) {
       if (!live(s)) continue;
       const Ws ws = slot(s).ws;
@@ -1040,7 +1052,7 @@ svd4_kernel(const WarpArgs wa, const int shared_doubles, const int series_double
     // the four measurement updates' SVDs: stack ((po + n) x n) -> (sS, sV)
     fold_status(oct_jacobi_svd(lane, n, po_mine + n, po_mine > 0 ? mine.ws.stk : nullptr, mine.sS,
                                mine.sV));
-#pragma unroll
+#pragma unroll 1
     for (int s = 0; s < kQuad; ++s) {
       if (!live(s)) continue;
       const Slot q = slot(s);
@@ -1073,7 +1085,7 @@ svd4_kernel(const WarpArgs wa, const int shared_doubles, const int series_double
   // ---- backward sampler: SvdSampler.sample (SvdSampler.scala:54-60), initialise (:38-45),
   // step (:15-36)
   if (OP == kOpSvdFfbs) {
-#pragma unroll
+#pragma unroll 1
     for (int s = 0; s < kQuad; ++s) {
       if (!live(s)) continue;
       const Ws ws = slot(s).ws;
@@ -1091,7 +1103,7 @@ svd4_kernel(const WarpArgs wa, const int shared_doubles, const int series_double
     for (int r = rows - 2; r >= 0; --r) {
       const int tobs = r + 1 - ki;
       load_model(lane, bt, mine.ws, tobs, false);
-#pragma unroll
+#pragma unroll 1
       for (int s = 0; s < kQuad; ++s) {
         if (!live(s)) continue;
         const Ws ws = slot(s).ws;
@@ -1111,7 +1123,7 @@ svd4_kernel(const WarpArgs wa, const int shared_doubles, const int series_double
         __syncwarp();
       }
       fold_status(oct_jacobi_svd(lane, n, 2 * n, mine_live ? mine.ws.stk : nullptr, mine.sS, mine.sV));
-#pragma unroll
+#pragma unroll 1
       for (int s = 0; s < kQuad; ++s) {
         if (!live(s)) continue;
         const Slot q = slot(s);
@@ -1144,22 +1156,17 @@ svd4_kernel(const WarpArgs wa, const int shared_doubles, const int series_double
     if (wa.stats.ssy.ptr || wa.stats.ny.ptr || wa.stats.ssw.ptr || wa.stats.scatter.ptr) {
       __threadfence_block();
       __syncwarp();
-#pragma unroll
+#pragma unroll 1
       for (int s = 0; s < kQuad; ++s)
         if (live(s)) gibbs_stats(lane, bt, slot(s).ws, wa.theta, wa.stats, b0 + s);
     }
   }
 
-  if (bt.status) {
-#pragma unroll
-    for (int s = 0; s < kQuad; ++s) {
-      if (!live(s) || lane != 0) continue;
-      const Ws ws = slot(s).ws;
-      const double *chk = (OP == kOpSvdFilter) ? ws.m : ws.th;
-      bool finite = true;
-      for (int k = 0; k < n; ++k) finite = finite && isfinite(chk[k]);
-      bt.status[b0 + s] = st[s] | (finite ? 0 : BDLM_ST_NONFINITE);
-    }
+  if (bt.status && mine_live && (lane & 7) == 0) {  // first lane of each octet: its own series
+    const double *chk = (OP == kOpSvdFilter) ? mine.ws.m : mine.ws.th;
+    bool finite = true;
+    for (int k = 0; k < n; ++k) finite = finite && isfinite(chk[k]);
+    bt.status[b0 + oct] = st_mine | (finite ? 0 : BDLM_ST_NONFINITE);
   }
 }
 

@@ -120,6 +120,9 @@ typedef struct bdlm_problem {
                          holds T matrices: host [T][p*p] when shared, or, with BDLM_PS_V, a
                          per-step array laid out like y with k = p*p.  Served by the
                          warp-per-series kernels.                               */
+  int32_t w_tv;       /* W varies with t (DlmFsvSystem.ffbs, DlmFsvSystem.scala:137-167): W holds T
+                         matrices, W[t] driving the transition INTO observation t; same layout
+                         rules as v_tv with BDLM_PS_W and k = n*n.                  */
   const double *t_init; /* host scalar or NULL.  NULL: the state (m0, C0) sits at min(times) - 1
                          (KalmanFilter.initialiseState).  Non-NULL: it sits at *t_init, i.e.
                          the call RESUMES a filter from a saved state -- folding

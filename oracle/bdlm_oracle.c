@@ -447,7 +447,7 @@ static double min_time(int T, const double *times) {
 static int kf_filter_impl(int n, int p, int T, const double *F, int f_tv,
                           const double *G, int g_tv, const double *V, int v_tv,
                           const double *t_init,
-                          const double *W, const double *m0,
+                          const double *W, int w_tv, const double *m0,
                           const double *C0, const double *times,
                           const double *y, int keep_init, double *times_out,
                           double *m, double *C, double *a, double *R,
@@ -476,7 +476,7 @@ static int kf_filter_impl(int n, int p, int T, const double *F, int f_tv,
     double dt = times[t] - tprev; /* KalmanFilter.step :99-107 */
     double *ar = a + (size_t)row * n, *Rr = R + (size_t)row * nn;
     double *mr = m + (size_t)row * n, *Cr = C + (size_t)row * nn;
-    kf_advance(n, Gt, W, dt, mc, Cc, ar, Rr, tmp);
+    kf_advance(n, Gt, W + (w_tv ? (size_t)t * nn : 0), dt, mc, Cc, ar, Rr, tmp);
     st |= kf_update(n, p, Ft, V + (v_tv ? (size_t)t * pp : 0), ar, Rr, y + (size_t)t * p,
                     f + (size_t)row * p, Q + (size_t)row * pp, mr, Cr);
     memcpy(mc, mr, sizeof(double) * n);
@@ -494,7 +494,7 @@ ORACLE_API int oracle_kf_filter(int n, int p, int T, const double *F, int f_tv,
                                 const double *y, int keep_init, double *times_out,
                                 double *m, double *C, double *a, double *R,
                                 double *f, double *Q) {
-  return kf_filter_impl(n, p, T, F, f_tv, G, g_tv, V, 0, NULL, W, m0, C0, times, y, keep_init,
+  return kf_filter_impl(n, p, T, F, f_tv, G, g_tv, V, 0, NULL, W, 0, m0, C0, times, y, keep_init,
                         times_out, m, C, a, R, f, Q);
 }
 
@@ -506,7 +506,7 @@ ORACLE_API int oracle_kf_filter_from(int n, int p, int T, const double *F, int f
                                      const double *y, int keep_init, double *times_out,
                                      double *m, double *C, double *a, double *R,
                                      double *f, double *Q) {
-  return kf_filter_impl(n, p, T, F, f_tv, G, g_tv, V, 0, &t_init, W, m0, C0, times, y,
+  return kf_filter_impl(n, p, T, F, f_tv, G, g_tv, V, 0, &t_init, W, 0, m0, C0, times, y,
                         keep_init, times_out, m, C, a, R, f, Q);
 }
 
@@ -520,8 +520,21 @@ ORACLE_API int oracle_kf_filter_vt(int n, int p, int T, const double *F, int f_t
                                    const double *y, int keep_init, double *times_out,
                                    double *m, double *C, double *a, double *R,
                                    double *f, double *Q) {
-  return kf_filter_impl(n, p, T, F, f_tv, G, g_tv, V, 1, NULL, W, m0, C0, times, y, keep_init,
+  return kf_filter_impl(n, p, T, F, f_tv, G, g_tv, V, 1, NULL, W, 0, m0, C0, times, y, keep_init,
                         times_out, m, C, a, R, f, Q);
+}
+
+/* Time-varying V_t and / or W_t: DlmFsvSystem.ffbs (DlmFsvSystem.scala:137-167) runs
+ * KalmanFilter.step with params.copy(w = W_t) at step t (W: T matrices of n x n). */
+ORACLE_API int oracle_kf_filter_tv(int n, int p, int T, const double *F, int f_tv,
+                                   const double *G, int g_tv, const double *V, int v_tv,
+                                   const double *W, int w_tv, const double *m0,
+                                   const double *C0, const double *times,
+                                   const double *y, int keep_init, double *times_out,
+                                   double *m, double *C, double *a, double *R,
+                                   double *f, double *Q) {
+  return kf_filter_impl(n, p, T, F, f_tv, G, g_tv, V, v_tv, NULL, W, w_tv, m0, C0, times, y,
+                        keep_init, times_out, m, C, a, R, f, Q);
 }
 
 /* B = (R1^T \ (G C^T))^T  -- Smoothing.scala:41 and :85 */
@@ -584,12 +597,12 @@ static int mvn_eig_draw(int n, const double *mu, const double *cov,
 /* Smoothing.sample :114-122 with Smoothing.step :74-103 / initialise :105-109.
  * z[rows][n]: the N(0,1) values consumed for row r (the reference draws row
  * rows-1 first).  dts[r] for r < rows-1 is time[r+1]-time[r]. */
-ORACLE_API int oracle_backward_sample(int n, int T, int keep_init, const double *G,
-                                      int g_tv, const double *W,
-                                      const double *times_rows, const double *m,
-                                      const double *C, const double *a,
-                                      const double *R, const double *z,
-                                      double *theta) {
+static int backward_sample_impl(int n, int T, int keep_init, const double *G,
+                                int g_tv, const double *W0, int w_tv,
+                                const double *times_rows, const double *m,
+                                const double *C, const double *a,
+                                const double *R, const double *z,
+                                double *theta) {
   int rows = T + keep_init, nn = n * n, st = ST_OK;
   double B[64 * 64], d[64], h[64], D[64 * 64], t1[64 * 64], t2[64 * 64],
       H[64 * 64], Hs[64 * 64];
@@ -598,6 +611,8 @@ ORACLE_API int oracle_backward_sample(int n, int T, int keep_init, const double 
   for (int r = rows - 2; r >= 0; --r) {
     int tobs = r + 1 - keep_init;
     const double *Gt = G + (g_tv ? (size_t)tobs * nn : 0);
+    /* W of the transition r -> r + 1 (DlmFsvSystem.scala:155-163 zips ps with filtered.init) */
+    const double *W = W0 + (w_tv ? (size_t)tobs * nn : 0);
     double dt = times_rows[r + 1] - times_rows[r];
     const double *a1 = a + (size_t)(r + 1) * n, *R1 = R + (size_t)(r + 1) * nn;
     const double *th1 = theta + (size_t)(r + 1) * n;
@@ -620,6 +635,33 @@ ORACLE_API int oracle_backward_sample(int n, int T, int keep_init, const double 
       for (int i = 0; i < n; ++i) Hs[i + j * n] = (H[i + j * n] + H[j + i * n]) / 2.0;
     st |= mvn_eig_draw(n, h, Hs, z + (size_t)r * n, theta + (size_t)r * n);
   }
+  return st;
+}
+
+ORACLE_API int oracle_backward_sample(int n, int T, int keep_init, const double *G,
+                                      int g_tv, const double *W,
+                                      const double *times_rows, const double *m,
+                                      const double *C, const double *a,
+                                      const double *R, const double *z,
+                                      double *theta) {
+  return backward_sample_impl(n, T, keep_init, G, g_tv, W, 0, times_rows, m, C, a, R, z, theta);
+}
+
+/* FFBS with time-varying V_t / W_t (StudentTGibbs.sampleState, DlmFsvSystem.ffbs). */
+ORACLE_API int oracle_ffbs_tv(int n, int p, int T, const double *F, int f_tv,
+                              const double *G, int g_tv, const double *V, int v_tv,
+                              const double *W, int w_tv, const double *m0, const double *C0,
+                              const double *times, const double *y, const double *z,
+                              double *times_out, double *theta, double *m, double *C,
+                              double *a, double *R) {
+  int rows = T + 1;
+  double *f = (double *)malloc(sizeof(double) * rows * p);
+  double *Q = (double *)malloc(sizeof(double) * rows * p * p);
+  int st = oracle_kf_filter_tv(n, p, T, F, f_tv, G, g_tv, V, v_tv, W, w_tv, m0, C0, times, y, 1,
+                               times_out, m, C, a, R, f, Q);
+  if (st >= 0)
+    st |= backward_sample_impl(n, T, 1, G, g_tv, W, w_tv, times_out, m, C, a, R, z, theta);
+  free(f); free(Q);
   return st;
 }
 

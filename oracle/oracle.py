@@ -64,12 +64,16 @@ def cm(M):
     return np.ascontiguousarray(np.asarray(M, dtype=np.float64).T).ravel()
 
 
-def kf_filter(n, p, F, G, V, W, m0, C0, times, y, keep_init=True, v_tv=False, t_init=None):
-    """v_tv: V holds T matrices (StudentTGibbs.filter, StudentTGibbs.scala:100-119)."""
+def kf_filter(n, p, F, G, V, W, m0, C0, times, y, keep_init=True, v_tv=False, t_init=None,
+              w_tv=False):
+    """v_tv / w_tv: V / W hold T matrices (StudentTGibbs.filter, StudentTGibbs.scala:100-119;
+    DlmFsvSystem.ffbs, DlmFsvSystem.scala:137-167)."""
     times = _a(times)
     T = times.size
     if v_tv:
         assert _a(V).size == T * p * p
+    if w_tv:
+        assert _a(W).size == T * n * n
     y = _a(y, (T, p))
     F, f_tv, G, g_tv = _model(F, G, n, p, T)
     rows = T + int(keep_init)
@@ -85,10 +89,9 @@ def kf_filter(n, p, F, G, V, W, m0, C0, times, y, keep_init=True, v_tv=False, t_
         out["time"] = tm
         out["status"] = st
         return out
-    fn = lib().oracle_kf_filter_vt if v_tv else lib().oracle_kf_filter
-    st = fn(
-        n, p, T, _p(F), f_tv, _p(G), g_tv, _p(_a(V)), _p(_a(W)), _p(_a(m0)), _p(_a(C0)),
-        _p(times), _p(y), int(keep_init), _p(tm),
+    st = lib().oracle_kf_filter_tv(
+        n, p, T, _p(F), f_tv, _p(G), g_tv, _p(_a(V)), int(v_tv), _p(_a(W)), int(w_tv),
+        _p(_a(m0)), _p(_a(C0)), _p(times), _p(y), int(keep_init), _p(tm),
         *(_p(out[k]) for k in ("m", "C", "a", "R", "f", "Q")))
     out["time"] = tm
     out["status"] = st
@@ -121,7 +124,7 @@ def backward_sample(n, G, W, filt, z, keep_init=True):
     return dict(theta=theta, status=st)
 
 
-def ffbs(n, p, F, G, V, W, m0, C0, times, y, z, v_tv=False):
+def ffbs(n, p, F, G, V, W, m0, C0, times, y, z, v_tv=False, w_tv=False):
     times = _a(times)
     T = times.size
     rows = T + 1
@@ -131,8 +134,7 @@ def ffbs(n, p, F, G, V, W, m0, C0, times, y, z, v_tv=False):
     out = {k: np.empty((rows, d)) for k, d in
            dict(theta=n, m=n, C=n * n, a=n, R=n * n).items()}
     tm = np.empty(rows)
-    fn = lib().oracle_ffbs_vt if v_tv else lib().oracle_ffbs
-    st = fn(n, p, T, _p(F), f_tv, _p(G), g_tv, _p(_a(V)), _p(_a(W)),
+    st = lib().oracle_ffbs_tv(n, p, T, _p(F), f_tv, _p(G), g_tv, _p(_a(V)), int(v_tv), _p(_a(W)), int(w_tv),
                            _p(_a(m0)), _p(_a(C0)), _p(times), _p(y), _p(z), _p(tm),
                            *(_p(out[k]) for k in ("theta", "m", "C", "a", "R")))
     out["time"] = tm

@@ -386,3 +386,38 @@ def test_filter_from_saved_state_and_forecast(eng, oracle):
         _exact(f, o["f"][h], "forecast mean"); _exact(q.ravel(), o["Q"][h], "forecast variance")
     # first forecast step is oneStepPrediction on the state itself (dt = 0)
     assert np.allclose(fc[0][1], mod.f(0.0).T @ full[-1].mt)
+
+
+@pytest.mark.parametrize("shared", [True, False])
+def test_time_varying_W_filter_and_ffbs(eng, oracle, shared):
+    """DlmFsvSystem.ffbs (DlmFsvSystem.scala:137-167): KalmanFilter.step with params.copy(w = W_t)
+    forward, Smoothing.step(model, W_t) for the transition t -> t + 1 backward; with V_t as well."""
+    from bayesian_dlms_b200 import Model, SERIES_MAJOR, dlm
+    rng = np.random.default_rng(77 + int(shared))
+    B, T, n, p = 4, 45, 3, 2
+    mod = dlm.polynomial(1) * dlm.polynomial(2)
+    m0, C0 = rng.standard_normal(n), H.spd(rng, n, 4.0)
+    times = np.cumsum(rng.choice([1.0, 2.0], T))
+    nb = 1 if shared else B
+    Wb = np.stack([np.stack([H.spd(rng, n, 0.4) for _ in range(T)]) for _ in range(nb)])
+    Vb = np.stack([np.stack([H.spd(rng, p, 2.0) for _ in range(T)]) for _ in range(nb)])
+    y = np.stack([H.simulate(mod, np.eye(p), Wb[0, 0], m0, C0, times, rng, missing=0.1) for _ in range(B)])
+    z = rng.standard_normal((B, T + 1, n))
+    model = Model.build(mod, times=times)
+    flat = lambda M, k: np.ascontiguousarray(M.transpose(0, 1, 3, 2).reshape(M.shape[0], T, k))  # noqa: E731
+    Wf, Vf = flat(Wb, n * n), flat(Vb, p * p)
+    if shared:
+        params = dict(V=Vf[0], W=Wf[0], m0=m0, C0=C0, v_tv=True, w_tv=True)
+    else:
+        params = dict(V=_cuda(Vf), W=_cuda(Wf), m0=m0, C0=C0, v_tv=True, w_tv=True, per_series=("V", "W"))
+    f = eng.filter(model, params, _cuda(y), layout=SERIES_MAJOR)
+    s = eng.ffbs(model, params, _cuda(y), _cuda(z), layout=SERIES_MAJOR)
+    assert int(f["status"].max()) == 0 and int(s["status"].max()) == 0
+    cm = oracle.oracle.cm
+    for b in range(B):
+        Vt, Wt = Vf[0 if shared else b], Wf[0 if shared else b]
+        o = oracle.kf_filter(n, p, model.F, model.G, Vt, Wt, m0, cm(C0), times, y[b], v_tv=True, w_tv=True)
+        for k in ("m", "C", "a", "R", "f", "Q"):
+            _exact(f[k][b].cpu().numpy()[1:], o[k][1:], k)
+        th = oracle.ffbs(n, p, model.F, model.G, Vt, Wt, m0, cm(C0), times, y[b], z[b], v_tv=True, w_tv=True)
+        _exact(s["theta"][b].cpu().numpy(), th["theta"], "theta")
