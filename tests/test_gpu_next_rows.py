@@ -421,3 +421,21 @@ def test_time_varying_W_filter_and_ffbs(eng, oracle, shared):
             _exact(f[k][b].cpu().numpy()[1:], o[k][1:], k)
         th = oracle.ffbs(n, p, model.F, model.G, Vt, Wt, m0, cm(C0), times, y[b], z[b], v_tv=True, w_tv=True)
         _exact(s["theta"][b].cpu().numpy(), th["theta"], "theta")
+
+
+def test_gibbs_draw_host_buffers_time_major(eng, oracle):
+    """Same call with HOST (numpy) buffers and the time-major layout: the library stages them."""
+    from bayesian_dlms_b200 import TIME_MAJOR
+    rng = np.random.default_rng(5)
+    B, n, p, T = 9, 4, 2, 120
+    stats = dict(ssy=rng.uniform(1, 50, (p, B)), ny=rng.integers(50, T, (p, B)).astype(float),
+                 ssw=rng.uniform(1, 50, (n, B)), scatter=np.zeros((n * n, B)))
+    gv, gw = rng.gamma(40.0, 1.0, (p, B)), rng.gamma(70.0, 1.0, (n, B))
+    out = eng.gibbs_draw(n, p, T, stats, dict(v_shape=5.0, v_scale=4.0, w_shape=17.0, w_scale=4.0),
+                         layout=TIME_MAJOR, inject=dict(gamma_v=gv, gamma_w=gw))
+    assert isinstance(out["V"], np.ndarray) and out["V"].shape == (p * p, B)
+    for b in range(B):
+        ov = oracle.gibbs_invgamma(5.0, 4.0, stats["ssy"][:, b], gv[:, b], count=stats["ny"][:, b])
+        ow = oracle.gibbs_invgamma(17.0, 4.0, stats["ssw"][:, b], gw[:, b], count_all=float(T))
+        _exact(out["V"][:, b], oracle.oracle.cm(np.diag(ov["draw"])), "V")
+        _exact(out["W"][:, b], oracle.oracle.cm(np.diag(ow["draw"])), "W")
