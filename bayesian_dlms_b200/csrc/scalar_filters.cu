@@ -12,6 +12,8 @@
 // Same arithmetic contract as the other bit-exact kernels (common.cuh): the reference's
 // operations in the reference's order, no FMA.  OU needs exp(): device exp() and the JVM's
 // differ in the last place, so OU parity is 1e-9 relative, AR(1) is bit exact.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "launch.h"
 #include "small_steps.cuh"
@@ -41,8 +43,8 @@ __device__ __forceinline__ void ar_predict(double phi, double mu, double sigma, 
   }
 }
 
-template <bool OU, bool FFBS>
-__global__ void __launch_bounds__(128)
+template <bool OU, bool FFBS, int kAhead, int MINB>
+__global__ void __launch_bounds__(128, MINB)
 ar_kernel(const ArArgs a) {
   const int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (b >= a.B) return;
@@ -57,7 +59,6 @@ ar_kernel(const ArArgs a) {
   const View &om = FFBS ? a.sm : a.m, &oC = FFBS ? a.sC : a.C;
   stv(om, b, 0, m); stv(oC, b, 0, C); stv(a.a, b, 0, m); stv(a.R, b, 0, C);
   // y (and v) do not depend on the recursion: keep kAhead steps of them in flight
-  constexpr int kAhead = 8;
   double yq[kAhead], vq[kAhead];
 #pragma unroll
   for (int i = 0; i < kAhead; ++i) {
@@ -220,16 +221,36 @@ cudaError_t launch_conj(const ConjArgs &a, const double *hG, const double *hF, c
 
 }  // namespace
 
+template <int AHEAD, int MINB>
+static void launch_ar_ahead(const ArArgs &a, unsigned blocks, int threads, cudaStream_t stream) {
+  if (a.ou) {
+    if (a.ffbs) ar_kernel<true, true, AHEAD, MINB><<<blocks, threads, 0, stream>>>(a);
+    else ar_kernel<true, false, AHEAD, MINB><<<blocks, threads, 0, stream>>>(a);
+  } else {
+    if (a.ffbs) ar_kernel<false, true, AHEAD, MINB><<<blocks, threads, 0, stream>>>(a);
+    else ar_kernel<false, false, AHEAD, MINB><<<blocks, threads, 0, stream>>>(a);
+  }
+}
+
 cudaError_t launch_ar(const ArArgs &a, cudaStream_t stream) {
   if (a.B == 0) return cudaSuccess;
-  const unsigned blocks = (unsigned)((a.B + 127) / 128);
-  if (a.ou) {
-    if (a.ffbs) ar_kernel<true, true><<<blocks, 128, 0, stream>>>(a);
-    else ar_kernel<true, false><<<blocks, 128, 0, stream>>>(a);
-  } else {
-    if (a.ffbs) ar_kernel<false, true><<<blocks, 128, 0, stream>>>(a);
-    else ar_kernel<false, false><<<blocks, 128, 0, stream>>>(a);
+  // tuning knobs (profiles/r1_tuning.txt): BDLM_AR_AHEAD = 1 | 2 | 4 | 8 prefetch depth,
+  // BDLM_AR_MINB = 1 | 8 resident blocks per SM asked of ptxas.  Measured: occupancy beats
+  // per-thread prefetch depth (depth 1 at 8 blocks/SM: 13.1 ms; depth 8 at 4 blocks: 21.5 ms).
+  static const int ahead = std::getenv("BDLM_AR_AHEAD") ? std::atoi(std::getenv("BDLM_AR_AHEAD")) : 1;
+  static const int minb = std::getenv("BDLM_AR_MINB") ? std::atoi(std::getenv("BDLM_AR_MINB")) : 8;
+  const int th = 128;
+  const unsigned blocks = (unsigned)((a.B + th - 1) / th);
+#define BDLM_AR_CASE(A_)                                              \
+  if (ahead == A_) {                                                  \
+    if (minb >= 8) launch_ar_ahead<A_, 8>(a, blocks, th, stream);     \
+    else launch_ar_ahead<A_, 1>(a, blocks, th, stream);               \
+    return cudaGetLastError();                                        \
   }
+  BDLM_AR_CASE(2) BDLM_AR_CASE(4) BDLM_AR_CASE(8)
+#undef BDLM_AR_CASE
+  if (minb >= 8) launch_ar_ahead<1, 8>(a, blocks, th, stream);
+  else launch_ar_ahead<1, 1>(a, blocks, th, stream);
   return cudaGetLastError();
 }
 
