@@ -630,8 +630,13 @@ __device__ __forceinline__ void fwd_row(const ScanModel<N> &md, const double (&W
   }
 }
 
+// BDLM_SCAN_MINB: resident blocks per SM asked of ptxas for the two apply sweeps (tuning knob,
+// profiles/r1_tuning.txt)
+#ifndef BDLM_SCAN_MINB
+#define BDLM_SCAN_MINB 1
+#endif
 template <int N, bool VEC, bool FUSE>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, BDLM_SCAN_MINB)
 fwd_apply_kernel(const ScanModel<N> md, const double *__restrict__ y, int64_t T, int64_t M,
                  const FElem<N> *pre /* [M+1] inclusive scan with slot 0 = start */,
                  int keep_init, KfViews kf, int32_t *status,
@@ -763,7 +768,7 @@ __device__ __forceinline__ void bwd_row(const ScanModel<N> &md, const double (&W
 }
 
 template <int N, bool VEC>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, BDLM_SCAN_MINB)
 bwd_apply_kernel(const ScanModel<N> md, View fm, View fC, int64_t nrows, int64_t M,
                  const SElem<N> *suf /* [M+1] suffix-inclusive scan, slot M = terminal */,
                  View sv, View Sv, int32_t *status,
