@@ -312,6 +312,39 @@ def gibbs_leg(eng, dev, B=4096, T=2000, sweeps=3):
             "posterior_mean_V_last": float(res["V"][-1].mean())}
 
 
+def gibbs_wishart_leg(eng, dev, B=65536, T=1000, sweeps=2):
+    """BASELINE.json config 4 as a sampler: correlated model n = p = 8, SVD filter + SVD sampler
+    (GibbsSampling.stepSvd's FFBS, Gibbs.scala:182-198) with an inverse-Wishart draw of the full W
+    (GibbsWishart.sampleSystemMatrix, GibbsWishart.scala:16-35) and inverse-gamma draws of diag(V),
+    65 536 series, every sweep device-resident."""
+    import torch
+    from bayesian_dlms_b200 import Model, SERIES_MAJOR, dlm, gibbs
+    mod = dlm.polynomial(1)
+    for _ in range(7):
+        mod = mod * dlm.polynomial(1)
+    n = 8
+    V = np.diag([1.0, 4.0] * 4)
+    W = np.diag([0.75, 1.25] * 4) + 0.5 * (np.eye(8, k=1) + np.eye(8, k=-1))
+    init = dict(V=V, W=W, m0=np.zeros(n), C0=np.eye(n))
+    prior = dict(v_shape=6.0, v_scale=5.0, w_nu=10.0, w_psi=np.eye(n))  # CorrelatedModel.scala:85-86
+    g = torch.Generator(device=dev).manual_seed(20260104)
+    y = torch.randn((B, T, n), generator=g, device=dev, dtype=torch.float64) * 2.0
+    model = Model.build(mod, T=T)
+    gibbs.sample(eng, model, y, prior, init, 1, seed=1, layout=SERIES_MAJOR, svd=True, record=False)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    res = gibbs.sample(eng, model, y, prior, init, sweeps, seed=2, layout=SERIES_MAJOR, svd=True,
+                       record=False)
+    e1.record()
+    torch.cuda.synchronize()
+    t = e0.elapsed_time(e1) * 1e-3
+    return {"config": "config4: %d series x T=%d, %d Gibbs sweeps (normals + SVD-FFBS + stats + "
+                      "inverse-Wishart W, inverse-gamma V), device-resident" % (B, T, sweeps),
+            "series_sweeps_per_s": B * sweeps / t, "ms_per_sweep": t * 1e3 / sweeps,
+            "status_max": int(res["status"].max())}
+
+
 def ar_leg(eng, dev, with_cpu=True, B=1_000_000, T=1000):
     """Next row f3: scalar AR(1) FFBS (FilterAr.ffbs, FilterAr.scala:77-83), the inner loop of the
     stochastic-volatility samplers, 1e6 series x T = 1000, per-series parameters and per-step
@@ -690,10 +723,12 @@ def main():
                 except Exception as ex:
                     line[key] = {"error": repr(ex)}
                 torch.cuda.empty_cache()
-            try:
-                line["gibbs"] = gibbs_leg(eng, dev)
-            except Exception as ex:
-                line["gibbs"] = {"error": repr(ex)}
+            for key, fn in (("gibbs", gibbs_leg), ("gibbs_wishart", gibbs_wishart_leg)):
+                try:
+                    line[key] = fn(eng, dev)
+                except Exception as ex:
+                    line[key] = {"error": repr(ex)}
+                torch.cuda.empty_cache()
         if scan_dist is not None:
             line["scan"] = scan_dist
         if not args.no_cpu and world >= 1:
