@@ -1193,7 +1193,9 @@ template <int OP, int NT, int PT>
 cudaError_t launch_dims(const WarpArgs &wa, cudaStream_t stream) {
   Ws sz(nullptr, wa.bt.n, wa.bt.p, OP);
   const int ws_doubles = (int)((sz.total + 1) & ~(size_t)1);
-  const int wpb = 2;
+  // two warps per block unless their workspaces would not fit one SM's shared memory (n or p
+  // close to 32: a single workspace is > 100 KB)
+  const int wpb = ((size_t)2 * ws_doubles * sizeof(double) <= (size_t)200 * 1024) ? 2 : 1;
   const size_t smem = (size_t)wpb * ws_doubles * sizeof(double);
   cudaError_t e = cudaFuncSetAttribute(warp_kernel<OP, NT, PT>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

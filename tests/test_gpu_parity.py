@@ -123,7 +123,23 @@ CASES = {
                                      np.eye(7)), 26, 0.1, True, 4),
     "seasonal13_irregular": (H.seasonal13, 21, 0.1, True, 5),
     "correlated8": (H.correlated8, 20, 0.2, True, 7),
+    # edge shapes: a single observation; more observations than states (eight sensors sharing a
+    # 7-dimensional state, Temperature.scala:41-44); the largest supported state (n = 32)
+    "single_step": (lambda: (_dlm().polynomial(2), np.array([[3.0]]), np.diag([2.0, 1.0]),
+                             np.zeros(2), 100.0 * np.eye(2)), 1, 0.0, False, 5),
+    "shared_state_p8_n7": (lambda: _shared_state(), 18, 0.25, True, 6),
+    "max_dim_n32": (lambda: (_dlm().seasonal(48, 16), np.array([[1.0]]),
+                             np.diag(np.linspace(0.05, 0.5, 32)), np.zeros(32), np.eye(32)),
+                    9, 0.1, False, 3),
 }
+
+
+def _shared_state():
+    dlm = _dlm()
+    base = dlm.polynomial(1) + dlm.seasonal(24, 3)
+    mod = dlm.Dlm(lambda t: np.tile(base.f(t), (1, 8)), base.g)
+    return (mod, np.diag(np.linspace(0.5, 2.0, 8)), np.diag([0.01, 0.2, 0.4, 0.5, 0.2, 0.1, 0.4]),
+            np.zeros(7), np.eye(7))
 
 
 def _make_case(name, seed=3):
@@ -265,7 +281,7 @@ def test_loglik_matches_oracle(eng, oracle, name):
 @pytest.mark.parametrize("name", ["first_order", "second_order", "second_order_irregular",
                                   "kat_bivariate", "seasonal13", "seasonal13_irregular",
                                   "seasonal7", "seasonal7_irregular",
-                                  "correlated8"])
+                                  "correlated8", "single_step", "shared_state_p8_n7", "max_dim_n32"])
 @pytest.mark.parametrize("svd", [False, True])
 def test_ffbs_bit_for_bit_with_injected_normals(eng, oracle, name, svd):
     from bayesian_dlms_b200 import Model, SERIES_MAJOR, TIME_MAJOR
