@@ -25,7 +25,7 @@ _ip = C.POINTER(C.c_int32)
 
 SYMBOLS = [
     "bdlm_create", "bdlm_destroy", "bdlm_last_error", "bdlm_version", "bdlm_set_stream",
-    "bdlm_sync", "bdlm_launch_count", "bdlm_set_staging_bytes", "bdlm_kf_filter",
+    "bdlm_sync", "bdlm_set_rng", "bdlm_launch_count", "bdlm_set_staging_bytes", "bdlm_kf_filter",
     "bdlm_rts_smooth", "bdlm_kf_filter_smooth", "bdlm_loglik", "bdlm_ffbs",
     "bdlm_svd_filter", "bdlm_svd_ffbs", "bdlm_gibbs_suffstats", "bdlm_wave_series",
     "bdlm_fp64_peak_tflops", "bdlm_scan_filter_smooth", "bdlm_scan_elem_doubles",
@@ -112,6 +112,7 @@ def load():
     lib.bdlm_last_error.restype = C.c_char_p
     lib.bdlm_set_stream.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     lib.bdlm_sync.argtypes = [C.c_void_p]
+    lib.bdlm_set_rng.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int64]
     lib.bdlm_launch_count.argtypes = [C.c_void_p]
     lib.bdlm_launch_count.restype = C.c_int64
     lib.bdlm_set_staging_bytes.argtypes = [C.c_void_p, C.c_int64]
@@ -199,6 +200,11 @@ class Context:
 
     def sync(self):
         self.check(load().bdlm_sync(self._h))
+
+    def set_rng(self, seed: int, sweep: int = 0, first_series: int = 0):
+        """Philox key of the FFBS calls' on-device RNG mode (z=None); ``first_series`` = global
+        index of the call's first series when a batch is sharded over ranks / calls."""
+        self.check(load().bdlm_set_rng(self._h, int(seed), int(sweep), int(first_series)))
 
     def launch_count(self) -> int:
         return int(load().bdlm_launch_count(self._h))

@@ -298,7 +298,10 @@ class Engine:
         mem, _ = _mem_and_ptr(y)
         B = self._batch_of(model, y, layout)
         rows = model.T + 1
-        assert tuple(z.shape) == self._shape(layout, B, rows, model.n), (z.shape, rows, model.n)
+        # z=None: the kernels draw their own normals (Philox, Context.set_rng(seed, sweep))
+        assert z is None or tuple(z.shape) == self._shape(layout, B, rows, model.n), \
+            (z.shape, rows, model.n)
+        zptr = None if z is None else _mem_and_ptr(z)[1]
         compat = capi.SVD_CONSISTENT_W if (svd and consistent_w) else 0
         pr, keep = self._problem(model, params, y, layout, True, compat, B, mem)
         theta = self._alloc(y, self._shape(layout, B, rows, model.n), pinned=pinned)
@@ -311,13 +314,13 @@ class Engine:
             fo, so = self._outs(capi.SvdOut, SVD_FIELDS, want_kf, y, layout, B, rows,
                                 self._svd_dims(model), pinned)
             out.update({"svd_" + k: v for k, v in fo.items()})
-            self.ctx.check(lib.bdlm_svd_ffbs(self.ctx.handle, pr, _mem_and_ptr(z)[1],
+            self.ctx.check(lib.bdlm_svd_ffbs(self.ctx.handle, pr, zptr,
                                              _mem_and_ptr(theta)[1], so, gs, stp))
         else:
             fo, ko = self._outs(capi.KfOut, KF_FIELDS, want_kf, y, layout, B, rows,
                                 self._kf_dims(model), pinned)
             out.update(fo)
-            self.ctx.check(lib.bdlm_ffbs(self.ctx.handle, pr, _mem_and_ptr(z)[1],
+            self.ctx.check(lib.bdlm_ffbs(self.ctx.handle, pr, zptr,
                                          _mem_and_ptr(theta)[1], ko, gs, stp))
         if st is not None:
             out["status"] = st

@@ -33,6 +33,8 @@ struct bdlm_ctx {
   size_t arena_bytes = 0;
   size_t staging_cap = (size_t)8 << 30;
   size_t workspace_cap = (size_t)48 << 30;  // device-mode spill/transposes per launch
+  unsigned long long rng_seed = 0, rng_sweep = 0;  // on-device RNG mode of the FFBS calls (z == NULL)
+  long long rng_first = 0;                         // global index of a call's first series
   void *scan_table = nullptr;          // scan.cu forward table of the model in scan_key
   std::vector<double> scan_key;
   bool use_group = std::getenv("BDLM_NO_GROUP_KERNEL") == nullptr;  // A/B switch for profiling
@@ -89,6 +91,7 @@ struct DevCall {
   int op;
   bdlm_problem pr;  // F, G, times: host; everything else device
   int64_t b0, Bc, Bp;
+  int64_t rng_b0 = 0;  // index of series b0 within the CALL (slabs / chunks restart b0 at 0)
   bdlm_kf_out kf{};
   bdlm_smooth_out sm{};
   bdlm_svd_out svd{};
@@ -412,7 +415,7 @@ int run_dev(bdlm_ctx *c, DevCall d, Bump bump) {
     a.gv = mk_rowview(const_cast<double *>(d.rng.gamma_v), L, d.b0, d.Bp, p.p);
     a.gw = mk_rowview(const_cast<double *>(d.rng.gamma_w), L, d.b0, d.Bp, n);
     a.bart = mk_rowview(const_cast<double *>(d.rng.bartlett), L, d.b0, d.Bp, n * n);
-    a.seed = d.rng.seed; a.sweep = d.rng.sweep;
+    a.seed = d.rng.seed; a.sweep = d.rng.sweep; a.base = c->rng_first + d.rng_b0;
     a.V = mk_rowview(d.V_out, L, d.b0, d.Bp, (int64_t)p.p * p.p);
     a.W = mk_rowview(d.W_out, L, d.b0, d.Bp, n * n);
     a.v_shape_rate = mk_rowview(d.v_sr, L, d.b0, d.Bp, 2 * p.p);
@@ -510,6 +513,8 @@ int run_dev(bdlm_ctx *c, DevCall d, Bump bump) {
   wa.s = mk_view(d.sm.s, L, d.b0, d.Bp, R, n);
   wa.S = mk_view(d.sm.S, L, d.b0, d.Bp, R, n * n);
   wa.z = mk_cview(d.z, L, d.b0, d.Bp, R, n);
+  wa.rng_seed = c->rng_seed; wa.rng_sweep = c->rng_sweep;
+  wa.rng_base = c->rng_first + d.rng_b0;
   wa.theta = mk_view(d.theta, L, d.b0, d.Bp, R, n);
   wa.svd.m = mk_view(d.svd.m, L, d.b0, d.Bp, R, n);
   wa.svd.dc = mk_view(d.svd.dc, L, d.b0, d.Bp, R, n);
@@ -579,7 +584,7 @@ int run_device_mode(bdlm_ctx *c, DevCall d) {
   if (rc) return rc;
   for (int64_t b0 = 0; b0 < B; b0 += chunk) {
     DevCall s = d;
-    s.b0 = b0; s.Bc = std::min(chunk, B - b0); s.Bp = B;
+    s.b0 = b0; s.Bc = std::min(chunk, B - b0); s.Bp = B; s.rng_b0 = b0;
     Bump bump{c->arena, 0, c->arena_bytes};
     rc = run_dev(c, s, bump);
     if (rc) return rc;
@@ -650,7 +655,7 @@ int run_host_mode(bdlm_ctx *c, DevCall d) {
     CU(cudaStreamWaitEvent(c->stream, c->ev_in[s], 0));
     if (it >= 2) CU(cudaStreamWaitEvent(c->stream, c->ev_out[s], 0));
     DevCall t = d;
-    t.pr.mem = BDLM_DEVICE; t.pr.B = Bs; t.b0 = 0; t.Bc = Bs; t.Bp = Bs;
+    t.pr.mem = BDLM_DEVICE; t.pr.B = Bs; t.b0 = 0; t.Bc = Bs; t.Bp = Bs; t.rng_b0 = b0;
     {
       std::vector<Field> tf;
       collect_fields(t, tf);
@@ -746,6 +751,12 @@ int bdlm_set_stream(bdlm_ctx *c, void *s, int use_own) {
   return 0;
 }
 
+int bdlm_set_rng(bdlm_ctx *c, uint64_t seed, uint64_t sweep, int64_t first_series) {
+  if (!c) return BDLM_E_ARG;
+  c->rng_seed = seed; c->rng_sweep = sweep; c->rng_first = first_series;
+  return 0;
+}
+
 int bdlm_sync(bdlm_ctx *c) {
   if (!c) return BDLM_E_ARG;
   CU(cudaSetDevice(c->device));
@@ -830,7 +841,7 @@ int bdlm_ffbs(bdlm_ctx *c, const bdlm_problem *p, const double *z, double *theta
               const bdlm_kf_out *kf, const bdlm_gibbs_stats *stats, int32_t *status) {
   int rc = validate(c, A_FFBS, p);
   if (rc) return rc;
-  if (!z || !theta) return fail(c, BDLM_E_ARG, "null z or theta");
+  if (!theta) return fail(c, BDLM_E_ARG, "null theta");  // z == NULL: on-device Philox normals
   DevCall d{}; d.op = A_FFBS; d.pr = *p; d.z = z; d.theta = theta;
   if (kf) d.kf = *kf;
   if (stats) d.stats = *stats;
@@ -851,7 +862,7 @@ int bdlm_svd_ffbs(bdlm_ctx *c, const bdlm_problem *p, const double *z, double *t
                   const bdlm_svd_out *filt, const bdlm_gibbs_stats *stats, int32_t *status) {
   int rc = validate(c, A_SVD_FFBS, p);
   if (rc) return rc;
-  if (!z || !theta) return fail(c, BDLM_E_ARG, "null z or theta");
+  if (!theta) return fail(c, BDLM_E_ARG, "null theta");  // z == NULL: on-device Philox normals
   DevCall d{}; d.op = A_SVD_FFBS; d.pr = *p; d.z = z; d.theta = theta;
   if (filt) d.svd = *filt;
   if (stats) d.stats = *stats;

@@ -26,6 +26,12 @@ namespace bdlm {
 
 namespace {
 
+// The FFBS kernels' normals (rng.cuh) use the caller's seed as the Philox key; the conjugate
+// draws use a different key so the two families of variates never share a counter block.
+__device__ __forceinline__ unsigned long long draw_key(unsigned long long seed) {
+  return seed ^ 0x9E3779B97F4A7C15ULL;
+}
+
 // Standard Gamma(shape, 1), Marsaglia & Tsang (2000); shape < 1 through the U^(1/shape) boost.
 __device__ double gamma_mt(curandStatePhilox4_32_10_t *rng, double shape) {
   double boost = 1.0;
@@ -84,7 +90,8 @@ invgamma_kernel(const GibbsDrawArgs a) {
       g = inj.ptr[b * inj.sb + i * inj.sk];
     } else {
       curandStatePhilox4_32_10_t rng;
-      curand_init(a.seed, (unsigned long long)(b * (a.p + a.n) + (is_v ? i : a.p + i)),
+      curand_init(draw_key(a.seed),
+                  (unsigned long long)((a.base + b) * (a.p + a.n) + (is_v ? i : a.p + i)),
                   a.sweep * 1024ULL, &rng);
       g = gamma_mt(&rng, shape);
     }
@@ -152,7 +159,7 @@ invwishart_kernel(const GibbsDrawArgs a) {
       v = 0.0;
       if (i >= j) {
         curandStatePhilox4_32_10_t rng;
-        curand_init(a.seed, (unsigned long long)((a.B * (a.p + a.n)) + b * nn + k),
+        curand_init(draw_key(a.seed) ^ 0x5DEECE66DULL, (unsigned long long)((a.base + b) * nn + k),
                     a.sweep * 1024ULL, &rng);
         // ChiSquared(k) = Gamma(k / 2, 2)
         v = (i == j) ? sqrt(2.0 * gamma_mt(&rng, 0.5 * (dof - i))) : curand_normal_double(&rng);

@@ -21,6 +21,7 @@
 // sufficient statistics (Gibbs.scala:29-43,63-73; GibbsWishart.scala:22-29).
 #include "common.cuh"
 #include "launch.h"
+#include "rng.cuh"
 #include "warp_linalg.cuh"
 
 namespace bdlm {
@@ -480,7 +481,8 @@ group_kernel(const WarpArgs wa) {
     }
     __syncwarp();
     {
-      const double z = wa.z.ptr[b * wa.z.sb + (int64_t)(rows - 1) * wa.z.sr + j * wa.z.sk];
+      const double z = wa.z.ptr ? wa.z.ptr[b * wa.z.sb + (int64_t)(rows - 1) * wa.z.sr + j * wa.z.sk]
+                                : philox_normal(RngKey{wa.rng_seed, wa.rng_sweep}, wa.rng_base + b, rows, rows - 1, N, j);
       th_j = eig_draw<N>(cx, m_j, z, st);
     }
     store_vec(wa.theta, rows - 1, th_j);
@@ -501,7 +503,8 @@ group_kernel(const WarpArgs wa) {
       }
       m_j = sp[j];
       const double a1_j = sp1[N + NN + j];
-      const double z = wa.z.ptr[b * wa.z.sb + (int64_t)r * wa.z.sr + j * wa.z.sk];
+      const double z = wa.z.ptr ? wa.z.ptr[b * wa.z.sb + (int64_t)r * wa.z.sr + j * wa.z.sk]
+                                : philox_normal(RngKey{wa.rng_seed, wa.rng_sweep}, wa.rng_base + b, rows, r, N, j);
       __syncwarp();
 #pragma unroll
       for (int k = 0; k < N; ++k) { Crow[k] = cx.S0[j + k * LD]; Arow[k] = cx.S1[j + k * LD]; }

@@ -15,6 +15,7 @@
 
 #include "common.cuh"
 #include "launch.h"
+#include "rng.cuh"
 #include "warp_linalg.cuh"
 
 namespace bdlm {
@@ -124,6 +125,14 @@ __device__ __forceinline__ void load_cview(int lane, const CView &v, int64_t b, 
                                            int cnt, double *dst) {
   const double *p = v.ptr + b * v.sb + row * v.sr;
   for (int k = lane; k < cnt; k += 32) dst[k] = p[k * v.sk];
+}
+
+// The n normals consumed when drawing theta[row]: injected, or generated (rng.cuh).
+__device__ __forceinline__ void load_z(int lane, const WarpArgs &wa, int64_t b, int64_t row, int rows,
+                                       int n, double *dst) {
+  if (wa.z.ptr) { load_cview(lane, wa.z, b, row, n, dst); return; }
+  const RngKey key{wa.rng_seed, wa.rng_sweep};
+  for (int k = lane; k < n; k += 32) dst[k] = philox_normal(key, wa.rng_base + b, rows, (int)row, n, k);
 }
 
 // Model matrices for observation t into the warp's G / F slots.
@@ -647,7 +656,7 @@ warp_kernel(const WarpArgs wa, const int ws_doubles) {
 
   if (OP == kOpFfbs) {
     // Smoothing.sample (Smoothing.scala:114-122), initialise (:105-109), step (:74-103)
-    load_cview(lane, wa.z, b, rows - 1, n, ws.v3);
+    load_z(lane, wa, b, rows - 1, rows, n, ws.v3);
     __syncwarp();
     st |= mvn_eig_draw(lane, n, ws, ws.m, ws.C, ws.v3, ws.th);
     store_view(lane, wa.theta, b, rows - 1, n, ws.th);
@@ -658,7 +667,7 @@ warp_kernel(const WarpArgs wa, const int ws_doubles) {
       const double *sp = spill + (size_t)r * wa.spill_k, *sp1 = sp + wa.spill_k;
       for (int k = lane; k < n; k += 32) { ws.m[k] = sp[k]; ws.a[k] = sp1[n + nn + k]; }
       for (int k = lane; k < nn; k += 32) { ws.C[k] = sp[n + k]; ws.R[k] = sp1[2 * n + nn + k]; }
-      load_cview(lane, wa.z, b, r, n, ws.v3);
+      load_z(lane, wa, b, r, rows, n, ws.v3);
       if (bt.w_tv) {  // W of the transition r -> r + 1 (DlmFsvSystem.scala:155-163)
         PView wt = bt.W;
         wt.ptr += (int64_t)tobs * bt.W_sr;
@@ -693,7 +702,7 @@ warp_kernel(const WarpArgs wa, const int ws_doubles) {
 
   if (OP == kOpSvdFfbs) {
     // SvdSampler.sample (SvdSampler.scala:54-60), initialise (:38-45), step (:15-36)
-    load_cview(lane, wa.z, b, rows - 1, n, ws.v3);
+    load_z(lane, wa, b, rows - 1, rows, n, ws.v3);
     for (ElemIter it(lane, n, n); it.ok(); it.next())
       ws.t1[it.i + it.j * n] = ws.C[it.i + it.j * n] * ws.dcv[it.j];
     __syncwarp();
@@ -709,7 +718,7 @@ warp_kernel(const WarpArgs wa, const int ws_doubles) {
         ws.m[k] = sp[k]; ws.dcv[k] = sp[n + k]; ws.a[k] = sp1[2 * n + nn + k];
       }
       for (int k = lane; k < nn; k += 32) ws.C[k] = sp[2 * n + k];
-      load_cview(lane, wa.z, b, r, n, ws.v3);
+      load_z(lane, wa, b, r, rows, n, ws.v3);
       __syncwarp();
       w_mm(lane, n, n, n, ws.Wsq, n, false, ws.G, n, false, ws.t1, n);
       w_mm(lane, n, n, n, ws.t1, n, false, ws.C, n, false, ws.t2, n);
@@ -1090,7 +1099,7 @@ svd4_kernel(const WarpArgs wa, const int shared_doubles, const int series_double
       if (!live(s)) continue;
       const Ws ws = slot(s).ws;
       const int64_t b = b0 + s;
-      load_cview(lane, wa.z, b, rows - 1, n, ws.v3);
+      load_z(lane, wa, b, rows - 1, rows, n, ws.v3);
       for (ElemIter it(lane, n, n); it.ok(); it.next())
         ws.t1[it.i + it.j * n] = ws.C[it.i + it.j * n] * ws.dcv[it.j];
       __syncwarp();
@@ -1128,7 +1137,7 @@ svd4_kernel(const WarpArgs wa, const int shared_doubles, const int series_double
         if (!live(s)) continue;
         const Slot q = slot(s);
         const Ws &ws = q.ws;
-        load_cview(lane, wa.z, b0 + s, r, n, ws.v3);
+        load_z(lane, wa, b0 + s, r, rows, n, ws.v3);
         w_mm(lane, n, n, n, ws.C, n, false, q.sV, n, false, ws.t5, n);  // uh
         for (int k = lane; k < n; k += 32) ws.v1[k] = 1.0 / q.sS[k];    // dh
         __syncwarp();

@@ -32,7 +32,9 @@ struct WarpArgs {
   Batch bt;
   KfViews kf;          // user-visible KfState outputs (any may be null)
   View s, S;           // smoother outputs
-  CView z;             // injected normals, rows x n
+  CView z;             // injected normals, rows x n; ptr == nullptr: generate them (rng)
+  unsigned long long rng_seed, rng_sweep;  // Philox key of the on-device RNG mode
+  long long rng_base;  // global index of series 0 of this launch (subsequence = rng_base + b)
   View theta;          // sampled path, rows x n (input for kOpStats)
   SvdViews svd;
   StatViews stats;
@@ -132,6 +134,7 @@ struct GibbsDrawArgs {
   StatViews stats;          // inputs (sb, sk strides)
   View gv, gw, bart;        // injected standard-gamma variates [p], [n] / Bartlett factor [n*n]
   unsigned long long seed, sweep;
+  long long base;           // global index of chain 0 of this launch (Philox subsequences)
   View V, W;                // outputs: per-chain p*p and n*n (column-major), either may be null
   View v_shape_rate, w_shape_rate;  // optional outputs [2p], [2n]: posterior shapes | rates
   int32_t *status;          // [B] or nullptr (OR-ed)

@@ -17,14 +17,15 @@ from .batch import Engine, Model, TIME_MAJOR
 
 def sample(eng: Engine, model: Model, y, prior: Dict, init: Dict, n_iters: int, *, seed: int = 0,
            layout=TIME_MAJOR, svd: bool = False, record: bool = True,
-           z: Optional[object] = None) -> Dict:
+           z: Optional[object] = None, first_series: int = 0) -> Dict:
     """Run ``n_iters`` Gibbs sweeps for every chain of the batch.
 
     y       CUDA tensor, (T, p, B) time-major or (B, T, p) series-major; NaN = missing
     prior   dict(v_shape, v_scale, and w_shape, w_scale  or  w_nu, w_psi)
     init    dict(V, W, m0, C0): initial DlmParameters shared by all chains (numpy)
-    z       optional pre-drawn normals (n_iters, *theta-shape) for reproducibility checks;
-            default: torch.randn on the device from ``seed``
+    z       optional pre-drawn normals (n_iters, *theta-shape) for bit-exact comparisons;
+            default: the FFBS kernels draw their own (Philox keyed by (seed, sweep)), so no
+            normals are materialised in HBM at all
     Returns dict(V=(iters, p, B) diagonals, W=(iters, n or n*n, B), theta=last path, status=...)
     in time-major orientation regardless of ``layout`` for the recorded chains.
     """
@@ -32,9 +33,6 @@ def sample(eng: Engine, model: Model, y, prior: Dict, init: Dict, n_iters: int, 
     n, p, T = model.n, model.p, model.T
     B = y.shape[2] if layout == TIME_MAJOR else y.shape[0]
     wishart = prior.get("w_psi") is not None
-    gen = torch.Generator(device=y.device)
-    gen.manual_seed(int(seed))
-    zshape = (T + 1, n, B) if layout == TIME_MAJOR else (B, T + 1, n)
     params = dict(init)
     chain_v = torch.empty((n_iters, p, B), dtype=torch.float64, device=y.device) if record else None
     wk = n * n if wishart else n
@@ -45,8 +43,8 @@ def sample(eng: Engine, model: Model, y, prior: Dict, init: Dict, n_iters: int, 
     vdiag = torch.arange(p, device=y.device) * (p + 1)
     wdiag = torch.arange(n, device=y.device) * (n + 1)
     for it in range(n_iters):
-        zi = z[it] if z is not None else torch.randn(zshape, dtype=torch.float64, device=y.device,
-                                                     generator=gen)
+        zi = z[it] if z is not None else None
+        eng.ctx.set_rng(seed, it, first_series)  # ranks sharding the chains pass their offset
         out = eng.ffbs(model, params, y, zi, layout=layout, stats=True, status=True, svd=svd)
         draw_out = eng.gibbs_draw(n, p, T, out, prior, layout=layout, seed=seed, sweep=it,
                                   out=draw_out)

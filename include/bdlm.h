@@ -169,6 +169,14 @@ BDLM_API int bdlm_version(void);
  * restores the context's own (non-blocking) stream. */
 BDLM_API int bdlm_set_stream(bdlm_ctx *ctx, void *cuda_stream, int use_own);
 BDLM_API int bdlm_sync(bdlm_ctx *ctx);
+/* On-device RNG mode of bdlm_ffbs / bdlm_svd_ffbs: when their `z` argument is NULL the kernels
+ * draw the N(0,1) values themselves -- Philox4x32-10 keyed by `seed`, one subsequence per series
+ * / chain (first_series + index within the call: ranks that shard a batch pass the global index
+ * of their first series), offset by (sweep, row, component), so a draw depends only on (seed,
+ * sweep, global series, row, component), not on the batch split, kernel variant or layout.
+ * Callers advance `sweep` once per Gibbs iteration.  Bit-for-bit parity with the reference
+ * needs injected `z`. */
+BDLM_API int bdlm_set_rng(bdlm_ctx *ctx, uint64_t seed, uint64_t sweep, int64_t first_series);
 /* Kernel launches issued by this context since creation (bench.py's gpu_launches). */
 BDLM_API int64_t bdlm_launch_count(bdlm_ctx *ctx);
 /* Cap on the device bytes a mem = BDLM_HOST call may use for staging (default 8 GiB). */
@@ -223,7 +231,8 @@ BDLM_API int bdlm_loglik(bdlm_ctx *ctx, const bdlm_problem *prob, double *transi
  * MultivariateGaussianSvd.draw (MultivariateGaussianSvd.scala:13-22).
  * prob->keep_init must be 1.  z: injected N(0,1) values, rows x n per series, z[row]
  * being the n values consumed when drawing theta[row] (the reference draws the last
- * row first, index 0..n-1 within a row).  theta: rows x n.  kf (optional) receives
+ * row first, index 0..n-1 within a row); NULL = draw them on the device (bdlm_set_rng).
+ * theta: rows x n.  kf (optional) receives
  * the SamplingState's filter moments; stats (optional) the Gibbs sufficient statistics
  * of the drawn path (Gibbs.scala:29-43,63-73; GibbsWishart.scala:22-29). */
 BDLM_API int bdlm_ffbs(bdlm_ctx *ctx, const bdlm_problem *prob, const double *z, double *theta,

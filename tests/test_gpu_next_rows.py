@@ -466,3 +466,50 @@ def test_device_resident_gibbs_wishart(eng, svd):
     assert (Wc[:, 0] > 0).all() and (det > 0).all()
     m = Wc[20:].mean(axis=(0, 2))
     assert 0.2 < m[0] < 2.5 and 0.3 < m[3] < 3.5, m
+
+
+# ------------------------------------------------------------------ on-device RNG mode (z = None)
+
+def test_ffbs_rng_mode_is_keyed_by_seed_sweep_series_row_component(eng):
+    """bdlm_set_rng: with z = NULL the kernels draw Philox normals that depend only on (seed, sweep,
+    global series, row, component): same key -> same path whatever the layout, batch split or
+    kernel (warp, group, four-series SVD); another sweep -> another path; N(0,1) marginals."""
+    import torch
+    from scipy import stats as sst
+    from bayesian_dlms_b200 import Model, SERIES_MAJOR, TIME_MAJOR, dlm
+    rng = np.random.default_rng(2)
+    # (a) n = 1: theta_T = m_T + sqrt(C_T) z  ->  recover z and test it
+    B, T = 40_000, 3
+    mod = dlm.polynomial(1)
+    params = dict(V=[[2.0]], W=[[3.0]], m0=[0.0], C0=[[10.0]])
+    y = _cuda(rng.standard_normal((T, 1, B)))
+    model = Model.build(mod, T=T)
+    eng.ctx.set_rng(11, 0)
+    a = eng.ffbs(model, params, y, None, want_kf=("m", "C"))
+    b = eng.ffbs(model, params, y, None, want_kf=("m", "C"))
+    eng.ctx.set_rng(11, 1)
+    c = eng.ffbs(model, params, y, None)
+    assert torch.equal(a["theta"], b["theta"]) and not torch.equal(a["theta"], c["theta"])
+    z = ((a["theta"][-1, 0] - a["m"][-1, 0]) / a["C"][-1, 0].sqrt()).cpu().numpy()
+    assert abs(z.mean()) < 0.03 and abs(z.var() - 1) < 0.03
+    assert sst.kstest(z, "norm").pvalue > 1e-3
+    assert abs(np.corrcoef(z[:-1], z[1:])[0, 1]) < 0.02          # neighbouring series independent
+    # (b) layout, batch split and kernel variant do not change a series' path
+    for mk, svd in ((H.seasonal7 if hasattr(H, "seasonal7") else None, False), (H.correlated8, True),
+                    (H.seasonal13, False)):
+        if mk is None:
+            continue
+        mod, V, W, m0, C0 = mk()
+        n, p, Bs, Ts = len(m0), V.shape[0], 7, 12
+        ys = np.stack([H.simulate(mod, V, W, m0, C0, np.arange(1.0, Ts + 1), rng, missing=0.1) for _ in range(Bs)])
+        model = Model.build(mod, T=Ts)
+        pr = dict(V=V, W=W, m0=m0, C0=C0)
+        eng.ctx.set_rng(5, 3)
+        s1 = eng.ffbs(model, pr, _cuda(ys), None, layout=SERIES_MAJOR, svd=svd)["theta"].cpu().numpy()
+        t1 = eng.ffbs(model, pr, _cuda(np.ascontiguousarray(ys.transpose(1, 2, 0))), None, layout=TIME_MAJOR,
+                      svd=svd)["theta"].cpu().numpy().transpose(2, 0, 1)
+        _exact(s1, t1, "layout")
+        eng.ctx.set_rng(5, 3, first_series=4)
+        s2 = eng.ffbs(model, pr, _cuda(ys[4:]), None, layout=SERIES_MAJOR, svd=svd)["theta"].cpu().numpy()
+        _exact(s2, s1[4:], "batch split with first_series")
+        eng.ctx.set_rng(5, 3)
