@@ -513,3 +513,41 @@ def test_ffbs_rng_mode_is_keyed_by_seed_sweep_series_row_component(eng):
         s2 = eng.ffbs(model, pr, _cuda(ys[4:]), None, layout=SERIES_MAJOR, svd=svd)["theta"].cpu().numpy()
         _exact(s2, s1[4:], "batch split with first_series")
         eng.ctx.set_rng(5, 3)
+
+
+# ------------------------------------------------------------------ Rao-Blackwellised step (f4)
+
+def test_rao_blackwell_kf_step_over_a_particle_cloud(eng, oracle):
+    """RaoBlackwellFilter.kfStep (RaoBlackwellFilter.scala:43-57) for every parameter particle in
+    ONE call: a batch of B particles, each with its own (V, W, m, C), one observation (T = 1)
+    arriving dt after the particles' common time -> (mt1, ct1) and the conditional likelihood
+    (KalmanFilter.conditionalLikelihood, KalmanFilter.scala:138-153) used as the new weight."""
+    from bayesian_dlms_b200 import Model, SERIES_MAJOR, dlm
+    rng = np.random.default_rng(4)
+    B, n, p = 300, 3, 2
+    mod = dlm.polynomial(1) * dlm.polynomial(2)
+    cm = oracle.oracle.cm
+    Vs = np.stack([cm(H.spd(rng, p, 2.0)) for _ in range(B)])
+    Ws = np.stack([cm(H.spd(rng, n, 0.5)) for _ in range(B)])
+    ms = rng.standard_normal((B, n))
+    Cs = np.stack([cm(H.spd(rng, n, 3.0)) for _ in range(B)])
+    y = np.tile(np.array([[[0.7, np.nan]]]), (B, 1, 1))        # second sensor missing
+    y[::2, 0, 1] = -1.3
+    t_prev, t_now = 41.0, 43.5
+    model = Model.build(mod, times=[t_now], t_init=t_prev)
+    params = dict(V=_cuda(Vs), W=_cuda(Ws), m0=_cuda(ms), C0=_cuda(Cs), per_series=("V", "W", "m0", "C0"))
+    f = eng.filter(model, params, _cuda(y), layout=SERIES_MAJOR, keep_init=False, want=("m", "C", "f", "Q"))
+    ll = eng.loglik(model, params, _cuda(y), layout=SERIES_MAJOR)
+    assert int(f["status"].max()) == 0
+    for b in range(0, B, 7):
+        o = oracle.kf_filter(n, p, model.F, model.G, Vs[b], Ws[b], ms[b], Cs[b], [t_now], y[b],
+                             keep_init=False, t_init=t_prev)
+        _exact(f["m"][b, 0].cpu().numpy(), o["m"][0], "mt1")
+        _exact(f["C"][b, 0].cpu().numpy(), o["C"][0], "ct1")
+        # conditional likelihood of the observed components
+        obs = ~np.isnan(y[b, 0])
+        Q = o["Q"][0].reshape(p, p).T[np.ix_(obs, obs)]
+        e = (y[b, 0] - o["f"][0])[obs]
+        want = -0.5 * (e @ np.linalg.solve(Q, e)) - 0.5 * (obs.sum() * np.log(2 * np.pi) + np.linalg.slogdet(Q)[1])
+        got = float(ll["innovations"][b])
+        assert abs(got - want) <= 1e-9 * max(1.0, abs(want)), (b, got, want)
