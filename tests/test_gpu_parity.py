@@ -395,6 +395,70 @@ def test_large_batch_properties_config2_shape(eng, oracle):
         _exact(S[:, :, b].cpu().numpy(), sm["S"], "S")
 
 
+def test_full_size_properties_config3_and_config4(eng, oracle):
+    """BASELINE configs 3 and 4 at (near) full size, where the oracle is too slow to be the checker:
+    size-independent properties plus bit-exact oracle spot checks on a few series.
+    * config 3 (n = 13, 4096 chains x T = 2000, 10 % missing): with z = 0 the backward sampler
+      returns its conditional means, which ARE the RTS-smoothed means -> FFBS(z = 0) equals the
+      smoother of the same data (different code path: eigen draw vs smoother gain) to 1e-8.
+    * config 4 (n = p = 8, 16 384 series x T = 1000): the SVD filter in its W-consistent mode is
+      the Kalman filter in another parametrisation -> same filtered means to 1e-7; covariance
+      rebuilt from (dc, uc) matches C.  Exercises the four-series kernel with a ragged last warp."""
+    import torch
+    from bayesian_dlms_b200 import Model, SERIES_MAJOR
+    dlm = _dlm()
+    # ---- config 3
+    mod, V, W, m0, C0 = H.seasonal13()
+    B, T, n = 4096, 2000, 13
+    g = torch.Generator(device="cuda").manual_seed(20260103)
+    y = torch.randn((B, T, 1), generator=g, device="cuda", dtype=torch.float64) * 2.0
+    y[torch.rand((B, T, 1), generator=g, device="cuda") < 0.1] = float("nan")
+    model = Model.build(mod, T=T)
+    params = dict(V=V, W=W, m0=m0, C0=C0)
+    z0 = torch.zeros((B, T + 1, n), device="cuda", dtype=torch.float64)
+    th = eng.ffbs(model, params, y, z0, layout=SERIES_MAJOR)
+    sm = eng.filter_smooth(model, params, y, layout=SERIES_MAJOR, want=("s",), textbook=True)
+    eng.sync()
+    assert int(th["status"].max()) == 0 and int(sm["status"].max()) == 0
+    err = ((th["theta"] - sm["s"]).abs() / sm["s"].abs().clamp_min(1e-3)).max().item()
+    assert err < 1e-8, err
+    F, _, G, _, _, p = dlm.materialise(mod, np.arange(1, T + 1.0))
+    for b in (0, B - 1):
+        o = oracle.ffbs(n, p, F, G, dlm.cm(V), dlm.cm(W), m0, dlm.cm(C0), np.arange(1, T + 1.0),
+                        y[b].cpu().numpy(), np.zeros((T + 1, n)))
+        _exact(th["theta"][b].cpu().numpy(), o["theta"], f"config3 theta[{b}]")
+    del th, sm, z0, y
+    torch.cuda.empty_cache()
+    # ---- config 4 (B not a multiple of 4: the last warp of the four-series kernel is ragged)
+    mod, V, W, m0, C0 = H.correlated8()
+    # distinct, DESCENDING variances: sqrtInvSvd(V) is then exactly diag(1 / sqrt(v)) (no
+    # permutation), so the reference's sub-selection under partial missingness (quirk Q6,
+    # SvdFilter.scala:51) picks the right entries and the SVD filter IS the Kalman filter
+    V = np.diag([5.5, 5.0, 4.5, 4.0, 2.5, 2.0, 1.5, 1.0])
+    B, T, n = 16383, 1000, 8
+    y = torch.randn((B, T, n), generator=g, device="cuda", dtype=torch.float64) * 2.0
+    y[torch.rand((B, T, n), generator=g, device="cuda") < 0.05] = float("nan")
+    model = Model.build(mod, T=T)
+    params = dict(V=V, W=W, m0=m0, C0=C0)
+    sv = eng.svd_filter(model, params, y, layout=SERIES_MAJOR, want=("m", "dc", "uc"), consistent_w=True)
+    kf = eng.filter(model, params, y, layout=SERIES_MAJOR, want=("m", "C"))
+    eng.sync()
+    assert int(sv["status"].max()) == 0 and int(kf["status"].max()) == 0
+    scale = kf["m"].abs().amax(dim=(1, 2), keepdim=True).clamp_min(1.0)
+    assert ((sv["m"] - kf["m"]).abs() / scale).max().item() < 1e-7
+    uc = sv["uc"][:64, -1].reshape(64, n, n).transpose(1, 2)          # column-major -> (i, j)
+    Crec = uc @ torch.diag_embed(sv["dc"][:64, -1] ** 2) @ uc.transpose(1, 2)
+    Ckf = kf["C"][:64, -1].reshape(64, n, n).transpose(1, 2)
+    assert torch.allclose(Crec, Ckf, rtol=1e-6, atol=1e-9)
+    Fm, _, Gm, _, _, p = dlm.materialise(mod, np.arange(1, T + 1.0))
+    sqrtW = oracle.sqrt_svd(dlm.cm(W))
+    for b in (0, B - 1):
+        o = oracle.svd_filter(n, p, Fm, Gm, dlm.cm(V), sqrtW, m0, dlm.cm(C0), np.arange(1, T + 1.0),
+                              y[b].cpu().numpy())
+        _exact(sv["m"][b].cpu().numpy(), o["m"], f"config4 svd m[{b}]")
+        _exact(sv["dc"][b].cpu().numpy(), o["dc"], f"config4 svd dc[{b}]")
+
+
 def test_wave_query_and_fp64_peak(eng):
     from bayesian_dlms_b200 import _capi as capi
     w2 = eng.ctx.wave_series(2, 1)
