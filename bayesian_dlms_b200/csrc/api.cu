@@ -501,6 +501,13 @@ int run_dev(bdlm_ctx *c, DevCall d, Bump bump) {
   // ---- warp-per-series path ----
   int rc = upload_model(c, d, bump, bt, hG0, hF0);
   if (rc) return rc;
+  if (d.op == A_LOGLIK && loglik_small_supported(bt) && std::getenv("BDLM_NO_SMALL_LOGLIK") == nullptr) {
+    // thread-per-series log-likelihoods (scalar_filters.cu): strided views serve both layouts
+    CU(launch_loglik_small(bt, hG0.data(), hF0.data(), d.ll_tr ? d.ll_tr + d.b0 : nullptr,
+                           d.ll_in ? d.ll_in + d.b0 : nullptr, c->stream));
+    ++c->launches;
+    return 0;
+  }
   WarpArgs wa{};
   wa.bt = bt;
   const int L = p.layout;

@@ -121,6 +121,10 @@ struct ConjArgs {
   View shape, scale;        // T + 1 rows, k = 1
 };
 bool conjugate_supported(int n, int p);
+// both log-likelihoods, one thread per series (n <= 4, p = 1, time-invariant model)
+bool loglik_small_supported(const Batch &bt);
+cudaError_t launch_loglik_small(const Batch &bt, const double *hG, const double *hF,
+                                double *ll_transition, double *ll_innov, cudaStream_t stream);
 cudaError_t launch_conjugate(const ConjArgs &a, const double *hG, const double *hF,
                              cudaStream_t stream);
 

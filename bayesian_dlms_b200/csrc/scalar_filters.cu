@@ -209,6 +209,109 @@ conjugate_kernel(const ConjModel<N> md, const ConjArgs a) {
   if (bt.status && st) bt.status[b] = st;
 }
 
+// ---- log-likelihoods, thread per series ------------------------------------------------------
+// KalmanFilter.likelihood (transition form, KalmanFilter.scala:299-306 with logLikelihood
+// :175-183) and the innovations form (conditionalLikelihood :138-153) for n <= 4, p = 1 and a
+// time-invariant F, G: what Metropolis / MetropolisHastings.dlm evaluate per proposal
+// (MetropolisHastings.scala:126-137,199-209).  Nothing is stored per step: the kernel reads y
+// (8 B / series-step) and is bound by FP64 issue; the warp-per-series kernel it replaces for
+// these shapes needs a whole warp and shared-memory round trips per series.
+// Operation order = oracle_loglik / mvn_logpdf / chol_logdet (dgesv solve, dpotrf log-determinant).
+template <int N>
+__device__ __forceinline__ int mvn_logpdf_small(const double (&x)[N], const double (&mu)[N],
+                                                const double (&S)[N * N], double &out) {
+  using namespace small;
+  int st = 0;
+  double c[N], slv[N], A[N * N], L[N * N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) { c[i] = x[i] - mu[i]; slv[i] = c[i]; }
+#pragma unroll
+  for (int k = 0; k < N * N; ++k) { A[k] = S[k]; L[k] = S[k]; }
+  st |= lu_solve<N, 1>(A, slv);
+  double dot = 0.0;
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const double prod = slv[i] * c[i];
+    dot = (i == 0) ? prod : dot + prod;
+  }
+  double ld = 0.0;
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    double d = L[j + j * N];
+#pragma unroll
+    for (int k = 0; k < j; ++k) d = d - L[j + k * N] * L[j + k * N];
+    if (!(d > 0.0)) st |= BDLM_ST_NOTPD;
+    d = sqrt(d);
+    L[j + j * N] = d;
+#pragma unroll
+    for (int i = j + 1; i < N; ++i) {
+      double v = L[i + j * N];
+#pragma unroll
+      for (int k = 0; k < j; ++k) v = v - L[i + k * N] * L[j + k * N];
+      L[i + j * N] = v / d;
+    }
+    ld = ld + log(d);
+  }
+  out = -dot / 2.0 - (N / 2.0 * 1.8378770664093453 + ld);
+  return st;
+}
+
+template <int N>
+__global__ void __launch_bounds__(128)
+loglik_small_kernel(const ConjModel<N> md, const Batch bt, double *ll_transition, double *ll_innov) {
+  using namespace small;
+  const int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (b >= bt.B) return;
+  double m[N], C[N * N], W[N * N];
+#pragma unroll
+  for (int k = 0; k < N; ++k) m[k] = bt.m0.ptr[b * bt.m0.sb + k * bt.m0.sk];
+#pragma unroll
+  for (int k = 0; k < N * N; ++k) {
+    C[k] = bt.C0.ptr[b * bt.C0.sb + k * bt.C0.sk];
+    W[k] = bt.W.ptr[b * bt.W.sb + k * bt.W.sk];
+  }
+  const double V = bt.V.ptr[b * bt.V.sb];
+  int st = 0;
+  double ll = 0.0, li = 0.0;
+  double ynext = ld_stream(bt.y.ptr + b * bt.y.sb);
+  for (int t = 0; t < bt.T; ++t) {
+    const double y = ynext;
+    if (t + 1 < bt.T) ynext = ld_stream(bt.y.ptr + b * bt.y.sb + (int64_t)(t + 1) * bt.y.sr);
+    const double dt = bt.dt ? bt.dt[t] : 1.0;
+    double a[N], R[N * N], mu[N], S[N * N], f, Q, v;
+    smm<N, N, 1, false, false>(md.G, m, mu);  // G m_{t-1}
+    advance<N, false>(md.G, W, dt, m, C, a, R);
+    update<N>(md.F, V, y, a, R, f, Q, m, C, st);
+#pragma unroll
+    for (int k = 0; k < N * N; ++k) S[k] = W[k] * dt;
+    st |= mvn_logpdf_small<N>(m, mu, S, v);
+    ll = (t == 0) ? v : ll + v;
+    if (!isnan(y)) {
+      const double sd = sqrt(Q);
+      const double dd = (y - f) / sd;
+      li += -dd * dd / 2.0 - log(sqrt(2.0 * 3.141592653589793) * sd);
+    }
+  }
+  if (ll_transition) ll_transition[b] = ll;
+  if (ll_innov) ll_innov[b] = li;
+  if (bt.status) {
+    bool finite = true;
+#pragma unroll
+    for (int k = 0; k < N; ++k) finite = finite && isfinite(m[k]);
+    bt.status[b] = st | (finite ? 0 : BDLM_ST_NONFINITE);
+  }
+}
+
+template <int N>
+cudaError_t launch_ll(const Batch &bt, const double *hG, const double *hF, double *tr, double *in,
+                      cudaStream_t s) {
+  ConjModel<N> md;
+  for (int k = 0; k < N * N; ++k) md.G[k] = hG[k];
+  for (int k = 0; k < N; ++k) md.F[k] = hF[k];
+  loglik_small_kernel<N><<<(unsigned)((bt.B + 127) / 128), 128, 0, s>>>(md, bt, tr, in);
+  return cudaGetLastError();
+}
+
 template <int N>
 cudaError_t launch_conj(const ConjArgs &a, const double *hG, const double *hF, cudaStream_t s) {
   ConjModel<N> md;
@@ -252,6 +355,22 @@ cudaError_t launch_ar(const ArArgs &a, cudaStream_t stream) {
   if (minb >= 8) launch_ar_ahead<1, 8>(a, blocks, th, stream);
   else launch_ar_ahead<1, 1>(a, blocks, th, stream);
   return cudaGetLastError();
+}
+
+bool loglik_small_supported(const Batch &bt) {
+  return bt.p == 1 && bt.n >= 1 && bt.n <= 4 && !bt.f_tv && !bt.g_tv && !bt.v_tv && !bt.w_tv;
+}
+
+cudaError_t launch_loglik_small(const Batch &bt, const double *hG, const double *hF,
+                                double *ll_transition, double *ll_innov, cudaStream_t stream) {
+  if (bt.B == 0) return cudaSuccess;
+  switch (bt.n) {
+    case 1: return launch_ll<1>(bt, hG, hF, ll_transition, ll_innov, stream);
+    case 2: return launch_ll<2>(bt, hG, hF, ll_transition, ll_innov, stream);
+    case 3: return launch_ll<3>(bt, hG, hF, ll_transition, ll_innov, stream);
+    case 4: return launch_ll<4>(bt, hG, hF, ll_transition, ll_innov, stream);
+    default: return cudaErrorInvalidValue;
+  }
 }
 
 bool conjugate_supported(int n, int p) { return p == 1 && n >= 1 && n <= 4; }

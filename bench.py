@@ -445,6 +445,46 @@ def scan_leg(eng, dev, with_cpu=True, logT=24):
     return res
 
 
+def loglik_leg(eng, dev, with_cpu=True, B=1_000_000, T=1000):
+    """Row a9 of the scope table: KalmanFilter.likelihood (what Metropolis-Hastings evaluates per
+    proposal, MetropolisHastings.scala:126-137) for the config-2 model, 1e6 series with their own
+    V, W: both log-likelihoods per series, nothing stored per step (FP64-issue bound)."""
+    import torch
+    from bayesian_dlms_b200 import Model, TIME_MAJOR, dlm
+    g = torch.Generator(device=dev).manual_seed(20260107)
+    y = torch.randn((T, 1, B), generator=g, device=dev, dtype=torch.float64).cumsum(0)
+    Vs_all, Ws_all = synth_params(B, 20260107, np)
+    params = dict(V=torch.from_numpy(Vs_all).to(dev), W=torch.from_numpy(Ws_all).to(dev),
+                  m0=np.zeros(2), C0=100.0 * np.eye(2), per_series=("V", "W"))
+    model = Model.build(dlm.polynomial(2), T=T)
+    eng.loglik(model, params, y, layout=TIME_MAJOR)
+    torch.cuda.synchronize()
+    ms = []
+    for _ in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = eng.loglik(model, params, y, layout=TIME_MAJOR)
+        e1.record()
+        torch.cuda.synchronize()
+        ms.append(e0.elapsed_time(e1))
+    t = float(np.median(ms)) * 1e-3
+    res = {"config": "a9: KalmanFilter.likelihood, polynomial(2), %d series x T=%d, per-series V, W" % (B, T),
+           "series_steps_per_s": B * T / t, "likelihoods_per_s": B / t, "ms": t * 1e3,
+           "status_max": int(out["status"].max())}
+    if with_cpu:
+        import oracle
+        F, _, G, _, n, p = dlm.materialise(dlm.polynomial(2), np.arange(1, T + 1.0))
+        yc = y[:, 0, :64].cpu().numpy().T.copy()
+        t0 = time.perf_counter()
+        for b in range(64):
+            oracle.loglik(n, p, F, G, [float(Vs_all[0, b])], Ws_all[:, b].copy(), np.zeros(2),
+                          dlm.cm(100.0 * np.eye(2)), np.arange(1, T + 1.0), yc[b])
+        dt = time.perf_counter() - t0
+        res["cpu_baseline"] = {"value": 64 * T / dt, "unit": "series-steps/s", "cores": 1, "kind": "port",
+                               "sample": f"64 series x T={T}, one core, {dt:.2f} s wall"}
+    return res
+
+
 def scan_dist_leg(eng, dev, rank, world, logT=24, reps=5):
     """BASELINE.json config 5 on N GPUs: ONE series, T = 2^24, time-sharded across the ranks
     (device-side protocol: two NCCL all-gathers of one <= 16-double aggregate per rank and pass,
@@ -717,7 +757,8 @@ def main():
                 line["ffbs"] = ffbs_leg(eng, dev, with_cpu=not args.no_cpu)
             except Exception as ex:  # secondary metric: never take the headline down
                 line["ffbs"] = {"error": repr(ex)}
-            for key, fn in (("svd_ffbs", svd_leg), ("scan", scan_leg), ("ar_ffbs", ar_leg)):
+            for key, fn in (("svd_ffbs", svd_leg), ("scan", scan_leg), ("ar_ffbs", ar_leg),
+                            ("loglik", loglik_leg)):
                 try:
                     line[key] = fn(eng, dev, with_cpu=not args.no_cpu)
                 except Exception as ex:
