@@ -501,6 +501,29 @@ int run_dev(bdlm_ctx *c, DevCall d, Bump bump) {
   // ---- warp-per-series path ----
   int rc = upload_model(c, d, bump, bt, hG0, hF0);
   if (rc) return rc;
+  if (d.op == A_FFBS && ffbs_small_supported(bt) && std::getenv("BDLM_NO_SMALL_FFBS") == nullptr) {
+    // one thread per chain (ffbs_small.cu); (m, C) spill in the caller's arrays when they are
+    // wanted, else dense time-major workspace
+    const int L = p.layout;
+    FfbsSmallArgs fa{};
+    fa.bt = bt;
+    fa.kf.a = mk_view(d.kf.a, L, d.b0, d.Bp, R, n); fa.kf.R = mk_view(d.kf.R, L, d.b0, d.Bp, R, n * n);
+    fa.kf.f = mk_view(d.kf.f, L, d.b0, d.Bp, R, 1); fa.kf.Q = mk_view(d.kf.Q, L, d.b0, d.Bp, R, 1);
+    fa.sm = d.kf.m ? mk_view(d.kf.m, L, d.b0, d.Bp, R, n)
+                   : mk_view(bump.take<double>((size_t)R * n * d.Bc), BDLM_TIME_MAJOR, 0, d.Bc, R, n);
+    fa.sC = d.kf.C ? mk_view(d.kf.C, L, d.b0, d.Bp, R, n * n)
+                   : mk_view(bump.take<double>((size_t)R * n * n * d.Bc), BDLM_TIME_MAJOR, 0, d.Bc, R, n * n);
+    fa.z = mk_cview(d.z, L, d.b0, d.Bp, R, n);
+    fa.theta = mk_view(d.theta, L, d.b0, d.Bp, R, n);
+    fa.stats.ssy = mk_rowview(d.stats.ssy, L, d.b0, d.Bp, 1);
+    fa.stats.ny = mk_rowview(d.stats.ny, L, d.b0, d.Bp, 1);
+    fa.stats.ssw = mk_rowview(d.stats.ssw, L, d.b0, d.Bp, n);
+    fa.stats.scatter = mk_rowview(d.stats.scatter, L, d.b0, d.Bp, n * n);
+    fa.rng_seed = c->rng_seed; fa.rng_sweep = c->rng_sweep; fa.rng_base = c->rng_first + d.rng_b0;
+    CU(launch_ffbs_small(fa, hG0.data(), hF0.data(), c->stream));
+    ++c->launches;
+    return 0;
+  }
   if (d.op == A_LOGLIK && loglik_small_supported(bt) && std::getenv("BDLM_NO_SMALL_LOGLIK") == nullptr) {
     // thread-per-series log-likelihoods (scalar_filters.cu): strided views serve both layouts
     CU(launch_loglik_small(bt, hG0.data(), hF0.data(), d.ll_tr ? d.ll_tr + d.b0 : nullptr,

@@ -45,6 +45,21 @@ struct WarpArgs {
 size_t warp_spill_doubles_per_row(int op, int n, int p);
 cudaError_t launch_warp(int op, const WarpArgs &wa, cudaStream_t stream);
 
+// ffbs_small.cu: FFBS with one thread per chain (n <= 4, p = 1, time-invariant F, G).
+struct FfbsSmallArgs {
+  Batch bt;
+  KfViews kf;          // optional a, R, f, Q outputs (m, C travel through sm / sC)
+  View sm, sC;         // (m, C) spill, rows x k: the caller's m / C arrays or workspace
+  CView z;             // injected normals or ptr == nullptr (Philox)
+  View theta;
+  StatViews stats;
+  unsigned long long rng_seed, rng_sweep;
+  long long rng_base;
+};
+bool ffbs_small_supported(const Batch &bt);
+cudaError_t launch_ffbs_small(const FfbsSmallArgs &a, const double *hG, const double *hF,
+                              cudaStream_t stream);
+
 // kf_group.cu: two series per warp, compile-time n, p = 1 (FFBS / filter, n in {7, 13}).
 bool group_supported(int op, int n, int p, int keep_init);
 cudaError_t launch_group(int op, const WarpArgs &wa, cudaStream_t stream);

@@ -445,6 +445,50 @@ def scan_leg(eng, dev, with_cpu=True, logT=24):
     return res
 
 
+def ffbs_small_leg(eng, dev, with_cpu=True, B=1_000_000, T=1000):
+    """FFBS for the config-2 model itself (polynomial(2), the reference's SecondOrder Gibbs example,
+    SecondOrder.scala:53-97): 1e6 chains x T = 1000, one thread per chain, on-device normals,
+    sufficient statistics fused."""
+    import torch
+    from bayesian_dlms_b200 import Model, TIME_MAJOR, dlm
+    g = torch.Generator(device=dev).manual_seed(20260108)
+    y = torch.randn((T, 1, B), generator=g, device=dev, dtype=torch.float64).cumsum(0)
+    params = dict(V=[[3.0]], W=np.diag([2.0, 1.0]), m0=np.zeros(2), C0=100.0 * np.eye(2))
+    model = Model.build(dlm.polynomial(2), T=T)
+    eng.ctx.set_rng(20260108, 0)
+    eng.ffbs(model, params, y, None, layout=TIME_MAJOR, stats=True)
+    torch.cuda.synchronize()
+    ms = []
+    for it in range(3):
+        eng.ctx.set_rng(20260108, it + 1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = eng.ffbs(model, params, y, None, layout=TIME_MAJOR, stats=True)
+        e1.record()
+        torch.cuda.synchronize()
+        ms.append(e0.elapsed_time(e1))
+    t = float(np.median(ms)) * 1e-3
+    res = {"config": "FFBS of the config-2 model: polynomial(2), %d chains x T=%d, Philox normals, "
+                     "Gibbs statistics fused" % (B, T),
+           "draws_per_s": B / t, "steps_per_s": B * (T + 1) / t, "ms_per_sweep": t * 1e3,
+           "status_max": int(out["status"].max())}
+    if with_cpu:
+        import oracle
+        F, _, G, _, n, p = dlm.materialise(dlm.polynomial(2), np.arange(1, T + 1.0))
+        threads = os.cpu_count()
+        Bs = 64 * threads
+        rng = np.random.default_rng(8)
+        yc = rng.standard_normal((Bs, T, 1)).cumsum(axis=1)
+        zc = rng.standard_normal((Bs, T + 1, 2))
+        t0 = time.perf_counter()
+        oracle.batch_ffbs(Bs, n, p, T, F, G, [3.0], dlm.cm(np.diag([2.0, 1.0])), np.zeros(2),
+                          dlm.cm(100.0 * np.eye(2)), np.arange(1, T + 1.0), yc, zc, nthreads=threads)
+        dt = time.perf_counter() - t0
+        res["cpu_baseline"] = {"value": Bs / dt, "unit": "draws/s", "cores": threads, "kind": "port",
+                               "sample": f"{Bs} chains x T={T}, {dt:.2f} s wall, oracle port OpenMP"}
+    return res
+
+
 def loglik_leg(eng, dev, with_cpu=True, B=1_000_000, T=1000):
     """Row a9 of the scope table: KalmanFilter.likelihood (what Metropolis-Hastings evaluates per
     proposal, MetropolisHastings.scala:126-137) for the config-2 model, 1e6 series with their own
@@ -758,7 +802,7 @@ def main():
             except Exception as ex:  # secondary metric: never take the headline down
                 line["ffbs"] = {"error": repr(ex)}
             for key, fn in (("svd_ffbs", svd_leg), ("scan", scan_leg), ("ar_ffbs", ar_leg),
-                            ("loglik", loglik_leg)):
+                            ("loglik", loglik_leg), ("ffbs_small", ffbs_small_leg)):
                 try:
                     line[key] = fn(eng, dev, with_cpu=not args.no_cpu)
                 except Exception as ex:

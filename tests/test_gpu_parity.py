@@ -279,6 +279,7 @@ def test_loglik_matches_oracle(eng, oracle, name):
 
 
 @pytest.mark.parametrize("name", ["first_order", "second_order", "second_order_irregular",
+                                  "third_order", "fourth_order",
                                   "kat_bivariate", "seasonal13", "seasonal13_irregular",
                                   "seasonal7", "seasonal7_irregular",
                                   "correlated8", "single_step", "shared_state_p8_n7", "max_dim_n32"])
