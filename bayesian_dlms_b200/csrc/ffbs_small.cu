@@ -158,7 +158,16 @@ ffbs_small_kernel(const FfbsModel<N> md, const FfbsSmallArgs a) {
     C[k] = bt.C0.ptr[b * bt.C0.sb + k * bt.C0.sk];
     W[k] = bt.W.ptr[b * bt.W.sb + k * bt.W.sk];
   }
-  const double V = bt.V.ptr[b * bt.V.sb];
+  double V = bt.V.ptr[b * bt.V.sb];
+  // time-varying V_t / W_t (StudentTGibbs.sampleState, DlmFsvSystem.ffbs): row t of the arrays
+  auto load_vw = [&](int t) {
+    if (bt.v_tv) V = bt.V.ptr[b * bt.V.sb + (int64_t)t * bt.V_sr];
+    if (bt.w_tv) {
+      const double *wp = bt.W.ptr + b * bt.W.sb + (int64_t)t * bt.W_sr;
+#pragma unroll
+      for (int k = 0; k < N * N; ++k) W[k] = wp[k * bt.W.sk];
+    }
+  };
   int st = 0;
   auto put = [&](const View &v, int64_t row, const double *x, int K, bool stream) {
     if (!v.ptr) return;
@@ -184,6 +193,7 @@ ffbs_small_kernel(const FfbsModel<N> md, const FfbsSmallArgs a) {
     if (t + 1 < T) ynext = ld_stream(bt.y.ptr + b * bt.y.sb + (int64_t)(t + 1) * bt.y.sr);
     const double dt = bt.dt ? bt.dt[t] : 1.0;
     double av[N], R[N * N], f, Q;
+    load_vw(t);
     advance<N, false>(md.G, W, dt, m, C, av, R);
     update<N>(md.F, V, y, av, R, f, Q, m, C, st);
     put(a.sm, t + 1, m, N, false); put(a.sC, t + 1, C, N * N, false);
@@ -212,6 +222,7 @@ ffbs_small_kernel(const FfbsModel<N> md, const FfbsSmallArgs a) {
     double mr[N], Cr[N * N], a1[N], R1[N * N];
     get(a.sm, r, mr, N); get(a.sC, r, Cr, N * N);
     normals(r, z);
+    load_vw(r);  // W of the transition r -> r + 1 (DlmFsvSystem.scala:155-163)
     advance<N, false>(md.G, W, dt, mr, Cr, a1, R1);  // == the forward (a, R) of row r + 1
     // smoothing_gain: B = (R1^T \ (G C^T))^T
     double rhs[N * N], At[N * N], Bg[N * N], d[N], t1[N * N], t2[N * N], h[N], D[N * N],
@@ -318,8 +329,7 @@ cudaError_t launch_n(const FfbsSmallArgs &a, const double *hG, const double *hF,
 }  // namespace
 
 bool ffbs_small_supported(const Batch &bt) {
-  return bt.p == 1 && bt.n >= 1 && bt.n <= 4 && bt.keep_init && !bt.f_tv && !bt.g_tv && !bt.v_tv &&
-         !bt.w_tv;
+  return bt.p == 1 && bt.n >= 1 && bt.n <= 4 && bt.keep_init && !bt.f_tv && !bt.g_tv;
 }
 
 cudaError_t launch_ffbs_small(const FfbsSmallArgs &a, const double *hG, const double *hF,

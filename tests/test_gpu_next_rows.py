@@ -388,14 +388,16 @@ def test_filter_from_saved_state_and_forecast(eng, oracle):
     assert np.allclose(fc[0][1], mod.f(0.0).T @ full[-1].mt)
 
 
+@pytest.mark.parametrize("shape", [(3, 2), (2, 1)])
 @pytest.mark.parametrize("shared", [True, False])
-def test_time_varying_W_filter_and_ffbs(eng, oracle, shared):
+def test_time_varying_W_filter_and_ffbs(eng, oracle, shared, shape):
     """DlmFsvSystem.ffbs (DlmFsvSystem.scala:137-167): KalmanFilter.step with params.copy(w = W_t)
     forward, Smoothing.step(model, W_t) for the transition t -> t + 1 backward; with V_t as well."""
     from bayesian_dlms_b200 import Model, SERIES_MAJOR, dlm
     rng = np.random.default_rng(77 + int(shared))
-    B, T, n, p = 4, 45, 3, 2
-    mod = dlm.polynomial(1) * dlm.polynomial(2)
+    B, T = 4, 45
+    n, p = shape
+    mod = dlm.polynomial(1) * dlm.polynomial(2) if p == 2 else dlm.polynomial(2)
     m0, C0 = rng.standard_normal(n), H.spd(rng, n, 4.0)
     times = np.cumsum(rng.choice([1.0, 2.0], T))
     nb = 1 if shared else B
