@@ -104,3 +104,44 @@ def test_time_major_host_buffers_use_strided_copies(eng):
             assert np.array_equal(out["m"][:, :, b], o["m"]) and np.array_equal(out["S"][:, :, b], s["S"])
     finally:
         eng.ctx.set_staging_bytes(8 << 30)
+
+
+def test_distinct_contexts_run_concurrently_from_two_threads():
+    """include/bdlm.h threading contract: a context is single-threaded-at-a-time, distinct contexts
+    are fully concurrent (the reference's `mapAsync(nChains)` callers, Streaming.scala:162-173).
+    Two host threads, one Engine each, hammer the same GPU; every result equals the
+    single-threaded one."""
+    import threading
+
+    import torch
+    from bayesian_dlms_b200 import Engine, Model, SERIES_MAJOR, dlm
+    rng = np.random.default_rng(0)
+    B, T = 257, 120
+    mod = dlm.polynomial(2)
+    params = dict(V=[[3.0]], W=np.diag([2.0, 1.0]), m0=np.zeros(2), C0=100.0 * np.eye(2))
+    y = rng.standard_normal((B, T, 1)).cumsum(axis=1)       # host buffers: the library stages them
+    z = rng.standard_normal((B, T + 1, 2))
+    model = Model.build(mod, T=T)
+    ref_eng = Engine(0)
+    ref_fs = ref_eng.filter_smooth(model, params, y, layout=SERIES_MAJOR)
+    ref_th = ref_eng.ffbs(model, params, y, z, layout=SERIES_MAJOR)["theta"]
+    errors = []
+
+    def worker(seed):
+        try:
+            eng = Engine(0)
+            for _ in range(6):
+                fs = eng.filter_smooth(model, params, y, layout=SERIES_MAJOR)
+                th = eng.ffbs(model, params, y, z, layout=SERIES_MAJOR)["theta"]
+                assert np.array_equal(fs["s"], ref_fs["s"]) and np.array_equal(fs["S"], ref_fs["S"])
+                assert np.array_equal(th, ref_th)
+        except Exception as ex:  # surfaced in the main thread
+            errors.append(repr(ex))
+
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    torch.cuda.synchronize()
+    assert not errors, errors
