@@ -26,7 +26,7 @@ _ip = C.POINTER(C.c_int32)
 SYMBOLS = [
     "bdlm_create", "bdlm_destroy", "bdlm_last_error", "bdlm_version", "bdlm_set_stream",
     "bdlm_sync", "bdlm_set_rng", "bdlm_launch_count", "bdlm_set_staging_bytes", "bdlm_kf_filter",
-    "bdlm_rts_smooth", "bdlm_kf_filter_smooth", "bdlm_loglik", "bdlm_ffbs",
+    "bdlm_rts_smooth", "bdlm_kf_filter_smooth", "bdlm_loglik", "bdlm_kf_filter_last", "bdlm_ffbs",
     "bdlm_svd_filter", "bdlm_svd_ffbs", "bdlm_gibbs_suffstats", "bdlm_wave_series",
     "bdlm_fp64_peak_tflops", "bdlm_scan_filter_smooth", "bdlm_scan_elem_doubles",
     "bdlm_scan_forward_reduce", "bdlm_scan_forward_apply", "bdlm_scan_backward_reduce",
@@ -126,6 +126,8 @@ def load():
     lib.bdlm_kf_filter_smooth.argtypes = [C.c_void_p, PP, C.POINTER(KfOut),
                                           C.POINTER(SmoothOut), C.c_void_p]
     lib.bdlm_loglik.argtypes = [C.c_void_p, PP, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.bdlm_kf_filter_last.argtypes = [C.c_void_p, PP, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_void_p]
     lib.bdlm_ffbs.argtypes = [C.c_void_p, PP, C.c_void_p, C.c_void_p, C.POINTER(KfOut),
                               C.POINTER(GibbsStats), C.c_void_p]
     lib.bdlm_svd_filter.argtypes = [C.c_void_p, PP, C.POINTER(SvdOut), C.c_void_p]

@@ -279,6 +279,27 @@ class Engine:
             out["status"] = st
         return out
 
+    def filter_last(self, model: Model, params: Dict, y, *, layout=TIME_MAJOR, loglik=False,
+                    status=True):
+        """``ys.foldLeft(init)(kf.step(mod, p))`` batched (NoModel.scala:153-155): only the state
+        after the last observation, nothing stored per step.  Returns m (n, B) / (B, n) and
+        C (n*n, B) / (B, n*n) [+ both log-likelihoods]."""
+        mem, _ = _mem_and_ptr(y)
+        B = self._batch_of(model, y, layout)
+        pr, keep = self._problem(model, params, y, layout, True, 0, B, mem)
+        n = model.n
+        row = (lambda k: (k, B)) if layout == TIME_MAJOR else (lambda k: (B, k))
+        out = dict(m=self._alloc(y, row(n)), C=self._alloc(y, row(n * n)))
+        if loglik:
+            out["transition"], out["innovations"] = self._alloc(y, (B,)), self._alloc(y, (B,))
+        st, stp = self._status(y, B, status)
+        ptr = lambda k: _mem_and_ptr(out[k])[1] if k in out else None  # noqa: E731
+        self.ctx.check(capi.load().bdlm_kf_filter_last(self.ctx.handle, pr, ptr("m"), ptr("C"),
+                                                       ptr("transition"), ptr("innovations"), stp))
+        if st is not None:
+            out["status"] = st
+        return out
+
     # ------------------------------------------------------------------ samplers
     def _stats(self, like, layout, B, model, want):
         if not want:

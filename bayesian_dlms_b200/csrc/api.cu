@@ -106,6 +106,8 @@ struct DevCall {
   // conjugate filter
   double cj_shape = 0, cj_scale = 0;
   double *cj_shape_out = nullptr, *cj_scale_out = nullptr;
+  // last filtered state only (rides on the log-likelihood kernels)
+  double *last_m = nullptr, *last_C = nullptr;
   // conjugate draws
   bdlm_gibbs_prior prior{};
   bdlm_gibbs_rng rng{};
@@ -220,6 +222,8 @@ void collect_fields(DevCall &d, std::vector<Field> &f) {
   add((const double *const *)&d.stats.scatter, 1, n * n, false, true);
   add((const double *const *)&d.ll_tr, 1, 1, false, true);
   add((const double *const *)&d.ll_in, 1, 1, false, true);
+  add((const double *const *)&d.last_m, 1, n, false, true);
+  add((const double *const *)&d.last_C, 1, n * n, false, true);
   add((const double *const *)&d.cj_shape_out, R, 1, false, true);
   add((const double *const *)&d.cj_scale_out, R, 1, false, true);
 }
@@ -527,7 +531,9 @@ int run_dev(bdlm_ctx *c, DevCall d, Bump bump) {
   if (d.op == A_LOGLIK && loglik_small_supported(bt) && std::getenv("BDLM_NO_SMALL_LOGLIK") == nullptr) {
     // thread-per-series log-likelihoods (scalar_filters.cu): strided views serve both layouts
     CU(launch_loglik_small(bt, hG0.data(), hF0.data(), d.ll_tr ? d.ll_tr + d.b0 : nullptr,
-                           d.ll_in ? d.ll_in + d.b0 : nullptr, c->stream));
+                           d.ll_in ? d.ll_in + d.b0 : nullptr,
+                           mk_rowview(d.last_m, p.layout, d.b0, d.Bp, n),
+                           mk_rowview(d.last_C, p.layout, d.b0, d.Bp, n * n), c->stream));
     ++c->launches;
     return 0;
   }
@@ -557,6 +563,8 @@ int run_dev(bdlm_ctx *c, DevCall d, Bump bump) {
   wa.stats.ny = mk_rowview(d.stats.ny, L, d.b0, d.Bp, p.p);
   wa.stats.ssw = mk_rowview(d.stats.ssw, L, d.b0, d.Bp, n);
   wa.stats.scatter = mk_rowview(d.stats.scatter, L, d.b0, d.Bp, n * n);
+  wa.last_m = mk_rowview(d.last_m, L, d.b0, d.Bp, n);
+  wa.last_C = mk_rowview(d.last_C, L, d.b0, d.Bp, n * n);
   wa.ll_transition = d.ll_tr ? d.ll_tr + d.b0 : nullptr;
   wa.ll_innov = d.ll_in ? d.ll_in + d.b0 : nullptr;
   const int wop = warp_op(d.op);
@@ -863,6 +871,18 @@ int bdlm_loglik(bdlm_ctx *c, const bdlm_problem *p, double *transition, double *
   if (rc) return rc;
   if (!transition && !innovations) return fail(c, BDLM_E_ARG, "no log-likelihood requested");
   DevCall d{}; d.op = A_LOGLIK; d.pr = *p; d.pr.keep_init = 1;
+  d.ll_tr = transition; d.ll_in = innovations; d.status = status;
+  return dispatch(c, d);
+}
+
+int bdlm_kf_filter_last(bdlm_ctx *c, const bdlm_problem *p, double *m_last, double *C_last,
+                        double *transition, double *innovations, int32_t *status) {
+  int rc = validate(c, A_LOGLIK, p);
+  if (rc) return rc;
+  if (!m_last && !C_last && !transition && !innovations)
+    return fail(c, BDLM_E_ARG, "nothing requested");
+  DevCall d{}; d.op = A_LOGLIK; d.pr = *p; d.pr.keep_init = 1;
+  d.last_m = m_last; d.last_C = C_last;
   d.ll_tr = transition; d.ll_in = innovations; d.status = status;
   return dispatch(c, d);
 }

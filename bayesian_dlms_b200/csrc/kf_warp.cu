@@ -602,6 +602,10 @@ warp_kernel(const WarpArgs wa, const int ws_doubles) {
       if (wa.ll_transition) wa.ll_transition[b] = ll_tr;
       if (wa.ll_innov) wa.ll_innov[b] = ll_in;
     }
+    {  // last filtered state only (bdlm_kf_filter_last): one row per series
+      store_view(lane, wa.last_m, b, 0, n, ws.m);
+      store_view(lane, wa.last_C, b, 0, nn, ws.C);
+    }
   }
 
   // ------------------------------------------------------------------ backward passes

@@ -39,6 +39,7 @@ struct WarpArgs {
   SvdViews svd;
   StatViews stats;
   double *ll_transition, *ll_innov;  // [B]
+  View last_m, last_C;               // kOpLoglik: final filtered state, one row per series
   double *spill;       // series-major workspace [B][rows][spill_k] or nullptr
   int64_t spill_k;
 };
@@ -139,7 +140,8 @@ bool conjugate_supported(int n, int p);
 // both log-likelihoods, one thread per series (n <= 4, p = 1, time-invariant model)
 bool loglik_small_supported(const Batch &bt);
 cudaError_t launch_loglik_small(const Batch &bt, const double *hG, const double *hF,
-                                double *ll_transition, double *ll_innov, cudaStream_t stream);
+                                double *ll_transition, double *ll_innov, const View &last_m,
+                                const View &last_C, cudaStream_t stream);
 cudaError_t launch_conjugate(const ConjArgs &a, const double *hG, const double *hF,
                              cudaStream_t stream);
 

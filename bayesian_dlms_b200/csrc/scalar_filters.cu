@@ -258,7 +258,8 @@ __device__ __forceinline__ int mvn_logpdf_small(const double (&x)[N], const doub
 
 template <int N>
 __global__ void __launch_bounds__(128)
-loglik_small_kernel(const ConjModel<N> md, const Batch bt, double *ll_transition, double *ll_innov) {
+loglik_small_kernel(const ConjModel<N> md, const Batch bt, double *ll_transition, double *ll_innov,
+                    const View last_m, const View last_C) {
   using namespace small;
   const int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (b >= bt.B) return;
@@ -294,6 +295,10 @@ loglik_small_kernel(const ConjModel<N> md, const Batch bt, double *ll_transition
   }
   if (ll_transition) ll_transition[b] = ll;
   if (ll_innov) ll_innov[b] = li;
+  if (last_m.ptr)  // final filtered state (bdlm_kf_filter_last)
+    for (int k = 0; k < N; ++k) last_m.ptr[b * last_m.sb + k * last_m.sk] = m[k];
+  if (last_C.ptr)
+    for (int k = 0; k < N * N; ++k) last_C.ptr[b * last_C.sb + k * last_C.sk] = C[k];
   if (bt.status) {
     bool finite = true;
 #pragma unroll
@@ -304,11 +309,11 @@ loglik_small_kernel(const ConjModel<N> md, const Batch bt, double *ll_transition
 
 template <int N>
 cudaError_t launch_ll(const Batch &bt, const double *hG, const double *hF, double *tr, double *in,
-                      cudaStream_t s) {
+                      const View &lm, const View &lC, cudaStream_t s) {
   ConjModel<N> md;
   for (int k = 0; k < N * N; ++k) md.G[k] = hG[k];
   for (int k = 0; k < N; ++k) md.F[k] = hF[k];
-  loglik_small_kernel<N><<<(unsigned)((bt.B + 127) / 128), 128, 0, s>>>(md, bt, tr, in);
+  loglik_small_kernel<N><<<(unsigned)((bt.B + 127) / 128), 128, 0, s>>>(md, bt, tr, in, lm, lC);
   return cudaGetLastError();
 }
 
@@ -362,13 +367,14 @@ bool loglik_small_supported(const Batch &bt) {
 }
 
 cudaError_t launch_loglik_small(const Batch &bt, const double *hG, const double *hF,
-                                double *ll_transition, double *ll_innov, cudaStream_t stream) {
+                                double *ll_transition, double *ll_innov, const View &last_m,
+                                const View &last_C, cudaStream_t stream) {
   if (bt.B == 0) return cudaSuccess;
   switch (bt.n) {
-    case 1: return launch_ll<1>(bt, hG, hF, ll_transition, ll_innov, stream);
-    case 2: return launch_ll<2>(bt, hG, hF, ll_transition, ll_innov, stream);
-    case 3: return launch_ll<3>(bt, hG, hF, ll_transition, ll_innov, stream);
-    case 4: return launch_ll<4>(bt, hG, hF, ll_transition, ll_innov, stream);
+    case 1: return launch_ll<1>(bt, hG, hF, ll_transition, ll_innov, last_m, last_C, stream);
+    case 2: return launch_ll<2>(bt, hG, hF, ll_transition, ll_innov, last_m, last_C, stream);
+    case 3: return launch_ll<3>(bt, hG, hF, ll_transition, ll_innov, last_m, last_C, stream);
+    case 4: return launch_ll<4>(bt, hG, hF, ll_transition, ll_innov, last_m, last_C, stream);
     default: return cudaErrorInvalidValue;
   }
 }

@@ -225,6 +225,16 @@ BDLM_API int bdlm_kf_filter_smooth(bdlm_ctx *ctx, const bdlm_problem *prob, cons
 BDLM_API int bdlm_loglik(bdlm_ctx *ctx, const bdlm_problem *prob, double *transition,
                 double *innovations, int32_t *status);
 
+/* ---- last filtered state only ----------------------------------------------------------
+ * `data.foldLeft(init)(kf.step(mod, p))` (NoModel.scala:153-155): the filter without any
+ * per-step store.  m_last [n] / C_last [n*n] per series ([k][B] or [B][k]) receive the state
+ * after the last observation; the two log-likelihoods of bdlm_loglik come for free.  Any output
+ * may be NULL.  Together with bdlm_problem.t_init this is the streaming pattern: keep the last
+ * state, resume when more data arrive. */
+BDLM_API int bdlm_kf_filter_last(bdlm_ctx *ctx, const bdlm_problem *prob, double *m_last,
+                                 double *C_last, double *transition, double *innovations,
+                                 int32_t *status);
+
 /* ---- FFBS ----------------------------------------------------------------------------
  * Smoothing.ffbs / ffbsDlm (Smoothing.scala:151-180): filter keeping the initial state,
  * then Smoothing.sample (:114-122) with Smoothing.step (:74-103) and

@@ -553,3 +553,33 @@ def test_rao_blackwell_kf_step_over_a_particle_cloud(eng, oracle):
         want = -0.5 * (e @ np.linalg.solve(Q, e)) - 0.5 * (obs.sum() * np.log(2 * np.pi) + np.linalg.slogdet(Q)[1])
         got = float(ll["innovations"][b])
         assert abs(got - want) <= 1e-9 * max(1.0, abs(want)), (b, got, want)
+
+
+@pytest.mark.parametrize("name", ["second_order", "seasonal7"])
+def test_filter_last_and_streaming_resume(eng, oracle, name):
+    """bdlm_kf_filter_last: only the final state (no per-step stores) == the last row of the full
+    filter, bit for bit; feeding it back with t_init continues the filter exactly (the streaming
+    pattern of NoModel.scala:153-155)."""
+    from bayesian_dlms_b200 import Model, SERIES_MAJOR, dlm
+    rng = np.random.default_rng(6)
+    if name == "second_order":
+        mod, V, W, m0, C0 = H.second_order()
+    else:
+        mod = dlm.polynomial(1) + dlm.seasonal(24, 3)
+        V, W, m0, C0 = np.array([[1.0]]), np.diag([0.01, 0.2, 0.4, 0.5, 0.2, 0.1, 0.4]), np.zeros(7), np.eye(7)
+    n, B, T, k = len(m0), 19, 70, 31
+    y = np.stack([H.simulate(mod, V, W, m0, C0, np.arange(1.0, T + 1), rng, missing=0.1) for _ in range(B)])
+    params = dict(V=V, W=W, m0=m0, C0=C0)
+    full = eng.filter(Model.build(mod, T=T), params, _cuda(y), layout=SERIES_MAJOR, want=("m", "C"))
+    last = eng.filter_last(Model.build(mod, T=k), params, _cuda(y[:, :k]), layout=SERIES_MAJOR, loglik=True)
+    assert int(last["status"].max()) == 0
+    _exact(last["m"].cpu().numpy(), full["m"][:, k].cpu().numpy(), "m_last")
+    _exact(last["C"].cpu().numpy(), full["C"][:, k].cpu().numpy(), "C_last")
+    ll = eng.loglik(Model.build(mod, T=k), params, _cuda(y[:, :k]), layout=SERIES_MAJOR)
+    assert np.array_equal(last["innovations"].cpu().numpy(), ll["innovations"].cpu().numpy())
+    # resume from the saved state
+    model2 = Model.build(mod, times=np.arange(k + 1.0, T + 1), t_init=float(k))
+    p2 = dict(V=V, W=W, m0=last["m"], C0=last["C"], per_series=("m0", "C0"))
+    rest = eng.filter(model2, p2, _cuda(y[:, k:]), layout=SERIES_MAJOR, keep_init=False, want=("m", "C"))
+    _exact(rest["m"].cpu().numpy(), full["m"][:, k + 1:].cpu().numpy(), "resumed m")
+    _exact(rest["C"].cpu().numpy(), full["C"][:, k + 1:].cpu().numpy(), "resumed C")
