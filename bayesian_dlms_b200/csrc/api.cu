@@ -586,7 +586,9 @@ int validate(bdlm_ctx *c, int op, const bdlm_problem *p) {
   if (p->T == 0) return fail(c, BDLM_E_EMPTY, "T == 0: empty observation vector");
   if (p->B < 0 || p->T < 0) return fail(c, BDLM_E_ARG, "negative B or T");
   if (p->n < 1 || p->n > BDLM_MAX_N || p->p < 1 || p->p > BDLM_MAX_P)
-    return fail(c, BDLM_E_ARG, "unsupported n or p (1..32)");
+    return fail(c, BDLM_E_ARG, "unsupported n (1..48) or p (1..32)");
+  if ((op == A_SVD_FILTER || op == A_SVD_FFBS) && p->n > 32)
+    return fail(c, BDLM_E_ARG, "the SVD entry points support n <= 32");
   if (p->layout != BDLM_TIME_MAJOR && p->layout != BDLM_SERIES_MAJOR)
     return fail(c, BDLM_E_ARG, "bad layout");
   if (p->mem != BDLM_DEVICE && p->mem != BDLM_HOST) return fail(c, BDLM_E_ARG, "bad mem");

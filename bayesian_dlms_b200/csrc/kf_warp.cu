@@ -267,8 +267,7 @@ __device__ __forceinline__ int w_chol_logdet(int lane, int n, const double *S, d
     d = sqrt(d);
     __syncwarp();
     if (lane == 0) L[j + j * n] = d;
-    const int i = j + 1 + lane;
-    if (i < n) {
+    for (int i = j + 1 + lane; i < n; i += 32) {
       double v = L[i + j * n];
       for (int k = 0; k < j; ++k) v = v - L[i + k * n] * L[j + k * n];
       L[i + j * n] = v / d;
@@ -390,8 +389,8 @@ __device__ __forceinline__ void gibbs_stats(int lane, const Batch &bt, const Ws 
                                             const View &theta, const StatViews &sv,
                                             int64_t b) {
   const int n = bt.n, p = bt.p, T = bt.T;
-  double ssy = 0.0, ny = 0.0, ssw = 0.0;
-  double sc[32];  // scatter elements idx = lane + 32 * q, q < 32 (n*n <= 1024)
+  double ssy = 0.0, ny = 0.0, ssw = 0.0, ssw_hi = 0.0;  // ssw_hi: component lane + 32 (n > 32)
+  double sc[72];  // scatter elements idx = lane + 32 * q, q < 72 (n*n <= 48*48)
   const int nsc = (n * n + 31) / 32;
   const bool want_sc = sv.scatter.ptr != nullptr;
   double tprev = 0.0;
@@ -417,6 +416,10 @@ __device__ __forceinline__ void gibbs_stats(int lane, const Batch &bt, const Ws 
       const double v = (ws.v3[lane] * ws.v3[lane]) / dt;
       ssw = (t == 0) ? v : ssw + v;
     }
+    if (lane + 32 < n) {
+      const double v = (ws.v3[lane + 32] * ws.v3[lane + 32]) / dt;
+      ssw_hi = (t == 0) ? v : ssw_hi + v;
+    }
     if (want_sc) {
 #pragma unroll 4
       for (int q = 0; q < nsc; ++q) {
@@ -435,6 +438,7 @@ __device__ __forceinline__ void gibbs_stats(int lane, const Batch &bt, const Ws 
   if (sv.ssy.ptr && lane < p) sv.ssy.ptr[b * sv.ssy.sb + lane * sv.ssy.sk] = ssy;
   if (sv.ny.ptr && lane < p) sv.ny.ptr[b * sv.ny.sb + lane * sv.ny.sk] = ny;
   if (sv.ssw.ptr && lane < n) sv.ssw.ptr[b * sv.ssw.sb + lane * sv.ssw.sk] = ssw;
+  if (sv.ssw.ptr && lane + 32 < n) sv.ssw.ptr[b * sv.ssw.sb + (lane + 32) * sv.ssw.sk] = ssw_hi;
   if (want_sc)
     for (int q = 0; q < nsc; ++q) {
       const int idx = lane + 32 * q;

@@ -73,8 +73,14 @@ __device__ __forceinline__ int w_lu_solve(int lane, int n, double *A, int nrhs, 
   int st = 0;
   for (int j = 0; j < n; ++j) {
     // idamax over rows j..n-1 of column j: first index of the maximum magnitude
-    double v = (lane >= j && lane < n) ? fabs(A[lane + j * n]) : -1.0;
+    // (rows beyond 31 wrap onto the lanes again: n <= 64; the first index of the maximum wins)
+    double v = -1.0;
     int idx = lane;
+    for (int i = lane; i < n; i += 32)
+      if (i >= j) {
+        const double a = fabs(A[i + j * n]);
+        if (a > v) { v = a; idx = i; }
+      }
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) {
       const double ov = __shfl_xor_sync(FULL, v, off);
@@ -95,7 +101,8 @@ __device__ __forceinline__ int w_lu_solve(int lane, int n, double *A, int nrhs, 
         __syncwarp();
       }
       const double r = 1.0 / A[j + j * n];
-      if (lane > j && lane < n) A[lane + j * n] = A[lane + j * n] * r;
+      for (int i = lane; i < n; i += 32)
+        if (i > j) A[i + j * n] = A[i + j * n] * r;
       __syncwarp();
     } else {
       st = BDLM_ST_SINGULAR;
@@ -211,21 +218,21 @@ __device__ __forceinline__ int w_jacobi_eigsym(int lane, int n, const double *Ai
     bool rotated = false;
     for (int round = 0; round < m - 1; ++round) {
       bool rot = false;
-      if (lane < n) {
-        const int q = rr_partner(n, round, lane);
+      for (int idx = lane; idx < n; idx += 32) {
+        const int q = rr_partner(n, round, idx);
         double c = 1.0, s = 0.0;
         if (q >= 0) {
-          const int lo = lane < q ? lane : q, hi = lane < q ? q : lane;
+          const int lo = idx < q ? idx : q, hi = idx < q ? q : idx;
           const double apq = A[hi + lo * n], app = A[lo + lo * n], aqq = A[hi + hi * n];
           if (apq * apq > kJacobiThr2 * fabs(app * aqq)) {
             double cc, ss;
             sym_rot(app, aqq, apq, cc, ss);
             c = cc;
-            s = (lane == lo) ? -ss : ss;
+            s = (idx == lo) ? -ss : ss;
             rot = true;
           }
         }
-        cs[lane] = c; sn[lane] = s; ipart[lane] = (q < 0) ? lane : q;
+        cs[idx] = c; sn[idx] = s; ipart[idx] = (q < 0) ? idx : q;
       }
       const bool any = __any_sync(FULL, rot);
       __syncwarp();
@@ -254,15 +261,15 @@ __device__ __forceinline__ int w_jacobi_eigsym(int lane, int n, const double *Ai
     if (!rotated) { st = 0; break; }
   }
   // eigenvalues ascending (dsyev order), sign rule
-  if (lane < n) cs[lane] = A[lane + lane * n];
+  for (int idx = lane; idx < n; idx += 32) cs[idx] = A[idx + idx * n];
   __syncwarp();
-  if (lane < n) {
-    const int rk = stable_rank(n, cs, lane, false);
-    ipart[rk] = lane;
-    lam[rk] = cs[lane];
+  for (int idx = lane; idx < n; idx += 32) {
+    const int rk = stable_rank(n, cs, idx, false);
+    ipart[rk] = idx;
+    lam[rk] = cs[idx];
   }
   __syncwarp();
-  if (lane < n) sn[lane] = col_flip(n, V + ipart[lane] * n) ? -1.0 : 1.0;
+  for (int idx = lane; idx < n; idx += 32) sn[idx] = col_flip(n, V + ipart[idx] * n) ? -1.0 : 1.0;
   __syncwarp();
   for (ElemIter it(lane, n, n); it.ok(); it.next()) {
     const double v = V[it.i + ipart[it.j] * n];

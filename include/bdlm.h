@@ -61,8 +61,8 @@ extern "C" {
 
 #define BDLM_VERSION 100
 
-#define BDLM_MAX_N 32 /* state dimension  */
-#define BDLM_MAX_P 32 /* observation dimension */
+#define BDLM_MAX_N 48 /* state dimension (the SVD entry points: 32)                     */
+#define BDLM_MAX_P 32 /* observation dimension                                          */
 
 enum { BDLM_TIME_MAJOR = 0, BDLM_SERIES_MAJOR = 1 };
 enum { BDLM_DEVICE = 0, BDLM_HOST = 1 };
