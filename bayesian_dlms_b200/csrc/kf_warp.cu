@@ -1,4 +1,4 @@
-// kf_warp.cu -- generic-dimension kernels (n, p <= 32): ONE WARP PER SERIES / CHAIN.
+// kf_warp.cu -- generic-dimension kernels (n <= 48, p <= 32; SVD ops n <= 32): ONE WARP PER SERIES / CHAIN.
 //
 // Covers every function of the hot path for any model shape: forward Kalman filter with
 // partially-missing observations, RTS smoother, FFBS with the Jacobi eigen draw, both

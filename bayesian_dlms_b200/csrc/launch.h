@@ -11,7 +11,7 @@ cudaError_t launch_kf_small(const Batch &bt, const double *hG, const double *hF,
                             bool do_filter, bool do_smooth, cudaStream_t stream,
                             int *wave_series = nullptr);  // non-null: occupancy query only
 
-// kf_warp.cu: warp-per-series shared-memory kernels (any n, p <= 32).
+// kf_warp.cu: warp-per-series shared-memory kernels (n <= 48, p <= 32; SVD ops n <= 32).
 struct SvdViews {
   View m, dc, uc, a, dr, ur, f;
 };

@@ -1,6 +1,6 @@
 // warp_linalg.cuh -- warp-cooperative dense linear algebra on shared-memory operands.
 //
-// One warp owns one series; its matrices (n, p <= 32) live in shared memory, column
+// One warp owns one series; its matrices (n <= 48, p <= 32) live in shared memory, column
 // major, and the 32 lanes split the OUTPUT elements of every operation.  Each output
 // element is produced by exactly one lane with the oracle's operation order (products
 // summed in increasing inner index, no FMA), so results are bit-identical to
