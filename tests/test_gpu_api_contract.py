@@ -35,7 +35,7 @@ def test_error_codes(eng):
     n0 = eng.ctx.launch_count()
     pr, keep = _problem(capi, T=0)
     assert lib.bdlm_kf_filter(h, pr, ko, None) == capi.E_EMPTY      # NoSuchElementException
-    pr, keep = _problem(capi, n=40)
+    pr, keep = _problem(capi, n=49)   # BDLM_MAX_N = 48
     assert lib.bdlm_kf_filter(h, pr, ko, None) == capi.E_ARG
     pr, keep = _problem(capi, layout=7)
     assert lib.bdlm_kf_filter(h, pr, ko, None) == capi.E_ARG
