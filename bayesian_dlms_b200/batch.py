@@ -12,6 +12,8 @@ Matrices are column-major inside a row (Breeze ``DenseMatrix.data`` order).
 """
 from __future__ import annotations
 
+import functools
+import threading
 from dataclasses import dataclass
 from typing import Dict, Optional, Sequence
 
@@ -60,13 +62,41 @@ class Model:
 
 
 _engines_by_device = {}
+_tls = threading.local()   # .engine: the Engine whose method is running on this thread
+
+
+class bound_engine:
+    """``with bound_engine(eng): ...`` -- device tensors marshalled inside the block make ``eng``
+    (and no other engine of that device) adopt torch's current stream."""
+
+    def __init__(self, eng):
+        self.eng = eng
+
+    def __enter__(self):
+        self.prev = getattr(_tls, "engine", None)
+        _tls.engine = self.eng
+        return self.eng
+
+    def __exit__(self, *exc):
+        _tls.engine = self.prev
+        return False
+
+
+def _on_engine_stream(fn):
+    @functools.wraps(fn)
+    def wrap(self, *args, **kwargs):
+        with bound_engine(self):
+            return fn(self, *args, **kwargs)
+    return wrap
 
 
 def _adopt_torch_stream(x):
     """Device-mode calls are enqueued on torch's CURRENT stream of the tensor's device, so they
-    are ordered with the torch ops that produced the inputs and consume the outputs."""
+    are ordered with the torch ops that produced the inputs and consume the outputs.  The engine
+    is the one whose method is running (thread-local); the per-device registry is only the
+    fallback for helpers called outside an Engine method."""
     import torch
-    eng = _engines_by_device.get(x.device.index)
+    eng = getattr(_tls, "engine", None) or _engines_by_device.get(x.device.index)
     if eng is not None:
         eng.ctx.set_stream(torch.cuda.current_stream(x.device).cuda_stream)
 
@@ -201,6 +231,7 @@ class Engine:
         return st, _mem_and_ptr(st)[1]
 
     # ------------------------------------------------------------------ filter / smoother
+    @_on_engine_stream
     def filter(self, model: Model, params: Dict, y, *, layout=TIME_MAJOR, keep_init=True,
                want=KF_FIELDS, status=True, pinned=False):
         """KalmanFilter.filterDlm / .filter batched (KalmanFilter.scala:291-294, Filter.scala:41-45)."""
@@ -216,6 +247,7 @@ class Engine:
             out["status"] = st
         return out
 
+    @_on_engine_stream
     def smooth(self, model: Model, params: Dict, filt: Dict, *, layout=TIME_MAJOR,
                keep_init=True, textbook=False, status=True, pinned=False):
         """Smoothing.backwardsSmoother batched (Smoothing.scala:57-64)."""
@@ -237,6 +269,7 @@ class Engine:
             out["status"] = st
         return out
 
+    @_on_engine_stream
     def filter_smooth(self, model: Model, params: Dict, y, *, layout=TIME_MAJOR, keep_init=True,
                       want=KF_FIELDS + ("s", "S"), textbook=False, status=True, pinned=False,
                       out: Optional[Dict] = None):
@@ -264,6 +297,7 @@ class Engine:
         self.ctx.check(capi.load().bdlm_kf_filter_smooth(self.ctx.handle, pr, ko, so, stp))
         return res
 
+    @_on_engine_stream
     def loglik(self, model: Model, params: Dict, y, *, layout=TIME_MAJOR, status=True):
         """KalmanFilter.likelihood (transition form, KalmanFilter.scala:299-306) and the
         innovations form (conditionalLikelihood, :138-153) per series."""
@@ -279,6 +313,7 @@ class Engine:
             out["status"] = st
         return out
 
+    @_on_engine_stream
     def filter_last(self, model: Model, params: Dict, y, *, layout=TIME_MAJOR, loglik=False,
                     status=True):
         """``ys.foldLeft(init)(kf.step(mod, p))`` batched (NoModel.scala:153-155): only the state
@@ -312,6 +347,7 @@ class Engine:
             setattr(gs, k, _mem_and_ptr(out[k])[1])
         return out, gs
 
+    @_on_engine_stream
     def ffbs(self, model: Model, params: Dict, y, z, *, layout=TIME_MAJOR, want_kf=(),
              stats=False, status=True, svd=False, consistent_w=False, pinned=False):
         """Smoothing.ffbsDlm (Smoothing.scala:173-180) or, with svd=True, SvdSampler.ffbsDlm
@@ -347,6 +383,7 @@ class Engine:
             out["status"] = st
         return out
 
+    @_on_engine_stream
     def svd_filter(self, model: Model, params: Dict, y, *, layout=TIME_MAJOR, keep_init=True,
                    want=SVD_FIELDS, consistent_w=False, status=True, pinned=False):
         """SvdFilter.filterDlm / .filter batched (SvdFilter.scala:100-119,158-161)."""
@@ -363,6 +400,7 @@ class Engine:
             out["status"] = st
         return out
 
+    @_on_engine_stream
     def gibbs_stats(self, model: Model, y, theta, *, layout=TIME_MAJOR):
         """Sufficient statistics of a given path (Gibbs.scala:29-43,63-73; GibbsWishart.scala:22-29)."""
         mem, _ = _mem_and_ptr(y)
@@ -415,6 +453,7 @@ class Engine:
         pr.y = yptr
         return pr, keep, B, T
 
+    @_on_engine_stream
     def ar_filter(self, sv: Dict, y, v, *, times=None, ou=False, layout=TIME_MAJOR,
                   want=("m", "C", "a", "R")):
         """FilterAr / FilterOu.filterUnivariate batched (FilterAr.scala:37-47, FilterOu.scala:30-45).
@@ -429,6 +468,7 @@ class Engine:
         self.ctx.check(capi.load().bdlm_ar_filter(self.ctx.handle, pr, ao))
         return out
 
+    @_on_engine_stream
     def ar_ffbs(self, sv: Dict, y, v, z, *, times=None, ou=False, layout=TIME_MAJOR, want=()):
         """FilterAr / FilterOu.ffbs batched (FilterAr.scala:77-83, FilterOu.scala:73-79) with
         injected normals z (T + 1 rows)."""
@@ -444,6 +484,7 @@ class Engine:
                                                 _mem_and_ptr(out["theta"])[1], ao))
         return out
 
+    @_on_engine_stream
     def conjugate_filter(self, model: Model, params: Dict, prior_shape: float, prior_scale: float,
                          y, *, layout=TIME_MAJOR, want=("m", "C"), status=True):
         """ConjugateFilter(prior, advanceState).filter batched (ConjugateFilter.scala:17-112)."""
@@ -462,6 +503,7 @@ class Engine:
             out["status"] = st
         return out
 
+    @_on_engine_stream
     def gibbs_draw(self, n: int, p: int, T: int, stats: Dict, prior: Dict, *, layout=TIME_MAJOR,
                    seed=0, sweep=0, inject: Optional[Dict] = None, want_shape_rate=False,
                    out: Optional[Dict] = None):

@@ -15,7 +15,7 @@ import numpy as np
 
 from . import _capi as capi
 from . import dlm as _dlm
-from .batch import Engine, Model, SERIES_MAJOR, _mem_and_ptr
+from .batch import Engine, Model, SERIES_MAJOR, _mem_and_ptr, bound_engine
 
 
 def _problem(model: Model, params: Dict, y, keep_init: bool):
@@ -42,7 +42,8 @@ def scan_filter_smooth(eng: Engine, model: Model, params: Dict, y, *, keep_init=
     """y: CUDA tensor [T] (or [T, 1]).  Returns [rows, k] tensors (+ int status)."""
     import torch
     n, rows = model.n, model.T + int(keep_init)
-    pr, keep = _problem(model, params, y, keep_init)
+    with bound_engine(eng):
+        pr, keep = _problem(model, params, y, keep_init)
     dims = dict(m=n, C=n * n, a=n, R=n * n, f=1, Q=1, s=n, S=n * n)
     out = {k: _alloc(y, rows, dims[k]) for k in want}
     ko, so = capi.KfOut(), capi.SmoothOut()
@@ -100,7 +101,8 @@ class ScanChunk:
         self.keep_init = keep_init
         self.rows = model.T + int(keep_init)
         self.y = y
-        self.pr, self._keep = _problem(model, params, y, keep_init)
+        with bound_engine(eng):
+            self.pr, self._keep = _problem(model, params, y, keep_init)
         n = self.n
         self.out = {k: _alloc(y, self.rows, d) for k, d in
                     dict(m=n, C=n * n, a=n, R=n * n, f=1, Q=1, s=n, S=n * n).items()}
@@ -186,7 +188,8 @@ class DistScan:
         self.model, self.y = model, y_chunk   # the problem struct points into model.F / model.G
         self.keep_init = rank == 0
         self.rows = model.T + int(self.keep_init)
-        self.pr, self._keep = _problem(model, params, y_chunk, self.keep_init)
+        with bound_engine(eng):
+            self.pr, self._keep = _problem(model, params, y_chunk, self.keep_init)
         n = self.n
         self.out = {k: _alloc(y_chunk, self.rows, d) for k, d in
                     dict(m=n, C=n * n, a=n, R=n * n, f=1, Q=1, s=n, S=n * n).items()}
