@@ -117,13 +117,12 @@ __device__ __forceinline__ int w_chol_lower(int lane, int n, const double *S, do
     d = sqrt(d);
     __syncwarp();
     if (lane == 0) L[j + j * n] = d;
-    const int i = j + 1 + lane;
-    if (i < n) {
+    for (int i = j + 1 + lane; i < n; i += 32) {  // rows strided over the lanes (n up to 48)
       double v = L[i + j * n];
       for (int k = 0; k < j; ++k) v = v - L[i + k * n] * L[j + k * n];
       L[i + j * n] = v / d;
     }
-    if (lane < j) L[lane + j * n] = 0.0;
+    for (int i = lane; i < j; i += 32) L[i + j * n] = 0.0;
     __syncwarp();
   }
   return st;
