@@ -184,10 +184,12 @@ def test_conjugate_filter_bit_exact(eng, oracle, n):
 
 # ------------------------------------------------------------------ conjugate draws
 
-def test_gibbs_draw_injected_bit_exact(eng, oracle):
+@pytest.mark.parametrize("dims", [(13, 5, 3), (3, 37, 7)])
+def test_gibbs_draw_injected_bit_exact(eng, oracle, dims):
     from bayesian_dlms_b200 import SERIES_MAJOR
     rng = np.random.default_rng(77)
-    B, n, p, T = 13, 5, 3, 250
+    B, n, p = dims
+    T = 250
     stats = dict(ssy=rng.uniform(1, 50, (B, p)), ny=rng.integers(100, T, (B, p)).astype(float),
                  ssw=rng.uniform(1, 50, (B, n)),
                  scatter=np.stack([oracle.oracle.cm(H.spd(rng, n, 5.0)) for _ in range(B)]))
