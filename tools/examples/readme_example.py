@@ -1,4 +1,8 @@
-import sys; sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__)))))
+"""The batched-use example of README.md as a runnable script (needs a B200)."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 from bayesian_dlms_b200 import Engine, Model, TIME_MAJOR, dlm, gibbs
 eng = Engine(0)
