@@ -102,3 +102,46 @@ def test_outer_sum_and_compose_shapes():
     assert b.f(1.0).shape == (7, 1) and b.g(1.0).shape == (7, 7)
     p = dlm.DlmParameters(3.0, 1.0, 0.0, 1.0) * dlm.DlmParameters(2.0, 1.0, 0.0, 1.0)
     assert p.v.shape == (2, 2) and p.m0.shape == (2,)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4])
+def test_scan_combine_is_associative_on_the_host(n):
+    """bdlm_scan_combine is host code (the carry folding of the time-sharded scan): the
+    filtering and smoothing operators of Sarkka & Garcia-Fernandez must be associative, with the
+    documented identity elements -- that is what makes chunks on different GPUs composable."""
+    lib = capi.load()
+    rng = np.random.default_rng(n)
+
+    def spd(scale):
+        a = rng.standard_normal((n, n))
+        return scale * (a @ a.T / n + 0.3 * np.eye(n))
+
+    def felem():   # [A | b | C | eta | J], matrices column-major
+        return np.concatenate([rng.standard_normal(n * n) * 0.5, rng.standard_normal(n),
+                               spd(1.0).T.ravel(), rng.standard_normal(n), spd(0.2).T.ravel()])
+
+    def selem():   # [E | g | L]
+        return np.concatenate([rng.standard_normal(n * n) * 0.5, rng.standard_normal(n), spd(1.0).T.ravel()])
+
+    def comb(backward, x, y):
+        out = np.empty_like(x)
+        assert lib.bdlm_scan_combine(n, backward, x.ctypes.data, y.ctypes.data, out.ctypes.data) == 0
+        return out
+
+    for backward, make in ((0, felem), (1, selem)):
+        assert lib.bdlm_scan_elem_doubles(n, backward) == make().size
+        a, b, c = make(), make(), make()
+        left = comb(backward, comb(backward, a, b), c)
+        right = comb(backward, a, comb(backward, b, c))
+        assert np.allclose(left, right, rtol=1e-9, atol=1e-11), (backward, np.abs(left - right).max())
+    # identities: forward (A = I, rest 0), backward (E = I, rest 0)
+    ident = np.zeros(3 * n * n + 2 * n)
+    ident[: n * n] = np.eye(n).ravel()
+    x = felem()
+    assert np.allclose(comb(0, ident, x), x, rtol=1e-12, atol=1e-14)
+    assert np.allclose(comb(0, x, ident), x, rtol=1e-12, atol=1e-14)
+    ident = np.zeros(2 * n * n + n)
+    ident[: n * n] = np.eye(n).ravel()
+    x = selem()
+    assert np.allclose(comb(1, ident, x), x, rtol=1e-12, atol=1e-14)
+    assert np.allclose(comb(1, x, ident), x, rtol=1e-12, atol=1e-14)
