@@ -250,3 +250,24 @@ def test_conjugate_filter_matches_numpy_for_n2():
         shape, scale = shape + 1, scale + v * e * e / qt
         assert np.allclose(o["m"][t + 1], m, rtol=1e-11) and np.allclose(o["C"][t + 1].reshape(n, n).T, C, rtol=1e-10)
         assert np.isclose(o["shape"][t + 1], shape) and np.isclose(o["scale"][t + 1], scale, rtol=1e-11)
+
+
+def test_ar_ffbs_is_the_dlm_ffbs_of_the_equivalent_model():
+    """An AR(1) state around mu = 0 with unit observation loading is the DLM F = 1, G = phi,
+    W = sigma^2 with m0 = 0, C0 = sigma^2 / (1 - phi^2): FilterAr.ffbs (scalar formulas) and
+    Smoothing.ffbs (matrix formulas + eigen draw) must agree to rounding on the same normals."""
+    from bayesian_dlms_b200 import dlm
+    rng = np.random.default_rng(31)
+    T, phi, sig, v = 300, 0.85, 0.6, 0.9
+    times = np.arange(1.0, T + 1)
+    y = rng.standard_normal(T)
+    y[rng.random(T) < 0.1] = np.nan
+    z = rng.standard_normal(T + 1)
+    f = oracle.ar_filter(phi, 0.0, sig, times, np.full(T, v), y)
+    th = oracle.ar_backward_sample(phi, f, z)
+    c0 = sig * sig / (1 - phi * phi)
+    o = oracle.ffbs(1, 1, [1.0], [phi], [v], [sig * sig], [0.0], [c0], times, y.reshape(T, 1),
+                    z.reshape(T + 1, 1))
+    assert np.allclose(o["m"][:, 0], f["m"], rtol=1e-12, atol=1e-14)
+    assert np.allclose(o["C"][:, 0], f["C"], rtol=1e-12, atol=1e-14)
+    assert np.allclose(o["theta"][:, 0], th, rtol=1e-9, atol=1e-11)
