@@ -36,7 +36,7 @@ struct bdlm_ctx {
   unsigned long long rng_seed = 0, rng_sweep = 0;  // on-device RNG mode of the FFBS calls (z == NULL)
   long long rng_first = 0;                         // global index of a call's first series
   void *scan_table = nullptr;          // scan.cu forward table of the model in scan_key
-  std::vector<double> scan_key;
+  std::vector<double> scan_key, scan_key_pending;
   bool use_group = std::getenv("BDLM_NO_GROUP_KERNEL") == nullptr;  // A/B switch for profiling
 };
 
@@ -658,6 +658,10 @@ int run_host_mode(bdlm_ctx *c, DevCall d) {
   while (slab > 128 && total_for(slab) > c->staging_cap) slab = ((slab / 2 + 127) / 128) * 128;
   int rc = ensure_arena(c, total_for(slab));
   if (rc) return rc;
+  // Device-mode calls return without synchronising and use the same arena (spill, transposes,
+  // model upload): the staged copies below run on other streams, so earlier work on the
+  // context's stream must have drained before the first of them touches the arena.
+  CU(cudaStreamSynchronize(c->stream));
 
   Bump bump{c->arena, 0, c->arena_bytes};
   std::vector<double *> dev_ptrs[2];
@@ -787,7 +791,9 @@ const char *bdlm_last_error(bdlm_ctx *c) { return c ? c->err.c_str() : g_create_
 
 int bdlm_set_stream(bdlm_ctx *c, void *s, int use_own) {
   if (!c) return BDLM_E_ARG;
-  c->stream = use_own ? c->own_stream : reinterpret_cast<cudaStream_t>(s);
+  cudaStream_t ns = use_own ? c->own_stream : reinterpret_cast<cudaStream_t>(s);
+  if (ns != c->stream) c->scan_key.clear();  // the table upload was ordered on the old stream
+  c->stream = ns;
   return 0;
 }
 
@@ -952,7 +958,17 @@ static int scan_fill(bdlm_ctx *c, const bdlm_problem *p, ScanArgs &a, bool forwa
   a.table = c->scan_table;
   a.table_upload = (key.size() != c->scan_key.size() ||
                     std::memcmp(key.data(), c->scan_key.data(), key.size() * sizeof(double)) != 0);
-  if (a.table_upload) c->scan_key = key;
+  if (a.table_upload) { c->scan_key.clear(); c->scan_key_pending = key; }
+  return 0;
+}
+
+// launch_scan for a forward pass: the table key is committed only once the upload is enqueued, so
+// a failed launch (or a finish phase without its local phase) can never leave a stale table that
+// a later call would trust.
+static int scan_launch_fwd(bdlm_ctx *c, ScanArgs &a) {
+  CU(launch_scan(a, c->stream, &c->launches));
+  if (a.table_upload) c->scan_key.swap(c->scan_key_pending);
+  c->scan_key_pending.clear();
   return 0;
 }
 
@@ -989,7 +1005,7 @@ int bdlm_scan_forward_reduce(bdlm_ctx *c, const bdlm_problem *p, double *agg_hos
   rc = scan_fill(c, p, a, true);
   if (rc) return rc;
   a.phase = kScanReduce; a.agg_out = agg_host; a.workspace = c->arena;
-  CU(launch_scan(a, c->stream, &c->launches));
+  { rc = scan_launch_fwd(c, a); if (rc) return rc; }
   return 0;
 }
 
@@ -1012,7 +1028,7 @@ int bdlm_scan_forward_apply(bdlm_ctx *c, const bdlm_problem *p, const double *st
   a.phase = kScanApply; a.start = start_mC_host ? start_mC_host : prior.data();
   a.kf = scan_kf_views(p, kf); a.status = status; a.workspace = c->arena;
   if (status) CU(cudaMemsetAsync(status, 0, sizeof(int32_t), c->stream));
-  CU(launch_scan(a, c->stream, &c->launches));  // start state travels by value: no sync needed
+  { rc = scan_launch_fwd(c, a); if (rc) return rc; }  // start state travels by value: no sync needed
   return 0;
 }
 
@@ -1085,7 +1101,7 @@ int bdlm_scan_filter_smooth(bdlm_ctx *c, const bdlm_problem *p, const bdlm_kf_ou
   a.kf = scan_kf_views(p, &k); a.status = status; a.workspace = c->arena;
   a.fuse_sagg = R > 1 ? c->arena + ws : nullptr;
   if (status) CU(cudaMemsetAsync(status, 0, sizeof(int32_t), c->stream));
-  CU(launch_scan(a, c->stream, &c->launches));
+  { rc = scan_launch_fwd(c, a); if (rc) return rc; }
   // backward: scan the aggregates, apply
   rc = scan_fill(c, p, a);
   if (rc) return rc;
@@ -1128,7 +1144,7 @@ int bdlm_scan_dist_forward_local(bdlm_ctx *c, const bdlm_problem *p, int32_t ran
   if (rc) return rc;
   a.phase = kScanDistLocal; a.agg_dev = agg_dev; a.workspace = c->arena;
   a.rank = rank; a.world = world;
-  CU(launch_scan(a, c->stream, &c->launches));
+  { rc = scan_launch_fwd(c, a); if (rc) return rc; }
   return 0;
 }
 
@@ -1145,13 +1161,12 @@ int bdlm_scan_dist_forward_finish(bdlm_ctx *c, const bdlm_problem *p, int32_t ra
   ScanArgs a;
   rc = scan_fill(c, p, a, true);
   if (rc) return rc;
-  a.table_upload = 0;  // built by the local phase
   a.phase = kScanDistFinish; a.aggs_dev = aggs_dev; a.rank = rank; a.world = world;
   a.start = prior.data(); a.has_successor = rank < world - 1;
   a.kf = scan_kf_views(p, kf); a.status = status; a.workspace = c->arena;
   a.fuse_sagg = c->arena + ws;  // smoother level-1 aggregates for the backward phases
   if (status) CU(cudaMemsetAsync(status, 0, sizeof(int32_t), c->stream));
-  CU(launch_scan(a, c->stream, &c->launches));
+  { rc = scan_launch_fwd(c, a); if (rc) return rc; }
   return 0;
 }
 

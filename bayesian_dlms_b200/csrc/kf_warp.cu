@@ -573,11 +573,13 @@ warp_kernel(const WarpArgs wa, const int ws_doubles) {
         if (OP == kOpLoglik) {
           // KalmanFilter.logLikelihood (KalmanFilter.scala:175-183): N(m_t; G m_{t-1}, W dt)
           double v;
-          w_mv(lane, n, n, ws.G, n, false, ws.th, ws.v3);
-          for (int k = lane; k < nn; k += 32) ws.t3[k] = ws.W[k] * dt;
-          __syncwarp();
-          st |= w_mvn_logpdf(lane, n, ws, ws.m, ws.v3, ws.t3, v);
-          ll_tr = (t == 0) ? v : ll_tr + v;
+          if (wa.ll_transition) {  // only when asked for: a rank-deficient W is fine otherwise
+            w_mv(lane, n, n, ws.G, n, false, ws.th, ws.v3);
+            for (int k = lane; k < nn; k += 32) ws.t3[k] = ws.W[k] * dt;
+            __syncwarp();
+            st |= w_mvn_logpdf(lane, n, ws, ws.m, ws.v3, ws.t3, v);
+            ll_tr = (t == 0) ? v : ll_tr + v;
+          }
           // conditionalLikelihood (:138-153)
           int *obs = ws.iscr + 32;
           const int po = observed(lane, p, ws.yrow, obs);

@@ -347,7 +347,11 @@ loglik_small_kernel(const ConjModel<N> md, const Batch bt, double *ll_transition
   // regular grid: S = W * 1.0 at every step -> factorise once
   MvnPrepared<N> mvn;
   const bool regular = bt.dt == nullptr;
-  if (regular) {
+  // the transition density N(m_t; G m_{t-1}, W dt) -- and the singular / not-PD status bits a
+  // rank-deficient W raises in it -- only when the caller asked for it (bdlm_kf_filter_last and
+  // innovations-only calls are valid for W = diag(s2, 0))
+  const bool want_tr = ll_transition != nullptr;
+  if (regular && want_tr) {
     double S[N * N];
 #pragma unroll
     for (int k = 0; k < N * N; ++k) S[k] = W[k] * 1.0;
@@ -362,15 +366,17 @@ loglik_small_kernel(const ConjModel<N> md, const Batch bt, double *ll_transition
     smm<N, N, 1, false, false>(md.G, m, mu);  // G m_{t-1}
     advance<N, false>(md.G, W, dt, m, C, a, R);
     update<N>(md.F, V, y, a, R, f, Q, m, C, st);
-    if (!regular) {
-      double S[N * N];
+    if (want_tr) {
+      if (!regular) {
+        double S[N * N];
 #pragma unroll
-      for (int k = 0; k < N * N; ++k) S[k] = W[k] * dt;
-      mvn.prepare(S);
+        for (int k = 0; k < N * N; ++k) S[k] = W[k] * dt;
+        mvn.prepare(S);
+      }
+      st |= mvn.st;
+      const double v = mvn.eval(m, mu);
+      ll = (t == 0) ? v : ll + v;
     }
-    st |= mvn.st;
-    const double v = mvn.eval(m, mu);
-    ll = (t == 0) ? v : ll + v;
     if (!isnan(y)) {
       const double sd = sqrt(Q);
       const double dd = (y - f) / sd;

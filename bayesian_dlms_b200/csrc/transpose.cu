@@ -10,7 +10,7 @@ namespace {
 
 __global__ void __launch_bounds__(256)
 transpose_kernel(const double *__restrict__ in, double *__restrict__ out, int64_t rows,
-                 int64_t cols) {
+                 int64_t cols, int64_t out_pitch) {
   __shared__ double tile[32][33];
   const int64_t c0 = (int64_t)blockIdx.x * 32, r0 = (int64_t)blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
@@ -23,7 +23,7 @@ transpose_kernel(const double *__restrict__ in, double *__restrict__ out, int64_
 #pragma unroll
   for (int k = 0; k < 32; k += 8) {
     const int64_t c = c0 + ty + k, r = r0 + tx;
-    if (r < rows && c < cols) st_stream(out + c * rows + r, tile[tx][ty + k]);
+    if (r < rows && c < cols) st_stream(out + c * out_pitch + r, tile[tx][ty + k]);
   }
 }
 
@@ -32,21 +32,20 @@ transpose_kernel(const double *__restrict__ in, double *__restrict__ out, int64_
 cudaError_t launch_transpose(const double *in, double *out, int64_t rows, int64_t cols,
                              cudaStream_t stream) {
   if (rows <= 0 || cols <= 0) return cudaSuccess;
-  const int64_t gx = (cols + 31) / 32, gy = (rows + 31) / 32;
-  if (gy > 65535) {  // put the long dimension on x
-    // out[c][r] = in[r][c]  <=>  transpose of the (cols x rows) view is not expressible
-    // by swapping arguments, so tile over y in chunks instead.
-    for (int64_t y0 = 0; y0 < gy; y0 += 65535) {
-      const int64_t ny = (gy - y0 < 65535) ? gy - y0 : 65535;
-      const int64_t rbeg = y0 * 32, rcnt = (rows - rbeg < ny * 32) ? rows - rbeg : ny * 32;
-      // rows [rbeg, rbeg + rcnt) of `in` -> columns [rbeg, ...) of `out`: needs the full
-      // output pitch, so use the strided kernel through pointer offsets.
-      (void)rcnt;
-      return cudaErrorInvalidValue;  // not needed by any caller (rows*k <= 2M)
-    }
+  // grid.y is limited to 65535 blocks: loop over bands of <= 65535 * 32 rows (a band of `in`
+  // rows is a contiguous block of `in` and a column range of `out`, reachable by pointer offset
+  // with the full pitches kept as kernel arguments)
+  const int64_t gx = (cols + 31) / 32;
+  if (gx > 2147483647LL) return cudaErrorInvalidValue;
+  const int64_t band = (int64_t)65535 * 32;
+  for (int64_t r0 = 0; r0 < rows; r0 += band) {
+    const int64_t rcnt = rows - r0 < band ? rows - r0 : band;
+    transpose_kernel<<<dim3((unsigned)gx, (unsigned)((rcnt + 31) / 32)), 256, 0, stream>>>(
+        in + r0 * cols, out + r0, rcnt, cols, rows);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
   }
-  transpose_kernel<<<dim3((unsigned)gx, (unsigned)gy), 256, 0, stream>>>(in, out, rows, cols);
-  return cudaGetLastError();
+  return cudaSuccess;
 }
 
 }  // namespace bdlm
