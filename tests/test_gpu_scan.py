@@ -60,6 +60,42 @@ def test_scan_equals_sequential(eng, n, T):
         assert H.rel_err(a, b) < TOL, (k, n, T, H.rel_err(a, b))
 
 
+@pytest.mark.slow
+@pytest.mark.parametrize("n", [1, 2])
+def test_scan_full_config5_size_vs_cpu_oracle(eng, n):
+    """BASELINE config 5 at its OWN size: one series, T = 2^24, against the CPU oracle's sequential
+    recursion (Filter.scala:41-62 order; KalmanFilter.scala:64-118 + Smoothing.scala:31-47 with the
+    textbook covariance, which for n = 1 is the reference itself) -- error growth of the scan over
+    2^24 combines is bounded here, not extrapolated from short series.  Tolerance 1e-9 relative."""
+    import oracle
+    import torch
+    from bayesian_dlms_b200 import Model, dlm
+    from bayesian_dlms_b200.scan import scan_filter_smooth
+    mod, V, W, m0, C0 = _models()[n]
+    T = 1 << 24
+    g = torch.Generator(device="cuda").manual_seed(20260105)
+    yd = torch.randn(T, generator=g, device="cuda", dtype=torch.float64).cumsum(0) * 0.1
+    yd[torch.rand(T, generator=g, device="cuda") < 0.001] = float("nan")   # missing observations too
+    model = Model.build(mod, T=T)
+    out = scan_filter_smooth(eng, model, dict(V=V, W=W, m0=m0, C0=C0), yd)
+    torch.cuda.synchronize()
+    assert int(out["status"][0]) == 0
+    F, _, G, _, _, p = dlm.materialise(mod, np.arange(1, 9.0))
+    y = yd.cpu().numpy()
+    o = oracle.kf_filter(n, 1, F, G, dlm.cm(V), dlm.cm(W), m0, dlm.cm(C0), np.arange(1, T + 1.0), y)
+    sm = oracle.rts_smooth(n, G, o, textbook=True)
+    o.update(s=sm["s"], S=sm["S"])
+    worst = {}
+    for k in ("m", "C", "a", "R", "f", "Q", "s", "S"):
+        a, b = out[k].cpu().numpy(), o[k]
+        if k in ("f", "Q"):
+            a, b = a[1:], b[1:]
+        worst[k] = H.rel_err(a, b)
+        del a
+    print("config-5 full-size max relative error vs CPU oracle, n = %d:" % n, worst)
+    assert max(worst.values()) < TOL, worst
+
+
 def test_scan_reproduces_golden_csv(eng):
     import torch
     from bayesian_dlms_b200 import Model, dlm
