@@ -587,8 +587,11 @@ int validate(bdlm_ctx *c, int op, const bdlm_problem *p) {
   if (p->B < 0 || p->T < 0) return fail(c, BDLM_E_ARG, "negative B or T");
   if (p->n < 1 || p->n > BDLM_MAX_N || p->p < 1 || p->p > BDLM_MAX_P)
     return fail(c, BDLM_E_ARG, "unsupported n (1..48) or p (1..32)");
-  if ((op == A_SVD_FILTER || op == A_SVD_FFBS) && p->n > 32)
-    return fail(c, BDLM_E_ARG, "the SVD entry points support n <= 32");
+  if (op != A_GIBBS_DRAW && op != A_AR_FILTER && op != A_AR_FFBS && op != A_CONJ_FILTER &&
+      warp_smem_bytes(warp_op(op), p->n, p->p) > (size_t)227 * 1024)
+    return fail(c, BDLM_E_ARG, "n and p together exceed one SM's shared memory (227 KB) for this "
+                               "operation: reduce p (n = 48 runs with p <= 16 on the Kalman path, "
+                               "p <= 8 on the SVD path)");
   if (p->layout != BDLM_TIME_MAJOR && p->layout != BDLM_SERIES_MAJOR)
     return fail(c, BDLM_E_ARG, "bad layout");
   if (p->mem != BDLM_DEVICE && p->mem != BDLM_HOST) return fail(c, BDLM_E_ARG, "bad mem");
@@ -602,10 +605,14 @@ int validate(bdlm_ctx *c, int op, const bdlm_problem *p) {
   if (op != A_SMOOTH && op != A_STATS && (!p->m0 || !p->C0))
     return fail(c, BDLM_E_ARG, "null m0 or C0");
   if (op != A_SMOOTH && !p->y) return fail(c, BDLM_E_ARG, "null y");
-  if (p->v_tv && op != A_FILTER && op != A_FILTER_SMOOTH && op != A_FFBS && op != A_LOGLIK)
-    return fail(c, BDLM_E_ARG, "v_tv: supported by filter, filter+smoother, log-likelihood and FFBS");
-  if (p->w_tv && op != A_FILTER && op != A_FILTER_SMOOTH && op != A_FFBS)
-    return fail(c, BDLM_E_ARG, "w_tv: supported by filter, filter+smoother and FFBS");
+  if (p->v_tv && op != A_FILTER && op != A_FILTER_SMOOTH && op != A_FFBS && op != A_LOGLIK &&
+      op != A_SVD_FILTER && op != A_SVD_FFBS)
+    return fail(c, BDLM_E_ARG, "v_tv: supported by filter, filter+smoother, log-likelihood, FFBS, "
+                               "SVD filter and SVD FFBS");
+  if (p->w_tv && op != A_FILTER && op != A_FILTER_SMOOTH && op != A_FFBS && op != A_SVD_FILTER &&
+      op != A_SVD_FFBS)
+    return fail(c, BDLM_E_ARG, "w_tv: supported by filter, filter+smoother, FFBS, SVD filter and "
+                               "SVD FFBS");
   if ((op == A_FFBS || op == A_SVD_FFBS || op == A_STATS) && !p->keep_init)
     return fail(c, BDLM_E_ARG, "FFBS keeps the initial state: keep_init must be 1");
   return 0;

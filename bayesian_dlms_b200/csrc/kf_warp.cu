@@ -1,4 +1,4 @@
-// kf_warp.cu -- generic-dimension kernels (n <= 48, p <= 32; SVD ops n <= 32): ONE WARP PER SERIES / CHAIN.
+// kf_warp.cu -- generic-dimension kernels (n <= 48, p <= 32): ONE WARP PER SERIES / CHAIN.
 //
 // Covers every function of the hot path for any model shape: forward Kalman filter with
 // partially-missing observations, RTS smoother, FFBS with the Jacobi eigen draw, both
@@ -42,7 +42,7 @@ struct Ws {
   // hides the serial rotation-parameter chain of the joint SVDs.
   static __host__ __device__ size_t svd4_shared_doubles(int n, int p) {
     const int L = imax(n, p), LL = L * L;
-    return (size_t)n * n + (size_t)n * p + 6 * (size_t)LL + 4 * (size_t)L + p + 96 + 32;
+    return (size_t)n * n + (size_t)n * p + 6 * (size_t)LL + 4 * (size_t)L + p + kScrDoubles + kIscrInts / 2;
   }
   static __host__ __device__ size_t svd4_series_doubles(int n, int p) {
     const int nn = n * n, L = imax(n, p);
@@ -57,8 +57,8 @@ struct Ws {
     w.G = take(nn); w.F = take((size_t)n * p);
     w.t1 = take(LL); w.t2 = take(LL); w.t3 = take(LL); w.t4 = take(LL); w.t5 = take(LL); w.t6 = take(LL);
     w.v1 = take(L); w.v2 = take(L); w.v3 = take(L); w.v4 = take(L); w.yrow = take(p);
-    w.scr = take(96);
-    w.iscr = reinterpret_cast<int *>(take(32));
+    w.scr = take(kScrDoubles);
+    w.iscr = reinterpret_cast<int *>(take(kIscrInts / 2));
     o = series;
     w.W = take(nn); w.Wsq = take(nn); w.V = take((size_t)p * p);
     w.m = take(n); w.a = take(n); w.th = take(n);
@@ -78,14 +78,20 @@ struct Ws {
     const bool svd = (op == kOpSvdFilter || op == kOpSvdFfbs);
     G = take(nn); F = take((size_t)n * p); W = take(nn); V = take((size_t)p * p);
     Wsq = svd ? take(nn) : nullptr;
-    m = take(n); C = take(nn); a = take(n); R = take(nn); f = take(p); Q = take((size_t)p * p);
+    m = take(n); C = take(nn); a = take(n); R = take(nn); f = take(p);
+    // The SVD operations never form Q or the smoothed covariance, and their sixth temporary is
+    // only live while t1 is dead (svd_update: the gain after Fm is consumed; SvdSampler.step:
+    // (du^T du) gWinv after G^T sqrtW^T is consumed) -- so t6 shares t1's storage there.  That is
+    // what lets n = 48 (12 n^2 + stack doubles) fit the 227 KB of one SM.
+    Q = svd ? nullptr : take((size_t)p * p);
     dcv = svd ? take(n) : nullptr; drv = svd ? take(n) : nullptr;
-    th = take(n); Sm = take(nn);
-    t1 = take(LL); t2 = take(LL); t3 = take(LL); t4 = take(LL); t5 = take(LL); t6 = take(LL);
+    th = take(n); Sm = svd ? nullptr : take(nn);
+    t1 = take(LL); t2 = take(LL); t3 = take(LL); t4 = take(LL); t5 = take(LL);
+    t6 = svd ? t1 : take(LL);
     stk = svd ? take((size_t)imax((n + L) * n, LL)) : nullptr;
     v1 = take(L); v2 = take(L); v3 = take(L); v4 = take(L); yrow = take(p);
-    scr = take(96);
-    iscr = reinterpret_cast<int *>(take(32));
+    scr = take(kScrDoubles);
+    iscr = reinterpret_cast<int *>(take(kIscrInts / 2));
     total = o;
   }
 };
@@ -186,7 +192,7 @@ __device__ __forceinline__ int kf_update(int lane, int n, int p, const Ws &ws) {
   w_mm(lane, p, n, p, ws.t1, p, false, ws.F, n, false, ws.Q, p);
   for (int k = lane; k < p * p; k += 32) ws.Q[k] = ws.Q[k] + ws.V[k];
   __syncwarp();
-  int *obs = ws.iscr + 32;
+  int *obs = ws.iscr + kObsOff;
   const int po = observed(lane, p, ws.yrow, obs);
   if (po == 0) {
     for (int k = lane; k < n; k += 32) ws.m[k] = ws.a[k];
@@ -315,6 +321,34 @@ __device__ __forceinline__ int w_sqrt_svd(int lane, int n, const Ws &ws, const d
   return st;
 }
 
+// Next row f2 on the SVD path: the parameters of observation t, transformed as the reference
+// transforms them at every step -- ps = vs.map(vi => transformParams(p.copy(v = vi)))
+// (DlmFsv.scala:213, DlmFsvSystem.scala:182): ws.V <- sqrtInvSvd(V_t), ws.Wsq <- sqrtSvd(W_t) and
+// ws.W <- the advance closure's factor (raw W_t, or sqrtSvd(W_t) with BDLM_SVD_CONSISTENT_W, which
+// is what those two callers use).  Clobbers stk, t3, t4, t5, v1, scr, iscr.
+__device__ __forceinline__ int svd_load_params_tv(int lane, const Batch &bt, const Ws &ws,
+                                                  int64_t b, int t, bool want_v) {
+  int st = 0;
+  const int n = bt.n, p = bt.p;
+  if (bt.v_tv && want_v) {
+    PView vt = bt.V;
+    vt.ptr += (int64_t)t * bt.V_sr;
+    load_pview(lane, vt, b, p * p, ws.V);
+    __syncwarp();
+    st |= w_sqrt_svd(lane, p, ws, ws.V, true, ws.t5);
+    w_copy(lane, p * p, ws.t5, ws.V);
+  }
+  if (bt.w_tv) {
+    PView wt = bt.W;
+    wt.ptr += (int64_t)t * bt.W_sr;
+    load_pview(lane, wt, b, n * n, ws.W);
+    __syncwarp();
+    st |= w_sqrt_svd(lane, n, ws, ws.W, false, ws.Wsq);
+    if (bt.compat & BDLM_SVD_CONSISTENT_W) w_copy(lane, n * n, ws.Wsq, ws.W);
+  }
+  return st;
+}
+
 // SvdFilter.advState (SvdFilter.scala:183-202): (m, dcv, C=uc) -> (a, drv, R=ur);
 // ws.W holds the advance closure's W factor.
 __device__ __forceinline__ int svd_advance(int lane, int n, const Ws &ws, double dt) {
@@ -341,7 +375,7 @@ __device__ __forceinline__ int svd_advance(int lane, int n, const Ws &ws, double
 // SvdFilter.updateState (SvdFilter.scala:38-68); ws.V holds V^{-1/2}.
 __device__ __forceinline__ int svd_update(int lane, int n, int p, const Ws &ws) {
   int st = 0;
-  int *obs = ws.iscr + 32;
+  int *obs = ws.iscr + kObsOff;
   const int po = observed(lane, p, ws.yrow, obs);
   if (po == 0) {
     for (int k = lane; k < n; k += 32) { ws.m[k] = ws.a[k]; ws.dcv[k] = ws.drv[k]; }
@@ -526,18 +560,19 @@ warp_kernel(const WarpArgs wa, const int ws_doubles) {
       load_model(lane, bt, ws, t, false);
       load_cview(lane, bt.y, b, t, p, ws.yrow);
       const double dt = bt.dt ? bt.dt[t] : 1.0;
-      if (bt.v_tv) {  // V_t: params.copy(v = V_t) at every step (StudentTGibbs.scala:105-118)
+      if (!kSvd && bt.v_tv) {  // V_t: params.copy(v = V_t) at every step (StudentTGibbs.scala:105-118)
         PView vt = bt.V;
         vt.ptr += (int64_t)t * bt.V_sr;
         load_pview(lane, vt, b, p * p, ws.V);
       }
-      if (bt.w_tv) {  // W_t: params.copy(w = W_t) (DlmFsvSystem.scala:142-153)
+      if (!kSvd && bt.w_tv) {  // W_t: params.copy(w = W_t) (DlmFsvSystem.scala:142-153)
         PView wt = bt.W;
         wt.ptr += (int64_t)t * bt.W_sr;
         load_pview(lane, wt, b, nn, ws.W);
       }
       __syncwarp();
       if (kSvd) {
+        if (bt.v_tv || bt.w_tv) st |= svd_load_params_tv(lane, bt, ws, b, t, true);
         st |= svd_advance(lane, n, ws, dt);
         w_mv(lane, p, n, ws.F, n, true, ws.a, ws.f);
         st |= svd_update(lane, n, p, ws);
@@ -581,7 +616,7 @@ warp_kernel(const WarpArgs wa, const int ws_doubles) {
             ll_tr = (t == 0) ? v : ll_tr + v;
           }
           // conditionalLikelihood (:138-153)
-          int *obs = ws.iscr + 32;
+          int *obs = ws.iscr + kObsOff;
           const int po = observed(lane, p, ws.yrow, obs);
           if (po == 1) {
             const int o = obs[0];
@@ -730,6 +765,8 @@ warp_kernel(const WarpArgs wa, const int ws_doubles) {
       for (int k = lane; k < nn; k += 32) ws.C[k] = sp[2 * n + k];
       load_z(lane, wa, b, r, rows, n, ws.v3);
       __syncwarp();
+      // W_t: the state of row r is stepped with sqrtSvd(W) of observation r (DlmFsvSystem.scala:193-201)
+      if (bt.w_tv) st |= svd_load_params_tv(lane, bt, ws, b, tobs, false);
       w_mm(lane, n, n, n, ws.Wsq, n, false, ws.G, n, false, ws.t1, n);
       w_mm(lane, n, n, n, ws.t1, n, false, ws.C, n, false, ws.t2, n);
       for (ElemIter it(lane, n, n); it.ok(); it.next()) {
@@ -914,7 +951,7 @@ __device__ __forceinline__ void svd_advance_pre(int lane, int n, const Ws &ws, d
 
 // svd_update split around its SVD.  pre returns po (0 = all missing: state copied, no SVD).
 __device__ __forceinline__ int svd_update_pre(int lane, int n, int p, const Ws &ws) {
-  int *obs = ws.iscr + 32;
+  int *obs = ws.iscr + kObsOff;
   const int po = observed(lane, p, ws.yrow, obs);
   if (po == 0) {
     for (int k = lane; k < n; k += 32) { ws.m[k] = ws.a[k]; ws.dcv[k] = ws.drv[k]; }
@@ -947,7 +984,7 @@ __device__ __forceinline__ int svd_update_pre(int lane, int n, int p, const Ws &
 // values and right vectors the joint SVD left for this series.
 __device__ __forceinline__ void svd_update_post(int lane, int n, int p, const Ws &ws,
                                                 const double *sS, const double *sV) {
-  int *obs = ws.iscr + 32;
+  int *obs = ws.iscr + kObsOff;
   const int po = observed(lane, p, ws.yrow, obs);
   double *Fm = ws.t1, *Vm = ws.t2;
   for (ElemIter it(lane, n, po); it.ok(); it.next()) Fm[it.i + it.j * n] = ws.F[it.i + obs[it.j] * n];
@@ -1053,7 +1090,10 @@ svd4_kernel(const WarpArgs wa, const int shared_doubles, const int series_double
     load_model(lane, bt, mine.ws, t, false);  // no-op unless F or G vary with t
 #pragma unroll 1
     for (int s = 0; s < kQuad; ++s)
-      if (live(s)) svd_advance_pre(lane, n, slot(s).ws, dt);
+      if (live(s)) {
+        if (bt.v_tv || bt.w_tv) add_status(s, svd_load_params_tv(lane, bt, slot(s).ws, b0 + s, t, true));
+        svd_advance_pre(lane, n, slot(s).ws, dt);
+      }
     if (dt != 0.0)  // the four time updates' SVDs together: stack (2n x n) -> (drv, R)
       fold_status(oct_jacobi_svd(lane, n, 2 * n, mine_live ? mine.ws.stk : nullptr, mine.ws.drv,
                                  mine.ws.R));
@@ -1133,6 +1173,7 @@ svd4_kernel(const WarpArgs wa, const int shared_doubles, const int series_double
         }
         for (int k = lane; k < nn; k += 32) ws.C[k] = sp[2 * n + k];
         __syncwarp();
+        if (bt.w_tv) add_status(s, svd_load_params_tv(lane, bt, ws, b, tobs, false));
         w_mm(lane, n, n, n, ws.Wsq, n, false, ws.G, n, false, ws.t1, n);
         w_mm(lane, n, n, n, ws.t1, n, false, ws.C, n, false, ws.t2, n);
         for (ElemIter it(lane, n, n); it.ok(); it.next()) {
@@ -1190,7 +1231,7 @@ svd4_kernel(const WarpArgs wa, const int shared_doubles, const int series_double
 }
 
 bool svd4_supported(int op, const Batch &bt) {
-  return (op == kOpSvdFilter || op == kOpSvdFfbs) && bt.n <= kOctN && bt.p <= kOctN && !bt.v_tv;
+  return (op == kOpSvdFilter || op == kOpSvdFfbs) && bt.n <= kOctN && bt.p <= kOctN;
 }
 
 template <int OP>
@@ -1243,6 +1284,11 @@ size_t warp_spill_doubles_per_row(int op, int n, int p) {
   if (op == kOpFilterSmooth || op == kOpFfbs) return (size_t)2 * n + 2 * n * n;
   if (op == kOpSvdFfbs) return (size_t)3 * n + n * n;
   return 0;
+}
+
+size_t warp_smem_bytes(int op, int n, int p) {
+  Ws sz(nullptr, n, p, op);
+  return ((sz.total + 1) & ~(size_t)1) * sizeof(double);
 }
 
 cudaError_t launch_warp(int op, const WarpArgs &wa, cudaStream_t stream) {

@@ -11,7 +11,7 @@ cudaError_t launch_kf_small(const Batch &bt, const double *hG, const double *hF,
                             bool do_filter, bool do_smooth, cudaStream_t stream,
                             int *wave_series = nullptr);  // non-null: occupancy query only
 
-// kf_warp.cu: warp-per-series shared-memory kernels (n <= 48, p <= 32; SVD ops n <= 32).
+// kf_warp.cu: warp-per-series shared-memory kernels (n <= 48, p <= 32).
 struct SvdViews {
   View m, dc, uc, a, dr, ur, f;
 };
@@ -44,6 +44,7 @@ struct WarpArgs {
   int64_t spill_k;
 };
 size_t warp_spill_doubles_per_row(int op, int n, int p);
+size_t warp_smem_bytes(int op, int n, int p);  // one warp's shared-memory workspace (<= 227 KB to launch)
 cudaError_t launch_warp(int op, const WarpArgs &wa, cudaStream_t stream);
 
 // ffbs_small.cu: FFBS with one thread per chain (n <= 4, p = 1, time-invariant F, G).

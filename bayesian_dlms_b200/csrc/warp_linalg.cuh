@@ -296,10 +296,15 @@ __device__ __forceinline__ bool rr_slot(int n, int round, int k, int &p, int &q)
   return true;
 }
 
+// Per-warp scratch of the Jacobi routines, sized for n <= 48 (24 column pairs per round).
+constexpr int kScrDoubles = 128;  // w_jacobi_svd: dots [72] | c [24] | s [24]; then norms [48] | flips [48]
+constexpr int kIscrInts = 128;    // pair p [48] | pair q [48] | observed-component list [32] at kObsOff
+constexpr int kObsOff = 96;
+
 // svd restatement (oracle jacobi_svd): one-sided Jacobi on the columns of U (r x n,
 // IN PLACE, destroyed); V: n x n work.  sv[n] descending, Vout (n x n) = right singular
-// vectors (Breeze rightVectors.t) ordered + sign-normalised.
-// scr: >= 80 doubles, iscr: >= 32 ints of per-warp scratch.
+// vectors (Breeze rightVectors.t) ordered + sign-normalised.  n <= 48.
+// scr: kScrDoubles doubles, iscr: the first kObsOff ints of the per-warp integer scratch.
 __device__ __forceinline__ int w_jacobi_svd(int lane, int r, int n, double *U, double *V,
                                             double *scr, int *iscr, double *sv,
                                             double *Vout) {
@@ -308,8 +313,8 @@ __device__ __forceinline__ int w_jacobi_svd(int lane, int r, int n, double *U, d
   __syncwarp();
   int st = (n == 1) ? 0 : BDLM_ST_NOTCONVERGED;
   const int m = (n + 1) & ~1, half = m / 2;
-  double *dots = scr, *pc = scr + 48, *ps = scr + 64;
-  int *pp = iscr, *pq = iscr + 16;
+  double *dots = scr, *pc = scr + 72, *ps = scr + 96;
+  int *pp = iscr, *pq = iscr + 48;
   for (int sweep = 0; sweep < kJacobiMaxSweeps && n > 1; ++sweep) {
     bool rotated = false;
     for (int round = 0; round < m - 1; ++round) {
@@ -330,7 +335,7 @@ __device__ __forceinline__ int w_jacobi_svd(int lane, int r, int n, double *U, d
       }
       __syncwarp();
       bool rot = false;
-      if (lane < half) {
+      if (lane < half) {  // half <= 24
         int p = -1, q = -1;
         double c = 1.0, s = 0.0;
         if (rr_slot(n, round, lane, p, q)) {
@@ -368,27 +373,27 @@ __device__ __forceinline__ int w_jacobi_svd(int lane, int r, int n, double *U, d
     }
     if (!rotated) { st = 0; break; }
   }
-  if (lane < n) {
-    const double *col = U + lane * r;
+  for (int j = lane; j < n; j += 32) {
+    const double *col = U + j * r;
     double acc = 0.0;
     for (int i = 0; i < r; ++i) {
       const double sq = col[i] * col[i];
       acc = (i == 0) ? sq : acc + sq;
     }
-    scr[lane] = sqrt(acc);
+    scr[j] = sqrt(acc);
   }
   __syncwarp();
-  if (lane < n) {
-    const int rk = stable_rank(n, scr, lane, true);
-    iscr[rk] = lane;
-    sv[rk] = scr[lane];
+  for (int j = lane; j < n; j += 32) {
+    const int rk = stable_rank(n, scr, j, true);
+    iscr[rk] = j;
+    sv[rk] = scr[j];
   }
   __syncwarp();
-  if (lane < n) scr[32 + lane] = col_flip(n, V + iscr[lane] * n) ? -1.0 : 1.0;
+  for (int j = lane; j < n; j += 32) scr[48 + j] = col_flip(n, V + iscr[j] * n) ? -1.0 : 1.0;
   __syncwarp();
   for (ElemIter it(lane, n, n); it.ok(); it.next()) {
     const double v = V[it.i + iscr[it.j] * n];
-    Vout[it.i + it.j * n] = (scr[32 + it.j] < 0.0) ? -v : v;
+    Vout[it.i + it.j * n] = (scr[48 + it.j] < 0.0) ? -v : v;
   }
   __syncwarp();
   return st;

@@ -129,6 +129,20 @@ def synth_params(B, seed, xp):
     return np.ascontiguousarray(Vs), np.ascontiguousarray(Ws)
 
 
+def timed_cpu(run, min_seconds=2.0, max_reps=100000):
+    """every CPU baseline is timed for >= 2 s of wall time AFTER one warm
+    pass (page faults, OpenMP team start-up, first-touch of the outputs).  `run()` does one pass
+    over the sample; returns (passes, seconds)."""
+    run()
+    reps, t0 = 0, time.perf_counter()
+    while True:
+        run()
+        reps += 1
+        dt = time.perf_counter() - t0
+        if dt >= min_seconds or reps >= max_reps:
+            return reps, dt
+
+
 def cpu_reference_leg(series, T, seconds_target=15.0, threads=None, warm_passes=1):
     """Time the CPU restatement of the reference (oracle, all host cores) on a bounded sample of
     the same workload.  The JVM reference itself cannot run here (no JDK): kind = "port"."""
@@ -218,12 +232,12 @@ def ffbs_leg(eng, dev, with_cpu=True, B=4096, T=2000):
         yc = rng.standard_normal((Bs, T, 1)) * 2.0
         yc[rng.random(yc.shape) < 0.1] = np.nan
         zc = rng.standard_normal((Bs, T + 1, n))
-        t0 = time.perf_counter()
-        oracle.batch_ffbs(Bs, n, p, T, F, G, [1.0], dlm.cm(W), np.zeros(n), dlm.cm(np.eye(n)),
-                          np.arange(1, T + 1.0), yc, zc, nthreads=threads)
-        dt = time.perf_counter() - t0
-        res["cpu_baseline"] = {"value": Bs / dt, "unit": "draws/s", "cores": threads, "kind": "port",
-                               "sample": f"{Bs} chains x T={T}, {dt:.2f} s wall, oracle port OpenMP"}
+        reps, dt = timed_cpu(lambda: oracle.batch_ffbs(
+            Bs, n, p, T, F, G, [1.0], dlm.cm(W), np.zeros(n), dlm.cm(np.eye(n)),
+            np.arange(1, T + 1.0), yc, zc, nthreads=threads))
+        res["cpu_baseline"] = {"value": reps * Bs / dt, "unit": "draws/s", "cores": threads, "kind": "port",
+                               "sample": f"{Bs} chains x T={T} x {reps} passes after one warm pass, "
+                                         f"{dt:.2f} s wall, oracle port OpenMP"}
     return res
 
 
@@ -270,12 +284,12 @@ def svd_leg(eng, dev, with_cpu=True, B=65536, T=1000):
         rng = np.random.default_rng(4)
         yc = rng.standard_normal((Bs, T, n)) * 2.0
         zc = rng.standard_normal((Bs, T + 1, n))
-        t0 = time.perf_counter()
-        oracle.batch_ffbs(Bs, n, p, T, F, G, dlm.cm(V), dlm.cm(W), np.zeros(n), dlm.cm(np.eye(n)),
-                          np.arange(1, T + 1.0), yc, zc, svd=True, nthreads=threads)
-        dt = time.perf_counter() - t0
-        res["cpu_baseline"] = {"value": Bs / dt, "unit": "draws/s", "cores": threads, "kind": "port",
-                               "sample": f"{Bs} series x T={T}, {dt:.2f} s wall, oracle port OpenMP"}
+        reps, dt = timed_cpu(lambda: oracle.batch_ffbs(
+            Bs, n, p, T, F, G, dlm.cm(V), dlm.cm(W), np.zeros(n), dlm.cm(np.eye(n)),
+            np.arange(1, T + 1.0), yc, zc, svd=True, nthreads=threads))
+        res["cpu_baseline"] = {"value": reps * Bs / dt, "unit": "draws/s", "cores": threads, "kind": "port",
+                               "sample": f"{Bs} series x T={T} x {reps} passes after one warm pass, "
+                                         f"{dt:.2f} s wall, oracle port OpenMP"}
     return res
 
 
@@ -383,15 +397,20 @@ def ar_leg(eng, dev, with_cpu=True, B=1_000_000, T=1000):
                         "unit": "GB/s", "frac": B * T * byt / t / 1e9 / peak, "bytes_per_step": byt}}
     if with_cpu:
         import oracle
-        Tc, reps = T, 2000
+        Tc, per = T, 500
         yc, vc, zc = np.random.default_rng(6).standard_normal((3, Tc + 1))
-        t0 = time.perf_counter()
-        for _ in range(reps):
-            f = oracle.ar_filter(0.8, 0.1, 0.3, np.arange(1.0, Tc + 1), np.abs(vc[:Tc]) + 0.5, yc[:Tc])
-            oracle.ar_backward_sample(0.8, f, zc)
-        dt = time.perf_counter() - t0
-        res["cpu_baseline"] = {"value": reps * Tc / dt, "unit": "series-steps/s", "cores": 1,
-                               "kind": "port", "sample": f"{reps} series x T={Tc}, one core, {dt:.2f} s wall"}
+        tt, vv = np.arange(1.0, Tc + 1), np.abs(vc[:Tc]) + 0.5
+
+        def run_ar():
+            for _ in range(per):
+                f = oracle.ar_filter(0.8, 0.1, 0.3, tt, vv, yc[:Tc])
+                oracle.ar_backward_sample(0.8, f, zc)
+
+        reps, dt = timed_cpu(run_ar)
+        res["cpu_baseline"] = {"value": reps * per * Tc / dt, "unit": "series-steps/s", "cores": 1,
+                               "kind": "port",
+                               "sample": f"{reps * per} series x T={Tc} after a warm pass of {per}, one "
+                                         f"core, {dt:.2f} s wall"}
     return res
 
 
@@ -434,14 +453,18 @@ def scan_leg(eng, dev, with_cpu=True, logT=24):
         Tc = 1 << 20  # the reference recursion is sequential: one core, bounded sample
         F, _, G, _, _, p = dlm.materialise(dlm.polynomial(2), np.arange(1, 9.0))
         yc = y[:Tc].cpu().numpy()
-        t0 = time.perf_counter()
-        o = oracle.kf_filter(2, 1, F, G, [3.0], dlm.cm(np.diag([2.0, 1.0])), np.zeros(2),
-                             dlm.cm(100.0 * np.eye(2)), np.arange(1, Tc + 1.0), yc)
-        oracle.rts_smooth(2, G, o)
-        dt = time.perf_counter() - t0
-        res["cpu_baseline"] = {"value": Tc / dt, "unit": "series-steps/s", "cores": 1, "kind": "port",
-                               "sample": f"first 2^20 steps, sequential (the reference has no "
-                                         f"parallel-in-time path), {dt:.2f} s wall"}
+        tc = np.arange(1, Tc + 1.0)
+
+        def run_seq():
+            o = oracle.kf_filter(2, 1, F, G, [3.0], dlm.cm(np.diag([2.0, 1.0])), np.zeros(2),
+                                 dlm.cm(100.0 * np.eye(2)), tc, yc)
+            oracle.rts_smooth(2, G, o)
+
+        reps, dt = timed_cpu(run_seq)
+        res["cpu_baseline"] = {"value": reps * Tc / dt, "unit": "series-steps/s", "cores": 1, "kind": "port",
+                               "sample": f"first 2^20 steps x {reps} passes after one warm pass, "
+                                         f"sequential (the reference has no parallel-in-time path), "
+                                         f"{dt:.2f} s wall"}
     return res
 
 
@@ -480,12 +503,12 @@ def ffbs_small_leg(eng, dev, with_cpu=True, B=1_000_000, T=1000):
         rng = np.random.default_rng(8)
         yc = rng.standard_normal((Bs, T, 1)).cumsum(axis=1)
         zc = rng.standard_normal((Bs, T + 1, 2))
-        t0 = time.perf_counter()
-        oracle.batch_ffbs(Bs, n, p, T, F, G, [3.0], dlm.cm(np.diag([2.0, 1.0])), np.zeros(2),
-                          dlm.cm(100.0 * np.eye(2)), np.arange(1, T + 1.0), yc, zc, nthreads=threads)
-        dt = time.perf_counter() - t0
-        res["cpu_baseline"] = {"value": Bs / dt, "unit": "draws/s", "cores": threads, "kind": "port",
-                               "sample": f"{Bs} chains x T={T}, {dt:.2f} s wall, oracle port OpenMP"}
+        reps, dt = timed_cpu(lambda: oracle.batch_ffbs(
+            Bs, n, p, T, F, G, [3.0], dlm.cm(np.diag([2.0, 1.0])), np.zeros(2),
+            dlm.cm(100.0 * np.eye(2)), np.arange(1, T + 1.0), yc, zc, nthreads=threads))
+        res["cpu_baseline"] = {"value": reps * Bs / dt, "unit": "draws/s", "cores": threads, "kind": "port",
+                               "sample": f"{Bs} chains x T={T} x {reps} passes after one warm pass, "
+                                         f"{dt:.2f} s wall, oracle port OpenMP"}
     return res
 
 
@@ -519,13 +542,85 @@ def loglik_leg(eng, dev, with_cpu=True, B=1_000_000, T=1000):
         import oracle
         F, _, G, _, n, p = dlm.materialise(dlm.polynomial(2), np.arange(1, T + 1.0))
         yc = y[:, 0, :64].cpu().numpy().T.copy()
-        t0 = time.perf_counter()
-        for b in range(64):
-            oracle.loglik(n, p, F, G, [float(Vs_all[0, b])], Ws_all[:, b].copy(), np.zeros(2),
-                          dlm.cm(100.0 * np.eye(2)), np.arange(1, T + 1.0), yc[b])
-        dt = time.perf_counter() - t0
-        res["cpu_baseline"] = {"value": 64 * T / dt, "unit": "series-steps/s", "cores": 1, "kind": "port",
-                               "sample": f"64 series x T={T}, one core, {dt:.2f} s wall"}
+        tt = np.arange(1, T + 1.0)
+
+        def run_ll():
+            for b in range(64):
+                oracle.loglik(n, p, F, G, [float(Vs_all[0, b])], Ws_all[:, b].copy(), np.zeros(2),
+                              dlm.cm(100.0 * np.eye(2)), tt, yc[b])
+
+        reps, dt = timed_cpu(run_ll)
+        res["cpu_baseline"] = {"value": reps * 64 * T / dt, "unit": "series-steps/s", "cores": 1, "kind": "port",
+                               "sample": f"64 series x T={T} x {reps} passes after one warm pass, one "
+                                         f"core, {dt:.2f} s wall"}
+    return res
+
+
+def jmh_leg(eng, with_cpu=True):
+    """The reference's own JMH shapes (benchmark/src/main/scala/bench/KalmanFilter.scala:10-33,
+    SvdFilter.scala:28-36, ffbs.scala:27-35): ONE series, polynomial(1), V = 3, W = 1, m0 = 0,
+    C0 = 1, T = 10 -- KalmanFilter.filterDlm, SvdFilter.filterDlm, Smoothing.ffbsDlm,
+    SvdSampler.ffbsDlm -- plus one series of T = 1000 (filterDlm + backwardsSmoother, the
+    FirstOrderDlm example).  Microseconds per call through (a) the drop-in mirror of the Scala API
+    (reference_api, host objects in and out), (b) the bare C ABI with host buffers, next to (c) the
+    CPU port on one core.  A single short series cannot fill a GPU: this leg exists to state the
+    per-call latency of the drop-in honestly, not to win."""
+    from bayesian_dlms_b200 import (Data, DlmParameters, KalmanFilter, Model, SERIES_MAJOR, Smoothing,
+                                    SvdFilter, SvdSampler, dlm, polynomial)
+    mod = polynomial(1)
+    p = DlmParameters(v=[[3.0]], w=[[1.0]], m0=[0.0], c0=[[1.0]])
+    rng = np.random.default_rng(10)
+
+    def series(T):
+        x = np.cumsum(rng.standard_normal(T))
+        return [Data(float(t + 1), np.array([x[t] + 1.7 * rng.standard_normal()])) for t in range(T)]
+
+    def us(fn, min_s=0.5):
+        fn(); fn()
+        n, t0 = 0, time.perf_counter()
+        while time.perf_counter() - t0 < min_s:
+            fn(); n += 1
+        return (time.perf_counter() - t0) / n * 1e6
+
+    res = {"model": "polynomial(1), V=3, W=1, m0=0, C0=1, one series (the JMH ModelState)", "unit": "us/call"}
+    for T in (10, 1000):
+        ys = series(T)
+        z = rng.standard_normal((T + 1, 1))
+        yarr = np.ascontiguousarray(np.array([d.observation for d in ys]).reshape(1, T, 1))
+        model = Model.build(mod, T=T)
+        par = dict(V=p.v, W=p.w, m0=p.m0, C0=p.c0)
+        zz = z.reshape(1, T + 1, 1).copy()
+        row = {}
+        row["kalmanFilter"] = {
+            "mirror": us(lambda: KalmanFilter.filterDlm(mod, ys, p)),
+            "c_abi": us(lambda: eng.filter(model, par, yarr, layout=SERIES_MAJOR, keep_init=False))}
+        row["svdFilter"] = {
+            "mirror": us(lambda: SvdFilter.filterDlm(mod, ys, p)),
+            "c_abi": us(lambda: eng.svd_filter(model, par, yarr, layout=SERIES_MAJOR, keep_init=False))}
+        row["naiveFfbs"] = {
+            "mirror": us(lambda: Smoothing.ffbsDlm(mod, ys, p, z=z)),
+            "c_abi": us(lambda: eng.ffbs(model, par, yarr, zz, layout=SERIES_MAJOR))}
+        row["svdFfbs"] = {
+            "mirror": us(lambda: SvdSampler.ffbsDlm(mod, ys, p, z=z)),
+            "c_abi": us(lambda: eng.ffbs(model, par, yarr, zz, layout=SERIES_MAJOR, svd=True))}
+        row["filterSmooth"] = {
+            "mirror": us(lambda: Smoothing.backwardsSmoother(mod)(KalmanFilter.filter(mod, ys, p))),
+            "c_abi": us(lambda: eng.filter_smooth(model, par, yarr, layout=SERIES_MAJOR))}
+        if with_cpu:
+            import oracle
+            F, _, G, _, n_, p_ = dlm.materialise(mod, np.arange(1, T + 1.0))
+            tt, y1 = np.arange(1, T + 1.0), yarr[0]
+            V, W, m0, C0 = [3.0], [1.0], [0.0], [1.0]
+            row["kalmanFilter"]["cpu_port"] = us(lambda: oracle.kf_filter(1, 1, F, G, V, W, m0, C0, tt, y1, keep_init=False))
+            row["svdFilter"]["cpu_port"] = us(lambda: oracle.svd_filter(1, 1, F, G, V, W, m0, C0, tt, y1, keep_init=False))
+            row["naiveFfbs"]["cpu_port"] = us(lambda: oracle.ffbs(1, 1, F, G, V, W, m0, C0, tt, y1, z))
+            row["svdFfbs"]["cpu_port"] = us(lambda: oracle.svd_ffbs(1, 1, F, G, V, W, m0, C0, tt, y1, z))
+            row["filterSmooth"]["cpu_port"] = us(
+                lambda: oracle.rts_smooth(1, G, oracle.kf_filter(1, 1, F, G, V, W, m0, C0, tt, y1)))
+        res["T=%d" % T] = row
+    res["note"] = ("c_abi = one bdlm_* call with numpy host buffers incl. ctypes marshalling; mirror adds "
+                   "Data/KfState object (un)packing; cpu_port = oracle C via ctypes, one core. The "
+                   "reference's JVM numbers for these harnesses are unpublished and no JVM exists here.")
     return res
 
 
@@ -587,11 +682,14 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     T, B = args.T, args.series
+    # identical in both arms (the driver compares the dicts); run-derived launch geometry goes to
+    # its own key
     config = {"workload": "config2: polynomial(2) n=2 p=1, %d series/GPU x T=%d, fused Kalman filter + "
                           "RTS smoother, full KfState+SmoothingState outputs" % (B, T),
-              "series_per_gpu": B, "T": T, "chunks_per_step": args.chunks,
+              "series_per_gpu": B, "T": T, "global_series": world * B,
               "device_layout": "time-major SoA [rows][k][B]",
               "l2": "inputs+outputs per launch >> 126 MB L2 (no flush needed)"}
+    geometry = {}
 
     if args.impl == "reference":
         if rank != 0:
@@ -638,9 +736,8 @@ def main():
         slabs = wave_aligned_slabs(0, B, eng.ctx.wave_series(N_STATE, N_OBS), args.waves)
         bounds = [s[0] for s in slabs] + [B]
         nch = len(bounds) - 1
-        config["global_series"] = world * B
-    config["chunks_per_step"] = nch
-    config["series_per_launch"] = bounds[1] - bounds[0]
+    geometry["launches_per_step"] = nch
+    geometry["series_per_launch"] = bounds[1] - bounds[0]
     Bc_max = max(bounds[i + 1] - bounds[i] for i in range(nch))
     rows = T + 1
     g = torch.Generator(device=dev).manual_seed(20260101 + rank)
@@ -768,6 +865,42 @@ def main():
                "host_layout": "series-major [B][T+1][k], pinned", "series_per_call": slab,
                "calls_per_step": ncall,
                "outputs": "full KfState (m,C,a,R,f,Q) + SmoothingState (s,S): 160 B/series-step over PCIe"}
+        # PCIe roofline of this leg, measured on the SAME buffers at this N: bare pinned-host
+        # copies (torch non_blocking copy_ = one cudaMemcpyAsync each), all ranks at once
+        dout = {k: torch.empty((slab, rows, d), device=dev, dtype=torch.float64) for k, d in dims.items()}
+        dy = torch.empty((slab, T, 1), device=dev, dtype=torch.float64)
+
+        def bare(direction):
+            barrier()
+            w0 = time.perf_counter()
+            for _ in range(2):
+                if direction in ("d2h", "both"):
+                    for k in dims:
+                        hout[k].copy_(dout[k], non_blocking=True)
+                if direction in ("h2d", "both"):
+                    dy.copy_(hy, non_blocking=True)
+            barrier()
+            w = torch.tensor([time.perf_counter() - w0], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(w, op=dist.ReduceOp.MAX)
+            nbytes = 0
+            if direction in ("d2h", "both"):
+                nbytes += slab * rows * sum(dims.values()) * 8
+            if direction in ("h2d", "both"):
+                nbytes += slab * T * 8
+            return 2 * nbytes / float(w.item()) / 1e9    # GB/s per rank, slowest rank
+
+        bare("d2h")
+        d2h_peak, h2d_peak = bare("d2h"), bare("h2d")
+        del dout, dy
+        per_rank_gbs = (h2d + d2h) * ksteps / wall / 1e9
+        e2e["roofline"] = {
+            "bound": "pcie", "achieved": per_rank_gbs, "peak": d2h_peak, "unit": "GB/s per GPU",
+            "frac": per_rank_gbs / d2h_peak,
+            "h2d_peak": h2d_peak,
+            "peak_source": "bare cudaMemcpyAsync D2H of the same pinned output buffers (8 fields x "
+                           "%d series), all %d ranks concurrently, slowest rank" % (slab, world),
+            "bytes_per_series_step": (h2d + d2h) / (ncall * slab * T)}
         # the same call asking only for what the reference's SmoothDlm app writes out
         # (smoothed mean and covariance, FirstOrderDlm.scala:248-254): 48 B/series-step D2H
         lean = {k: hout[k] for k in ("s", "S", "status")}
@@ -795,6 +928,7 @@ def main():
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+            "launch_geometry": geometry,
             "gpu_launches": int(launches), "clocks": clocks, "status_max": status_max,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak,
@@ -804,8 +938,10 @@ def main():
                          # to this run's average launch
                          "traffic": 0.9987 * ALGO_BYTES_PER_STEP * float(np.mean(kern_steps)) / 1e9,
                          "traffic_unit": "GB per launch",
-                         "traffic_source": "profiles/r1_kf_small_full.txt (61.298 GB measured / "
-                                           "61.379 GB algorithmic for its 284160-series launch)",
+                         "traffic_source": "NOT measured by this run: ratio from the ncu --set full "
+                                           "capture profiles/r1_kf_small_full.txt (kernel as of commit 48f6a5e; "
+                                           "61.298 GB measured / 61.379 GB algorithmic for its "
+                                           "284160-series launch); kf_small.cu unchanged since",
                          "kernel": "kf_small_kernel<2,true> (fused filter+smoother)",
                          "algorithmic_bytes_per_series_step": ALGO_BYTES_PER_STEP,
                          "launch_ms_avg": float(np.mean(kern_ms)),
@@ -827,6 +963,10 @@ def main():
                 except Exception as ex:
                     line[key] = {"error": repr(ex)}
                 torch.cuda.empty_cache()
+            try:
+                line["jmh"] = jmh_leg(eng, with_cpu=not args.no_cpu)
+            except Exception as ex:
+                line["jmh"] = {"error": repr(ex)}
             for key, fn in (("gibbs", gibbs_leg), ("gibbs_wishart", gibbs_wishart_leg)):
                 try:
                     line[key] = fn(eng, dev)

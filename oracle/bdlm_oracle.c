@@ -840,20 +840,28 @@ static int svd_update(int n, int p, const double *F, const double *Vfac,
  * parameters, V^{-1/2} is derived here) or filterDecomp :134-140 (transform =
  * 0: Vfac is passed in already transformed).  Wadv is the W factor used by the
  * advance closure.  keep_init as for the Kalman filter.  Outputs per row:
- * m[n], dc[n], uc[n*n], a[n], dr[n], ur[n*n], f[p]. */
-ORACLE_API int oracle_svd_filter(int n, int p, int T, const double *F, int f_tv,
-                                 const double *G, int g_tv, const double *V,
-                                 int transform, const double *Wadv,
-                                 const double *m0, const double *C0,
-                                 const double *times, const double *y,
-                                 int keep_init, double *times_out, double *m,
-                                 double *dc, double *uc, double *a, double *dr,
-                                 double *ur, double *f) {
+ * m[n], dc[n], uc[n*n], a[n], dr[n], ur[n*n], f[p].
+ *
+ * v_tv / w_tv (next row f2): V / Wadv hold T matrices, one per observation, as in
+ * DlmFsv.ffbsSvd (DlmFsv.scala:208-229: ps = vs.map(vi => transformParams(p.copy(v = vi))),
+ * the step for observation t runs with ps(t)) and DlmFsvSystem.ffbsSvd
+ * (DlmFsvSystem.scala:177-207, the same with W_t).  With transform = 1 every V_t goes
+ * through sqrtInvSvd at its own step. */
+static int svd_filter_impl(int n, int p, int T, const double *F, int f_tv,
+                           const double *G, int g_tv, const double *V, int v_tv,
+                           int transform, const double *Wadv, int w_tv,
+                           const double *m0, const double *C0,
+                           const double *times, const double *y,
+                           int keep_init, double *times_out, double *m,
+                           double *dc, double *uc, double *a, double *dr,
+                           double *ur, double *f) {
   if (T <= 0) return -1;
   int st = ST_OK, nn = n * n;
   double Vfac[64 * 64], mc[64], dcc[64], ucc[64 * 64], sv[64];
-  if (transform) st |= oracle_sqrt_svd(p, V, 1, Vfac);
-  else memcpy(Vfac, V, sizeof(double) * p * p);
+  if (!v_tv) {
+    if (transform) st |= oracle_sqrt_svd(p, V, 1, Vfac);
+    else memcpy(Vfac, V, sizeof(double) * p * p);
+  }
   /* initialiseState :83-95 */
   st |= jacobi_svd(n, n, C0, sv, ucc);
   for (int i = 0; i < n; ++i) dcc[i] = sqrt(sv[i]);
@@ -872,10 +880,16 @@ ORACLE_API int oracle_svd_filter(int n, int p, int T, const double *F, int f_tv,
   for (int t = 0; t < T; ++t, ++row) {
     const double *Ft = F + (f_tv ? (size_t)t * n * p : 0);
     const double *Gt = G + (g_tv ? (size_t)t * nn : 0);
+    const double *Wt = Wadv + (w_tv ? (size_t)t * nn : 0);
+    if (v_tv) {
+      const double *Vt = V + (size_t)t * p * p;
+      if (transform) st |= oracle_sqrt_svd(p, Vt, 1, Vfac);
+      else memcpy(Vfac, Vt, sizeof(double) * p * p);
+    }
     double dt = times[t] - tprev;
     double *ar = a + (size_t)row * n, *drr = dr + (size_t)row * n,
            *urr = ur + (size_t)row * nn;
-    st |= svd_advance(n, Gt, Wadv, dt, mc, dcc, ucc, ar, drr, urr);
+    st |= svd_advance(n, Gt, Wt, dt, mc, dcc, ucc, ar, drr, urr);
     mv(p, n, Ft, n, 1, ar, f + (size_t)row * p); /* :74 */
     st |= svd_update(n, p, Ft, Vfac, ar, drr, urr, y + (size_t)t * p,
                      m + (size_t)row * n, dc + (size_t)row * n, uc + (size_t)row * nn);
@@ -888,14 +902,26 @@ ORACLE_API int oracle_svd_filter(int n, int p, int T, const double *F, int f_tv,
   return st;
 }
 
+ORACLE_API int oracle_svd_filter(int n, int p, int T, const double *F, int f_tv,
+                                 const double *G, int g_tv, const double *V,
+                                 int transform, const double *Wadv,
+                                 const double *m0, const double *C0,
+                                 const double *times, const double *y,
+                                 int keep_init, double *times_out, double *m,
+                                 double *dc, double *uc, double *a, double *dr,
+                                 double *ur, double *f) {
+  return svd_filter_impl(n, p, T, F, f_tv, G, g_tv, V, 0, transform, Wadv, 0, m0, C0, times,
+                         y, keep_init, times_out, m, dc, uc, a, dr, ur, f);
+}
+
 /* SvdSampler.sample :54-60 with step :15-36, initialise :38-45, rnorm :94-102.
  * sqrtW is the matrix handed to SvdSampler.step (W^{1/2} on the ffbs path). */
-ORACLE_API int oracle_svd_backward_sample(int n, int T, int keep_init,
-                                          const double *G, int g_tv,
-                                          const double *sqrtW, const double *m,
-                                          const double *dc, const double *uc,
-                                          const double *a, const double *z,
-                                          double *theta) {
+static int svd_backward_sample_impl(int n, int T, int keep_init,
+                                    const double *G, int g_tv,
+                                    const double *sqrtW_all, int w_tv, const double *m,
+                                    const double *dc, const double *uc,
+                                    const double *a, const double *z,
+                                    double *theta) {
   int rows = T + keep_init, nn = n * n, st = ST_OK;
   double M[64 * 64], x[64], t1[64 * 64], t2[64 * 64], stack[128 * 64], sv[64],
       Vr[64 * 64], uh[64 * 64], dh[64], gW[64 * 64], du[64 * 64], dd[64 * 64],
@@ -911,6 +937,9 @@ ORACLE_API int oracle_svd_backward_sample(int n, int T, int keep_init,
   for (int r = rows - 2; r >= 0; --r) {
     int tobs = r + 1 - keep_init;
     const double *Gt = G + (g_tv ? (size_t)tobs * nn : 0);
+    /* w_tv: (ps, filtered.init).zipped.scanRight -- the state of row r is stepped with the
+     * parameters of observation r, i.e. of the transition r -> r + 1 (DlmFsvSystem.scala:193-201) */
+    const double *sqrtW = sqrtW_all + (w_tv ? (size_t)tobs * nn : 0);
     const double *ucr = uc + (size_t)r * nn, *dcr = dc + (size_t)r * n;
     mm(n, n, n, sqrtW, n, 0, Gt, n, 0, t1, n); /* sqrtW * G        */
     mm(n, n, n, t1, n, 0, ucr, n, 0, t2, n);   /* (sqrtW G) * uc   */
@@ -941,6 +970,15 @@ ORACLE_API int oracle_svd_backward_sample(int n, int T, int keep_init,
   return st;
 }
 
+ORACLE_API int oracle_svd_backward_sample(int n, int T, int keep_init,
+                                          const double *G, int g_tv,
+                                          const double *sqrtW, const double *m,
+                                          const double *dc, const double *uc,
+                                          const double *a, const double *z,
+                                          double *theta) {
+  return svd_backward_sample_impl(n, T, keep_init, G, g_tv, sqrtW, 0, m, dc, uc, a, z, theta);
+}
+
 /* SvdSampler.ffbs :66-74 as called by ffbsDlm :79-82 / Gibbs.stepSvd
  * (Gibbs.scala:187-190): params transformed, advance closure holds RAW W (Q2)
  * unless consistent != 0, sampler gets W^{1/2}. */
@@ -963,6 +1001,53 @@ ORACLE_API int oracle_svd_ffbs(int n, int p, int T, const double *F, int f_tv,
   if (s2 < 0) return s2;
   st |= s2;
   st |= oracle_svd_backward_sample(n, T, 1, G, g_tv, sqrtW, m, dc, uc, a, z, theta);
+  return st;
+}
+
+/* Next row f2 on the SVD path.  V: [T][p*p] when v_tv, W: [T][n*n] when w_tv (raw matrices).
+ *  - DlmFsv.ffbsSvd (DlmFsv.scala:208-229): v_tv = 1, w_tv = 0, consistent = 1 -- every step runs
+ *    with transformParams(p.copy(v = V_t)), the advance closure is built from the TRANSFORMED
+ *    parameters (so it stacks sqrtSvd(W), not the raw W of quirk Q2), the sampler gets ps.head.w.
+ *  - DlmFsvSystem.ffbsSvd (DlmFsvSystem.scala:177-207): w_tv = 1, consistent = 1; the backward
+ *    step of row r uses sqrtSvd(W) of observation r.
+ * consistent = 0 keeps the raw-W advance of filterDlm / ffbsDlm for callers that mix the two. */
+ORACLE_API int oracle_svd_filter_tv(int n, int p, int T, const double *F, int f_tv,
+                                    const double *G, int g_tv, const double *V, int v_tv,
+                                    const double *W, int w_tv, int consistent,
+                                    const double *m0, const double *C0,
+                                    const double *times, const double *y, int keep_init,
+                                    double *times_out, double *m, double *dc, double *uc,
+                                    double *a, double *dr, double *ur, double *f) {
+  int nn = n * n, st = ST_OK, nW = w_tv ? T : 1;
+  double *Wadv = (double *)malloc(sizeof(double) * nn * nW);
+  for (int t = 0; t < nW; ++t) {
+    if (consistent) st |= oracle_sqrt_svd(n, W + (size_t)t * nn, 0, Wadv + (size_t)t * nn);
+    else memcpy(Wadv + (size_t)t * nn, W + (size_t)t * nn, sizeof(double) * nn);
+  }
+  int s2 = svd_filter_impl(n, p, T, F, f_tv, G, g_tv, V, v_tv, 1, Wadv, w_tv, m0, C0, times, y,
+                           keep_init, times_out, m, dc, uc, a, dr, ur, f);
+  free(Wadv);
+  return s2 < 0 ? s2 : (st | s2);
+}
+
+ORACLE_API int oracle_svd_ffbs_tv(int n, int p, int T, const double *F, int f_tv,
+                                  const double *G, int g_tv, const double *V, int v_tv,
+                                  const double *W, int w_tv, int consistent,
+                                  const double *m0, const double *C0, const double *times,
+                                  const double *y, const double *z, double *times_out,
+                                  double *theta, double *m, double *dc, double *uc,
+                                  double *a, double *dr, double *ur) {
+  int rows = T + 1, nn = n * n, st = ST_OK, nW = w_tv ? T : 1;
+  double *sqrtW = (double *)malloc(sizeof(double) * nn * nW);
+  for (int t = 0; t < nW; ++t) st |= oracle_sqrt_svd(n, W + (size_t)t * nn, 0, sqrtW + (size_t)t * nn);
+  double *f = (double *)malloc(sizeof(double) * rows * p);
+  int s2 = svd_filter_impl(n, p, T, F, f_tv, G, g_tv, V, v_tv, 1, consistent ? sqrtW : W, w_tv,
+                           m0, C0, times, y, 1, times_out, m, dc, uc, a, dr, ur, f);
+  free(f);
+  if (s2 < 0) { free(sqrtW); return s2; }
+  st |= s2;
+  st |= svd_backward_sample_impl(n, T, 1, G, g_tv, sqrtW, w_tv, m, dc, uc, a, z, theta);
+  free(sqrtW);
   return st;
 }
 

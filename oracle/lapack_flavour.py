@@ -113,7 +113,11 @@ def sqrt_svd(M, inv=False):
 
 
 def svd_filter(Fs, Gs, Vfac, Wadv, m0, C0, times, y, keep_init=True):
+    """Vfac / Wadv: matrices, or callables t -> matrix (per-step V_t / W_t, DlmFsv.scala:208-229)."""
     T = len(times)
+    Vfac_c, Wadv_c = Vfac, Wadv
+    Vf = Vfac_c if callable(Vfac_c) else (lambda t: Vfac_c)
+    Wa = Wadv_c if callable(Wadv_c) else (lambda t: Wadv_c)
     s, vt = _svd(np.array(C0, float))
     m, dc, uc = np.array(m0, float), np.sqrt(s), vt.T
     tprev = np.min(times) - 1.0
@@ -127,14 +131,14 @@ def svd_filter(Fs, Gs, Vfac, Wadv, m0, C0, times, y, keep_init=True):
             a, dr, ur = m, dc, uc
         else:
             a = G @ m
-            sv, vt = _svd(np.vstack([np.diag(dc) @ uc.T @ G.T, Wadv * np.sqrt(dt)]))
+            sv, vt = _svd(np.vstack([np.diag(dc) @ uc.T @ G.T, Wa(t) * np.sqrt(dt)]))
             ur, dr = vt.T, sv
         f = F.T @ a
         o = [i for i in range(F.shape[1]) if not np.isnan(y[t][i])]
         if not o:
             m, dc, uc = a, dr, ur
         else:
-            Vm, Fm = Vfac[np.ix_(o, o)], F[:, o]
+            Vm, Fm = Vf(t)[np.ix_(o, o)], F[:, o]
             sv, vt = _svd(np.vstack([Vm @ Fm.T @ ur, np.diag(1.0 / dr)]))
             uc = ur @ vt.T
             e = y[t][o] - Fm.T @ a

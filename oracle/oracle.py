@@ -181,6 +181,48 @@ def svd_filter(n, p, F, G, V, Wadv, m0, C0, times, y, keep_init=True, transform=
     return out
 
 
+def svd_filter_tv(n, p, F, G, V, W, m0, C0, times, y, keep_init=True, v_tv=False, w_tv=False,
+                  consistent=True):
+    """Next row f2 on the SVD path: V [T][p*p] / W [T][n*n] raw matrices per observation
+    (DlmFsv.ffbsSvd, DlmFsv.scala:208-229; DlmFsvSystem.ffbsSvd, DlmFsvSystem.scala:177-207)."""
+    times = _a(times)
+    T = times.size
+    y = _a(y, (T, p))
+    F, f_tv, G, g_tv = _model(F, G, n, p, T)
+    assert _a(V).size == (T if v_tv else 1) * p * p and _a(W).size == (T if w_tv else 1) * n * n
+    rows = T + int(keep_init)
+    out = {k: np.empty((rows, d)) for k, d in
+           dict(m=n, dc=n, uc=n * n, a=n, dr=n, ur=n * n, f=p).items()}
+    tm = np.empty(rows)
+    st = lib().oracle_svd_filter_tv(
+        n, p, T, _p(F), f_tv, _p(G), g_tv, _p(_a(V)), int(v_tv), _p(_a(W)), int(w_tv),
+        int(consistent), _p(_a(m0)), _p(_a(C0)), _p(times), _p(y), int(keep_init), _p(tm),
+        *(_p(out[k]) for k in ("m", "dc", "uc", "a", "dr", "ur", "f")))
+    out["time"] = tm
+    out["status"] = st
+    return out
+
+
+def svd_ffbs_tv(n, p, F, G, V, W, m0, C0, times, y, z, v_tv=False, w_tv=False, consistent=True):
+    times = _a(times)
+    T = times.size
+    rows = T + 1
+    y = _a(y, (T, p))
+    z = _a(z, (rows, n))
+    F, f_tv, G, g_tv = _model(F, G, n, p, T)
+    assert _a(V).size == (T if v_tv else 1) * p * p and _a(W).size == (T if w_tv else 1) * n * n
+    out = {k: np.empty((rows, d)) for k, d in
+           dict(theta=n, m=n, dc=n, uc=n * n, a=n, dr=n, ur=n * n).items()}
+    tm = np.empty(rows)
+    st = lib().oracle_svd_ffbs_tv(
+        n, p, T, _p(F), f_tv, _p(G), g_tv, _p(_a(V)), int(v_tv), _p(_a(W)), int(w_tv),
+        int(consistent), _p(_a(m0)), _p(_a(C0)), _p(times), _p(y), _p(z), _p(tm),
+        *(_p(out[k]) for k in ("theta", "m", "dc", "uc", "a", "dr", "ur")))
+    out["time"] = tm
+    out["status"] = st
+    return out
+
+
 def svd_backward_sample(n, G, sqrtW, filt, z, keep_init=True):
     rows = filt["m"].shape[0]
     T = rows - int(keep_init)

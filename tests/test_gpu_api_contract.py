@@ -145,3 +145,75 @@ def test_distinct_contexts_run_concurrently_from_two_threads():
         t.join()
     torch.cuda.synchronize()
     assert not errors, errors
+
+
+def test_device_call_then_host_call_share_the_arena_safely(eng):
+    """A device-mode call returns without synchronising and keeps using the context's workspace
+    (spill, transposes); a host-mode call right behind it stages its slabs through the same arena
+    on other streams.  The second must not start before the first has drained."""
+    import oracle
+    import torch
+    from bayesian_dlms_b200 import Model, SERIES_MAJOR
+    oracle.build()
+    mod, V, W, m0, C0 = H.second_order()
+    rng = np.random.default_rng(3)
+    B, T = 40_000, 200
+    y = rng.standard_normal((B, T, 1)).cumsum(axis=1)
+    model = Model.build(mod, T=T)
+    params = dict(V=V, W=W, m0=m0, C0=C0)
+    yd = torch.from_numpy(y).cuda()
+    for _ in range(3):
+        d = eng.filter_smooth(model, params, yd, layout=SERIES_MAJOR, want=("s", "S"))   # async
+        h = eng.filter_smooth(model, params, y[:64].copy(), layout=SERIES_MAJOR, want=("s", "S"))
+        eng.sync()
+        F, _, G, _, n, p = __import__("bayesian_dlms_b200").dlm.materialise(mod, np.arange(1, T + 1.0))
+        cm = oracle.oracle.cm
+        for b in (0, 63, B - 1):
+            o = oracle.kf_filter(n, p, F, G, cm(V), cm(W), m0, cm(C0), np.arange(1, T + 1.0), y[b])
+            s = oracle.rts_smooth(n, G, o)
+            assert np.array_equal(d["S"][b].cpu().numpy(), s["S"]), b
+            if b < 64:
+                assert np.array_equal(h["S"][b], s["S"]), b
+
+
+def test_filter_last_with_rank_deficient_W_reports_no_failure(eng):
+    """W = diag(s2, 0) (trend / seasonal DLMs): the last filtered state and the innovations
+    log-likelihood are well defined; only the transition density N(m_t; G m_{t-1}, W dt) is not,
+    and it is evaluated -- and its status bits raised -- only when asked for."""
+    import torch
+    from bayesian_dlms_b200 import Model, SERIES_MAJOR
+    from bayesian_dlms_b200 import _capi as capi
+    mod, V, W, m0, C0 = H.second_order()
+    W = np.diag([2.0, 0.0])
+    rng = np.random.default_rng(4)
+    for n_, model_mod, Wm in ((2, mod, W), (13, H.seasonal13()[0], np.diag([0.0] + [0.1] * 12))):
+        Vm, m0m, C0m = np.array([[1.0]]), np.zeros(n_), np.eye(n_)
+        T, B = 30, 5
+        y = torch.from_numpy(rng.standard_normal((B, T, 1))).cuda()
+        model = Model.build(model_mod, T=T)
+        out = eng.filter_last(model, dict(V=Vm, W=Wm, m0=m0m, C0=C0m), y, layout=SERIES_MAJOR)
+        eng.sync()
+        assert int(out["status"].max()) == 0, n_
+        full = eng.filter_last(model, dict(V=Vm, W=Wm, m0=m0m, C0=C0m), y, layout=SERIES_MAJOR,
+                               loglik=True)
+        eng.sync()
+        assert int(full["status"].max()) & (capi.ST_SINGULAR | capi.ST_NOTPD), n_
+        assert np.array_equal(out["m"].cpu().numpy(), full["m"].cpu().numpy())
+
+
+def test_series_major_transposes_beyond_65535_row_tiles(eng):
+    """Series-major register-kernel calls transpose through workspace; B > 65535 * 32 series used
+    to exceed grid.y."""
+    import torch
+    from bayesian_dlms_b200 import Model, SERIES_MAJOR, TIME_MAJOR
+    mod, V, W, m0, C0 = H.second_order()
+    B, T = 65535 * 32 + 4097, 3
+    g = torch.Generator(device="cuda").manual_seed(1)
+    y = torch.randn((B, T, 1), generator=g, device="cuda", dtype=torch.float64)
+    model = Model.build(mod, T=T)
+    params = dict(V=V, W=W, m0=m0, C0=C0)
+    a = eng.filter_smooth(model, params, y, layout=SERIES_MAJOR, want=("m", "S"))
+    b = eng.filter_smooth(model, params, y.permute(1, 2, 0).contiguous(), layout=TIME_MAJOR,
+                          want=("m", "S"))
+    eng.sync()
+    assert torch.equal(a["S"], b["S"].permute(2, 0, 1)) and torch.equal(a["m"], b["m"].permute(2, 0, 1))

@@ -585,3 +585,92 @@ def test_filter_last_and_streaming_resume(eng, oracle, name):
     rest = eng.filter(model2, p2, _cuda(y[:, k:]), layout=SERIES_MAJOR, keep_init=False, want=("m", "C"))
     _exact(rest["m"].cpu().numpy(), full["m"][:, k + 1:].cpu().numpy(), "resumed m")
     _exact(rest["C"].cpu().numpy(), full["C"][:, k + 1:].cpu().numpy(), "resumed C")
+
+
+# ------------------------------------------------------------------ f2 on the SVD path
+
+@pytest.mark.parametrize("shape", [(2, 1), (3, 2), (8, 8), (13, 1)])   # <= 8: four-series kernel
+@pytest.mark.parametrize("tv", ["v", "w", "vw"])
+@pytest.mark.parametrize("shared", [True, False])
+def test_svd_path_time_varying_V_W(eng, oracle, shape, tv, shared):
+    """DlmFsv.ffbsSvd (DlmFsv.scala:208-229: SvdFilter.step with transformParams(p.copy(v = V_t)),
+    sampler on ps.head.w) and DlmFsvSystem.ffbsSvd (DlmFsvSystem.scala:177-207: W_t forward and in
+    SvdSampler.step of the transition t -> t + 1), both closures self-consistent (BDLM_SVD_CONSISTENT_W);
+    the raw-W (quirk Q2) closure with per-step parameters as well.  Bit-exact against the oracle."""
+    from bayesian_dlms_b200 import Model, SERIES_MAJOR, dlm
+    n, p = shape
+    rng = np.random.default_rng(1000 * n + 10 * p + len(tv) + int(shared))
+    B, T = 6, 30
+    if n == 13:
+        mod = H.seasonal13()[0]
+    elif n == 8:
+        mod = H.correlated8()[0]
+    else:
+        mod = dlm.polynomial(2) if p == 1 else dlm.polynomial(1) * dlm.polynomial(2)
+    m0, C0 = rng.standard_normal(n), H.spd(rng, n, 4.0)
+    times = np.cumsum(rng.choice([1.0, 2.0], T))
+    v_tv, w_tv = "v" in tv, "w" in tv
+    nb = 1 if shared else B
+    Vb = np.stack([np.stack([H.spd(rng, p, 2.0) for _ in range(T if v_tv else 1)]) for _ in range(nb)])
+    Wb = np.stack([np.stack([H.spd(rng, n, 0.4) for _ in range(T if w_tv else 1)]) for _ in range(nb)])
+    y = np.stack([H.simulate(mod, np.eye(p), Wb[0, 0], m0, C0, times, rng, missing=0.1) for _ in range(B)])
+    z = rng.standard_normal((B, T + 1, n))
+    model = Model.build(mod, times=times)
+    flat = lambda M, k: np.ascontiguousarray(M.transpose(0, 1, 3, 2).reshape(M.shape[0], -1, k))  # noqa: E731
+    Vf, Wf = flat(Vb, p * p), flat(Wb, n * n)
+    params = dict(m0=m0, C0=C0, v_tv=v_tv, w_tv=w_tv)
+    per = []
+    for name, arr, is_tv in (("V", Vf, v_tv), ("W", Wf, w_tv)):
+        if shared:
+            params[name] = arr[0] if is_tv else arr[0, 0]
+        else:
+            params[name] = _cuda(arr if is_tv else arr[:, 0])
+            per.append(name)
+    if per:
+        params["per_series"] = tuple(per)
+    for consistent in (True, False):
+        f = eng.svd_filter(model, params, _cuda(y), layout=SERIES_MAJOR, consistent_w=consistent)
+        s = eng.ffbs(model, params, _cuda(y), _cuda(z), layout=SERIES_MAJOR, svd=True,
+                     consistent_w=consistent, want_kf=("m", "dc"))
+        assert int(f["status"].max()) == 0 and int(s["status"].max()) == 0
+        for b in range(B):
+            Vt = Vf[0 if shared else b] if v_tv else Vf[0 if shared else b][0]
+            Wt = Wf[0 if shared else b] if w_tv else Wf[0 if shared else b][0]
+            o = oracle.svd_ffbs_tv(n, p, model.F, model.G, Vt, Wt, m0, oracle.oracle.cm(C0), times,
+                                   y[b], z[b], v_tv=v_tv, w_tv=w_tv, consistent=consistent)
+            for k in ("m", "dc", "uc", "a", "dr", "ur"):
+                _exact(f[k][b].cpu().numpy(), o[k], "%s consistent=%s" % (k, consistent))
+            _exact(s["theta"][b].cpu().numpy(), o["theta"], "theta consistent=%s" % consistent)
+            _exact(s["svd_m"][b].cpu().numpy(), o["m"], "ffbs m")
+
+
+@pytest.mark.parametrize("shape", [(37, 7), (40, 3), (48, 2)])
+def test_svd_path_beyond_32_states(eng, oracle, shape):
+    """The SVD entry points at the reference's largest example (n = 37, p = 7 with missing sensors
+    and fractional irregular times, AqMeshExample.scala:86-127) and up to BDLM_MAX_N = 48."""
+    from bayesian_dlms_b200 import Model, SERIES_MAJOR, dlm
+    n, p = shape
+    rng = np.random.default_rng(n + p)
+    B, T = 3, 12
+    # p sensors loading on n states: a dense 0/1-ish F and a dt-dependent G (damped levels with a
+    # weak coupling to the next state), so every irregular step has its own G
+    Fm = (rng.random((n, p)) < 0.3).astype(float) + np.eye(n, p)
+    mod = dlm.Dlm(lambda t: Fm,
+                  lambda dt: np.exp(-0.05 * dt) * np.eye(n) + 0.1 * dt * np.eye(n, k=1))
+    times = np.cumsum(rng.uniform(0.25, 1.5, T))
+    V, W = H.spd(rng, p, 1.0), H.spd(rng, n, 0.2)
+    m0, C0 = rng.standard_normal(n), H.spd(rng, n, 2.0)
+    y = np.stack([H.simulate(mod, V, W, m0, C0, times, rng, missing=0.2) for _ in range(B)])
+    z = rng.standard_normal((B, T + 1, n))
+    model = Model.build(mod, times=times)
+    assert model.n == n and model.p == p
+    params = dict(V=V, W=W, m0=m0, C0=C0)
+    f = eng.svd_filter(model, params, _cuda(y), layout=SERIES_MAJOR)
+    s = eng.ffbs(model, params, _cuda(y), _cuda(z), layout=SERIES_MAJOR, svd=True)
+    assert int(f["status"].max()) == 0 and int(s["status"].max()) == 0
+    cm = oracle.oracle.cm
+    for b in range(B):
+        o = oracle.svd_ffbs(n, p, model.F, model.G, cm(V), cm(W), m0, cm(C0), times, y[b], z[b])
+        for key in ("m", "dc", "uc", "a", "dr", "ur"):
+            _exact(f[key][b].cpu().numpy(), o[key], key)
+        _exact(s["theta"][b].cpu().numpy(), o["theta"], "theta")

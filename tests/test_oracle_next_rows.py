@@ -8,6 +8,7 @@
   GibbsWishart.scala:16-35; InverseWishart.scala:17-25) against numpy/LAPACK.
 """
 import numpy as np
+import pytest
 
 import helpers as H
 import oracle
@@ -271,3 +272,67 @@ def test_ar_ffbs_is_the_dlm_ffbs_of_the_equivalent_model():
     assert np.allclose(o["m"][:, 0], f["m"], rtol=1e-12, atol=1e-14)
     assert np.allclose(o["C"][:, 0], f["C"], rtol=1e-12, atol=1e-14)
     assert np.allclose(o["theta"][:, 0], th, rtol=1e-9, atol=1e-11)
+
+
+# ------------------------------------------------------------------ f2 on the SVD path
+
+@pytest.mark.parametrize("shape", [(2, 1), (3, 2)])
+@pytest.mark.parametrize("tv", ["v", "w", "vw"])
+def test_svd_filter_time_varying_params_vs_lapack_and_kalman(shape, tv):
+    """DlmFsv.ffbsSvd (DlmFsv.scala:208-229) / DlmFsvSystem.ffbsSvd (DlmFsvSystem.scala:177-207):
+    the SVD filter stepped with transformParams(p.copy(v = V_t)) [w = W_t] per observation, advance
+    closure built from the transformed parameters.  Pins: (1) constant arrays reproduce the
+    time-invariant oracle bit for bit; (2) the numpy + LAPACK restatement at 1e-8; (3) with the
+    self-consistent closure and no partially missing rows the SVD filter is the Kalman filter in
+    factored form, so the Kalman oracle with V_t / W_t must agree at 1e-7."""
+    import oracle
+    from oracle import lapack_flavour as lf
+    from bayesian_dlms_b200 import dlm
+    n, p = shape
+    rng = np.random.default_rng(31 * n + p + len(tv))
+    T = 40
+    mod = dlm.polynomial(2) if p == 1 else dlm.polynomial(1) * dlm.polynomial(2)
+    times = np.cumsum(rng.choice([1.0, 2.0], T))
+    m0, C0 = rng.standard_normal(n), H.spd(rng, n, 4.0)
+    v_tv, w_tv = "v" in tv, "w" in tv
+    Vs = np.stack([H.spd(rng, p, 2.0) for _ in range(T if v_tv else 1)])
+    Ws = np.stack([H.spd(rng, n, 0.4) for _ in range(T if w_tv else 1)])
+    y = H.simulate(mod, Vs[0], Ws[0], m0, C0, times, rng)
+    y[rng.random(T) < 0.15] = np.nan          # whole rows missing (Q6 needs no partial rows)
+    F, _, G, _, _, _ = dlm.materialise(mod, times)
+    cmT = lambda M: np.ascontiguousarray(M.transpose(0, 2, 1).reshape(M.shape[0], -1))  # noqa: E731
+    z = rng.standard_normal((T + 1, n))
+    o = oracle.svd_ffbs_tv(n, p, F, G, cmT(Vs), cmT(Ws), m0, dlm.cm(C0), times, y, z,
+                           v_tv=v_tv, w_tv=w_tv, consistent=True)
+    assert o["status"] == 0
+    # (1) constant per-step arrays == the time-invariant entry point, bit for bit
+    Vc, Wc = np.repeat(Vs[:1], T, 0), np.repeat(Ws[:1], T, 0)
+    a = oracle.svd_ffbs_tv(n, p, F, G, cmT(Vc), cmT(Wc), m0, dlm.cm(C0), times, y, z,
+                           v_tv=True, w_tv=True, consistent=True)
+    b = oracle.svd_ffbs(n, p, F, G, dlm.cm(Vs[0]), dlm.cm(Ws[0]), m0, dlm.cm(C0), times, y, z,
+                        consistent=True)
+    for k in ("theta", "m", "dc", "uc", "a", "dr", "ur"):
+        assert np.array_equal(a[k], b[k]), k
+    # (2) LAPACK flavour
+    Fs = lambda t: mod.f(times[t])                                      # noqa: E731
+    tp = np.concatenate([[times.min() - 1.0], times])
+    Gs = lambda t: mod.g(tp[t + 1] - tp[t])                             # noqa: E731
+    Vf = lambda t: lf.sqrt_svd(Vs[t if v_tv else 0], inv=True)          # noqa: E731
+    Wa = lambda t: lf.sqrt_svd(Ws[t if w_tv else 0])                    # noqa: E731
+    ref = lf.svd_filter(Fs, Gs, Vf, Wa, m0, C0, times, y)
+    assert H.rel_err(o["m"], np.stack([k["m"] for k in ref])) < 1e-8
+    assert H.rel_err(o["dc"], np.stack([k["dc"] for k in ref])) < 1e-8
+    # (3) Kalman filter with the same V_t, W_t
+    kf = oracle.kf_filter(n, p, F, G, cmT(Vs) if v_tv else dlm.cm(Vs[0]),
+                          cmT(Ws) if w_tv else dlm.cm(Ws[0]), m0, dlm.cm(C0), times, y,
+                          v_tv=v_tv, w_tv=w_tv)
+    assert H.rel_err(o["m"], kf["m"]) < 1e-7
+    for r in range(T + 1):
+        uc = dlm.from_cm(o["uc"][r], n, n)
+        assert H.rel_err(uc @ np.diag(o["dc"][r] ** 2) @ uc.T, dlm.from_cm(kf["C"][r], n, n)) < 1e-6
+    # the sampler's mean recursion (z = 0) against the LAPACK flavour, per-step sqrtW
+    o0 = oracle.svd_ffbs_tv(n, p, F, G, cmT(Vs), cmT(Ws), m0, dlm.cm(C0), times, y, 0 * z,
+                            v_tv=v_tv, w_tv=w_tv, consistent=True)
+    if not w_tv:
+        mom0 = lf.svd_sampler_moments(Gs, lf.sqrt_svd(Ws[0]), ref, o0["theta"])
+        assert H.rel_err(o0["theta"], np.stack([x[0] for x in mom0])) < 1e-7
