@@ -8,7 +8,8 @@ implementation, and nothing here imports ``oracle/``.
 """
 from .dlm import (Data, Dlm, DlmParameters, autoregressive, polynomial, regression,  # noqa: F401
                   seasonal)
-from .batch import Engine, Model, SERIES_MAJOR, TIME_MAJOR, default_engine  # noqa: F401
+from .batch import (Engine, Model, SERIES_MAJOR, TIME_MAJOR, build_batch_model,  # noqa: F401
+                    default_engine, model_to_device)
 from .reference_api import (ConjugateFilter, FilterAr, FilterOu, GibbsSampling,  # noqa: F401
                             InverseGamma, InverseWishart, KalmanFilter, KfState, SamplingState,
                             Smoothing, SmoothingState, SvParameters, SvdFilter, SvdSampler,
@@ -16,7 +17,8 @@ from .reference_api import (ConjugateFilter, FilterAr, FilterOu, GibbsSampling, 
 
 __all__ = [
     "Data", "Dlm", "DlmParameters", "polynomial", "regression", "autoregressive", "seasonal",
-    "Engine", "Model", "TIME_MAJOR", "SERIES_MAJOR", "default_engine",
+    "Engine", "Model", "TIME_MAJOR", "SERIES_MAJOR", "default_engine", "build_batch_model",
+    "model_to_device",
     "KalmanFilter", "Smoothing", "SvdFilter", "SvdSampler", "GibbsSampling",
     "KfState", "SmoothingState", "SamplingState", "SvdState",
     "FilterAr", "FilterOu", "SvParameters", "ConjugateFilter", "InverseGamma", "InverseWishart",

@@ -16,6 +16,7 @@ LIB_PATH = os.environ.get("BDLM_LIB_PATH") or os.path.join(HERE, "libbdlm.so")
 TIME_MAJOR, SERIES_MAJOR = 0, 1
 DEVICE, HOST = 0, 1
 PS_V, PS_W, PS_M0, PS_C0 = 1, 2, 4, 8
+PS_TIMES, PS_F, PS_G = 16, 32, 64   # Data.time / mod.f(time) / mod.g(dt) given per series
 TEXTBOOK_SMOOTHER, SVD_CONSISTENT_W = 1, 2
 ST_SINGULAR, ST_NOTCONVERGED, ST_NOTPD, ST_NONFINITE = 1, 2, 4, 8
 E_ARG, E_EMPTY, E_CUDA, E_NODEVICE = -1, -2, -3, -4
@@ -251,7 +252,7 @@ def make_problem(*, B, T, n, p, layout, mem, keep_init, F, G, times, V, W, m0, C
             return None
         return host_ptr(x) if isinstance(x, np.ndarray) else int(x)
 
-    pr.F, pr.G, pr.times = addr(F), addr(G), addr(times)
+    pr.F, pr.G, pr.times = addr(F), addr(G), addr(times)   # ints when given per series (PS_*)
     pr.V, pr.W, pr.m0, pr.C0, pr.y = addr(V), addr(W), addr(m0), addr(C0), addr(y)
     pr.v_tv = int(bool(v_tv))
     pr.w_tv = int(bool(w_tv))

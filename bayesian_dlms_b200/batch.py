@@ -41,6 +41,9 @@ class Model:
     T: int
     times: Optional[np.ndarray]  # None = regular grid 1..T
     t_init: Optional[np.ndarray] = None  # 1-element array: time of the saved state to resume from
+    # names among ("times", "F", "G") that are given PER SERIES: arrays laid out like y with
+    # k = 1 / n*p / n*n, living in the same memory space as y (numpy or torch)
+    per_series: tuple = ()
 
     @staticmethod
     def build(mod: _dlm.Dlm, times: Optional[Sequence[float]] = None, T: Optional[int] = None,
@@ -59,6 +62,46 @@ class Model:
                      bool(f_tv), bool(g_tv), n, p, int(tgrid.size),
                      None if regular else tgrid,
                      None if t_init is None else np.array([float(t_init)]))
+
+
+def build_batch_model(mod: _dlm.Dlm, times, layout=capi.SERIES_MAJOR) -> Model:
+    """Model for a batch whose series sit on DIFFERENT time grids (``Data(time, observation)`` is
+    per series in the reference, Dlm.scala:94; AqMeshExample.scala:86-127 has per-sensor irregular
+    times): ``times`` is (B, T).  The closures are evaluated per series on the host; F / G are
+    passed per series only where they really differ (polynomial G does not depend on dt,
+    regression F depends on time).  Ragged batches: pad a short series at the end with its last
+    time (dt = 0 passes the state through) and NaN observations."""
+    times = np.ascontiguousarray(times, dtype=np.float64)
+    assert times.ndim == 2 and times.shape[1] > 0
+    B, T = times.shape
+    mods = list(mod) if isinstance(mod, (list, tuple)) else [mod] * B   # one Dlm per series, e.g.
+    assert len(mods) == B                                              # regression covariates
+    Fs, Gs, f_any, g_any = [], [], False, False
+    n = p = None
+    for b in range(B):
+        F, f_tv, G, g_tv, n, p = _dlm.materialise(mods[b], times[b])
+        Fs.append(np.broadcast_to(F.reshape(-1, n * p), (T, n * p)))
+        Gs.append(np.broadcast_to(G.reshape(-1, n * n), (T, n * n)))
+        f_any, g_any = f_any or bool(f_tv), g_any or bool(g_tv)
+    Fs, Gs = np.stack(Fs), np.stack(Gs)          # (B, T, k)
+    f_ps = f_any or not np.array_equal(Fs, np.broadcast_to(Fs[:1, :1], Fs.shape))
+    g_ps = g_any or not np.array_equal(Gs, np.broadcast_to(Gs[:1, :1], Gs.shape))
+    lay = (lambda a: np.ascontiguousarray(a.transpose(1, 2, 0))) if layout == capi.TIME_MAJOR \
+        else np.ascontiguousarray
+    per = ["times"] + (["F"] if f_ps else []) + (["G"] if g_ps else [])
+    return Model(lay(Fs) if f_ps else np.ascontiguousarray(Fs[0, 0]),
+                 lay(Gs) if g_ps else np.ascontiguousarray(Gs[0, 0]),
+                 bool(f_ps), bool(g_ps), n, p, T, lay(times[:, :, None]), None, tuple(per))
+
+
+def model_to_device(model: Model, device) -> Model:
+    """Copy of ``model`` whose per-series arrays are CUDA tensors (for device-resident calls)."""
+    import torch
+    kw = {k: getattr(model, k) for k in ("F", "G", "f_tv", "g_tv", "n", "p", "T", "times", "t_init",
+                                         "per_series")}
+    for name in model.per_series:
+        kw[name] = torch.from_numpy(np.ascontiguousarray(kw[name])).to(device)
+    return Model(**kw)
 
 
 _engines_by_device = {}
@@ -190,8 +233,19 @@ class Engine:
                 keep.append(a)
                 ptrs[name] = a
         _, yptr = _mem_and_ptr(y)
+        grid = {"F": model.F, "G": model.G, "times": model.times}
+        for name, bit, k in (("times", capi.PS_TIMES, 1), ("F", capi.PS_F, n * p),
+                             ("G", capi.PS_G, n * n)):
+            if name in model.per_series:
+                x = grid[name]
+                expect = self._shape(layout, B, model.T, k)
+                assert tuple(x.shape) == expect, (name, tuple(x.shape), expect)
+                m_, ptr = _mem_and_ptr(x)
+                assert m_ == mem, f"per-series {name} lives in a different memory space than the data"
+                per |= bit
+                grid[name] = ptr
         pr = capi.make_problem(B=B, T=model.T, n=n, p=p, layout=layout, mem=mem,
-                               keep_init=keep_init, F=model.F, G=model.G, times=model.times,
+                               keep_init=keep_init, F=grid["F"], G=grid["G"], times=grid["times"],
                                V=ptrs["V"], W=ptrs["W"], m0=ptrs["m0"], C0=ptrs["C0"], y=yptr,
                                per_series=per, compat=compat, f_tv=model.f_tv, g_tv=model.g_tv,
                                v_tv=v_tv, w_tv=w_tv, t_init=model.t_init)

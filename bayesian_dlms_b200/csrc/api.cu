@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "ctx_internal.h"
 #include "launch.h"
 
 using namespace bdlm;
@@ -38,6 +39,7 @@ struct bdlm_ctx {
   void *scan_table = nullptr;          // scan.cu forward table of the model in scan_key
   std::vector<double> scan_key, scan_key_pending;
   bool use_group = std::getenv("BDLM_NO_GROUP_KERNEL") == nullptr;  // A/B switch for profiling
+  int64_t range_lo = -1, range_hi = -1;  // ctx_set_range: sub-batch of the next call (comm.cu)
 };
 
 static std::string g_create_err;
@@ -195,6 +197,10 @@ void collect_fields(DevCall &d, std::vector<Field> &f) {
   }
   const bool smooth_in = d.op == A_SMOOTH;
   if (d.op != A_SMOOTH) add(&d.pr.y, p.T, pp, true, false);
+  // per-series time grids / model matrices travel (and are transposed / staged) like y
+  if (p.per_series & BDLM_PS_TIMES) add(&d.pr.times, p.T, 1, true, false);
+  if (p.per_series & BDLM_PS_F) add(&d.pr.F, p.T, n * pp, true, false);
+  if (p.per_series & BDLM_PS_G) add(&d.pr.G, p.T, n * n, true, false);
   if (p.per_series & BDLM_PS_V) add(&d.pr.V, p.v_tv ? p.T : 1, pp * pp, true, false);
   if (p.per_series & BDLM_PS_W) add(&d.pr.W, p.w_tv ? p.T : 1, n * n, true, false);
   if (p.per_series & BDLM_PS_M0) add(&d.pr.m0, 1, n, true, false);
@@ -242,6 +248,7 @@ size_t dev_workspace_bytes(const DevCall &d, int64_t Bc) {
     if (d.op == A_AR_FFBS) bytes += 2 * align_up(sizeof(double) * (size_t)R * Bc);  // (m, C) spill
     return bytes + 8192;
   }
+  if (p.per_series & BDLM_PS_TIMES) bytes += align_up(sizeof(double) * (size_t)p.T * Bc);  // dt
   if (d.op == A_GIBBS_DRAW || d.op == A_CONJ_FILTER) return bytes + 8192;
   if (small_path(d.op, p)) {
     if (p.layout == BDLM_SERIES_MAJOR) {  // time-major mirrors of every field
@@ -272,12 +279,15 @@ int upload_model(bdlm_ctx *c, const DevCall &d, Bump &bump, Batch &bt,
     host.insert(host.end(), src, src + cnt);
     return o;
   };
-  const size_t oF = push(p.F, (size_t)(p.f_tv ? T : 1) * n * pp);
-  const size_t oG = push(p.G, (size_t)(p.g_tv ? T : 1) * n * n);
-  hF0.assign(p.F, p.F + (size_t)n * pp);
-  hG0.assign(p.G, p.G + (size_t)n * n);
+  const bool psF = (p.per_series & BDLM_PS_F) != 0, psG = (p.per_series & BDLM_PS_G) != 0,
+             psT = (p.per_series & BDLM_PS_TIMES) != 0;
+  const size_t oF = psF ? 0 : push(p.F, (size_t)(p.f_tv ? T : 1) * n * pp);
+  const size_t oG = psG ? 0 : push(p.G, (size_t)(p.g_tv ? T : 1) * n * n);
+  // constant-bank copies of the first F, G for the register kernels (unused when they vary)
+  if (psF) hF0.assign((size_t)n * pp, 0.0); else hF0.assign(p.F, p.F + (size_t)n * pp);
+  if (psG) hG0.assign((size_t)n * n, 0.0); else hG0.assign(p.G, p.G + (size_t)n * n);
   size_t oDt = (size_t)-1;
-  if (p.times) {
+  if (p.times && !psT) {
     double tmin = p.times[0];
     for (int t = 1; t < T; ++t) tmin = std::fmin(tmin, p.times[t]);
     // KalmanFilter.initialiseState, KalmanFilter.scala:116-117 -- or the time of a saved state
@@ -302,9 +312,31 @@ int upload_model(bdlm_ctx *c, const DevCall &d, Bump &bump, Batch &bt,
   CU(cudaMemcpyAsync(dev, host.data(), host.size() * sizeof(double), cudaMemcpyHostToDevice,
                      c->stream));
   bt.B = d.Bc; bt.T = T; bt.n = n; bt.p = pp; bt.keep_init = p.keep_init ? 1 : 0;
-  bt.compat = p.compat; bt.F = dev + oF; bt.G = dev + oG;
-  bt.dt = (oDt == (size_t)-1) ? nullptr : dev + oDt;
+  bt.compat = p.compat;
   bt.f_tv = p.f_tv; bt.g_tv = p.g_tv;
+  bt.ps_model = (psF || psG) ? 1 : 0;
+  // per-step per-series array laid out like y with k components: strides of element (b, t, k)
+  auto ps_strides = [&](const double *user, int64_t k, const double *&ptr, int64_t &sb, int64_t &sr,
+                        int64_t &sk) {
+    if (p.layout == BDLM_TIME_MAJOR) { ptr = user + d.b0; sb = 1; sk = d.Bp; sr = k * d.Bp; }
+    else { ptr = user + d.b0 * (int64_t)T * k; sb = (int64_t)T * k; sr = k; sk = 1; }
+  };
+  if (psF) ps_strides(p.F, (int64_t)n * pp, bt.F, bt.F_sb, bt.F_sr, bt.F_sk);
+  else { bt.F = dev + oF; bt.F_sb = 0; bt.F_sr = p.f_tv ? (int64_t)n * pp : 0; bt.F_sk = 1; }
+  if (psG) ps_strides(p.G, (int64_t)n * n, bt.G, bt.G_sb, bt.G_sr, bt.G_sk);
+  else { bt.G = dev + oG; bt.G_sb = 0; bt.G_sr = p.g_tv ? (int64_t)n * n : 0; bt.G_sk = 1; }
+  bt.dt = (oDt == (size_t)-1) ? nullptr : dev + oDt;
+  bt.dt_sb = 0; bt.dt_sr = 1;
+  if (psT) {  // dt of every series on the device, in the layout of the times array
+    const double *tp; int64_t tsb, tsr, tsk;
+    ps_strides(p.times, 1, tp, tsb, tsr, tsk);
+    double *dtw = bump.take<double>((size_t)T * d.Bc);
+    if (p.layout == BDLM_TIME_MAJOR) { bt.dt_sb = 1; bt.dt_sr = d.Bc; }
+    else { bt.dt_sb = T; bt.dt_sr = 1; }
+    CU(launch_dt_from_times(tp, tsb, tsr, dtw, bt.dt_sb, bt.dt_sr, d.Bc, T, p.t_init, c->stream));
+    ++c->launches;
+    bt.dt = dtw;
+  }
   auto pv = [&](const double *user, size_t off, int64_t k) {
     PView v{nullptr, 0, 1};
     if (off != (size_t)-1) { v.ptr = dev + off; v.sb = 0; v.sk = 1; }
@@ -570,7 +602,8 @@ int run_dev(bdlm_ctx *c, DevCall d, Bump bump) {
   const int wop = warp_op(d.op);
   wa.spill_k = (int64_t)warp_spill_doubles_per_row(wop, p.n, p.p);
   wa.spill = wa.spill_k ? bump.take<double>((size_t)wa.spill_k * R * d.Bc) : nullptr;
-  if (c->use_group && !p.v_tv && !p.w_tv && group_supported(wop, p.n, p.p, p.keep_init ? 1 : 0)) {
+  if (c->use_group && !p.v_tv && !p.w_tv && !bt.ps_model && bt.dt_sb == 0 &&
+      group_supported(wop, p.n, p.p, p.keep_init ? 1 : 0)) {
     CU(launch_group(wop, wa, c->stream));  // two series per warp, compile-time n (kf_group.cu)
     ++c->launches;
     return 0;
@@ -596,6 +629,19 @@ int validate(bdlm_ctx *c, int op, const bdlm_problem *p) {
     return fail(c, BDLM_E_ARG, "bad layout");
   if (p->mem != BDLM_DEVICE && p->mem != BDLM_HOST) return fail(c, BDLM_E_ARG, "bad mem");
   if (op != A_GIBBS_DRAW && (!p->F || !p->G)) return fail(c, BDLM_E_ARG, "null F or G");
+  if (p->per_series & ~(BDLM_PS_V | BDLM_PS_W | BDLM_PS_M0 | BDLM_PS_C0 | BDLM_PS_TIMES | BDLM_PS_F |
+                        BDLM_PS_G))
+    return fail(c, BDLM_E_ARG, "unknown per_series bit");
+  if ((p->per_series & BDLM_PS_TIMES) && !p->times)
+    return fail(c, BDLM_E_ARG, "BDLM_PS_TIMES without a times array");
+  if ((p->per_series & BDLM_PS_TIMES) && p->g_tv && !(p->per_series & BDLM_PS_G))
+    return fail(c, BDLM_E_ARG, "per-series time grids with a dt-dependent G need per-series G "
+                               "(BDLM_PS_G): g(dt) differs by series");
+  if ((p->per_series & BDLM_PS_F) && !p->f_tv) return fail(c, BDLM_E_ARG, "BDLM_PS_F needs f_tv = 1");
+  if ((p->per_series & BDLM_PS_G) && !p->g_tv) return fail(c, BDLM_E_ARG, "BDLM_PS_G needs g_tv = 1");
+  if ((p->per_series & (BDLM_PS_TIMES | BDLM_PS_F | BDLM_PS_G)) &&
+      (op == A_CONJ_FILTER || op == A_GIBBS_DRAW))
+    return fail(c, BDLM_E_ARG, "per-series grids / models: not supported by this entry point");
   if (op == A_GIBBS_DRAW) return 0;
   if (op == A_CONJ_FILTER) {
     if (!p->W || !p->m0 || !p->C0 || !p->y) return fail(c, BDLM_E_ARG, "null W, m0, C0 or y");
@@ -619,19 +665,19 @@ int validate(bdlm_ctx *c, int op, const bdlm_problem *p) {
 }
 
 // Device-mode entry: loop over series chunks that fit the workspace cap.
-int run_device_mode(bdlm_ctx *c, DevCall d) {
+int run_device_mode(bdlm_ctx *c, DevCall d, int64_t lo, int64_t hi) {
   const int64_t B = d.pr.B;
-  if (B == 0) return 0;
-  int64_t chunk = B;
+  if (hi <= lo) return 0;
+  int64_t chunk = hi - lo;
   while (chunk > 128 && dev_workspace_bytes(d, chunk) > c->workspace_cap)
     chunk = ((chunk / 2 + 127) / 128) * 128;
   // series-major small path transposes are addressed per chunk; any chunk size works
   const size_t need = dev_workspace_bytes(d, chunk);
   int rc = ensure_arena(c, need);
   if (rc) return rc;
-  for (int64_t b0 = 0; b0 < B; b0 += chunk) {
+  for (int64_t b0 = lo; b0 < hi; b0 += chunk) {
     DevCall s = d;
-    s.b0 = b0; s.Bc = std::min(chunk, B - b0); s.Bp = B; s.rng_b0 = b0;
+    s.b0 = b0; s.Bc = std::min(chunk, hi - b0); s.Bp = B; s.rng_b0 = b0;
     Bump bump{c->arena, 0, c->arena_bytes};
     rc = run_dev(c, s, bump);
     if (rc) return rc;
@@ -641,10 +687,10 @@ int run_device_mode(bdlm_ctx *c, DevCall d) {
 
 // Host-mode entry: stage slabs of series through the arena with two buffer sets so the
 // H2D copy of slab i+1, the kernels of slab i and the D2H copy of slab i-1 overlap.
-int run_host_mode(bdlm_ctx *c, DevCall d) {
+int run_host_mode(bdlm_ctx *c, DevCall d, int64_t lo, int64_t hi) {
   const bdlm_problem &p = d.pr;
   const int64_t B = p.B;
-  if (B == 0) return 0;
+  if (hi <= lo) return 0;
   std::vector<Field> fields;
   collect_fields(d, fields);
   std::vector<double *> host_ptrs;
@@ -654,7 +700,7 @@ int run_host_mode(bdlm_ctx *c, DevCall d) {
   for (auto &f : fields) per_series += sizeof(double) * (size_t)f.rows * f.k;
 
   // slab size: two staged sets + one device workspace within the staging cap
-  int64_t slab = std::min<int64_t>(B, 1 << 20);
+  int64_t slab = std::min<int64_t>(hi - lo, 1 << 20);
   auto total_for = [&](int64_t s) {
     DevCall t = d; t.pr.mem = BDLM_DEVICE;
     size_t staged = 0;
@@ -695,9 +741,9 @@ int run_host_mode(bdlm_ctx *c, DevCall d) {
   };
 
   int it = 0;
-  for (int64_t b0 = 0; b0 < B; b0 += slab, ++it) {
+  for (int64_t b0 = lo; b0 < hi; b0 += slab, ++it) {
     const int s = it & 1;
-    const int64_t Bs = std::min(slab, B - b0);
+    const int64_t Bs = std::min(slab, hi - b0);
     // the set's buffers are free once the D2H of the slab that used them has finished
     if (it >= 2) CU(cudaStreamWaitEvent(c->s_in, c->ev_out[s], 0));
     for (size_t i = 0; i < fields.size(); ++i)
@@ -732,10 +778,21 @@ int run_host_mode(bdlm_ctx *c, DevCall d) {
 int dispatch(bdlm_ctx *c, DevCall &d) {
   CU(cudaSetDevice(c->device));
   d.b0 = 0; d.Bc = d.pr.B; d.Bp = d.pr.B;
-  return d.pr.mem == BDLM_HOST ? run_host_mode(c, d) : run_device_mode(c, d);
+  int64_t lo = 0, hi = d.pr.B;
+  if (c->range_lo >= 0) {  // one shard of a batch cut over several contexts (comm.cu)
+    lo = std::min(c->range_lo, d.pr.B); hi = std::min(c->range_hi, d.pr.B);
+    c->range_lo = c->range_hi = -1;
+  }
+  return d.pr.mem == BDLM_HOST ? run_host_mode(c, d, lo, hi) : run_device_mode(c, d, lo, hi);
 }
 
 }  // namespace
+
+namespace bdlm {
+cudaStream_t ctx_stream(bdlm_ctx *c) { return c->stream; }
+void ctx_set_range(bdlm_ctx *c, int64_t lo, int64_t hi) { c->range_lo = lo; c->range_hi = lo < 0 ? -1 : hi; }
+void ctx_count_launches(bdlm_ctx *c, int64_t n) { c->launches += n; }
+}  // namespace bdlm
 
 // ------------------------------------------------------------------------- C ABI
 

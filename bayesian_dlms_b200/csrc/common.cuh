@@ -42,9 +42,13 @@ struct Batch {
   int n, p;
   int keep_init;   // rows = T + keep_init
   int compat;      // BDLM_TEXTBOOK_* | BDLM_SVD_*
-  const double *F; // device [n*p] or [T][n*p]
-  const double *G; // device [n*n] or [T][n*n]
-  const double *dt;// device [T] (dt into observation t) or nullptr = all 1.0
+  const double *F; // device [n*p] or [T][n*p]; per series: element (b, t, k) at F[b*F_sb + t*F_sr + k*F_sk]
+  const double *G; // device [n*n] or [T][n*n]; per series: G[b*G_sb + t*G_sr + k*G_sk]
+  const double *dt;// device (dt into observation t) or nullptr = all 1.0; element (b, t) at
+                   // dt[b*dt_sb + t*dt_sr] -- shared by the batch: dt_sb = 0, dt_sr = 1
+  int64_t dt_sb, dt_sr;
+  int64_t F_sb, F_sr, F_sk, G_sb, G_sr, G_sk;  // shared: sb = 0, sr = (tv ? k : 0), sk = 1
+  int ps_model;    // F or G given per series (Data.time / regression covariates differ by series)
   int f_tv, g_tv;
   int v_tv;        // V varies with t (StudentTGibbs.filter): V holds T matrices, row stride V_sr
   int64_t V_sr;
@@ -54,6 +58,11 @@ struct Batch {
   CView y;         // T rows
   int32_t *status; // [B] or nullptr
 };
+
+// dt into observation t of series b (1.0 on the regular grid)
+__device__ __forceinline__ double dt_at(const Batch &bt, int64_t b, int t) {
+  return bt.dt ? bt.dt[b * bt.dt_sb + (int64_t)t * bt.dt_sr] : 1.0;
+}
 
 __host__ __device__ inline int64_t vidx(int64_t sb, int64_t sr, int64_t sk, int64_t b,
                                         int64_t r, int64_t k) {

@@ -191,7 +191,7 @@ ffbs_small_kernel(const FfbsModel<N> md, const FfbsSmallArgs a) {
   for (int t = 0; t < T; ++t) {
     const double y = ynext;
     if (t + 1 < T) ynext = ld_stream(bt.y.ptr + b * bt.y.sb + (int64_t)(t + 1) * bt.y.sr);
-    const double dt = bt.dt ? bt.dt[t] : 1.0;
+    const double dt = dt_at(bt, b, t);
     double av[N], R[N * N], f, Q;
     load_vw(t);
     advance<N, false>(md.G, W, dt, m, C, av, R);
@@ -218,7 +218,7 @@ ffbs_small_kernel(const FfbsModel<N> md, const FfbsSmallArgs a) {
   st |= eig_draw_small<N>(m, C, z, th);
   put(a.theta, T, th, N, false);
   for (int r = T - 1; r >= 0; --r) {
-    const double dt = bt.dt ? bt.dt[r] : 1.0;  // transition r -> r + 1 = the step into observation r
+    const double dt = dt_at(bt, b, r);  // transition r -> r + 1 = the step into observation r
     double mr[N], Cr[N * N], a1[N], R1[N * N];
     get(a.sm, r, mr, N); get(a.sC, r, Cr, N * N);
     normals(r, z);
@@ -281,7 +281,7 @@ ffbs_small_kernel(const FfbsModel<N> md, const FfbsSmallArgs a) {
       double res = 0.0;
       if (!isnan(y)) { res = (y - ft) * (y - ft); ny += 1.0; }
       ssy = (t == 0) ? res : ssy + res;
-      const double dt = bt.dt ? bt.dt[t] : 1.0;
+      const double dt = dt_at(bt, b, t);
       double gx[N], diff[N];
       smm<N, N, 1, false, false>(md.G, prev, gx);
 #pragma unroll
@@ -329,7 +329,7 @@ cudaError_t launch_n(const FfbsSmallArgs &a, const double *hG, const double *hF,
 }  // namespace
 
 bool ffbs_small_supported(const Batch &bt) {
-  return bt.p == 1 && bt.n >= 1 && bt.n <= 4 && bt.keep_init && !bt.f_tv && !bt.g_tv;
+  return bt.p == 1 && bt.n >= 1 && bt.n <= 4 && bt.keep_init && !bt.f_tv && !bt.g_tv && !bt.ps_model;
 }
 
 cudaError_t launch_ffbs_small(const FfbsSmallArgs &a, const double *hG, const double *hF,

@@ -63,20 +63,20 @@ struct SmallModel {
 // Model matrices for observation t: kernel-parameter constant bank when time-invariant
 // (static indices, no address taken), uniform global loads when they vary with t.
 template <int N, bool REG>
-__device__ __forceinline__ void load_model(const Batch &bt, const SmallModel<N> &mdl, int t,
+__device__ __forceinline__ void load_model(const Batch &bt, const SmallModel<N> &mdl, int64_t b, int t,
                                            double (&G)[N * N], double (&F)[N]) {
-  if (!REG && bt.g_tv) {
-    const double *g = bt.G + (int64_t)t * N * N;
+  if (!REG && bt.g_tv) {  // shared [T][n*n] (uniform loads) or per series (coalesced, time-major)
+    const double *g = bt.G + b * bt.G_sb + (int64_t)t * bt.G_sr;
 #pragma unroll
-    for (int k = 0; k < N * N; ++k) G[k] = __ldg(g + k);
+    for (int k = 0; k < N * N; ++k) G[k] = __ldg(g + k * bt.G_sk);
   } else {
 #pragma unroll
     for (int k = 0; k < N * N; ++k) G[k] = mdl.G[k];
   }
   if (!REG && bt.f_tv) {
-    const double *f = bt.F + (int64_t)t * N;
+    const double *f = bt.F + b * bt.F_sb + (int64_t)t * bt.F_sr;
 #pragma unroll
-    for (int k = 0; k < N; ++k) F[k] = __ldg(f + k);
+    for (int k = 0; k < N; ++k) F[k] = __ldg(f + k * bt.F_sk);
   } else {
 #pragma unroll
     for (int k = 0; k < N; ++k) F[k] = mdl.F[k];
@@ -149,9 +149,9 @@ kf_small_kernel(const Batch bt, const SmallModel<N> mdl, const KfViews kf, const
         const int t = t0 + u;
         if (t < T) {
           double a[N], R[N * N], f, Q;
-          const double dt = REG ? 1.0 : (bt.dt ? bt.dt[t] : 1.0);
+          const double dt = REG ? 1.0 : dt_at(bt, b, t);
           double G[N * N], F[N];
-          load_model<N, REG>(bt, mdl, t, G, F);
+          load_model<N, REG>(bt, mdl, b, t, G, F);
           advance<N, REG>(G, W, dt, m, C, a, R);
           update<N>(F, V, ycur[u], a, R, f, Q, m, C, st);
           const int64_t row = t + ki;
@@ -227,9 +227,9 @@ kf_small_kernel(const Batch bt, const SmallModel<N> mdl, const KfViews kf, const
         }
       }
       const int tobs = r + 1 - ki;  // observation index of row r + 1
-      const double dt = REG ? 1.0 : (bt.dt ? bt.dt[tobs] : 1.0);
+      const double dt = REG ? 1.0 : dt_at(bt, b, tobs);
       double G[N * N], F[N];
-      load_model<N, REG>(bt, mdl, tobs, G, F);
+      load_model<N, REG>(bt, mdl, b, tobs, G, F);
       if (!RELOAD) advance<N, REG>(G, W, dt, m, C, a1, R1);  // bit-identical to the forward a, R
       rts_step<N>(G, m, C, a1, R1, textbook, s, S, st);
       store_vec<N>(sv, b, r, s);

@@ -141,17 +141,17 @@ __device__ __forceinline__ void load_z(int lane, const WarpArgs &wa, int64_t b, 
   for (int k = lane; k < n; k += 32) dst[k] = philox_normal(key, wa.rng_base + b, rows, (int)row, n, k);
 }
 
-// Model matrices for observation t into the warp's G / F slots.
-__device__ __forceinline__ void load_model(int lane, const Batch &bt, const Ws &ws, int t,
+// Model matrices for observation t of series b into the warp's G / F slots.
+__device__ __forceinline__ void load_model(int lane, const Batch &bt, const Ws &ws, int64_t b, int t,
                                            bool first) {
   const int n = bt.n, p = bt.p;
   if (bt.g_tv || first) {
-    const double *g = bt.G + (bt.g_tv ? (int64_t)t * n * n : 0);
-    for (int k = lane; k < n * n; k += 32) ws.G[k] = g[k];
+    const double *g = bt.G + b * bt.G_sb + (int64_t)t * bt.G_sr;
+    for (int k = lane; k < n * n; k += 32) ws.G[k] = g[k * bt.G_sk];
   }
   if (bt.f_tv || first) {
-    const double *f = bt.F + (bt.f_tv ? (int64_t)t * n * p : 0);
-    for (int k = lane; k < n * p; k += 32) ws.F[k] = f[k];
+    const double *f = bt.F + b * bt.F_sb + (int64_t)t * bt.F_sr;
+    for (int k = lane; k < n * p; k += 32) ws.F[k] = f[k * bt.F_sk];
   }
   __syncwarp();
 }
@@ -431,7 +431,7 @@ __device__ __forceinline__ void gibbs_stats(int lane, const Batch &bt, const Ws 
   load_view(lane, theta, b, 0, n, ws.th);  // theta_0
   __syncwarp();
   for (int t = 0; t < T; ++t) {
-    load_model(lane, bt, ws, t, t == 0);
+    load_model(lane, bt, ws, b, t, t == 0);
     load_view(lane, theta, b, t + 1, n, ws.v4);
     load_cview(lane, bt.y, b, t, p, ws.yrow);
     __syncwarp();
@@ -442,7 +442,7 @@ __device__ __forceinline__ void gibbs_stats(int lane, const Batch &bt, const Ws 
       if (!isnan(yi)) { const double d = yi - ws.v1[lane]; res = d * d; ny += 1.0; }
       ssy = (t == 0) ? res : ssy + res;
     }
-    const double dt = bt.dt ? bt.dt[t] : 1.0;
+    const double dt = dt_at(bt, b, t);
     w_mv(lane, n, n, ws.G, n, false, ws.th, ws.v2);
     for (int k = lane; k < n; k += 32) ws.v3[k] = ws.v4[k] - ws.v2[k];
     __syncwarp();
@@ -514,7 +514,7 @@ warp_kernel(const WarpArgs wa, const int ws_doubles) {
     load_pview(lane, bt.m0, b, n, ws.m);
     load_pview(lane, bt.C0, b, nn, ws.C);
     __syncwarp();
-    load_model(lane, bt, ws, 0, true);
+    load_model(lane, bt, ws, b, 0, true);
     if (kSvd) {
       // transformParams (SvdFilter.scala:232-236) + initialiseState (:83-95)
       st |= w_sqrt_svd(lane, p, ws, ws.V, true, ws.t5);
@@ -557,9 +557,9 @@ warp_kernel(const WarpArgs wa, const int ws_doubles) {
 
     for (int t = 0; t < T; ++t) {
       const int64_t row = t + ki;
-      load_model(lane, bt, ws, t, false);
+      load_model(lane, bt, ws, b, t, false);
       load_cview(lane, bt.y, b, t, p, ws.yrow);
-      const double dt = bt.dt ? bt.dt[t] : 1.0;
+      const double dt = dt_at(bt, b, t);
       if (!kSvd && bt.v_tv) {  // V_t: params.copy(v = V_t) at every step (StudentTGibbs.scala:105-118)
         PView vt = bt.V;
         vt.ptr += (int64_t)t * bt.V_sr;
@@ -653,7 +653,7 @@ warp_kernel(const WarpArgs wa, const int ws_doubles) {
   if (OP == kOpSmooth || OP == kOpFilterSmooth) {
     // Smoothing.backwardsSmoother (Smoothing.scala:57-64)
     if (OP == kOpSmooth) {
-      load_model(lane, bt, ws, 0, true);  // no forward pass ran: G, F are not in smem yet
+      load_model(lane, bt, ws, b, 0, true);  // no forward pass ran: G, F are not in smem yet
       load_view(lane, wa.kf.m, b, rows - 1, n, ws.m);
       load_view(lane, wa.kf.C, b, rows - 1, nn, ws.C);
       __syncwarp();
@@ -665,7 +665,7 @@ warp_kernel(const WarpArgs wa, const int ws_doubles) {
     const bool textbook = (bt.compat & BDLM_TEXTBOOK_SMOOTHER) != 0;
     for (int r = rows - 2; r >= 0; --r) {
       const int tobs = r + 1 - ki;
-      load_model(lane, bt, ws, tobs, false);
+      load_model(lane, bt, ws, b, tobs, false);
       if (OP == kOpFilterSmooth) {
         const double *sp = spill + (size_t)r * wa.spill_k, *sp1 = sp + wa.spill_k;
         for (int k = lane; k < n; k += 32) { ws.m[k] = sp[k]; ws.a[k] = sp1[n + nn + k]; }
@@ -680,7 +680,7 @@ warp_kernel(const WarpArgs wa, const int ws_doubles) {
           __syncwarp();
         } else {
           __syncwarp();
-          const double dt = bt.dt ? bt.dt[tobs] : 1.0;
+          const double dt = dt_at(bt, b, tobs);
           kf_advance(lane, n, ws, dt, ws.m, ws.C, ws.a, ws.R);
         }
       }
@@ -707,8 +707,8 @@ warp_kernel(const WarpArgs wa, const int ws_doubles) {
     store_view(lane, wa.theta, b, rows - 1, n, ws.th);
     for (int r = rows - 2; r >= 0; --r) {
       const int tobs = r + 1 - ki;
-      load_model(lane, bt, ws, tobs, false);
-      const double dt = bt.dt ? bt.dt[tobs] : 1.0;
+      load_model(lane, bt, ws, b, tobs, false);
+      const double dt = dt_at(bt, b, tobs);
       const double *sp = spill + (size_t)r * wa.spill_k, *sp1 = sp + wa.spill_k;
       for (int k = lane; k < n; k += 32) { ws.m[k] = sp[k]; ws.a[k] = sp1[n + nn + k]; }
       for (int k = lane; k < nn; k += 32) { ws.C[k] = sp[n + k]; ws.R[k] = sp1[2 * n + nn + k]; }
@@ -757,7 +757,7 @@ warp_kernel(const WarpArgs wa, const int ws_doubles) {
     store_view(lane, wa.theta, b, rows - 1, n, ws.th);
     for (int r = rows - 2; r >= 0; --r) {
       const int tobs = r + 1 - ki;
-      load_model(lane, bt, ws, tobs, false);
+      load_model(lane, bt, ws, b, tobs, false);
       const double *sp = spill + (size_t)r * wa.spill_k, *sp1 = sp + wa.spill_k;
       for (int k = lane; k < n; k += 32) {
         ws.m[k] = sp[k]; ws.dcv[k] = sp[n + k]; ws.a[k] = sp1[2 * n + nn + k];
@@ -1040,7 +1040,7 @@ svd4_kernel(const WarpArgs wa, const int shared_doubles, const int series_double
   auto add_status = [&](int s, int bits) { if (oct == s) st_mine |= bits; };
   {  // the model is shared by the batch: one copy per warp
     const Ws ws = mine.ws;
-    load_model(lane, bt, ws, 0, true);
+    load_model(lane, bt, ws, b0, 0, true);  // (svd4 is only chosen for batch-shared F, G, dt)
   }
 
   // ---- initial state: transformParams (SvdFilter.scala:232-236) + initialiseState (:83-95);
@@ -1086,8 +1086,8 @@ svd4_kernel(const WarpArgs wa, const int shared_doubles, const int series_double
   // ---- forward filter
   for (int t = 0; t < T; ++t) {
     const int64_t row = t + ki;
-    const double dt = bt.dt ? bt.dt[t] : 1.0;
-    load_model(lane, bt, mine.ws, t, false);  // no-op unless F or G vary with t
+    const double dt = dt_at(bt, b0, t);
+    load_model(lane, bt, mine.ws, b0, t, false);  // no-op unless F or G vary with t
 #pragma unroll 1
     for (int s = 0; s < kQuad; ++s)
       if (live(s)) {
@@ -1161,7 +1161,7 @@ svd4_kernel(const WarpArgs wa, const int shared_doubles, const int series_double
     }
     for (int r = rows - 2; r >= 0; --r) {
       const int tobs = r + 1 - ki;
-      load_model(lane, bt, mine.ws, tobs, false);
+      load_model(lane, bt, mine.ws, b0, tobs, false);
 #pragma unroll 1
       for (int s = 0; s < kQuad; ++s) {
         if (!live(s)) continue;
@@ -1231,7 +1231,9 @@ svd4_kernel(const WarpArgs wa, const int shared_doubles, const int series_double
 }
 
 bool svd4_supported(int op, const Batch &bt) {
-  return (op == kOpSvdFilter || op == kOpSvdFfbs) && bt.n <= kOctN && bt.p <= kOctN;
+  // one copy of F, G and one dt per warp: per-series grids / models go to the warp-per-series kernel
+  return (op == kOpSvdFilter || op == kOpSvdFfbs) && bt.n <= kOctN && bt.p <= kOctN &&
+         !bt.ps_model && bt.dt_sb == 0;
 }
 
 template <int OP>

@@ -70,6 +70,11 @@ cudaError_t launch_group(int op, const WarpArgs &wa, cudaStream_t stream);
 cudaError_t launch_transpose(const double *in, double *out, int64_t rows, int64_t cols,
                              cudaStream_t stream);
 
+// transpose.cu: dt[b][t] from per-series observation times (element (b, t) at base[b*sb + t*sr]).
+cudaError_t launch_dt_from_times(const double *times, int64_t tsb, int64_t tsr, double *dt,
+                                 int64_t dsb, int64_t dsr, int64_t B, int T, const double *t_init,
+                                 cudaStream_t stream);
+
 // scan.cu: parallel-in-time filter / smoother for one long series (n <= 4, p = 1, regular
 // grid, time-invariant model).
 enum { kScanReduce = 0, kScanApply = 1,

@@ -169,7 +169,7 @@ conjugate_kernel(const ConjModel<N> md, const ConjArgs a) {
   store(a.kf.f, 0, &nanv, 1); store(a.kf.Q, 0, &nanv, 1);
   store(a.shape, 0, &shape, 1); store(a.scale, 0, &scale, 1);
   for (int t = 0; t < bt.T; ++t) {
-    const double dt = bt.dt ? bt.dt[t] : 1.0;
+    const double dt = dt_at(bt, b, t);
     const double y = ld_stream(bt.y.ptr + b * bt.y.sb + t * bt.y.sr);
     double av[N], R[N * N];
     advance<N, false>(md.G, W, dt, m, C, av, R);
@@ -361,7 +361,7 @@ loglik_small_kernel(const ConjModel<N> md, const Batch bt, double *ll_transition
   for (int t = 0; t < bt.T; ++t) {
     const double y = ynext;
     if (t + 1 < bt.T) ynext = ld_stream(bt.y.ptr + b * bt.y.sb + (int64_t)(t + 1) * bt.y.sr);
-    const double dt = bt.dt ? bt.dt[t] : 1.0;
+    const double dt = dt_at(bt, b, t);
     double a[N], R[N * N], mu[N], f, Q;
     smm<N, N, 1, false, false>(md.G, m, mu);  // G m_{t-1}
     advance<N, false>(md.G, W, dt, m, C, a, R);
@@ -453,7 +453,7 @@ cudaError_t launch_ar(const ArArgs &a, cudaStream_t stream) {
 }
 
 bool loglik_small_supported(const Batch &bt) {
-  return bt.p == 1 && bt.n >= 1 && bt.n <= 4 && !bt.f_tv && !bt.g_tv && !bt.v_tv && !bt.w_tv;
+  return bt.p == 1 && bt.n >= 1 && bt.n <= 4 && !bt.f_tv && !bt.g_tv && !bt.v_tv && !bt.w_tv && !bt.ps_model;
 }
 
 cudaError_t launch_loglik_small(const Batch &bt, const double *hG, const double *hF,

@@ -27,7 +27,42 @@ transpose_kernel(const double *__restrict__ in, double *__restrict__ out, int64_
   }
 }
 
+// Per-series time grids (Data.time differs by series, Dlm.scala:94): dt into every observation,
+// computed exactly as the host does for a shared grid -- prev = min(times) - 1.0
+// (KalmanFilter.initialiseState, KalmanFilter.scala:112-118) or the saved state's time, then
+// dt[t] = times[t] - prev, prev = times[t].  One thread per series.
+__global__ void __launch_bounds__(128)
+dt_kernel(const double *__restrict__ times, int64_t tsb, int64_t tsr, double *__restrict__ dt,
+          int64_t dsb, int64_t dsr, int64_t B, int T, int has_init, double t_init) {
+  const int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const double *tp = times + b * tsb;
+  double prev;
+  if (has_init) {
+    prev = t_init;
+  } else {
+    double tmin = tp[0];
+    for (int t = 1; t < T; ++t) tmin = fmin(tmin, tp[(int64_t)t * tsr]);
+    prev = tmin - 1.0;
+  }
+  double *dp = dt + b * dsb;
+  for (int t = 0; t < T; ++t) {
+    const double cur = tp[(int64_t)t * tsr];
+    dp[(int64_t)t * dsr] = cur - prev;
+    prev = cur;
+  }
+}
+
 }  // namespace
+
+cudaError_t launch_dt_from_times(const double *times, int64_t tsb, int64_t tsr, double *dt,
+                                 int64_t dsb, int64_t dsr, int64_t B, int T, const double *t_init,
+                                 cudaStream_t stream) {
+  if (B <= 0 || T <= 0) return cudaSuccess;
+  dt_kernel<<<(unsigned)((B + 127) / 128), 128, 0, stream>>>(times, tsb, tsr, dt, dsb, dsr, B, T,
+                                                             t_init != nullptr, t_init ? *t_init : 0.0);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_transpose(const double *in, double *out, int64_t rows, int64_t cols,
                              cudaStream_t stream) {

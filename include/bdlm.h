@@ -24,7 +24,8 @@
  *    (host pointers, tiny) or given per series, [k][B] for TIME_MAJOR and [B][k] for
  *    SERIES_MAJOR, in the same memory space as the data.
  *  - F, G, times are model-assembly products evaluated from the Scala closures
- *    mod.f(time_t), mod.g(dt_t) on the host: always HOST pointers, shared by the batch.
+ *    mod.f(time_t), mod.g(dt_t) on the host: HOST pointers shared by the batch, unless the
+ *    BDLM_PS_TIMES / BDLM_PS_F / BDLM_PS_G bits of per_series say they are given per series.
  *    g_tv / f_tv = 1 when they vary with t: G[T][n*n] with G[t] = g(times[t]-times[t-1]),
  *    times[-1] := min(times) - 1 (KalmanFilter.initialiseState, KalmanFilter.scala:112-118).
  *    times == NULL means the regular grid 1..T (every dt = 1).
@@ -91,7 +92,22 @@ enum {
 };
 
 /* which params are per series (bit mask for bdlm_problem.per_series) */
-enum { BDLM_PS_V = 1, BDLM_PS_W = 2, BDLM_PS_M0 = 4, BDLM_PS_C0 = 8 };
+enum { BDLM_PS_V = 1, BDLM_PS_W = 2, BDLM_PS_M0 = 4, BDLM_PS_C0 = 8,
+       /* Data(time, observation) is per series in the reference (Dlm.scala:94): a batch whose
+        * series sit on DIFFERENT (irregular) grids or carry different covariates runs as one call.
+        *  BDLM_PS_TIMES: `times` is a per-step per-series array laid out like y with k = 1, in the
+        *                 data's memory space; every series starts from its own min(times) - 1
+        *                 (KalmanFilter.scala:112-118) unless t_init is given.  Needs a
+        *                 dt-independent G (g_tv = 0: polynomial, regression, autoregressive) or
+        *                 BDLM_PS_G.
+        *  BDLM_PS_F:     F (with f_tv = 1) is laid out like y with k = n*p -- mod.f(time_t) of each
+        *                 series, e.g. Dlm.regression's F_t = (1, x_t) (Dlm.scala:159-169).
+        *  BDLM_PS_G:     G (with g_tv = 1) is laid out like y with k = n*n -- mod.g(dt_t) of each
+        *                 series (seasonal models on per-series irregular grids,
+        *                 AqMeshExample.scala:86-127).
+        * Ragged batches: pad a short series at the END with NaN observations at its last time
+        * (dt = 0: advState passes the state through, an all-missing update leaves it unchanged). */
+       BDLM_PS_TIMES = 16, BDLM_PS_F = 32, BDLM_PS_G = 64 };
 
 typedef struct bdlm_ctx bdlm_ctx;
 
@@ -107,9 +123,9 @@ typedef struct bdlm_problem {
   int32_t f_tv, g_tv; /* F / G vary with t                                  */
   int32_t per_series; /* BDLM_PS_* mask                                     */
   int32_t compat;     /* BDLM_TEXTBOOK_* / BDLM_SVD_* mask                  */
-  const double *F;    /* host [n*p] or [T][n*p]                             */
-  const double *G;    /* host [n*n] or [T][n*n]                             */
-  const double *times;/* host [T] or NULL (regular grid)                    */
+  const double *F;    /* host [n*p] or [T][n*p]   (or per series: BDLM_PS_F)  */
+  const double *G;    /* host [n*n] or [T][n*n]   (or per series: BDLM_PS_G)  */
+  const double *times;/* host [T] or NULL (regular grid) (or BDLM_PS_TIMES)   */
   const double *V;    /* DlmParameters.v  (Dlm.scala:36)                    */
   const double *W;    /* DlmParameters.w                                    */
   const double *m0;   /* DlmParameters.m0                                   */
