@@ -18,8 +18,8 @@ DEVICE, HOST = 0, 1
 PS_V, PS_W, PS_M0, PS_C0 = 1, 2, 4, 8
 PS_TIMES, PS_F, PS_G = 16, 32, 64   # Data.time / mod.f(time) / mod.g(dt) given per series
 TEXTBOOK_SMOOTHER, SVD_CONSISTENT_W = 1, 2
-ST_SINGULAR, ST_NOTCONVERGED, ST_NOTPD, ST_NONFINITE = 1, 2, 4, 8
-E_ARG, E_EMPTY, E_CUDA, E_NODEVICE = -1, -2, -3, -4
+ST_SINGULAR, ST_NOTCONVERGED, ST_NOTPD, ST_NONFINITE, ST_TIMEOUT = 1, 2, 4, 8, 16
+E_ARG, E_EMPTY, E_CUDA, E_NODEVICE, E_NCCL = -1, -2, -3, -4, -5
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)
@@ -35,7 +35,14 @@ SYMBOLS = [
     "bdlm_scan_dist_forward_local", "bdlm_scan_dist_forward_finish",
     "bdlm_scan_dist_backward_local", "bdlm_scan_dist_backward_finish",
     "bdlm_ar_filter", "bdlm_ar_ffbs", "bdlm_conjugate_filter", "bdlm_gibbs_draw",
+    # multi-GPU communicator
+    "bdlm_comm_unique_id", "bdlm_comm_create", "bdlm_comm_destroy", "bdlm_comm_last_error",
+    "bdlm_comm_size", "bdlm_comm_local_size", "bdlm_comm_ctx", "bdlm_comm_sync",
+    "bdlm_comm_uses_peer_exchange", "bdlm_comm_allreduce_sum", "bdlm_comm_allreduce_sum_device",
+    "bdlm_comm_kf_filter_smooth", "bdlm_comm_loglik", "bdlm_comm_ffbs", "bdlm_comm_svd_ffbs",
+    "bdlm_comm_scan_filter_smooth",
 ]
+COMM_ID_BYTES = 128
 AR1, OU = 0, 1
 V_SCALAR, V_PER_STEP, V_PER_SERIES_STEP = 0, 1, 2
 
@@ -161,26 +168,54 @@ def load():
     lib.bdlm_gibbs_draw.argtypes = [C.c_void_p, PP, C.POINTER(GibbsStats), C.POINTER(GibbsPrior),
                                     C.POINTER(GibbsRng), C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p]
+    lib.bdlm_comm_unique_id.argtypes = [C.c_void_p]
+    lib.bdlm_comm_create.argtypes = [C.POINTER(C.c_int32), C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                     C.POINTER(C.c_void_p)]
+    lib.bdlm_comm_destroy.argtypes = [C.c_void_p]
+    lib.bdlm_comm_destroy.restype = None
+    lib.bdlm_comm_last_error.argtypes = [C.c_void_p]
+    lib.bdlm_comm_last_error.restype = C.c_char_p
+    for name in ("bdlm_comm_size", "bdlm_comm_local_size", "bdlm_comm_sync",
+                 "bdlm_comm_uses_peer_exchange"):
+        getattr(lib, name).argtypes = [C.c_void_p]
+    lib.bdlm_comm_ctx.argtypes = [C.c_void_p, C.c_int32]
+    lib.bdlm_comm_ctx.restype = C.c_void_p
+    lib.bdlm_comm_allreduce_sum.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
+    lib.bdlm_comm_allreduce_sum_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
+    lib.bdlm_comm_kf_filter_smooth.argtypes = [C.c_void_p, PP, C.POINTER(KfOut), C.POINTER(SmoothOut),
+                                               C.c_void_p]
+    lib.bdlm_comm_loglik.argtypes = [C.c_void_p, PP, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.bdlm_comm_ffbs.argtypes = [C.c_void_p, PP, C.c_void_p, C.c_void_p, C.POINTER(KfOut),
+                                   C.POINTER(GibbsStats), C.c_void_p, C.POINTER(GibbsStats)]
+    lib.bdlm_comm_svd_ffbs.argtypes = [C.c_void_p, PP, C.c_void_p, C.c_void_p, C.POINTER(SvdOut),
+                                       C.POINTER(GibbsStats), C.c_void_p, C.POINTER(GibbsStats)]
+    lib.bdlm_comm_scan_filter_smooth.argtypes = [C.c_void_p, C.POINTER(Problem), C.POINTER(KfOut),
+                                                 C.POINTER(SmoothOut), C.POINTER(C.c_void_p)]
     _lib = lib
     return lib
 
 
 class Context:
-    """Owns one bdlm_ctx (one GPU, one stream)."""
+    """Owns one bdlm_ctx (one GPU, one stream) -- or borrows one that a communicator owns."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device: int = 0, borrowed_handle=None):
         lib = load()
-        h = C.c_void_p()
-        rc = lib.bdlm_create(int(device), C.byref(h))
-        if rc != 0:
-            raise BdlmError(rc, lib.bdlm_last_error(None).decode())
+        self._owned = borrowed_handle is None
+        if self._owned:
+            h = C.c_void_p()
+            rc = lib.bdlm_create(int(device), C.byref(h))
+            if rc != 0:
+                raise BdlmError(rc, lib.bdlm_last_error(None).decode())
+        else:
+            h = C.c_void_p(borrowed_handle)
         self._h = h
         self.device = device
         self._keep = []
 
     def close(self):
         if getattr(self, "_h", None):
-            load().bdlm_destroy(self._h)
+            if self._owned:
+                load().bdlm_destroy(self._h)
             self._h = None
 
     def __del__(self):

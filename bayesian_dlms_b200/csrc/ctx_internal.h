@@ -16,5 +16,8 @@ cudaStream_t ctx_stream(bdlm_ctx *c);
 // lo < 0 clears the restriction; the restriction is consumed by one call.
 void ctx_set_range(bdlm_ctx *c, int64_t lo, int64_t hi);
 void ctx_count_launches(bdlm_ctx *c, int64_t n);
+// Peer mailboxes the bdlm_scan_dist_* calls of this context use until cleared (peers == nullptr).
+struct ScanPeers;
+void scan_set_peers(bdlm_ctx *c, const ScanPeers *peers, unsigned long long epoch);
 
 }  // namespace bdlm

@@ -82,6 +82,17 @@ enum { kScanReduce = 0, kScanApply = 1,
        // identity carry, chunk aggregate left in DEVICE memory for the all-gather; finish = fold
        // the gathered aggregates of the other ranks on the device and apply
        kScanDistLocal = 2, kScanDistFinish = 3 };
+// Peer mailboxes of a single-process communicator (comm.cu): box[r] / flag[r] live in rank r's
+// device memory and are mapped into every other device (cudaDeviceEnablePeerAccess).  A rank
+// PUBLISHES its chunk aggregate by storing it into slot [its rank] of every peer's box over
+// NVLink, followed by a system-scope release of flag[r][its rank] = epoch; the carry-folding
+// thread of the finish phase spins on its own flags.  world == 0: not in use (NCCL all-gather).
+struct ScanPeers {
+  int world;
+  double *box[BDLM_COMM_MAX_WORLD];
+  unsigned long long *flag[BDLM_COMM_MAX_WORLD];
+};
+
 struct ScanArgs {
   int n;
   int64_t T;           // observations in this chunk
@@ -105,6 +116,8 @@ struct ScanArgs {
   double *agg_dev;     // dist local: device [elem doubles], this rank's chunk aggregate (out)
   const double *aggs_dev;  // dist finish: device [world][elem doubles], all ranks' aggregates
   int rank, world;     // dist phases
+  ScanPeers peers;     // dist phases: peer mailboxes instead of agg_dev + all-gather (world > 0)
+  unsigned long long epoch;  // value the mailbox flags take for this call
   void *table;         // device, scan_table_bytes(): y-independent parts of the level-1 aggregates
   int table_upload;    // 1 = (re)build the table for this model before the forward pass
 };

@@ -874,21 +874,81 @@ __global__ void copy_last_row(View fm, View fC, int64_t row, View sv, View Sv, d
   }
 }
 
-// Carry folding on the device (multi-GPU): one thread, at most world - 1 combines.
+// ---- peer-mailbox exchange of the chunk aggregates (single-process communicators, comm.cu) ----
+// Publish: block d stores this rank's aggregate into slot [rank] of rank d's box with plain 8-byte
+// stores over NVLink (or locally for d == rank), fences at system scope, then one thread releases
+// flag[d][rank] = epoch.  One launch replaces the device-to-device copy + the NCCL all-gather.
+template <class E>
+__global__ void __launch_bounds__(64)
+publish_kernel(const E *src, const ScanPeers peers, int rank, unsigned long long epoch) {
+  constexpr int kD = (int)(sizeof(E) / sizeof(double));
+  const int d = blockIdx.x;
+  const double *s = reinterpret_cast<const double *>(src);
+  double *dst = peers.box[d] + (size_t)rank * kD;
+  for (int k = threadIdx.x; k < kD; k += blockDim.x) dst[k] = s[k];
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    volatile unsigned long long *f = peers.flag[d] + rank;
+    *f = epoch;
+  }
+}
+
+// Acquire side: spin (bounded -- a peer that died must not hang this GPU) until the slot of
+// `src_rank` in MY box carries this call's epoch, then read it with volatile loads.
+constexpr int kPeerSpinMax = 1 << 24;
+template <class E>
+__device__ bool peer_wait_read(const ScanPeers &peers, int my_rank, int src_rank,
+                               unsigned long long epoch, E &out) {
+  constexpr int kD = (int)(sizeof(E) / sizeof(double));
+  volatile unsigned long long *f = peers.flag[my_rank] + src_rank;
+  int spins = 0;
+  while (*f < epoch) {
+    if (++spins > kPeerSpinMax) return false;
+    __nanosleep(64);
+  }
+  __threadfence_system();
+  const volatile double *s = peers.box[my_rank] + (size_t)src_rank * kD;
+  double *o = reinterpret_cast<double *>(&out);
+  for (int k = 0; k < kD; ++k) o[k] = s[k];
+  return true;
+}
+
+// Carry folding on the device (multi-GPU): one thread, at most world - 1 combines.  The aggregates
+// come from `aggs` (NCCL all-gather already done on this stream) or, with peers.world > 0, from
+// this rank's mailbox as the peers publish them.
 template <int N>
 __global__ void fold_forward_kernel(const FElem<N> *aggs, int rank, const StateArg<N> prior,
-                                    FElem<N> *carry) {
-  FElem<N> e, t;
+                                    FElem<N> *carry, const ScanPeers peers,
+                                    unsigned long long epoch, int32_t *status) {
+  FElem<N> e, t, in;
   f_state<N>(e, prior.v, prior.v + N);  // the state before the first observation of rank 0
-  for (int r = 0; r < rank; ++r) { f_combine<N>(e, aggs[r], t); e = t; }
+  for (int r = 0; r < rank; ++r) {
+    if (peers.world > 0) {
+      if (!peer_wait_read(peers, rank, r, epoch, in)) { if (status) atomicOr(status, BDLM_ST_TIMEOUT); break; }
+    } else {
+      in = aggs[r];
+    }
+    f_combine<N>(e, in, t); e = t;
+  }
   *carry = e;
 }
 // carry of rank r = agg_{r+1} (x) ... (x) agg_{world-1}; the last rank's aggregate already ends in
 // its terminal state s_T = m_T, S_T = C_T.
 template <int N>
-__global__ void fold_backward_kernel(const SElem<N> *aggs, int rank, int world, SElem<N> *carry) {
-  SElem<N> e = aggs[world - 1], t;
-  for (int r = world - 2; r > rank; --r) { s_combine<N>(aggs[r], e, t); e = t; }
+__global__ void fold_backward_kernel(const SElem<N> *aggs, int rank, int world, SElem<N> *carry,
+                                     const ScanPeers peers, unsigned long long epoch,
+                                     int32_t *status) {
+  SElem<N> e, t, in;
+  bool ok = true;
+  if (peers.world > 0) ok = peer_wait_read(peers, rank, world - 1, epoch, e);
+  else e = aggs[world - 1];
+  for (int r = world - 2; r > rank && ok; --r) {
+    if (peers.world > 0) ok = peer_wait_read(peers, rank, r, epoch, in);
+    else in = aggs[r];
+    if (ok) { s_combine<N>(in, e, t); e = t; }
+  }
+  if (!ok && status) atomicOr(status, BDLM_ST_TIMEOUT);
   *carry = e;
 }
 
@@ -942,12 +1002,20 @@ cudaError_t scan_forward(const ScanArgs &a, cudaStream_t stream, int64_t *launch
       CK(cudaMemcpyAsync(a.agg_out, X + M, sizeof(FElem<N>), cudaMemcpyDeviceToHost, stream));
       return cudaStreamSynchronize(stream);
     }
-    if (local)  // stays on the device: the caller all-gathers it (NCCL) on the same stream
+    if (local) {
+      if (a.peers.world > 0) {  // straight into every peer's mailbox over NVLink
+        publish_kernel<FElem<N>><<<a.peers.world, 64, 0, stream>>>(X + M, a.peers, a.rank, a.epoch);
+        ++*launches;
+        return cudaGetLastError();
+      }
+      // stays on the device: the caller all-gathers it (NCCL) on the same stream
       return cudaMemcpyAsync(a.agg_dev, X + M, sizeof(FElem<N>), cudaMemcpyDeviceToDevice, stream);
+    }
   } else {
     // X still holds this rank's scanned prefixes from the local phase
     fold_forward_kernel<N><<<1, 1, 0, stream>>>(reinterpret_cast<const FElem<N> *>(a.aggs_dev),
-                                                a.rank, state_arg<N>(a.start), carry);
+                                                a.rank, state_arg<N>(a.start), carry, a.peers,
+                                                a.epoch, a.status);
     ++*launches;
   }
   const bool vec = dense_aligned(a.kf.m, N) && dense_aligned(a.kf.C, N * N) &&
@@ -1011,11 +1079,17 @@ cudaError_t scan_backward(const ScanArgs &a, cudaStream_t stream, int64_t *launc
       CK(cudaMemcpyAsync(a.agg_out, X, sizeof(SElem<N>), cudaMemcpyDeviceToHost, stream));
       return cudaStreamSynchronize(stream);
     }
-    if (local)
+    if (local) {
+      if (a.peers.world > 0) {
+        publish_kernel<SElem<N>><<<a.peers.world, 64, 0, stream>>>(X, a.peers, a.rank, a.epoch);
+        ++*launches;
+        return cudaGetLastError();
+      }
       return cudaMemcpyAsync(a.agg_dev, X, sizeof(SElem<N>), cudaMemcpyDeviceToDevice, stream);
+    }
   } else if (a.has_successor) {
     fold_backward_kernel<N><<<1, 1, 0, stream>>>(reinterpret_cast<const SElem<N> *>(a.aggs_dev),
-                                                 a.rank, a.world, carry);
+                                                 a.rank, a.world, carry, a.peers, a.epoch, a.status);
     ++*launches;
   }
   const SElem<N> *cr = (finish && a.has_successor) ? carry : nullptr;

@@ -624,14 +624,18 @@ def jmh_leg(eng, with_cpu=True):
     return res
 
 
-def scan_dist_leg(eng, dev, rank, world, logT=24, reps=5):
-    """BASELINE.json config 5 on N GPUs: ONE series, T = 2^24, time-sharded across the ranks
-    (device-side protocol: two NCCL all-gathers of one <= 16-double aggregate per rank and pass,
-    no host synchronisation).  Strong scaling: total work is fixed.  Time = max over ranks."""
+def scan_dist_leg(comm, eng, dev, rank, world, logT=24, reps=5):
+    """BASELINE.json config 5 on N GPUs: ONE series, T = 2^24, time-sharded across the ranks through
+    the library's communicator (bdlm_comm_scan_filter_smooth: per pass one exchange of a <= 16-double
+    chunk aggregate per rank, no host synchronisation).  Strong scaling: total work is fixed.
+    Time = max over ranks.  Two variants: one process per GPU (this torchrun job; NCCL all-gathers
+    issued by libbdlm.so) and, on rank 0 alone, ONE process driving all N GPUs with the aggregates
+    stored straight into the peers' mailboxes over NVLink (no NCCL call on the path)."""
     import torch
     import torch.distributed as dist
     from bayesian_dlms_b200 import Model, dlm
-    from bayesian_dlms_b200.scan import DistScan
+    from bayesian_dlms_b200.comm import Comm
+    from bayesian_dlms_b200.scan import scan_filter_smooth
     from bayesian_dlms_b200.sharding import shard_range
     T = 1 << logT
     params = dict(V=[[3.0]], W=np.diag([2.0, 1.0]), m0=np.zeros(2), C0=100.0 * np.eye(2))
@@ -641,39 +645,111 @@ def scan_dist_leg(eng, dev, rank, world, logT=24, reps=5):
     g = torch.Generator(device=dev).manual_seed(20260105)
     yfull = torch.randn(T, generator=g, device=dev, dtype=torch.float64).cumsum(0) * 0.1
     yc = yfull[lo:hi].contiguous()
-    ds = DistScan(eng, Model.build(dlm.polynomial(2), T=hi - lo), params, yc, rank, world)
-    ds.run(); ds.run()
+    h = comm.scan_setup([Model.build(dlm.polynomial(2), T=hi - lo)], params, [yc])
+    comm.scan_run(h); comm.scan_run(h)
     ms = []
     for _ in range(reps):
         dist.barrier(); torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); ds.run(); e1.record()
+        e0.record(); comm.scan_run(h); e1.record()
         torch.cuda.synchronize()
         t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms.append(float(t.item()))
-    st = ds.status.clone()
+    st = h["status"][0].clone()
     dist.all_reduce(st, op=dist.ReduceOp.MAX)
-    # parity on REAL ranks: this rank's rows of the NCCL-exchanged run against the same rows of
-    # the single-GPU scan of the whole series (itself checked against the CPU oracle at this
-    # size by tests/test_gpu_scan.py::test_scan_full_config5_size_vs_cpu_oracle)
-    from bayesian_dlms_b200.scan import scan_filter_smooth
+    # parity on REAL ranks: this rank's rows of the exchanged run against the same rows of the
+    # single-GPU scan of the whole series (itself checked against the CPU oracle at this size by
+    # tests/test_gpu_scan.py::test_scan_full_config5_size_vs_cpu_oracle)
     one = scan_filter_smooth(eng, Model.build(dlm.polynomial(2), T=T), params, yfull)
     torch.cuda.synchronize()
-    r0 = 0 if rank == 0 else lo + 1          # global row of this chunk's first output row
-    worst = torch.zeros(1, device=dev, dtype=torch.float64)
-    for k in ("m", "C", "a", "R", "s", "S"):
-        a, b = ds.out[k], one[k][r0:r0 + ds.rows]
-        den = torch.maximum(b.abs(), 1e-6 * one[k].abs().max())
-        worst = torch.maximum(worst, ((a - b).abs() / den).max().reshape(1))
+
+    def worst_vs_one(out, r):
+        lo_r, hi_r = shard_range(T, r, world)
+        r0 = 0 if r == 0 else lo_r + 1      # global row of the chunk's first output row
+        w = torch.zeros(1, device=dev, dtype=torch.float64)
+        for k in ("m", "C", "a", "R", "s", "S"):
+            a = out[k].to(dev)
+            b = one[k][r0:r0 + a.shape[0]]
+            den = torch.maximum(b.abs(), 1e-6 * one[k].abs().max())
+            w = torch.maximum(w, ((a - b).abs() / den).max().reshape(1))
+        return w
+
+    worst = worst_vs_one(h["outs"][0], rank)
     dist.all_reduce(worst, op=dist.ReduceOp.MAX)
     t = float(np.median(ms)) * 1e-3
-    return {"config": "config5: one series, T=2^%d, polynomial(2), time-sharded over %d GPUs" % (logT, world),
-            "scaling": "strong", "steps_per_s": T / t, "ms": t * 1e3, "status": int(st.item()),
-            "max_rel_err": float(worst.item()),
-            "max_rel_err_of": "every rank's (m, C, a, R, s, S) rows vs the single-GPU scan of the "
-                              "whole series, max over ranks (NCCL all-reduce); bar 1e-9",
-            "collectives": "2 NCCL all-gathers of <= 16 doubles per rank per call"}
+    res = {"config": "config5: one series, T=2^%d, polynomial(2), time-sharded over %d GPUs" % (logT, world),
+           "scaling": "strong", "steps_per_s": T / t, "ms": t * 1e3, "status": int(st.item()),
+           "max_rel_err": float(worst.item()),
+           "max_rel_err_of": "every rank's (m, C, a, R, s, S) rows vs the single-GPU scan of the "
+                             "whole series, max over ranks; bar 1e-9",
+           "exchange": "bdlm_comm_scan_filter_smooth, one process per GPU: 2 ncclAllGather of <= 16 "
+                       "doubles per rank per call, issued by libbdlm.so"}
+    # ---- the same job from ONE process driving all N GPUs (a JVM host): peer-mailbox exchange
+    dist.barrier()
+    if rank == 0:
+        try:
+            pc = Comm.single_process(list(range(world)))
+            models, chunks = [], []
+            for r in range(world):
+                lo_r, hi_r = shard_range(T, r, world)
+                models.append(Model.build(dlm.polynomial(2), T=hi_r - lo_r))
+                chunks.append(yfull[lo_r:hi_r].to(torch.device("cuda", r)).contiguous())
+            hp = pc.scan_setup(models, params, chunks)
+            pc.scan_run(hp); pc.scan_run(hp); pc.sync()
+            wall = []
+            for _ in range(reps):
+                pc.sync()
+                # the communicator's contexts run on their own streams: time with the host clock
+                # around enqueue + sync of all devices (includes launch latency, like the caller sees)
+                w0 = time.perf_counter()
+                pc.scan_run(hp)
+                pc.sync()
+                wall.append((time.perf_counter() - w0) * 1e3)
+            worst_p = max(float(worst_vs_one(hp["outs"][r], r).item()) for r in range(world))
+            res["single_process"] = {
+                "ms": float(np.median(wall)), "peer_mailboxes": pc.uses_peer_exchange,
+                "status": max(int(s_.item()) for s_ in hp["status"]), "max_rel_err": worst_p,
+                "timing": "host clock around enqueue + sync of all %d devices (median of %d)" % (world, reps),
+                "exchange": "aggregates stored into the peers' mailboxes over NVLink + flag "
+                            "(no NCCL call)" if pc.uses_peer_exchange else "NCCL all-gathers"}
+            pc.close()
+        except Exception as ex:
+            res["single_process"] = {"error": repr(ex)}
+    dist.barrier()
+    return res
+
+
+def loglik_dist_leg(comm, eng, dev, rank, world, B=1_000_000, T=1000):
+    """The reduction north_star names: KalmanFilter.likelihood of every series of every rank and
+    ONE ncclAllReduce of the two sums inside the library (bdlm_comm_loglik) -- the pooled
+    log-likelihood a Metropolis step over shared parameters needs (MetropolisHastings.scala:126-137)."""
+    import torch
+    import torch.distributed as dist
+    from bayesian_dlms_b200 import Model, TIME_MAJOR, dlm
+    g = torch.Generator(device=dev).manual_seed(20260107 + rank)
+    y = torch.randn((T, 1, B), generator=g, device=dev, dtype=torch.float64).cumsum(0)
+    params = dict(V=[[3.0]], W=np.diag([2.0, 1.0]), m0=np.zeros(2), C0=100.0 * np.eye(2))
+    model = Model.build(dlm.polynomial(2), T=T)
+    out = comm.loglik(model, params, y, layout=TIME_MAJOR)
+    ms = []
+    for _ in range(3):
+        dist.barrier(); torch.cuda.synchronize()
+        w0 = time.perf_counter()
+        out = comm.loglik(model, params, y, layout=TIME_MAJOR)   # returns after the all-reduce
+        w = torch.tensor([time.perf_counter() - w0], device=dev, dtype=torch.float64)
+        dist.all_reduce(w, op=dist.ReduceOp.MAX)
+        ms.append(float(w.item()) * 1e3)
+    local = torch.stack([out["transition"].sum(), out["innovations"].sum()])
+    dist.all_reduce(local)   # torch's own reduce as the cross-check of the library's
+    t = float(np.median(ms)) * 1e-3
+    return {"config": "a9 on %d GPUs: %d series/GPU x T=%d, sums reduced by ncclAllReduce inside "
+                      "libbdlm.so" % (world, B, T),
+            "series_steps_per_s": world * B * T / t, "ms": t * 1e3,
+            "sum_innovations": out["sum_innovations"], "sum_transition": out["sum_transition"],
+            "rel_diff_vs_torch_allreduce": float(max(
+                abs(out["sum_transition"] - local[0].item()) / abs(local[0].item()),
+                abs(out["sum_innovations"] - local[1].item()) / abs(local[1].item())))}
 
 
 def main():
@@ -717,10 +793,17 @@ def main():
     from bayesian_dlms_b200 import Engine, Model, TIME_MAJOR, dlm
 
     torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
-    eng = Engine(local)
+    comm = None
+    if world > 1:
+        # torch.distributed is plumbing (rendezvous, barriers, max-over-ranks of the timings); the
+        # data-path collectives go through the library's own communicator (bdlm_comm_*)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        from bayesian_dlms_b200.comm import Comm
+        comm = Comm.from_torch_distributed(local)
+        eng = comm.engines[0]
+    else:
+        eng = Engine(local)
     eng.use_torch_stream()
 
     # ---- synthetic inputs, resident in HBM (Dlm.simStep generative model, Dlm.scala:245-282)
@@ -786,7 +869,9 @@ def main():
         chk[0] = o["s"][0, 0, 0]; chk[1] = o["S"][0, 0, 0]; chk[2] = o["m"][-1, 0, 0]
         chk[3] = o["status"].max().double()
         if world > 1:
-            dist.all_reduce(chk)  # the only inter-GPU traffic: a 4-double checksum reduce
+            # the only inter-GPU traffic of a step: ncclAllReduce of 4 doubles, issued by libbdlm.so
+            # on the stream the kernels run on
+            comm.allreduce_sum_device(chk)
 
     def barrier():
         if world > 1:
@@ -916,11 +1001,20 @@ def main():
         e2e["lean_outputs_value"] = world * ncall * slab * T / float(wl.item())
         e2e["lean_outputs"] = "s, S only (what SmoothDlm writes): 48 B/series-step over PCIe"
 
-    scan_dist = None
+    scan_dist = loglik_dist = None
     if world > 1 and not args.no_ffbs:  # collective: every rank takes part
         outbuf.clear(); ys.clear(); pars.clear()
         torch.cuda.empty_cache()
-        scan_dist = scan_dist_leg(eng, dev, rank, world)
+        try:
+            scan_dist = scan_dist_leg(comm, eng, dev, rank, world)
+        except Exception as ex:
+            scan_dist = {"error": repr(ex)}
+        torch.cuda.empty_cache()
+        try:
+            loglik_dist = loglik_dist_leg(comm, eng, dev, rank, world)
+        except Exception as ex:
+            loglik_dist = {"error": repr(ex)}
+        torch.cuda.empty_cache()
 
     if rank == 0:
         line = {
@@ -975,6 +1069,8 @@ def main():
                 torch.cuda.empty_cache()
         if scan_dist is not None:
             line["scan"] = scan_dist
+        if loglik_dist is not None:
+            line["loglik"] = loglik_dist
         if not args.no_cpu and world >= 1:
             try:
                 base, _, _ = cpu_reference_leg(B, T)

@@ -62,8 +62,10 @@ extern "C" {
 
 #define BDLM_VERSION 100
 
-#define BDLM_MAX_N 48 /* state dimension (the SVD entry points: 32)                     */
+#define BDLM_MAX_N 48 /* state dimension (n and p together must fit one SM's 227 KB)     */
 #define BDLM_MAX_P 32 /* observation dimension                                          */
+#define BDLM_COMM_ID_BYTES 128  /* opaque rendezvous id of a multi-process communicator     */
+#define BDLM_COMM_MAX_WORLD 64  /* ranks (GPUs) per communicator                            */
 
 enum { BDLM_TIME_MAJOR = 0, BDLM_SERIES_MAJOR = 1 };
 enum { BDLM_DEVICE = 0, BDLM_HOST = 1 };
@@ -73,7 +75,8 @@ enum {
   BDLM_E_ARG = -1,       /* null pointer / bad dims / unsupported n,p / bad flag  */
   BDLM_E_EMPTY = -2,     /* T == 0: NoSuchElementException (KalmanFilter.scala:116-117) */
   BDLM_E_CUDA = -3,      /* CUDA runtime error, see bdlm_last_error                */
-  BDLM_E_NODEVICE = -4   /* no usable CUDA device: there is no CPU fallback        */
+  BDLM_E_NODEVICE = -4,  /* no usable CUDA device: there is no CPU fallback        */
+  BDLM_E_NCCL = -5       /* NCCL could not be loaded or a collective failed        */
 };
 
 /* per-series status bits */
@@ -81,7 +84,8 @@ enum {
   BDLM_ST_SINGULAR = 1,     /* zero pivot in `\`  (Breeze MatrixSingularException)    */
   BDLM_ST_NOTCONVERGED = 2, /* Jacobi sweep cap   (Breeze NotConvergedException)      */
   BDLM_ST_NOTPD = 4,        /* Cholesky failed    (MultivariateGaussian on W*dt)      */
-  BDLM_ST_NONFINITE = 8     /* NaN/Inf in the final state                             */
+  BDLM_ST_NONFINITE = 8,    /* NaN/Inf in the final state                             */
+  BDLM_ST_TIMEOUT = 16      /* time-sharded scan: a peer's aggregate never arrived    */
 };
 
 /* compat flags: default 0 = reference-verbatim behaviour (what parity is judged on) */
@@ -340,6 +344,70 @@ BDLM_API int bdlm_scan_dist_backward_finish(bdlm_ctx *ctx, const bdlm_problem *p
 /* out = earlier (x) later on the host (carry folding between ranks; a few dozen flops). */
 BDLM_API int bdlm_scan_combine(int32_t n, int32_t backward, const double *earlier,
                                const double *later, double *out);
+
+/* ======================================================================================
+ * Multi-GPU communicator (SURVEY.md 8b "Threading", 8e): one context per device, NCCL behind
+ * one object.  Series and chains are independent -- the reference fits one model per sensor
+ * (UoModel.scala:69-104) and its only parallel driver maps chains over futures
+ * (Streaming.scala:162-173) -- so batches are cut into contiguous blocks of series, one per GPU,
+ * with NO data-path collective; the only inter-GPU traffic is an ncclAllReduce of summed
+ * log-likelihoods / pooled Gibbs statistics, and the chunk aggregates of the time-sharded scan.
+ * NCCL is dlopen'ed (libnccl.so.2; BDLM_NCCL_LIB overrides): libbdlm.so does not link it.
+ *
+ *  single process, n GPUs (a JVM host):  bdlm_comm_create(devs, n, 0, n, NULL, &comm)
+ *  one process per GPU (rank r of w):    rank 0: bdlm_comm_unique_id(id), broadcast id, then
+ *                                        every rank: bdlm_comm_create(&dev, 1, r, w, id, &comm)
+ *
+ * Sharded calls take the problem of THIS PROCESS (prob->B = the series it owns): host buffers
+ * (mem = BDLM_HOST) are cut over the process's devices and run concurrently, one host thread and
+ * one slab pipeline per device; device buffers need one device per process.  Results are those
+ * of one bdlm_* call on the whole batch (status, per-series parameters and the Philox
+ * subsequences are indexed by the position in the call; bdlm_set_rng(first_series) on each
+ * context makes them global across processes).
+ * ==================================================================================== */
+typedef struct bdlm_comm bdlm_comm;
+BDLM_API int bdlm_comm_unique_id(void *id /* BDLM_COMM_ID_BYTES */);
+BDLM_API int bdlm_comm_create(const int32_t *devices, int32_t n_local, int32_t first_rank,
+                              int32_t world, const void *id, bdlm_comm **out);
+BDLM_API void bdlm_comm_destroy(bdlm_comm *comm);
+BDLM_API const char *bdlm_comm_last_error(bdlm_comm *comm); /* NULL: last create error */
+BDLM_API int32_t bdlm_comm_size(bdlm_comm *comm);           /* ranks of the whole job      */
+BDLM_API int32_t bdlm_comm_local_size(bdlm_comm *comm);     /* devices driven by this process */
+BDLM_API bdlm_ctx *bdlm_comm_ctx(bdlm_comm *comm, int32_t local_index); /* owned by the comm */
+BDLM_API int bdlm_comm_sync(bdlm_comm *comm);               /* bdlm_sync on every local context */
+/* 1 when the time-sharded scan exchanges its aggregates through peer mailboxes (direct NVLink
+ * stores + flag, single-process communicators with full peer access) instead of NCCL. */
+BDLM_API int32_t bdlm_comm_uses_peer_exchange(bdlm_comm *comm);
+/* values[count] (host) <- sum over all PROCESSES of their values (ncclAllReduce, fp64). */
+BDLM_API int bdlm_comm_allreduce_sum(bdlm_comm *comm, double *values, int32_t count);
+/* Same on device memory of a one-device-per-process communicator; enqueue-only. */
+BDLM_API int bdlm_comm_allreduce_sum_device(bdlm_comm *comm, double *values_dev, int32_t count);
+/* bdlm_kf_filter_smooth over the communicator's devices. */
+BDLM_API int bdlm_comm_kf_filter_smooth(bdlm_comm *comm, const bdlm_problem *prob,
+                                        const bdlm_kf_out *kf, const bdlm_smooth_out *sm,
+                                        int32_t *status);
+/* bdlm_loglik over the devices; sums (host [2], optional) receives Sum_b transition[b] and
+ * Sum_b innovations[b] over every series of EVERY rank -- the pooled log-likelihood a
+ * Metropolis step over shared parameters evaluates (MetropolisHastings.scala:126-137). */
+BDLM_API int bdlm_comm_loglik(bdlm_comm *comm, const bdlm_problem *prob, double *transition,
+                              double *innovations, int32_t *status, double *sums);
+/* bdlm_ffbs / bdlm_svd_ffbs over the devices; pooled (host arrays ssy[p], ny[p], ssw[n],
+ * scatter[n*n], any may be NULL) receives the sufficient statistics summed over the chains of
+ * every rank (needs the per-chain `stats` arrays). */
+BDLM_API int bdlm_comm_ffbs(bdlm_comm *comm, const bdlm_problem *prob, const double *z, double *theta,
+                            const bdlm_kf_out *kf, const bdlm_gibbs_stats *stats, int32_t *status,
+                            const bdlm_gibbs_stats *pooled);
+BDLM_API int bdlm_comm_svd_ffbs(bdlm_comm *comm, const bdlm_problem *prob, const double *z,
+                                double *theta, const bdlm_svd_out *filt,
+                                const bdlm_gibbs_stats *stats, int32_t *status,
+                                const bdlm_gibbs_stats *pooled);
+/* ONE long series cut along time over the ranks (BASELINE config 5): the six-phase protocol of
+ * bdlm_scan_dist_* behind one call.  probs / kfs / sms / status have one entry per LOCAL device
+ * (rank order) describing that rank's contiguous time chunk in that device's memory; keep_init =
+ * 1 on global rank 0 only; kf->m and kf->C are required.  Enqueue-only (bdlm_comm_sync). */
+BDLM_API int bdlm_comm_scan_filter_smooth(bdlm_comm *comm, const bdlm_problem *probs,
+                                          const bdlm_kf_out *kfs, const bdlm_smooth_out *sms,
+                                          int32_t *const *status);
 
 /* ======================================================================================
  * "Next" rows: the callers and neighbours of the hot path.

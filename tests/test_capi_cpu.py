@@ -145,3 +145,18 @@ def test_scan_combine_is_associative_on_the_host(n):
     x = selem()
     assert np.allclose(comb(1, ident, x), x, rtol=1e-12, atol=1e-14)
     assert np.allclose(comb(1, x, ident), x, rtol=1e-12, atol=1e-14)
+
+
+def test_communicator_needs_a_gpu_and_says_so():
+    """bdlm_comm_create wraps bdlm_create per device: no GPU, no communicator, no fallback."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    lib = capi.load()
+    h = C.c_void_p()
+    devs = (C.c_int32 * 1)(0)
+    rc = lib.bdlm_comm_create(devs, 1, 0, 1, None, C.byref(h))
+    assert rc in (capi.E_NODEVICE, capi.E_NCCL) and not h.value
+    assert lib.bdlm_comm_last_error(None)
+    assert lib.bdlm_comm_create(devs, 1, 0, 2, None, C.byref(h)) == capi.E_ARG   # several processes need an id
+    assert lib.bdlm_comm_size(None) == 0 and lib.bdlm_comm_ctx(None, 0) is None
