@@ -40,6 +40,14 @@ struct bdlm_ctx {
   std::vector<double> scan_key, scan_key_pending;
   bool use_group = std::getenv("BDLM_NO_GROUP_KERNEL") == nullptr;  // A/B switch for profiling
   int64_t range_lo = -1, range_hi = -1;  // ctx_set_range: sub-batch of the next call (comm.cu)
+  // Pinned staging for small transfers: the model upload of every call (F, G, dt, shared
+  // parameters: a pageable source would make cudaMemcpyAsync stage it synchronously) goes through
+  // a ring of pinned slots, and host-buffer calls whose arrays total <= kTinyBytes travel as ONE
+  // H2D and ONE D2H copy through `bounce` instead of one copy per field.
+  struct PinSlot { char *host = nullptr; cudaEvent_t done = nullptr; };
+  PinSlot pin[4];
+  int pin_next = 0;
+  char *bounce = nullptr;
   ScanPeers scan_peers{};                // scan_set_peers: mailbox exchange of the dist scan phases
   unsigned long long scan_epoch = 0;
 };
@@ -66,6 +74,32 @@ int fail(bdlm_ctx *c, int code, const std::string &msg) {
   } while (0)
 
 size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+constexpr size_t kPinSlotBytes = 64 << 10;   // model upload slots
+constexpr size_t kTinyBytes = 512 << 10;     // host-buffer calls below this use the bounce path
+
+// Host -> device copy of a small block the caller is about to free (std::vector): through a pinned
+// slot when it fits (really asynchronous), else straight from pageable memory (the driver stages it
+// before returning).
+int upload_small(bdlm_ctx *c, void *dev, const void *host, size_t bytes) {
+  if (bytes == 0) return 0;
+  if (bytes <= kPinSlotBytes) {
+    bdlm_ctx::PinSlot &sl = c->pin[c->pin_next];
+    c->pin_next = (c->pin_next + 1) & 3;
+    if (!sl.host) {
+      CU(cudaHostAlloc(reinterpret_cast<void **>(&sl.host), kPinSlotBytes, cudaHostAllocDefault));
+      CU(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+    } else {
+      CU(cudaEventSynchronize(sl.done));  // the copy that last used this slot has left it
+    }
+    std::memcpy(sl.host, host, bytes);
+    CU(cudaMemcpyAsync(dev, sl.host, bytes, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaEventRecord(sl.done, c->stream));
+    return 0;
+  }
+  CU(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, c->stream));
+  return 0;
+}
 
 int ensure_arena(bdlm_ctx *c, size_t bytes) {
   if (bytes <= c->arena_bytes) return 0;
@@ -311,8 +345,10 @@ int upload_model(bdlm_ctx *c, const DevCall &d, Bump &bump, Batch &bt,
   const size_t oM = shared(p.m0, BDLM_PS_M0, n);
   const size_t oC = shared(p.C0, BDLM_PS_C0, (size_t)n * n);
   double *dev = bump.take<double>(host.size());
-  CU(cudaMemcpyAsync(dev, host.data(), host.size() * sizeof(double), cudaMemcpyHostToDevice,
-                     c->stream));
+  {
+    int rc = upload_small(c, dev, host.data(), host.size() * sizeof(double));
+    if (rc) return rc;
+  }
   bt.B = d.Bc; bt.T = T; bt.n = n; bt.p = pp; bt.keep_init = p.keep_init ? 1 : 0;
   bt.compat = p.compat;
   bt.f_tv = p.f_tv; bt.g_tv = p.g_tv;
@@ -401,8 +437,10 @@ int run_dev(bdlm_ctx *c, DevCall d, Bump bump) {
     if (ap.v_mode == BDLM_V_PER_STEP) { oV = host.size(); host.insert(host.end(), ap.v, ap.v + T); }
     if (!host.empty()) {
       double *dev = bump.take<double>(host.size());
-      CU(cudaMemcpyAsync(dev, host.data(), host.size() * sizeof(double), cudaMemcpyHostToDevice,
-                         c->stream));
+      {
+        int rc = upload_small(c, dev, host.data(), host.size() * sizeof(double));
+        if (rc) return rc;
+      }
       if (oDt != (size_t)-1) a.dt = dev + oDt;
       if (oV != (size_t)-1) a.v_shared = dev + oV;
     }
@@ -701,6 +739,54 @@ int run_host_mode(bdlm_ctx *c, DevCall d, int64_t lo, int64_t hi) {
   size_t per_series = sizeof(int32_t);
   for (auto &f : fields) per_series += sizeof(double) * (size_t)f.rows * f.k;
 
+  // ---- small calls (one series of T = 10 ... 1000, a few hundred short series): every field
+  // packed into one pinned block, ONE copy in, ONE copy out, everything on the context's stream.
+  // The per-field pipeline below costs one cudaMemcpyAsync (5-10 us from pageable memory) per
+  // field and three streams' worth of events, which dominates calls of this size.
+  if (lo == 0 && hi == B && per_series * (size_t)B + 256 * (fields.size() + 2) <= kTinyBytes) {
+    std::vector<size_t> off(fields.size());
+    size_t in_end = 0, pos = 0;
+    for (int pass = 0; pass < 2; ++pass) {  // inputs first, then outputs: two contiguous regions
+      for (size_t i = 0; i < fields.size(); ++i) {
+        if ((pass == 0) != fields[i].in) continue;
+        off[i] = pos;
+        pos = align_up(pos + sizeof(double) * (size_t)fields[i].rows * fields[i].k * B);
+      }
+      if (pass == 0) in_end = pos;
+    }
+    const size_t st_off = pos;
+    pos = align_up(pos + sizeof(int32_t) * (size_t)B);
+    const size_t staged = pos;
+    DevCall t = d;
+    t.pr.mem = BDLM_DEVICE;
+    int rc = ensure_arena(c, staged + dev_workspace_bytes(t, B) + 65536);
+    if (rc) return rc;
+    if (!c->bounce) CU(cudaHostAlloc(reinterpret_cast<void **>(&c->bounce), 2 * kTinyBytes, cudaHostAllocDefault));
+    CU(cudaStreamSynchronize(c->stream));  // earlier device-mode work may still use the arena / bounce
+    for (size_t i = 0; i < fields.size(); ++i)
+      if (fields[i].in)
+        std::memcpy(c->bounce + off[i], host_ptrs[i], sizeof(double) * (size_t)fields[i].rows * fields[i].k * B);
+    if (in_end) CU(cudaMemcpyAsync(c->arena, c->bounce, in_end, cudaMemcpyHostToDevice, c->stream));
+    {
+      std::vector<Field> tf;
+      collect_fields(t, tf);
+      for (size_t i = 0; i < tf.size(); ++i) *tf[i].slot = reinterpret_cast<double *>(c->arena + off[i]);
+      t.status = host_status ? reinterpret_cast<int32_t *>(c->arena + st_off) : nullptr;
+      t.b0 = 0; t.Bc = B; t.Bp = B; t.rng_b0 = 0;
+      Bump work{c->arena, staged, c->arena_bytes};
+      rc = run_dev(c, t, work);
+      if (rc) return rc;
+    }
+    if (staged > in_end)
+      CU(cudaMemcpyAsync(c->bounce + in_end, c->arena + in_end, staged - in_end, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    for (size_t i = 0; i < fields.size(); ++i)
+      if (fields[i].out)
+        std::memcpy(host_ptrs[i], c->bounce + off[i], sizeof(double) * (size_t)fields[i].rows * fields[i].k * B);
+    if (host_status) std::memcpy(host_status, c->bounce + st_off, sizeof(int32_t) * (size_t)B);
+    return 0;
+  }
+
   // slab size: two staged sets + one device workspace within the staging cap
   int64_t slab = std::min<int64_t>(hi - lo, 1 << 20);
   auto total_for = [&](int64_t s) {
@@ -846,6 +932,11 @@ void bdlm_destroy(bdlm_ctx *c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->arena) cudaFree(c->arena);
   if (c->scan_table) cudaFree(c->scan_table);
+  if (c->bounce) cudaFreeHost(c->bounce);
+  for (auto &sl : c->pin) {
+    if (sl.host) cudaFreeHost(sl.host);
+    if (sl.done) cudaEventDestroy(sl.done);
+  }
   for (int i = 0; i < 2; ++i) {
     if (c->ev_in[i]) cudaEventDestroy(c->ev_in[i]);
     if (c->ev_comp[i]) cudaEventDestroy(c->ev_comp[i]);

@@ -35,9 +35,11 @@ struct GSmem {               // per SERIES shared memory (doubles)
   static constexpr int LD = N | 1;  // odd leading dimension: column reads by 16 lanes hit 16 banks
   static constexpr int MAT = LD * N;
   static constexpr int VEC = 16;
-  static constexpr int kMats = 6;   // S0..S3, SW (per-series W), SG (model G copy per series)
-  static constexpr int kVecs = 10;
-  static constexpr int total = kMats * MAT + kVecs * VEC + 16;
+  static constexpr int kMats = 4;   // S0..S3 per series (W is read from global / L1 where it is
+                                    // used: one column per lane per step; G: one copy per WARP)
+  static constexpr int kVecs = 7;
+  static constexpr int total = kMats * MAT + kVecs * VEC;   // per series
+  static constexpr int warp_total = 2 * total + MAT;        // two series + the shared model G
 };
 
 // out[i] = sum_k X[i + k*LD] * y[k]   (X in shared memory, broadcast reads)
@@ -60,81 +62,110 @@ struct Ctx {
   int lane, gl, grp;       // lane in warp, lane in group, group in warp
   bool act;                // gl < N
   int jj;                  // min(gl, N-1): safe index for addressing
-  double *S0, *S1, *S2, *S3, *SW, *SG;
-  double *VA, *VB, *VC, *VS, *VD, *VK, *VL, *VZ, *VX, *VY;
-  int *IP;
+  double *S0, *S1, *S2, *S3, *SG;
+  // VC / VS (two buffers of Jacobi rotation parameters each) share storage with the forward
+  // filter's VA, VB / VX, VK: the eigen-decomposition only runs in the backward pass
+  double *VA, *VB, *VC, *VS, *VD, *VK, *VL, *VZ, *VX;
 };
 
-// One round of the round-robin Jacobi schedule for both series of the warp.  `round` is a
-// run-time value on purpose: unrolling the rounds made the kernel 29 k instructions (466 KB)
-// and ncu showed 87 % of all stall samples as "no instruction" (I-cache misses).  Own-column
-// elements at run-time row indices come from the shared-memory copy of A instead.
+// ---- Jacobi eigen-decomposition on REGISTER columns ------------------------------------------
+// Lane j owns column j of A and of V for the whole decomposition.  The round-robin schedule of the
+// oracle (rr_partners) pairs, in round r, the indices r + k and r - k (mod N, N odd; index r is
+// idle): in the frame "position = index - r (mod N)" the pairs are ALWAYS (e, N - e).  Every lane
+// therefore keeps the rows of its A column in position order -- register e holds row (e + r) mod N
+// -- and rotates them by one register per round, which makes every row index of the update a
+// compile-time register index although the round is a run-time loop (unrolling the rounds made the
+// first version of this kernel 466 KB of code and instruction-fetch bound).  The partner's column
+// arrives by width-16 shuffles; nothing of A or V lives in shared memory, and the only barrier of
+// a round is the one that publishes the 13 rotation parameters.  Each element is still produced
+// by one lane with the oracle's operations in the oracle's order, so the bits do not change.
+//
+// (Before: A and V double-buffered through shared memory with run-time row indices, three
+// __syncwarp per round, 254 registers -> 8 warps/SM; ncu: issue active 37 %, 1.8 warps per issue
+// waiting on fixed latencies and 1.5 on local memory, profiles/r1_group_kernel_full.txt.)
 template <int N>
-__device__ __forceinline__ void jacobi_round(const Ctx<N> &cx, int round, double (&Acol)[N],
-                                             double (&Vcol)[N], bool &rot_any_grp) {
-  constexpr int LD = GSmem<N>::LD;
+__device__ __forceinline__ void jacobi_round(const Ctx<N> &cx, int r, double (&Ac)[N],
+                                             double (&Vc)[N], bool &rot_any_grp) {
+  static_assert(N % 2 == 1, "position frame below assumes an odd dimension (idle index = round)");
   const int j = cx.jj;
-  // --- rotation parameters of my pair (both members compute the same c, s)
-  const int q = rr_partner(N, round, j);
+  const unsigned gmask = 0xffffu << (cx.grp * GW);
+  int d = j - r; if (d < 0) d += N;                 // my position in this round
+  const bool paired = d != 0;
+  int q = 2 * r - j; if (q < 0) q += N; if (q >= N) q -= N;   // partner index (= r - d mod N)
+  const int src = paired ? q : j;                    // lane (in group) whose column I mix with
+  // own diagonal A[j, j] sits in register d, A[q, j] in register N - d
+  double ajj = Ac[0], aqj = Ac[0];
+#pragma unroll
+  for (int e = 1; e < N; ++e) {
+    ajj = (e == d) ? Ac[e] : ajj;
+    aqj = (e == N - d) ? Ac[e] : aqj;
+  }
+  const double aqq = __shfl_sync(FULL, ajj, src, GW);
   double c = 1.0, s = 0.0;
   bool rot = false;
-  if (cx.act && q >= 0) {
-    const int lo = j < q ? j : q, hi = j < q ? q : j;
-    const double apq = cx.S1[hi + lo * LD], app = cx.S1[lo + lo * LD], aqq = cx.S1[hi + hi * LD];
-    if (apq * apq > kJacobiThr2 * fabs(app * aqq)) {
+  if (cx.act && paired) {
+    const bool lo = j < q;
+    const double app = lo ? ajj : aqq, aqq2 = lo ? aqq : ajj;
+    if (aqj * aqj > kJacobiThr2 * fabs(app * aqq2)) {
       double cc, ss;
-      sym_rot(app, aqq, apq, cc, ss);
+      sym_rot(app, aqq2, aqj, cc, ss);
       c = cc;
-      s = (j == lo) ? -ss : ss;
+      s = lo ? -ss : ss;
       rot = true;
     }
   }
-  const int pj = (q < 0) ? j : q;
-  if (cx.act) { cx.VC[j] = c; cx.VS[j] = s; cx.IP[j] = pj; }
+  double *pc = cx.VC + (r & 1) * GW, *ps = cx.VS + (r & 1) * GW;   // double-buffered: one barrier
+  if (cx.act) { pc[j] = c; ps[j] = s; }
   const unsigned bal = __ballot_sync(FULL, rot);
   const bool any = ((bal >> (cx.grp * GW)) & 0xffffu) != 0;
   __syncwarp();
-  double nA[N];
-  if (any) {
+  if (any) {  // uniform within the 16-lane group: the shuffles below name only the group's lanes
     rot_any_grp = true;
     const double cj = c, sj = s;
-    const double *Aj = cx.S1 + j * LD, *Ap = cx.S1 + pj * LD, *Vp = cx.S2 + pj * LD;
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-      // new (i, j) element of J^T A J from the old x1 = A[i,j], x2 = A[pi,j], x3 = A[i,pj],
-      // x4 = A[pi,pj]:
-      //   i >= j: v = cj*(ci*x1 + si*x2) + sj*(ci*x3 + si*x4)   (element (i, j), lower triangle)
-      //   i <  j: v = ci*(cj*x1 + sj*x3) + si*(cj*x2 + sj*x4)   (mirror of element (j, i))
-      const int pi = cx.IP[i];
-      const double ci = cx.VC[i], si = cx.VS[i];
-      const double x1 = Acol[i], x2 = Aj[pi], x3 = Ap[i], x4 = Ap[pi];
+    auto elem = [&](int e, double x1, double x2, double x3, double x4) {
+      // new A[i, j], i = (e + r) mod N, from x1 = A[i,j], x2 = A[pi,j], x3 = A[i,pj], x4 = A[pi,pj]:
+      //   i >= j: cj*(ci*x1 + si*x2) + sj*(ci*x3 + si*x4)   (lower triangle, as the oracle)
+      //   i <  j: ci*(cj*x1 + sj*x3) + si*(cj*x2 + sj*x4)   (mirror of element (j, i))
+      int i = e + r; if (i >= N) i -= N;
+      const double ci = pc[i], si = ps[i];
       const bool low = i >= j;
       const double co = low ? cj : ci, so = low ? sj : si;
       const double cn = low ? ci : cj, sn = low ? si : sj;
       const double y2 = low ? x2 : x3, y3 = low ? x3 : x2;
       const double t1 = cn * x1 + sn * y2;
       const double t2 = cn * y3 + sn * x4;
-      nA[i] = co * t1 + so * t2;
-      Vcol[i] = cj * Vcol[i] + sj * Vp[i];
+      return co * t1 + so * t2;
+    };
+    {  // position 0: the idle row (pi = i)
+      const double x3 = __shfl_sync(gmask, Ac[0], src, GW);
+      Ac[0] = elem(0, Ac[0], Ac[0], x3, x3);
+    }
+#pragma unroll
+    for (int e = 1; e <= N / 2; ++e) {  // rows e and N - e are each other's partners: in place
+      const double a1 = Ac[e], a2 = Ac[N - e];
+      const double p1 = __shfl_sync(gmask, a1, src, GW), p2 = __shfl_sync(gmask, a2, src, GW);
+      Ac[e] = elem(e, a1, a2, p1, p2);
+      Ac[N - e] = elem(N - e, a2, a1, p2, p1);
+    }
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      const double vp = __shfl_sync(gmask, Vc[k], src, GW);
+      Vc[k] = cj * Vc[k] + sj * vp;
     }
   }
-  __syncwarp();  // all shared-memory reads of the old columns done before anyone publishes
-  if (any) {
+  // next round's frame: register e <- row (e + r + 1) mod N
+  const double first = Ac[0];
 #pragma unroll
-    for (int i = 0; i < N; ++i) Acol[i] = nA[i];
-    if (cx.act) {
-#pragma unroll
-      for (int i = 0; i < N; ++i) { cx.S1[i + j * LD] = Acol[i]; cx.S2[i + j * LD] = Vcol[i]; }
-    }
-  }
-  __syncwarp();
+  for (int e = 0; e < N - 1; ++e) Ac[e] = Ac[e + 1];
+  Ac[N - 1] = first;
 }
 
 // MultivariateGaussianSvd(mu, cov).draw with injected normals.  Input: the symmetric matrix
 // whose LOWER triangle is read sits in S0 (column-major, ld LD); mu_j, z_j per lane.
-// Uses S1 (A), S2 (V), S3 (M), VC, VS, VL, VZ.  Returns the draw element of lane j.
+// Uses S3 (M = V diag(sqrt lam)), VC, VS (rotation parameters, double-buffered), VL, VZ.
+// Returns the draw element of lane j.
 template <int N>
-__device__ __noinline__ double eig_draw(const Ctx<N> &cx, double mu_j, double z_j, int &st) {
+__device__ __noinline__ double eig_draw(const Ctx<N> cx, double mu_j, double z_j, int &st) {
   constexpr int LD = GSmem<N>::LD;
   const int j = cx.jj;
   double Acol[N], Vcol[N];
@@ -143,17 +174,13 @@ __device__ __noinline__ double eig_draw(const Ctx<N> &cx, double mu_j, double z_
     Acol[i] = (i >= j) ? cx.S0[i + j * LD] : cx.S0[j + i * LD];
     Vcol[i] = (i == j) ? 1.0 : 0.0;
   }
-  __syncwarp();
-  if (cx.act) {
-#pragma unroll
-    for (int i = 0; i < N; ++i) { cx.S1[i + j * LD] = Acol[i]; cx.S2[i + j * LD] = Vcol[i]; }
-    cx.VZ[j] = z_j;
-  }
+  if (cx.act) cx.VZ[j] = z_j;
   __syncwarp();
   constexpr int M = (N + 1) & ~1;
   bool converged_grp = (N == 1);
   for (int sweep = 0; sweep < kJacobiMaxSweeps && N > 1; ++sweep) {
     bool rot = false;
+    // M - 1 = N rounds bring the row frame back to register e = row e
     for (int round = 0; round < M - 1; ++round) jacobi_round<N>(cx, round, Acol, Vcol, rot);
     if (!rot) converged_grp = true;
     // continue while either series of the warp still rotates (a converged series only
@@ -162,7 +189,9 @@ __device__ __noinline__ double eig_draw(const Ctx<N> &cx, double mu_j, double z_
   }
   if (!converged_grp) st |= BDLM_ST_NOTCONVERGED;
   // eigenvalues ascending (stable), sign rule, M = V diag(sqrt lam) in sorted order
-  const double lam = cx.S1[j + j * LD];
+  double lam = Acol[0];
+#pragma unroll
+  for (int e = 1; e < N; ++e) lam = (e == j) ? Acol[e] : lam;
   if (cx.act) cx.VL[j] = lam;
   __syncwarp();
   int rank = 0;
@@ -263,8 +292,13 @@ __device__ __forceinline__ int lu_cols(const Ctx<N> &cx, double (&A)[N], double 
   return st;
 }
 
+// 14 warps per SM (7 blocks): 148 x 14 x 2 = 4144 chains resident, so BASELINE config 3 (4096
+// chains) is ONE wave; ptxas gets 65536 / (14 x 32) = 146 registers per thread.
+#ifndef BDLM_GROUP_MINB
+#define BDLM_GROUP_MINB 7
+#endif
 template <int N, int OP>
-__global__ void __launch_bounds__(kWpb * 32)
+__global__ void __launch_bounds__(kWpb * 32, BDLM_GROUP_MINB)
 group_kernel(const WarpArgs wa) {
   extern __shared__ double smem[];
   constexpr int LD = GSmem<N>::LD, MAT = GSmem<N>::MAT, VEC = GSmem<N>::VEC, NN = N * N;
@@ -282,14 +316,15 @@ group_kernel(const WarpArgs wa) {
   const bool ghost = b >= bt.B;
   if (ghost) b = bt.B - 1;
   if (((int64_t)blockIdx.x * kWpb + wib) * 2 >= bt.B) return;  // whole warp beyond the batch
-  double *base = smem + (size_t)sib * GSmem<N>::total;
+  double *wbase = smem + (size_t)wib * GSmem<N>::warp_total;
+  double *base = wbase + MAT + (size_t)cx.grp * GSmem<N>::total;
+  cx.SG = wbase;  // both series of the warp share the model
   cx.S0 = base; cx.S1 = base + MAT; cx.S2 = base + 2 * MAT; cx.S3 = base + 3 * MAT;
-  cx.SW = base + 4 * MAT; cx.SG = base + 5 * MAT;
   double *v = base + GSmem<N>::kMats * MAT;
-  cx.VA = v; cx.VB = v + VEC; cx.VC = v + 2 * VEC; cx.VS = v + 3 * VEC; cx.VD = v + 4 * VEC;
-  cx.VK = v + 5 * VEC; cx.VL = v + 6 * VEC; cx.VZ = v + 7 * VEC; cx.VX = v + 8 * VEC;
-  cx.VY = v + 9 * VEC;
-  cx.IP = reinterpret_cast<int *>(v + GSmem<N>::kVecs * VEC);
+  cx.VA = v; cx.VB = v + VEC; cx.VX = v + 2 * VEC; cx.VK = v + 3 * VEC;
+  cx.VC = v; cx.VS = v + 2 * VEC;   // 2 x VEC each (double-buffered), backward pass only
+  cx.VD = v + 4 * VEC; cx.VL = v + 5 * VEC; cx.VZ = v + 6 * VEC;
+  (void)sib;
   const int j = cx.jj;
   const bool wr = cx.act && !ghost;  // lane may write global memory
   const int T = bt.T, rows = T + 1;
@@ -297,18 +332,16 @@ group_kernel(const WarpArgs wa) {
   double Fk[N];  // F (n x 1), shared model
 
   // ---- per-series parameters
-  double V;
-  {
-    const double *wp = bt.W.ptr + b * bt.W.sb;
-#pragma unroll
-    for (int i = 0; i < N; ++i) cx.SW[i + j * LD] = wp[(i + j * N) * bt.W.sk];
-    V = bt.V.ptr[b * bt.V.sb];
-  }
+  const double V = bt.V.ptr[b * bt.V.sb];
+  const double *wcolp = bt.W.ptr + b * bt.W.sb + (int64_t)j * N * bt.W.sk;  // column j of W
   auto load_model = [&](int t, bool first) {
     if (bt.g_tv || first) {
       const double *g = bt.G + (bt.g_tv ? (int64_t)t * NN : 0);
+      __syncwarp();  // the other series may still be reading the previous G
+      if (cx.grp == 0) {
 #pragma unroll
-      for (int i = 0; i < N; ++i) cx.SG[i + j * LD] = g[i + j * N];
+        for (int i = 0; i < N; ++i) cx.SG[i + j * LD] = g[i + j * N];
+      }
     }
     if (bt.f_tv || first) {
       const double *f = bt.F + (bt.f_tv ? (int64_t)t * N : 0);
@@ -393,7 +426,7 @@ group_kernel(const WarpArgs wa) {
       __syncwarp();
       mm_sx<N, LD>(cx.S0, Grow, Rcol);
 #pragma unroll
-      for (int i = 0; i < N; ++i) Rcol[i] = Rcol[i] + cx.SW[i + j * LD] * dt;
+      for (int i = 0; i < N; ++i) Rcol[i] = Rcol[i] + wcolp[i * bt.W.sk] * dt;
     }
     // f = F^T a ; Q = (F^T R) F + V
     __syncwarp();
@@ -532,7 +565,7 @@ group_kernel(const WarpArgs wa) {
       // diff = I - B G
       double Gcol[N], t1[N], Dcol[N], Drow[N], H1[N], H2[N], Wcol[N];
 #pragma unroll
-      for (int k = 0; k < N; ++k) { Gcol[k] = cx.SG[k + j * LD]; Wcol[k] = cx.SW[k + j * LD]; }
+      for (int k = 0; k < N; ++k) { Gcol[k] = cx.SG[k + j * LD]; Wcol[k] = wcolp[k * bt.W.sk]; }
       mm_sx<N, LD>(cx.S3, Gcol, t1);
 #pragma unroll
       for (int i = 0; i < N; ++i) Dcol[i] = ((i == j) ? 1.0 : 0.0) - t1[i];
@@ -648,7 +681,7 @@ group_kernel(const WarpArgs wa) {
 
 template <int N, int OP>
 cudaError_t launch_group_n(const WarpArgs &wa, cudaStream_t stream) {
-  const size_t smem = (size_t)kWpb * 2 * GSmem<N>::total * sizeof(double);
+  const size_t smem = (size_t)kWpb * GSmem<N>::warp_total * sizeof(double);
   cudaError_t e = cudaFuncSetAttribute(group_kernel<N, OP>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;

@@ -202,3 +202,72 @@ object GpuGibbs {
   // struct bdlm_gibbs_prior { double v_shape, v_scale, w_shape, w_scale, w_nu; const double *w_psi; }
   // struct bdlm_gibbs_rng   { uint64 seed, sweep; const double *gamma_v, *gamma_w, *bartlett; }
 }
+
+/** All GPUs of a node behind one object: `bdlm_comm_*` (include/bdlm.h).  The reference's only
+  * parallel driver maps chains over futures on CPU cores (Streaming.scala:162-173); here one JVM
+  * hands the whole batch to the library, which cuts it into contiguous blocks of series, one per
+  * GPU, and runs them on its own host threads.  NCCL lives inside libbdlm.so (dlopen): the only
+  * collectives are the sums of log-likelihoods / pooled Gibbs statistics and the chunk aggregates
+  * of the time-sharded scan.  NOT compiled in this repository (no JVM in the image); the same calls
+  * are exercised by bayesian_dlms_b200/comm.py in tests/test_gpu_comm.py. */
+final class GpuComm(devices: Seq[Int]) extends AutoCloseable {
+  import java.lang.foreign._
+  import ValueLayout._
+  private val linker = Linker.nativeLinker()
+  private val lib    = SymbolLookup.libraryLookup("libbdlm.so", Arena.global())
+  private def h(name: String, fd: FunctionDescriptor) = linker.downcallHandle(lib.find(name).get, fd)
+  private val commCreate  = h("bdlm_comm_create", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, JAVA_INT, JAVA_INT, ADDRESS, ADDRESS))
+  private val commDestroy = h("bdlm_comm_destroy", FunctionDescriptor.ofVoid(ADDRESS))
+  private val commErr     = h("bdlm_comm_last_error", FunctionDescriptor.of(ADDRESS, ADDRESS))
+  private val commFs      = h("bdlm_comm_kf_filter_smooth", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS))
+  private val commLoglik  = h("bdlm_comm_loglik", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS))
+  private val commFfbs    = h("bdlm_comm_ffbs", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS))
+  private val commScan    = h("bdlm_comm_scan_filter_smooth", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS))
+  private val commSync    = h("bdlm_comm_sync", FunctionDescriptor.of(JAVA_INT, ADDRESS))
+
+  private val handle: MemorySegment = {
+    val a = Arena.ofConfined()
+    try {
+      val devs = a.allocateFrom(JAVA_INT, devices.toArray: _*)
+      val out  = a.allocate(ADDRESS)
+      val rc = commCreate.invoke(devs, devices.size, 0, devices.size, MemorySegment.NULL, out).asInstanceOf[Int]
+      if (rc != 0) throw new IllegalStateException(
+        commErr.invoke(MemorySegment.NULL).asInstanceOf[MemorySegment].reinterpret(4096).getString(0))
+      out.get(ADDRESS, 0)
+    } finally a.close()
+  }
+
+  /** Σ_b KalmanFilter.likelihood over EVERY series of the batch (all GPUs), e.g. the pooled
+    * log-likelihood of a Metropolis step over parameters shared by the series
+    * (MetropolisHastings.scala:126-137).  `problem` is a host-memory bdlm_problem for the whole
+    * batch built exactly like GpuKalman.problem (B = number of series). */
+  def loglikSums(problem: MemorySegment, transition: MemorySegment, innovations: MemorySegment,
+                 status: MemorySegment): (Double, Double) = {
+    val a = Arena.ofConfined()
+    try {
+      val sums = a.allocate(JAVA_DOUBLE, 2)
+      val rc = commLoglik.invoke(handle, problem, transition, innovations, status, sums).asInstanceOf[Int]
+      if (rc < 0) throw new IllegalArgumentException(
+        commErr.invoke(handle).asInstanceOf[MemorySegment].reinterpret(4096).getString(0))
+      (sums.getAtIndex(JAVA_DOUBLE, 0), sums.getAtIndex(JAVA_DOUBLE, 1))
+    } finally a.close()
+  }
+
+  /** bdlm_comm_kf_filter_smooth: host arrays for the whole batch, cut over the GPUs. */
+  def filterSmooth(problem: MemorySegment, kf: MemorySegment, sm: MemorySegment, status: MemorySegment): Int =
+    commFs.invoke(handle, problem, kf, sm, status).asInstanceOf[Int]
+
+  /** bdlm_comm_ffbs with pooled sufficient statistics (ss_y, n_y, ss_w, scatter summed over all chains). */
+  def ffbs(problem: MemorySegment, z: MemorySegment, theta: MemorySegment, kf: MemorySegment,
+           stats: MemorySegment, status: MemorySegment, pooled: MemorySegment): Int =
+    commFfbs.invoke(handle, problem, z, theta, kf, stats, status, pooled).asInstanceOf[Int]
+
+  /** ONE long series cut along time, one chunk per GPU (BASELINE config 5): enqueue-only. */
+  def scanFilterSmooth(chunkProblems: MemorySegment, kfOuts: MemorySegment, smOuts: MemorySegment,
+                       status: MemorySegment): Int = {
+    val rc = commScan.invoke(handle, chunkProblems, kfOuts, smOuts, status).asInstanceOf[Int]
+    if (rc == 0) commSync.invoke(handle).asInstanceOf[Int] else rc
+  }
+
+  override def close(): Unit = commDestroy.invoke(handle)
+}
