@@ -25,7 +25,8 @@ namespace {
 
 using namespace small;
 
-// eigSym restatement (oracle jacobi_eigsym): lower triangle of Ain read, lam ascending, Vout
+// eigSym restatement (oracle jacobi_eigsym): one-sided Jacobi on the columns of U = A (lower
+// triangle of Ain read) with V accumulated from I; lam_j = sign(v_j . u_j) |u_j| ascending, Vout
 // columns = sign-normalised eigenvectors.  All indices are compile-time after unrolling.
 template <int N>
 __device__ __forceinline__ int jacobi_eigsym_small(const double (&Ain)[N * N], double (&lam)[N],
@@ -44,55 +45,52 @@ __device__ __forceinline__ int jacobi_eigsym_small(const double (&Ain)[N * N], d
     bool rotated = false;
 #pragma unroll
     for (int round = 0; round < M - 1; ++round) {
-      double cs[N], sn[N];
-      bool any = false;
 #pragma unroll
-      for (int i = 0; i < N; ++i) {
-        const int q = rr_partner(N, round, i);
-        cs[i] = 1.0; sn[i] = 0.0;
-        if (q >= 0) {
-          const int lo = i < q ? i : q, hi = i < q ? q : i;
-          const double apq = A[hi + lo * N], app = A[lo + lo * N], aqq = A[hi + hi * N];
-          if (apq * apq > kJacobiThr2 * fabs(app * aqq)) {
-            double c, s;
-            sym_rot(app, aqq, apq, c, s);
-            cs[i] = c;
-            sn[i] = (i == lo) ? -s : s;
-            any = true;
+      for (int p = 0; p < N; ++p) {
+        const int q = rr_partner(N, round, p);
+        if (q < 0 || q < p) continue;   // compile-time after unrolling
+        double alpha = 0.0, beta = 0.0, gamma = 0.0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+          const double up = A[i + p * N], uq = A[i + q * N];
+          const double pp = up * up, qq = uq * uq, pq = up * uq;
+          alpha = (i == 0) ? pp : alpha + pp;
+          beta = (i == 0) ? qq : beta + qq;
+          gamma = (i == 0) ? pq : gamma + pq;
+        }
+        if (gamma * gamma > kJacobiThr2 * (alpha * beta)) {
+          rotated = true;
+          double c, s;
+          sym_rot(alpha, beta, gamma, c, s);
+#pragma unroll
+          for (int i = 0; i < N; ++i) {
+            const double up = A[i + p * N], uq = A[i + q * N];
+            A[i + p * N] = c * up - s * uq;
+            A[i + q * N] = s * up + c * uq;
+            const double vp = V[i + p * N], vq = V[i + q * N];
+            V[i + p * N] = c * vp - s * vq;
+            V[i + q * N] = s * vp + c * vq;
           }
         }
       }
-      if (!any) continue;
-      rotated = true;
-      double A2[N * N], V2[N * N];
-#pragma unroll
-      for (int j = 0; j < N; ++j) {
-        const int qj = rr_partner(N, round, j);
-        const int pj = qj < 0 ? j : qj;
-#pragma unroll
-        for (int i = j; i < N; ++i) {
-          const int qi = rr_partner(N, round, i);
-          const int pi = qi < 0 ? i : qi;
-#define BDLM_SYM(r, c_) ((r) >= (c_) ? A[(r) + (c_) * N] : A[(c_) + (r) * N])
-          const double t_ij = cs[i] * BDLM_SYM(i, j) + sn[i] * BDLM_SYM(pi, j);
-          const double t_ipj = cs[i] * BDLM_SYM(i, pj) + sn[i] * BDLM_SYM(pi, pj);
-#undef BDLM_SYM
-          const double v = cs[j] * t_ij + sn[j] * t_ipj;
-          A2[i + j * N] = v;
-          A2[j + i * N] = v;
-        }
-#pragma unroll
-        for (int i = 0; i < N; ++i) V2[i + j * N] = cs[j] * V[i + j * N] + sn[j] * V[i + pj * N];
-      }
-#pragma unroll
-      for (int k = 0; k < N * N; ++k) { A[k] = A2[k]; V[k] = V2[k]; }
     }
     if (!rotated) { st = 0; break; }
   }
-  // eigenvalues ascending (stable), sign rule: largest-|component| (first such) positive
   double d[N];
 #pragma unroll
-  for (int i = 0; i < N; ++i) d[i] = A[i + i * N];
+  for (int j = 0; j < N; ++j) {
+    double nn = 0.0, dot = 0.0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      const double u = A[i + j * N];
+      const double sq = u * u, vu = V[i + j * N] * u;
+      nn = (i == 0) ? sq : nn + sq;
+      dot = (i == 0) ? vu : dot + vu;
+    }
+    const double nrm = sqrt(nn);
+    d[j] = (dot < 0.0) ? -nrm : nrm;
+  }
+  // eigenvalues ascending (stable), sign rule: largest-|component| (first such) positive
 #pragma unroll
   for (int k = 0; k < N; ++k) {
     int rank = 0;

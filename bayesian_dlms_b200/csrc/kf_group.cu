@@ -37,7 +37,7 @@ struct GSmem {               // per SERIES shared memory (doubles)
   static constexpr int VEC = 16;
   static constexpr int kMats = 4;   // S0..S3 per series (W is read from global / L1 where it is
                                     // used: one column per lane per step; G: one copy per WARP)
-  static constexpr int kVecs = 7;
+  static constexpr int kVecs = 6;
   static constexpr int total = kMats * MAT + kVecs * VEC;   // per series
   static constexpr int warp_total = 2 * total + MAT;        // two series + the shared model G
 };
@@ -63,160 +63,119 @@ struct Ctx {
   bool act;                // gl < N
   int jj;                  // min(gl, N-1): safe index for addressing
   double *S0, *S1, *S2, *S3, *SG;
-  // VC / VS (two buffers of Jacobi rotation parameters each) share storage with the forward
-  // filter's VA, VB / VX, VK: the eigen-decomposition only runs in the backward pass
-  double *VA, *VB, *VC, *VS, *VD, *VK, *VL, *VZ, *VX;
+  double *VA, *VB, *VD, *VK, *VZ, *VX;
 };
 
-// ---- Jacobi eigen-decomposition on REGISTER columns ------------------------------------------
-// Lane j owns column j of A and of V for the whole decomposition.  The round-robin schedule of the
-// oracle (rr_partners) pairs, in round r, the indices r + k and r - k (mod N, N odd; index r is
-// idle): in the frame "position = index - r (mod N)" the pairs are ALWAYS (e, N - e).  Every lane
-// therefore keeps the rows of its A column in position order -- register e holds row (e + r) mod N
-// -- and rotates them by one register per round, which makes every row index of the update a
-// compile-time register index although the round is a run-time loop (unrolling the rounds made the
-// first version of this kernel 466 KB of code and instruction-fetch bound).  The partner's column
-// arrives by width-16 shuffles; nothing of A or V lives in shared memory, and the only barrier of
-// a round is the one that publishes the 13 rotation parameters.  Each element is still produced
-// by one lane with the oracle's operations in the oracle's order, so the bits do not change.
-//
-// (Before: A and V double-buffered through shared memory with run-time row indices, three
-// __syncwarp per round, 254 registers -> 8 warps/SM; ncu: issue active 37 %, 1.8 warps per issue
-// waiting on fixed latencies and 1.5 on local memory, profiles/r1_group_kernel_full.txt.)
+// ---- eigSym (oracle jacobi_eigsym) on REGISTER columns --------------------------------------
+// One-sided Jacobi: lane j owns column j of U (= A at the start) and of V for the whole
+// decomposition.  Per round a lane fetches its partner's U column by width-16 shuffles, forms
+// |own|^2 and own . partner (the partner's norm arrives by one more shuffle: it sums the same
+// squares in the same order, so alpha / beta / gamma are the oracle's bits in both lanes of the
+// pair), derives (c, s) and rotates its own U and V columns:  own' = c * own + s' * partner with
+// s' = -s in the lower-index lane (c*up - s*uq) and +s in the higher one (s*up + c*uq).  Nothing
+// lives in shared memory, there is no barrier inside a sweep, no dependence on the OTHER pairs'
+// rotation parameters and no lower / upper-triangle case split: about 300 instructions per round
+// against 1000 for the two-sided update J^T A J this kernel used in round 1 (ncu, n = 13: 83 k
+// instructions per FFBS step, 21 % of them FP64; profiles/r2_group_twosided_full.txt).
 template <int N>
-__device__ __forceinline__ void jacobi_round(const Ctx<N> &cx, int r, double (&Ac)[N],
-                                             double (&Vc)[N], bool &rot_any_grp) {
-  static_assert(N % 2 == 1, "position frame below assumes an odd dimension (idle index = round)");
+__device__ __forceinline__ bool jacobi_round(const Ctx<N> &cx, int round, double (&u)[N],
+                                             double (&v)[N]) {
   const int j = cx.jj;
-  const unsigned gmask = 0xffffu << (cx.grp * GW);
-  int d = j - r; if (d < 0) d += N;                 // my position in this round
-  const bool paired = d != 0;
-  int q = 2 * r - j; if (q < 0) q += N; if (q >= N) q -= N;   // partner index (= r - d mod N)
-  const int src = paired ? q : j;                    // lane (in group) whose column I mix with
-  // own diagonal A[j, j] sits in register d, A[q, j] in register N - d
-  double ajj = Ac[0], aqj = Ac[0];
+  const int q = cx.act ? rr_partner(N, round, j) : -1;
+  const int src = q < 0 ? cx.gl : q;   // lane (in the 16-lane group) holding the partner column
+  const bool low = j < q;
+  double w[N];
+  double own = 0.0, gamma = 0.0;
 #pragma unroll
-  for (int e = 1; e < N; ++e) {
-    ajj = (e == d) ? Ac[e] : ajj;
-    aqj = (e == N - d) ? Ac[e] : aqj;
+  for (int i = 0; i < N; ++i) {
+    w[i] = __shfl_sync(FULL, u[i], src, GW);
+    const double sq = u[i] * u[i], pq = u[i] * w[i];
+    own = (i == 0) ? sq : own + sq;
+    gamma = (i == 0) ? pq : gamma + pq;
   }
-  const double aqq = __shfl_sync(FULL, ajj, src, GW);
-  double c = 1.0, s = 0.0;
-  bool rot = false;
-  if (cx.act && paired) {
-    const bool lo = j < q;
-    const double app = lo ? ajj : aqq, aqq2 = lo ? aqq : ajj;
-    if (aqj * aqj > kJacobiThr2 * fabs(app * aqq2)) {
-      double cc, ss;
-      sym_rot(app, aqq2, aqj, cc, ss);
-      c = cc;
-      s = lo ? -ss : ss;
-      rot = true;
-    }
+  const double other = __shfl_sync(FULL, own, src, GW);
+  const double alpha = low ? own : other, beta = low ? other : own;
+  const bool rot = q >= 0 && (gamma * gamma > kJacobiThr2 * (alpha * beta));
+  // nobody in the warp rotates (the last sweep of both series): skip the V exchange as well
+  if (__ballot_sync(FULL, rot) == 0u) return false;
+  double c = 1.0, sp = 0.0;
+  if (rot) {
+    double cc, ss;
+    sym_rot(alpha, beta, gamma, cc, ss);
+    c = cc;
+    sp = low ? -ss : ss;
   }
-  double *pc = cx.VC + (r & 1) * GW, *ps = cx.VS + (r & 1) * GW;   // double-buffered: one barrier
-  if (cx.act) { pc[j] = c; ps[j] = s; }
-  const unsigned bal = __ballot_sync(FULL, rot);
-  const bool any = ((bal >> (cx.grp * GW)) & 0xffffu) != 0;
-  __syncwarp();
-  if (any) {  // uniform within the 16-lane group: the shuffles below name only the group's lanes
-    rot_any_grp = true;
-    const double cj = c, sj = s;
-    auto elem = [&](int e, double x1, double x2, double x3, double x4) {
-      // new A[i, j], i = (e + r) mod N, from x1 = A[i,j], x2 = A[pi,j], x3 = A[i,pj], x4 = A[pi,pj]:
-      //   i >= j: cj*(ci*x1 + si*x2) + sj*(ci*x3 + si*x4)   (lower triangle, as the oracle)
-      //   i <  j: ci*(cj*x1 + sj*x3) + si*(cj*x2 + sj*x4)   (mirror of element (j, i))
-      int i = e + r; if (i >= N) i -= N;
-      const double ci = pc[i], si = ps[i];
-      const bool low = i >= j;
-      const double co = low ? cj : ci, so = low ? sj : si;
-      const double cn = low ? ci : cj, sn = low ? si : sj;
-      const double y2 = low ? x2 : x3, y3 = low ? x3 : x2;
-      const double t1 = cn * x1 + sn * y2;
-      const double t2 = cn * y3 + sn * x4;
-      return co * t1 + so * t2;
-    };
-    {  // position 0: the idle row (pi = i)
-      const double x3 = __shfl_sync(gmask, Ac[0], src, GW);
-      Ac[0] = elem(0, Ac[0], Ac[0], x3, x3);
-    }
 #pragma unroll
-    for (int e = 1; e <= N / 2; ++e) {  // rows e and N - e are each other's partners: in place
-      const double a1 = Ac[e], a2 = Ac[N - e];
-      const double p1 = __shfl_sync(gmask, a1, src, GW), p2 = __shfl_sync(gmask, a2, src, GW);
-      Ac[e] = elem(e, a1, a2, p1, p2);
-      Ac[N - e] = elem(N - e, a2, a1, p2, p1);
-    }
-#pragma unroll
-    for (int k = 0; k < N; ++k) {
-      const double vp = __shfl_sync(gmask, Vc[k], src, GW);
-      Vc[k] = cj * Vc[k] + sj * vp;
+  for (int i = 0; i < N; ++i) {
+    const double vw = __shfl_sync(FULL, v[i], src, GW);
+    if (rot) {
+      u[i] = c * u[i] + sp * w[i];
+      v[i] = c * v[i] + sp * vw;
     }
   }
-  // next round's frame: register e <- row (e + r + 1) mod N
-  const double first = Ac[0];
-#pragma unroll
-  for (int e = 0; e < N - 1; ++e) Ac[e] = Ac[e + 1];
-  Ac[N - 1] = first;
+  return rot;
 }
 
 // MultivariateGaussianSvd(mu, cov).draw with injected normals.  Input: the symmetric matrix
 // whose LOWER triangle is read sits in S0 (column-major, ld LD); mu_j, z_j per lane.
-// Uses S3 (M = V diag(sqrt lam)), VC, VS (rotation parameters, double-buffered), VL, VZ.
-// Returns the draw element of lane j.
+// Uses S3 (M = V diag(sqrt lam)), VL, VZ.  Returns the draw element of lane j.
 template <int N>
 __device__ __noinline__ double eig_draw(const Ctx<N> cx, double mu_j, double z_j, int &st) {
   constexpr int LD = GSmem<N>::LD;
   const int j = cx.jj;
-  double Acol[N], Vcol[N];
+  double u[N], v[N];
 #pragma unroll
   for (int i = 0; i < N; ++i) {
-    Acol[i] = (i >= j) ? cx.S0[i + j * LD] : cx.S0[j + i * LD];
-    Vcol[i] = (i == j) ? 1.0 : 0.0;
+    u[i] = (i >= j) ? cx.S0[i + j * LD] : cx.S0[j + i * LD];
+    v[i] = (i == j) ? 1.0 : 0.0;
   }
   if (cx.act) cx.VZ[j] = z_j;
-  __syncwarp();
   constexpr int M = (N + 1) & ~1;
   bool converged_grp = (N == 1);
+  const unsigned gbits = 0xffffu << (cx.grp * GW);
   for (int sweep = 0; sweep < kJacobiMaxSweeps && N > 1; ++sweep) {
     bool rot = false;
-    // M - 1 = N rounds bring the row frame back to register e = row e
-    for (int round = 0; round < M - 1; ++round) jacobi_round<N>(cx, round, Acol, Vcol, rot);
-    if (!rot) converged_grp = true;
-    // continue while either series of the warp still rotates (a converged series only
-    // executes no-op rounds, exactly like the oracle's `continue`)
-    if (!__any_sync(FULL, rot)) break;
+    for (int round = 0; round < M - 1; ++round) rot = jacobi_round<N>(cx, round, u, v) || rot;
+    const unsigned bal = __ballot_sync(FULL, rot);
+    if ((bal & gbits) == 0u) converged_grp = true;  // this series saw a sweep without a rotation
+    // continue while either series of the warp still rotates (a converged series only executes
+    // no-op rounds, exactly like the oracle's `continue`)
+    if (bal == 0u) break;
   }
   if (!converged_grp) st |= BDLM_ST_NOTCONVERGED;
-  // eigenvalues ascending (stable), sign rule, M = V diag(sqrt lam) in sorted order
-  double lam = Acol[0];
+  // lam_j = sign(v_j . u_j) |u_j|; ascending (stable), sign rule, M = V diag(sqrt lam) sorted
+  double nn = 0.0, dot = 0.0;
 #pragma unroll
-  for (int e = 1; e < N; ++e) lam = (e == j) ? Acol[e] : lam;
-  if (cx.act) cx.VL[j] = lam;
-  __syncwarp();
+  for (int i = 0; i < N; ++i) {
+    const double sq = u[i] * u[i], vu = v[i] * u[i];
+    nn = (i == 0) ? sq : nn + sq;
+    dot = (i == 0) ? vu : dot + vu;
+  }
+  const double nrm = sqrt(nn);
+  const double lam = (dot < 0.0) ? -nrm : nrm;
   int rank = 0;
 #pragma unroll
   for (int k = 0; k < N; ++k) {
-    const double lk = cx.VL[k];
+    const double lk = __shfl_sync(FULL, lam, k, GW);
     rank += ((lk < lam) || (lk == lam && k < j)) ? 1 : 0;
   }
   int im = 0;
-  double best = fabs(Vcol[0]);
+  double best = fabs(v[0]);
 #pragma unroll
   for (int i = 1; i < N; ++i) {
-    const double a = fabs(Vcol[i]);
+    const double a = fabs(v[i]);
     if (a > best) { best = a; im = i; }
   }
-  double vim = Vcol[0];
+  double vim = v[0];
 #pragma unroll
-  for (int i = 1; i < N; ++i) vim = (im == i) ? Vcol[i] : vim;
+  for (int i = 1; i < N; ++i) vim = (im == i) ? v[i] : vim;
   const bool flip = vim < 0.0;
   const double sq = sqrt(lam);
   if (cx.act) {
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-      const double v = flip ? -Vcol[i] : Vcol[i];
-      cx.S3[i + rank * LD] = v * sq;
+      const double x = flip ? -v[i] : v[i];
+      cx.S3[i + rank * LD] = x * sq;
     }
   }
   __syncwarp();
@@ -322,8 +281,7 @@ group_kernel(const WarpArgs wa) {
   cx.S0 = base; cx.S1 = base + MAT; cx.S2 = base + 2 * MAT; cx.S3 = base + 3 * MAT;
   double *v = base + GSmem<N>::kMats * MAT;
   cx.VA = v; cx.VB = v + VEC; cx.VX = v + 2 * VEC; cx.VK = v + 3 * VEC;
-  cx.VC = v; cx.VS = v + 2 * VEC;   // 2 x VEC each (double-buffered), backward pass only
-  cx.VD = v + 4 * VEC; cx.VL = v + 5 * VEC; cx.VZ = v + 6 * VEC;
+  cx.VD = v + 4 * VEC; cx.VZ = v + 5 * VEC;
   (void)sib;
   const int j = cx.jj;
   const bool wr = cx.act && !ghost;  // lane may write global memory

@@ -245,11 +245,10 @@ __device__ __forceinline__ int smoothing_gain(int lane, int n, const Ws &ws, con
 }
 
 // MultivariateGaussianSvd(mu, cov).draw with injected normals z -> out (n).
-// cov must not alias t1..t6; uses t2..t6, v1, v2, v4, scr, iscr.
+// cov must not alias t2, t3, t6; uses t2, t3, t6, v1, v2, scr, iscr.
 __device__ __forceinline__ int mvn_eig_draw(int lane, int n, const Ws &ws, const double *mu,
                                             const double *cov, const double *z, double *out) {
-  const int st = w_jacobi_eigsym(lane, n, cov, ws.t2, ws.t3, ws.t4, ws.t5, ws.v2, ws.v4,
-                                 ws.iscr, ws.v1, ws.t6);
+  const int st = w_jacobi_eigsym(lane, n, cov, ws.t2, ws.t3, ws.scr, ws.iscr, ws.v1, ws.t6);
   for (ElemIter it(lane, n, n); it.ok(); it.next())
     ws.t2[it.i + it.j * n] = ws.t6[it.i + it.j * n] * sqrt(ws.v1[it.j]);
   __syncwarp();

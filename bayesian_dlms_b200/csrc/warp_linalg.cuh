@@ -197,88 +197,6 @@ __device__ __forceinline__ bool col_flip(int rows, const double *col) {
   return col[im] < 0.0;
 }
 
-// eigSym restatement (oracle jacobi_eigsym).  Ain: n x n, lower triangle read.
-// Workspaces A, A2, V, V2: n*n each; cs, sn: n each; ipart: n ints.
-// Results: lam[n] ascending, Vout (n x n) ordered + sign-normalised eigenvectors.
-// Vout may alias A2 or V2's final "other" buffer is handled internally: pass a distinct
-// buffer.  Returns status bits.
-__device__ __forceinline__ int w_jacobi_eigsym(int lane, int n, const double *Ain, double *A,
-                                               double *A2, double *V, double *V2, double *cs,
-                                               double *sn, int *ipart, double *lam,
-                                               double *Vout) {
-  for (ElemIter it(lane, n, n); it.ok(); it.next()) {
-    const int i = it.i, j = it.j;
-    A[i + j * n] = (i >= j) ? Ain[i + j * n] : Ain[j + i * n];
-    V[i + j * n] = (i == j) ? 1.0 : 0.0;
-  }
-  __syncwarp();
-  int st = (n == 1) ? 0 : BDLM_ST_NOTCONVERGED;
-  const int m = (n + 1) & ~1;
-  for (int sweep = 0; sweep < kJacobiMaxSweeps && n > 1; ++sweep) {
-    bool rotated = false;
-    for (int round = 0; round < m - 1; ++round) {
-      bool rot = false;
-      for (int idx = lane; idx < n; idx += 32) {
-        const int q = rr_partner(n, round, idx);
-        double c = 1.0, s = 0.0;
-        if (q >= 0) {
-          const int lo = idx < q ? idx : q, hi = idx < q ? q : idx;
-          const double apq = A[hi + lo * n], app = A[lo + lo * n], aqq = A[hi + hi * n];
-          if (apq * apq > kJacobiThr2 * fabs(app * aqq)) {
-            double cc, ss;
-            sym_rot(app, aqq, apq, cc, ss);
-            c = cc;
-            s = (idx == lo) ? -ss : ss;
-            rot = true;
-          }
-        }
-        cs[idx] = c; sn[idx] = s; ipart[idx] = (q < 0) ? idx : q;
-      }
-      const bool any = __any_sync(FULL, rot);
-      __syncwarp();
-      if (!any) continue;
-      rotated = true;
-      // (J^T A J) for i >= j, mirrored; V J for all elements
-      for (ElemIter it(lane, n, n); it.ok(); it.next()) {
-        const int i = it.i, j = it.j;
-        const int pj = ipart[j];
-        const double cj = cs[j], sj = sn[j];
-        if (i >= j) {
-          const int pi = ipart[i];
-          const double ci = cs[i], si = sn[i];
-          const double t_ij = ci * A[i + j * n] + si * A[pi + j * n];
-          const double t_ipj = ci * A[i + pj * n] + si * A[pi + pj * n];
-          const double v = cj * t_ij + sj * t_ipj;
-          A2[i + j * n] = v;
-          A2[j + i * n] = v;
-        }
-        V2[i + j * n] = cj * V[i + j * n] + sj * V[i + pj * n];
-      }
-      __syncwarp();
-      double *t = A; A = A2; A2 = t;
-      t = V; V = V2; V2 = t;
-    }
-    if (!rotated) { st = 0; break; }
-  }
-  // eigenvalues ascending (dsyev order), sign rule
-  for (int idx = lane; idx < n; idx += 32) cs[idx] = A[idx + idx * n];
-  __syncwarp();
-  for (int idx = lane; idx < n; idx += 32) {
-    const int rk = stable_rank(n, cs, idx, false);
-    ipart[rk] = idx;
-    lam[rk] = cs[idx];
-  }
-  __syncwarp();
-  for (int idx = lane; idx < n; idx += 32) sn[idx] = col_flip(n, V + ipart[idx] * n) ? -1.0 : 1.0;
-  __syncwarp();
-  for (ElemIter it(lane, n, n); it.ok(); it.next()) {
-    const double v = V[it.i + ipart[it.j] * n];
-    Vout[it.i + it.j * n] = (sn[it.j] < 0.0) ? -v : v;
-  }
-  __syncwarp();
-  return st;
-}
-
 // Pair of round-robin slot k in `round` (oracle rr_partners enumeration): returns false
 // when the slot touches a dummy index; p < q otherwise.
 __device__ __forceinline__ bool rr_slot(int n, int round, int k, int &p, int &q) {
@@ -301,13 +219,11 @@ constexpr int kScrDoubles = 128;  // w_jacobi_svd: dots [72] | c [24] | s [24]; 
 constexpr int kIscrInts = 128;    // pair p [48] | pair q [48] | observed-component list [32] at kObsOff
 constexpr int kObsOff = 96;
 
-// svd restatement (oracle jacobi_svd): one-sided Jacobi on the columns of U (r x n,
-// IN PLACE, destroyed); V: n x n work.  sv[n] descending, Vout (n x n) = right singular
-// vectors (Breeze rightVectors.t) ordered + sign-normalised.  n <= 48.
+// One-sided (Hestenes) Jacobi iteration (oracle jacobi_onesided) on the columns of U (r x n, IN
+// PLACE) with the rotations accumulated in V (n x n, set to I here).  n <= 48.
 // scr: kScrDoubles doubles, iscr: the first kObsOff ints of the per-warp integer scratch.
-__device__ __forceinline__ int w_jacobi_svd(int lane, int r, int n, double *U, double *V,
-                                            double *scr, int *iscr, double *sv,
-                                            double *Vout) {
+__device__ __forceinline__ int w_jacobi_onesided(int lane, int r, int n, double *U, double *V,
+                                                 double *scr, int *iscr) {
   for (ElemIter it(lane, n, n); it.ok(); it.next())
     V[it.i + it.j * n] = (it.i == it.j) ? 1.0 : 0.0;
   __syncwarp();
@@ -373,6 +289,36 @@ __device__ __forceinline__ int w_jacobi_svd(int lane, int r, int n, double *U, d
     }
     if (!rotated) { st = 0; break; }
   }
+  return st;
+}
+
+// Common finish of the SVD / eigSym restatements: keys scr[0..n) are ranked (descending for
+// singular values, ascending for eigenvalues; stable), out_key[rank] = key, Vout = the columns of
+// V in that order with the oracle's sign rule (largest-|component| positive).
+__device__ __forceinline__ void w_order_and_sign(int lane, int n, const double *V, double *scr,
+                                                 int *iscr, bool desc, double *out_key,
+                                                 double *Vout) {
+  for (int j = lane; j < n; j += 32) {
+    const int rk = stable_rank(n, scr, j, desc);
+    iscr[rk] = j;
+    out_key[rk] = scr[j];
+  }
+  __syncwarp();
+  for (int j = lane; j < n; j += 32) scr[48 + j] = col_flip(n, V + iscr[j] * n) ? -1.0 : 1.0;
+  __syncwarp();
+  for (ElemIter it(lane, n, n); it.ok(); it.next()) {
+    const double v = V[it.i + iscr[it.j] * n];
+    Vout[it.i + it.j * n] = (scr[48 + it.j] < 0.0) ? -v : v;
+  }
+  __syncwarp();
+}
+
+// svd restatement (oracle jacobi_svd): U (r x n) IN PLACE, destroyed; V: n x n work.  sv[n]
+// descending, Vout (n x n) = right singular vectors (Breeze rightVectors.t).
+__device__ __forceinline__ int w_jacobi_svd(int lane, int r, int n, double *U, double *V,
+                                            double *scr, int *iscr, double *sv,
+                                            double *Vout) {
+  const int st = w_jacobi_onesided(lane, r, n, U, V, scr, iscr);
   for (int j = lane; j < n; j += 32) {
     const double *col = U + j * r;
     double acc = 0.0;
@@ -383,19 +329,35 @@ __device__ __forceinline__ int w_jacobi_svd(int lane, int r, int n, double *U, d
     scr[j] = sqrt(acc);
   }
   __syncwarp();
-  for (int j = lane; j < n; j += 32) {
-    const int rk = stable_rank(n, scr, j, true);
-    iscr[rk] = j;
-    sv[rk] = scr[j];
-  }
-  __syncwarp();
-  for (int j = lane; j < n; j += 32) scr[48 + j] = col_flip(n, V + iscr[j] * n) ? -1.0 : 1.0;
-  __syncwarp();
+  w_order_and_sign(lane, n, V, scr, iscr, true, sv, Vout);
+  return st;
+}
+
+// eigSym restatement (oracle jacobi_eigsym): one-sided Jacobi on U = A (lower triangle of Ain
+// read), lam_j = sign(v_j . u_j) |u_j| ascending, Vout = sign-normalised eigenvectors.
+// U, V: n*n work each (distinct from Ain and Vout).
+__device__ __forceinline__ int w_jacobi_eigsym(int lane, int n, const double *Ain, double *U,
+                                               double *V, double *scr, int *iscr, double *lam,
+                                               double *Vout) {
   for (ElemIter it(lane, n, n); it.ok(); it.next()) {
-    const double v = V[it.i + iscr[it.j] * n];
-    Vout[it.i + it.j * n] = (scr[48 + it.j] < 0.0) ? -v : v;
+    const int i = it.i, j = it.j;
+    U[i + j * n] = (i >= j) ? Ain[i + j * n] : Ain[j + i * n];
   }
   __syncwarp();
+  const int st = w_jacobi_onesided(lane, n, n, U, V, scr, iscr);
+  for (int j = lane; j < n; j += 32) {
+    const double *u = U + j * n, *v = V + j * n;
+    double nn = 0.0, dot = 0.0;
+    for (int i = 0; i < n; ++i) {
+      const double sq = u[i] * u[i], vu = v[i] * u[i];
+      nn = (i == 0) ? sq : nn + sq;
+      dot = (i == 0) ? vu : dot + vu;
+    }
+    const double nrm = sqrt(nn);
+    scr[j] = (dot < 0.0) ? -nrm : nrm;
+  }
+  __syncwarp();
+  w_order_and_sign(lane, n, V, scr, iscr, false, lam, Vout);
   return st;
 }
 

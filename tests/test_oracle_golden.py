@@ -267,12 +267,19 @@ def test_ffbs_matches_lapack_flavour(name):
         if n > 1 and np.min(np.diff(w)) < 1e-3 * w[-1]:
             continue
         checked += 1
-        # dsyev's eigenvector signs are implementation-defined: align them with the
-        # oracle's documented rule (largest-|component| positive; ties can flip on rounding)
+        # dsyev's eigenvector signs are implementation-defined, and the oracle's rule (largest-
+        # |component| positive) is decided by rounding when two components tie in magnitude
+        # (symmetric models): compare sign-free.  theta - h = sum_k (+-) sqrt(w_k) z_k v_k, so
+        # the coordinates of the draw in LAPACK's eigenbasis must be +- z_k, one by one.
+        coord = (v.T @ d) / np.sqrt(w)
+        assert np.max(np.abs(np.abs(coord) - np.abs(z[r]))) < 1e-7 * max(1.0, np.max(np.abs(z[r]))), r
+        # and where the oracle's own eigenvectors of LAPACK's H have no such tie, bit-level signs too
         _, Vo, _ = oracle.eigsym(dlm.cm(Hc))
-        v = v * np.sign(np.sum(v * Vo, axis=0))
-        draw = h + (v @ np.diag(np.sqrt(w))) @ z[r]
-        assert H.rel_err(o["theta"][r], draw) < 1e-7, r
+        top2 = np.sort(np.abs(Vo), axis=0)[-2:]
+        if np.all(top2[1] - top2[0] > 1e-6):
+            va = v * np.sign(np.sum(v * Vo, axis=0))
+            draw = h + (va @ np.diag(np.sqrt(w))) @ z[r]
+            assert H.rel_err(o["theta"][r], draw) < 1e-7, r
     assert checked > len(ref) // 2
     # z = 0: theta_t = h_t exactly -> the mean recursion alone, at full tolerance
     o0 = oracle.ffbs(n, p, F, G, dlm.cm(V), dlm.cm(W), m0, dlm.cm(C0), times, y, 0 * z)
