@@ -326,7 +326,7 @@ __device__ __forceinline__ int w_sqrt_svd(int lane, int n, const Ws &ws, const d
 // ws.W <- the advance closure's factor (raw W_t, or sqrtSvd(W_t) with BDLM_SVD_CONSISTENT_W, which
 // is what those two callers use).  Clobbers stk, t3, t4, t5, v1, scr, iscr.
 __device__ __forceinline__ int svd_load_params_tv(int lane, const Batch &bt, const Ws &ws,
-                                                  int64_t b, int t, bool want_v) {
+                                               int64_t b, int t, bool want_v) {
   int st = 0;
   const int n = bt.n, p = bt.p;
   if (bt.v_tv && want_v) {
@@ -874,17 +874,14 @@ __device__ __noinline__ int oct_jacobi_svd(int lane, int n, int r, const double 
       if (rot) {
         double c, sn;
         sym_rot(alpha, beta, gamma, c, sn);
-        if (low) {
+        // lower-index lane: c*up - s*uq; higher: s*up + c*uq.  Both are own' = c*own + s'*partner
+        // with s' = -+s (a - b == a + (-b) and (-s)*w == -(s*w) exactly; + commutes), so the two
+        // lanes of a pair run ONE instruction stream instead of two divergent ones.
+        const double sp = low ? -sn : sn;
 #pragma unroll
-          for (int i = 0; i < kOctRows; ++i) u[i] = c * u[i] - sn * w[i];
+        for (int i = 0; i < kOctRows; ++i) u[i] = c * u[i] + sp * w[i];
 #pragma unroll
-          for (int i = 0; i < kOctN; ++i) v[i] = c * v[i] - sn * vw[i];
-        } else {
-#pragma unroll
-          for (int i = 0; i < kOctRows; ++i) u[i] = sn * w[i] + c * u[i];
-#pragma unroll
-          for (int i = 0; i < kOctN; ++i) v[i] = sn * vw[i] + c * v[i];
-        }
+        for (int i = 0; i < kOctN; ++i) v[i] = c * v[i] + sp * vw[i];
       }
       rotated = rotated || rot;
     }
