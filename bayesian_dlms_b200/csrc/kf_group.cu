@@ -57,6 +57,27 @@ __device__ __forceinline__ void mm_sx(const double *X, const double (&y)[N], dou
   }
 }
 
+// out[i] = sum_k X[i + k*LD] * y[k*ys] with the k loop at RUN time (rows i stay compile-time
+// register indices): the same products summed in the same order as mm_sx, in 1/12 of the code.
+// The straight-line body of an FFBS step was 150 KB of SASS that every warp streamed once per
+// step (ncu: 2.7 warps per issue-active cycle stalled on instruction fetch,
+// profiles/r2_group_onesided_full.txt); y comes from shared memory (or, for W, global memory).
+template <int N, int LD>
+__device__ __forceinline__ void mm_sy(const double *X, const double *y, int64_t ys, double (&out)[N]) {
+  {
+    const double y0 = y[0];
+#pragma unroll
+    for (int i = 0; i < N; ++i) out[i] = X[i] * y0;
+  }
+#pragma unroll 1
+  for (int k = 1; k < N; ++k) {
+    const double yk = y[k * ys];
+    const double *xc = X + k * LD;
+#pragma unroll
+    for (int i = 0; i < N; ++i) out[i] = out[i] + xc[i] * yk;
+  }
+}
+
 template <int N>
 struct Ctx {
   int lane, gl, grp;       // lane in warp, lane in group, group in warp
@@ -372,17 +393,20 @@ group_kernel(const WarpArgs wa) {
         a_j = acc;
       }
       // R = (G C) G^T + W dt
-      double t1[N], Grow[N];
-      mm_sx<N, LD>(cx.SG, Ccol, t1);
+      double t1[N];
+      if (cx.act) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) cx.S1[i + j * LD] = Ccol[i];
+      }
+      __syncwarp();
+      mm_sy<N, LD>(cx.SG, cx.S1 + j * LD, 1, t1);        // column j of G C
       __syncwarp();
       if (cx.act) {
 #pragma unroll
         for (int i = 0; i < N; ++i) cx.S0[i + j * LD] = t1[i];
       }
-#pragma unroll
-      for (int k = 0; k < N; ++k) Grow[k] = cx.SG[j + k * LD];
       __syncwarp();
-      mm_sx<N, LD>(cx.S0, Grow, Rcol);
+      mm_sy<N, LD>(cx.S0, cx.SG + j, LD, Rcol);           // (G C) x row j of G
 #pragma unroll
       for (int i = 0; i < N; ++i) Rcol[i] = Rcol[i] + wcolp[i * bt.W.sk] * dt;
     }
@@ -424,28 +448,25 @@ group_kernel(const WarpArgs wa) {
     const double mn_j = a_j + K_j * e;
     if (cx.act) cx.VK[j] = K_j;
     __syncwarp();
-    double Dcol[N], Drow[N], t1[N], Cn[N];
+    double Dcol[N], t1[N], Cn[N];
     double F_j = Fk[0];  // F element of this lane's column index
 #pragma unroll
     for (int i = 1; i < N; ++i) F_j = (j == i) ? Fk[i] : F_j;
 #pragma unroll
-    for (int i = 0; i < N; ++i) {
-      Dcol[i] = ((i == j) ? 1.0 : 0.0) - cx.VK[i] * F_j;
-      Drow[i] = ((i == j) ? 1.0 : 0.0) - K_j * Fk[i];
-    }
+    for (int i = 0; i < N; ++i) Dcol[i] = ((i == j) ? 1.0 : 0.0) - cx.VK[i] * F_j;
     if (cx.act) {
 #pragma unroll
       for (int i = 0; i < N; ++i) cx.S0[i + j * LD] = Dcol[i];
     }
     __syncwarp();
-    mm_sx<N, LD>(cx.S0, Rcol, t1);  // D R
+    mm_sy<N, LD>(cx.S0, cx.S1 + j * LD, 1, t1);  // D R   (S1 holds R)
     __syncwarp();
     if (cx.act) {
 #pragma unroll
       for (int i = 0; i < N; ++i) cx.S2[i + j * LD] = t1[i];
     }
     __syncwarp();
-    mm_sx<N, LD>(cx.S2, Drow, Cn);  // (D R) D^T
+    mm_sy<N, LD>(cx.S2, cx.S0 + j, LD, Cn);  // (D R) D^T : row j of D from S0
 #pragma unroll
     for (int i = 0; i < N; ++i) Cn[i] = Cn[i] + (cx.VK[i] * V) * K_j;
     m_j = obs ? mn_j : a_j;
@@ -485,7 +506,7 @@ group_kernel(const WarpArgs wa) {
       const double *sp = spill + (size_t)r * wa.spill_k, *sp1 = sp + wa.spill_k;
       __syncwarp();
       // C_t -> S0, R_{t+1} -> S1 (both needed by rows and by columns)
-      double Ccur[N], Crow[N], Arow[N];
+      double Ccur[N], Arow[N];
 #pragma unroll
       for (int i = 0; i < N; ++i) {
         Ccur[i] = sp[N + i + j * N];
@@ -498,10 +519,10 @@ group_kernel(const WarpArgs wa) {
                                 : philox_normal(RngKey{wa.rng_seed, wa.rng_sweep}, wa.rng_base + b, rows, r, N, j);
       __syncwarp();
 #pragma unroll
-      for (int k = 0; k < N; ++k) { Crow[k] = cx.S0[j + k * LD]; Arow[k] = cx.S1[j + k * LD]; }
+      for (int k = 0; k < N; ++k) Arow[k] = cx.S1[j + k * LD];
       // B = (R1^T \ (G C^T))^T
       double X[N];
-      mm_sx<N, LD>(cx.SG, Crow, X);  // column j of G C^T
+      mm_sy<N, LD>(cx.SG, cx.S0 + j, LD, X);  // column j of G C^T (row j of C from S0)
       st |= lu_cols<N>(cx, Arow, X);  // X = column j of the solution = row j of B
       // B -> S3
       if (cx.act) {
@@ -521,10 +542,8 @@ group_kernel(const WarpArgs wa) {
         h_j = m_j + acc;
       }
       // diff = I - B G
-      double Gcol[N], t1[N], Dcol[N], Drow[N], H1[N], H2[N], Wcol[N];
-#pragma unroll
-      for (int k = 0; k < N; ++k) { Gcol[k] = cx.SG[k + j * LD]; Wcol[k] = wcolp[k * bt.W.sk]; }
-      mm_sx<N, LD>(cx.S3, Gcol, t1);
+      double t1[N], Dcol[N], H1[N], H2[N];
+      mm_sy<N, LD>(cx.S3, cx.SG + j * LD, 1, t1);   // B x column j of G
 #pragma unroll
       for (int i = 0; i < N; ++i) Dcol[i] = ((i == j) ? 1.0 : 0.0) - t1[i];
       if (cx.act) {
@@ -532,17 +551,15 @@ group_kernel(const WarpArgs wa) {
         for (int i = 0; i < N; ++i) cx.S2[i + j * LD] = Dcol[i];
       }
       __syncwarp();
-      mm_sx<N, LD>(cx.S2, Ccur, t1);  // diff C
-#pragma unroll
-      for (int k = 0; k < N; ++k) Drow[k] = cx.S2[j + k * LD];
+      mm_sy<N, LD>(cx.S2, cx.S0 + j * LD, 1, t1);  // diff C   (column j of C_t from S0)
       __syncwarp();
       if (cx.act) {
 #pragma unroll
         for (int i = 0; i < N; ++i) cx.S0[i + j * LD] = t1[i];
       }
       __syncwarp();
-      mm_sx<N, LD>(cx.S0, Drow, H1);  // (diff C) diff^T
-      mm_sx<N, LD>(cx.S3, Wcol, t1);  // B W
+      mm_sy<N, LD>(cx.S0, cx.S2 + j, LD, H1);      // (diff C) diff^T : row j of diff from S2
+      mm_sy<N, LD>(cx.S3, wcolp, bt.W.sk, t1);     // B W : column j of W
 #pragma unroll
       for (int i = 0; i < N; ++i) t1[i] = t1[i] * dt;
       __syncwarp();
@@ -551,7 +568,7 @@ group_kernel(const WarpArgs wa) {
         for (int i = 0; i < N; ++i) cx.S1[i + j * LD] = t1[i];
       }
       __syncwarp();
-      mm_sx<N, LD>(cx.S1, X, H2);  // ((B W) dt) B^T : column j of B^T = row j of B = X
+      mm_sy<N, LD>(cx.S1, cx.S3 + j, LD, H2);  // ((B W) dt) B^T : column j of B^T = row j of B
       __syncwarp();
       if (cx.act) {
 #pragma unroll
