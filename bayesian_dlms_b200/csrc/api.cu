@@ -16,6 +16,8 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>  // header-only NVTX 3: no link dependency, no cost without a tool attached
+
 #include "common.cuh"
 #include "ctx_internal.h"
 #include "launch.h"
@@ -53,6 +55,15 @@ struct bdlm_ctx {
 };
 
 static std::string g_create_err;
+
+// NVTX range around every ABI call and every slab phase of the host-buffer pipeline (SURVEY.md
+// section 5, tracing row): shows up in Nsight Systems / ncu --nvtx as bdlm_* ranges.
+struct NvtxRange {
+  explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange &) = delete;
+  NvtxRange &operator=(const NvtxRange &) = delete;
+};
 
 namespace {
 
@@ -834,8 +845,11 @@ int run_host_mode(bdlm_ctx *c, DevCall d, int64_t lo, int64_t hi) {
     const int64_t Bs = std::min(slab, hi - b0);
     // the set's buffers are free once the D2H of the slab that used them has finished
     if (it >= 2) CU(cudaStreamWaitEvent(c->s_in, c->ev_out[s], 0));
-    for (size_t i = 0; i < fields.size(); ++i)
-      if (fields[i].in) CU(copy(fields[i], host_ptrs[i], dev_ptrs[s][i], b0, Bs, true, c->s_in));
+    {
+      NvtxRange r_("bdlm slab H2D");
+      for (size_t i = 0; i < fields.size(); ++i)
+        if (fields[i].in) CU(copy(fields[i], host_ptrs[i], dev_ptrs[s][i], b0, Bs, true, c->s_in));
+    }
     CU(cudaEventRecord(c->ev_in[s], c->s_in));
     CU(cudaStreamWaitEvent(c->stream, c->ev_in[s], 0));
     if (it >= 2) CU(cudaStreamWaitEvent(c->stream, c->ev_out[s], 0));
@@ -846,11 +860,13 @@ int run_host_mode(bdlm_ctx *c, DevCall d, int64_t lo, int64_t hi) {
       collect_fields(t, tf);
       for (size_t i = 0; i < tf.size(); ++i) *tf[i].slot = dev_ptrs[s][i];
       t.status = host_status ? dev_status[s] : nullptr;
+      NvtxRange r_("bdlm slab kernels");
       rc = run_dev(c, t, work);
       if (rc) return rc;
     }
     CU(cudaEventRecord(c->ev_comp[s], c->stream));
     CU(cudaStreamWaitEvent(c->s_out, c->ev_comp[s], 0));
+    NvtxRange r_("bdlm slab D2H");
     for (size_t i = 0; i < fields.size(); ++i)
       if (fields[i].out) CU(copy(fields[i], host_ptrs[i], dev_ptrs[s][i], b0, Bs, false, c->s_out));
     if (host_status)
@@ -1005,6 +1021,7 @@ int bdlm_set_staging_bytes(bdlm_ctx *c, int64_t bytes) {
 
 int bdlm_kf_filter(bdlm_ctx *c, const bdlm_problem *p, const bdlm_kf_out *out,
                    int32_t *status) {
+  NvtxRange nvtx_("bdlm_kf_filter");
   int rc = validate(c, A_FILTER, p);
   if (rc) return rc;
   if (!out) return fail(c, BDLM_E_ARG, "null output struct");
@@ -1014,6 +1031,7 @@ int bdlm_kf_filter(bdlm_ctx *c, const bdlm_problem *p, const bdlm_kf_out *out,
 
 int bdlm_rts_smooth(bdlm_ctx *c, const bdlm_problem *p, const bdlm_kf_out *filt,
                     const bdlm_smooth_out *out, int32_t *status) {
+  NvtxRange nvtx_("bdlm_rts_smooth");
   int rc = validate(c, A_SMOOTH, p);
   if (rc) return rc;
   if (!filt || !out || !filt->m || !filt->C)
@@ -1026,6 +1044,7 @@ int bdlm_rts_smooth(bdlm_ctx *c, const bdlm_problem *p, const bdlm_kf_out *filt,
 
 int bdlm_kf_filter_smooth(bdlm_ctx *c, const bdlm_problem *p, const bdlm_kf_out *kf,
                           const bdlm_smooth_out *sm, int32_t *status) {
+  NvtxRange nvtx_("bdlm_kf_filter_smooth");
   int rc = validate(c, A_FILTER_SMOOTH, p);
   if (rc) return rc;
   if (!sm) return fail(c, BDLM_E_ARG, "null smoother output struct");
@@ -1036,6 +1055,7 @@ int bdlm_kf_filter_smooth(bdlm_ctx *c, const bdlm_problem *p, const bdlm_kf_out 
 
 int bdlm_loglik(bdlm_ctx *c, const bdlm_problem *p, double *transition, double *innovations,
                 int32_t *status) {
+  NvtxRange nvtx_("bdlm_loglik");
   int rc = validate(c, A_LOGLIK, p);
   if (rc) return rc;
   if (!transition && !innovations) return fail(c, BDLM_E_ARG, "no log-likelihood requested");
@@ -1046,6 +1066,7 @@ int bdlm_loglik(bdlm_ctx *c, const bdlm_problem *p, double *transition, double *
 
 int bdlm_kf_filter_last(bdlm_ctx *c, const bdlm_problem *p, double *m_last, double *C_last,
                         double *transition, double *innovations, int32_t *status) {
+  NvtxRange nvtx_("bdlm_kf_filter_last");
   int rc = validate(c, A_LOGLIK, p);
   if (rc) return rc;
   if (!m_last && !C_last && !transition && !innovations)
@@ -1058,6 +1079,7 @@ int bdlm_kf_filter_last(bdlm_ctx *c, const bdlm_problem *p, double *m_last, doub
 
 int bdlm_ffbs(bdlm_ctx *c, const bdlm_problem *p, const double *z, double *theta,
               const bdlm_kf_out *kf, const bdlm_gibbs_stats *stats, int32_t *status) {
+  NvtxRange nvtx_("bdlm_ffbs");
   int rc = validate(c, A_FFBS, p);
   if (rc) return rc;
   if (!theta) return fail(c, BDLM_E_ARG, "null theta");  // z == NULL: on-device Philox normals
@@ -1070,6 +1092,7 @@ int bdlm_ffbs(bdlm_ctx *c, const bdlm_problem *p, const double *z, double *theta
 
 int bdlm_svd_filter(bdlm_ctx *c, const bdlm_problem *p, const bdlm_svd_out *out,
                     int32_t *status) {
+  NvtxRange nvtx_("bdlm_svd_filter");
   int rc = validate(c, A_SVD_FILTER, p);
   if (rc) return rc;
   if (!out) return fail(c, BDLM_E_ARG, "null output struct");
@@ -1079,6 +1102,7 @@ int bdlm_svd_filter(bdlm_ctx *c, const bdlm_problem *p, const bdlm_svd_out *out,
 
 int bdlm_svd_ffbs(bdlm_ctx *c, const bdlm_problem *p, const double *z, double *theta,
                   const bdlm_svd_out *filt, const bdlm_gibbs_stats *stats, int32_t *status) {
+  NvtxRange nvtx_("bdlm_svd_ffbs");
   int rc = validate(c, A_SVD_FFBS, p);
   if (rc) return rc;
   if (!theta) return fail(c, BDLM_E_ARG, "null theta");  // z == NULL: on-device Philox normals
@@ -1156,6 +1180,7 @@ int bdlm_scan_combine(int32_t n, int32_t backward, const double *earlier, const 
 }
 
 int bdlm_scan_forward_reduce(bdlm_ctx *c, const bdlm_problem *p, double *agg_host) {
+  NvtxRange nvtx_("bdlm_scan_forward_reduce");
   int rc = scan_validate(c, p);
   if (rc) return rc;
   if (!agg_host) return fail(c, BDLM_E_ARG, "null aggregate pointer");
@@ -1172,6 +1197,7 @@ int bdlm_scan_forward_reduce(bdlm_ctx *c, const bdlm_problem *p, double *agg_hos
 
 int bdlm_scan_forward_apply(bdlm_ctx *c, const bdlm_problem *p, const double *start_mC_host,
                             const bdlm_kf_out *kf, int32_t *status) {
+  NvtxRange nvtx_("bdlm_scan_forward_apply");
   int rc = scan_validate(c, p);
   if (rc) return rc;
   if (!kf) return fail(c, BDLM_E_ARG, "null output struct");
@@ -1195,6 +1221,7 @@ int bdlm_scan_forward_apply(bdlm_ctx *c, const bdlm_problem *p, const double *st
 
 int bdlm_scan_backward_reduce(bdlm_ctx *c, const bdlm_problem *p, const bdlm_kf_out *filt,
                               int32_t has_successor, double *agg_host) {
+  NvtxRange nvtx_("bdlm_scan_backward_reduce");
   int rc = scan_validate(c, p);
   if (rc) return rc;
   if (!filt || !filt->m || !filt->C || !agg_host)
@@ -1214,6 +1241,7 @@ int bdlm_scan_backward_reduce(bdlm_ctx *c, const bdlm_problem *p, const bdlm_kf_
 int bdlm_scan_backward_apply(bdlm_ctx *c, const bdlm_problem *p, const bdlm_kf_out *filt,
                              const double *next_sS_host, const bdlm_smooth_out *sm,
                              int32_t *status) {
+  NvtxRange nvtx_("bdlm_scan_backward_apply");
   int rc = scan_validate(c, p);
   if (rc) return rc;
   if (!filt || !filt->m || !filt->C || !sm)
@@ -1235,6 +1263,7 @@ int bdlm_scan_backward_apply(bdlm_ctx *c, const bdlm_problem *p, const bdlm_kf_o
 
 int bdlm_scan_filter_smooth(bdlm_ctx *c, const bdlm_problem *p, const bdlm_kf_out *kf,
                             const bdlm_smooth_out *sm, int32_t *status) {
+  NvtxRange nvtx_("bdlm_scan_filter_smooth");
   int rc = scan_validate(c, p);
   if (rc) return rc;
   if (!sm) return fail(c, BDLM_E_ARG, "null smoother output struct");
@@ -1296,6 +1325,7 @@ static int scan_dist_common(bdlm_ctx *c, const bdlm_problem *p, const bdlm_kf_ou
 
 int bdlm_scan_dist_forward_local(bdlm_ctx *c, const bdlm_problem *p, int32_t rank, int32_t world,
                                  double *agg_dev) {
+  NvtxRange nvtx_("bdlm_scan_dist_forward_local");
   size_t ws;
   int rc = scan_dist_common(c, p, nullptr, rank, world, &ws);
   if (rc) return rc;
@@ -1311,6 +1341,7 @@ int bdlm_scan_dist_forward_local(bdlm_ctx *c, const bdlm_problem *p, int32_t ran
 
 int bdlm_scan_dist_forward_finish(bdlm_ctx *c, const bdlm_problem *p, int32_t rank, int32_t world,
                                   const double *aggs_dev, const bdlm_kf_out *kf, int32_t *status) {
+  NvtxRange nvtx_("bdlm_scan_dist_forward_finish");
   size_t ws;
   if (!kf) return fail(c, BDLM_E_ARG, "null output struct");
   int rc = scan_dist_common(c, p, kf, rank, world, &ws);
@@ -1335,6 +1366,7 @@ int bdlm_scan_dist_forward_finish(bdlm_ctx *c, const bdlm_problem *p, int32_t ra
 int bdlm_scan_dist_backward_local(bdlm_ctx *c, const bdlm_problem *p, int32_t rank, int32_t world,
                                   const bdlm_kf_out *filt, const bdlm_smooth_out *sm,
                                   double *agg_dev) {
+  NvtxRange nvtx_("bdlm_scan_dist_backward_local");
   size_t ws;
   if (!filt) return fail(c, BDLM_E_ARG, "null filtered-state struct");
   int rc = scan_dist_common(c, p, filt, rank, world, &ws);
@@ -1357,6 +1389,7 @@ int bdlm_scan_dist_backward_local(bdlm_ctx *c, const bdlm_problem *p, int32_t ra
 int bdlm_scan_dist_backward_finish(bdlm_ctx *c, const bdlm_problem *p, int32_t rank, int32_t world,
                                    const double *aggs_dev, const bdlm_kf_out *filt,
                                    const bdlm_smooth_out *sm, int32_t *status) {
+  NvtxRange nvtx_("bdlm_scan_dist_backward_finish");
   size_t ws;
   if (!filt) return fail(c, BDLM_E_ARG, "null filtered-state struct");
   int rc = scan_dist_common(c, p, filt, rank, world, &ws);
@@ -1404,17 +1437,20 @@ static int ar_call(bdlm_ctx *c, int op, const bdlm_ar_problem *ap, const bdlm_ar
 }
 
 int bdlm_ar_filter(bdlm_ctx *c, const bdlm_ar_problem *ap, const bdlm_ar_out *out) {
+  NvtxRange nvtx_("bdlm_ar_filter");
   return ar_call(c, A_AR_FILTER, ap, out, nullptr, nullptr);
 }
 
 int bdlm_ar_ffbs(bdlm_ctx *c, const bdlm_ar_problem *ap, const double *z, double *theta,
                  const bdlm_ar_out *filt) {
+  NvtxRange nvtx_("bdlm_ar_ffbs");
   return ar_call(c, A_AR_FFBS, ap, filt, z, theta);
 }
 
 int bdlm_conjugate_filter(bdlm_ctx *c, const bdlm_problem *p, double prior_shape,
                           double prior_scale, const bdlm_kf_out *out, double *shape,
                           double *scale, int32_t *status) {
+  NvtxRange nvtx_("bdlm_conjugate_filter");
   int rc = validate(c, A_CONJ_FILTER, p);
   if (rc) return rc;
   if (!conjugate_supported(p->n, p->p) || p->f_tv || p->g_tv || !p->keep_init)
@@ -1433,6 +1469,7 @@ int bdlm_conjugate_filter(bdlm_ctx *c, const bdlm_problem *p, double prior_shape
 int bdlm_gibbs_draw(bdlm_ctx *c, const bdlm_problem *p, const bdlm_gibbs_stats *stats,
                     const bdlm_gibbs_prior *prior, const bdlm_gibbs_rng *rng, double *V_out,
                     double *W_out, double *v_shape_rate, double *w_shape_rate, int32_t *status) {
+  NvtxRange nvtx_("bdlm_gibbs_draw");
   int rc = validate(c, A_GIBBS_DRAW, p);
   if (rc) return rc;
   if (!stats || !prior || !rng) return fail(c, BDLM_E_ARG, "null stats, prior or rng");
@@ -1450,6 +1487,7 @@ int bdlm_gibbs_draw(bdlm_ctx *c, const bdlm_problem *p, const bdlm_gibbs_stats *
 
 int bdlm_gibbs_suffstats(bdlm_ctx *c, const bdlm_problem *p, const double *theta,
                          const bdlm_gibbs_stats *stats) {
+  NvtxRange nvtx_("bdlm_gibbs_suffstats");
   int rc = validate(c, A_STATS, p);
   if (rc) return rc;
   if (!theta || !stats) return fail(c, BDLM_E_ARG, "null theta or stats");

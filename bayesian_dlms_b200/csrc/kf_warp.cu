@@ -828,6 +828,27 @@ warp_kernel(const WarpArgs wa, const int ws_doubles) {
 // (16 rows) and of V (8 rows) in registers; partners exchange columns with width-8 shuffles.
 // No shared-memory traffic and no barrier inside a sweep, all 32 lanes busy.
 
+// Out-of-line products for the four-series kernel: its ~25 small-matrix products per series-step
+// were inlined copies of w_mm (the kernel was 30 k SASS instructions = 480 KB, and ncu showed 2.35
+// warps per issue-active cycle stalled on instruction fetch, profiles/r2_svd4_before_full.txt).
+// One copy, strides instead of transpose flags; same products summed in the same order.
+__device__ __noinline__ void q_mm(int lane, int ar, int ac, int bc, const double *A, int lda,
+                                  bool ta, const double *B, int ldb, bool tb, double *out, int ldo) {
+  const int a_si = ta ? lda : 1, a_sk = ta ? 1 : lda;
+  const int b_sk = tb ? ldb : 1, b_sj = tb ? 1 : ldb;
+  for (ElemIter it(lane, ar, bc); it.ok(); it.next()) {
+    const double *ap = A + it.i * a_si, *bp = B + it.j * b_sj;
+    double acc = ap[0] * bp[0];
+    for (int k = 1; k < ac; ++k) acc = acc + ap[k * a_sk] * bp[k * b_sk];
+    out[it.i + it.j * ldo] = acc;
+  }
+  __syncwarp();
+}
+__device__ __forceinline__ void q_mv(int lane, int ar, int ac, const double *A, int lda, bool ta,
+                                     const double *x, double *y) {
+  q_mm(lane, ar, ac, 1, A, lda, ta, x, ac, false, y, ar);
+}
+
 constexpr int kQuad = 4;     // series per warp
 constexpr int kOctRows = 16; // max rows of a stacked matrix: (p + n) or 2n with n, p <= 8
 constexpr int kOctN = 8;
@@ -932,11 +953,11 @@ __device__ __forceinline__ void svd_advance_pre(int lane, int n, const Ws &ws, d
     __syncwarp();
     return;
   }
-  w_mv(lane, n, n, ws.G, n, false, ws.m, ws.a);
+  q_mv(lane, n, n, ws.G, n, false, ws.m, ws.a);
   for (ElemIter it(lane, n, n); it.ok(); it.next())
     ws.t1[it.i + it.j * n] = ws.dcv[it.i] * ws.C[it.j + it.i * n];
   __syncwarp();
-  w_mm(lane, n, n, n, ws.t1, n, false, ws.G, n, true, ws.t2, n);
+  q_mm(lane, n, n, n, ws.t1, n, false, ws.G, n, true, ws.t2, n);
   const double sq = sqrt(dt);
   for (ElemIter it(lane, n, n); it.ok(); it.next()) {
     ws.stk[it.i + it.j * 2 * n] = ws.t2[it.i + it.j * n];
@@ -960,9 +981,9 @@ __device__ __forceinline__ int svd_update_pre(int lane, int n, int p, const Ws &
   for (ElemIter it(lane, po, po); it.ok(); it.next())
     Vm[it.i + it.j * po] = ws.V[obs[it.i] + obs[it.j] * p];
   __syncwarp();
-  w_mv(lane, po, n, Fm, n, true, ws.a, ws.v1);  // fm
-  w_mm(lane, po, po, n, Vm, po, false, Fm, n, true, ws.t3, po);
-  w_mm(lane, po, n, n, ws.t3, po, false, ws.R, n, false, ws.t4, po);
+  q_mv(lane, po, n, Fm, n, true, ws.a, ws.v1);  // fm
+  q_mm(lane, po, po, n, Vm, po, false, Fm, n, true, ws.t3, po);
+  q_mm(lane, po, n, n, ws.t3, po, false, ws.R, n, false, ws.t4, po);
   const int r = po + n;
   for (ElemIter it(lane, r, n); it.ok(); it.next()) {
     const int i = it.i, j = it.j;
@@ -987,25 +1008,27 @@ __device__ __forceinline__ void svd_update_post(int lane, int n, int p, const Ws
   for (ElemIter it(lane, po, po); it.ok(); it.next())
     Vm[it.i + it.j * po] = ws.V[obs[it.i] + obs[it.j] * p];
   __syncwarp();
-  w_mv(lane, po, n, Fm, n, true, ws.a, ws.v1);  // fm
+  q_mv(lane, po, n, Fm, n, true, ws.a, ws.v1);  // fm
   if (lane < po) ws.v1[lane] = ws.yrow[obs[lane]] - ws.v1[lane];  // e
   __syncwarp();
-  w_mm(lane, n, n, n, ws.R, n, false, sV, n, false, ws.C, n);  // uc = ur * V
-  w_mm(lane, n, po, po, Fm, n, false, Vm, po, true, ws.t3, n);
-  w_mm(lane, n, po, po, ws.t3, n, false, Vm, po, false, ws.t4, n);  // fv
+  q_mm(lane, n, n, n, ws.R, n, false, sV, n, false, ws.C, n);  // uc = ur * V
+  q_mm(lane, n, po, po, Fm, n, false, Vm, po, true, ws.t3, n);
+  q_mm(lane, n, po, po, ws.t3, n, false, Vm, po, false, ws.t4, n);  // fv
   for (int k = lane; k < n; k += 32) ws.dcv[k] = 1.0 / sS[k];
   __syncwarp();
   for (ElemIter it(lane, n, n); it.ok(); it.next())
     ws.t3[it.i + it.j * n] = ws.dcv[it.i] * ws.C[it.j + it.i * n];  // X = diag(dc) uc^T
   __syncwarp();
-  w_mm(lane, n, n, n, ws.t3, n, true, ws.t3, n, false, ws.t5, n);
-  w_mm(lane, n, n, po, ws.t5, n, false, ws.t4, n, false, ws.t6, n);  // gain
-  w_mv(lane, n, po, ws.t6, n, false, ws.v1, ws.v3);
+  q_mm(lane, n, n, n, ws.t3, n, true, ws.t3, n, false, ws.t5, n);
+  q_mm(lane, n, n, po, ws.t5, n, false, ws.t4, n, false, ws.t6, n);  // gain
+  q_mv(lane, n, po, ws.t6, n, false, ws.v1, ws.v3);
   for (int k = lane; k < n; k += 32) ws.m[k] = ws.a[k] + ws.v3[k];
   __syncwarp();
 }
 
-template <int OP>
+// NP > 0: n = p = NP known at compile time (BASELINE config 4 is n = p = 8): the element loops of
+// the per-series phases fold their index arithmetic (they were 3/4 integer instructions).
+template <int OP, int NP>
 __global__ void __launch_bounds__(32)  // (32, 9) caps ptxas at 168 registers -> spills, 16 % slower
 svd4_kernel(const WarpArgs wa, const int shared_doubles, const int series_doubles) {
   extern __shared__ double smem[];
@@ -1013,7 +1036,8 @@ svd4_kernel(const WarpArgs wa, const int shared_doubles, const int series_double
   const int lane = threadIdx.x;
   const int64_t b0 = (int64_t)blockIdx.x * kQuad;
   if (b0 >= bt.B) return;
-  const int n = bt.n, p = bt.p, nn = n * n, T = bt.T, ki = bt.keep_init, rows = T + ki;
+  const int n = NP > 0 ? NP : bt.n, p = NP > 0 ? NP : bt.p;
+  const int nn = n * n, T = bt.T, ki = bt.keep_init, rows = T + ki;
   const int oct = lane >> 3;
   constexpr bool kSpill = OP == kOpSvdFfbs;
   // series s of this warp: shared temporaries + its own state slice; series past the end of the
@@ -1060,7 +1084,7 @@ svd4_kernel(const WarpArgs wa, const int shared_doubles, const int series_double
     for (int k = lane; k < n; k += 32) ws.dcv[k] = sqrt(ws.v1[k]);
     w_copy(lane, nn, ws.t4, ws.C);
     if (ki) {
-      w_mv(lane, p, n, ws.F, n, true, ws.m, ws.f);
+      q_mv(lane, p, n, ws.F, n, true, ws.m, ws.f);
       store_view(lane, wa.svd.m, b, 0, n, ws.m);
       store_view(lane, wa.svd.a, b, 0, n, ws.m);
       store_view(lane, wa.svd.dc, b, 0, n, ws.dcv);
@@ -1100,7 +1124,7 @@ svd4_kernel(const WarpArgs wa, const int shared_doubles, const int series_double
       const Ws ws = slot(s).ws;
       load_cview(lane, bt.y, b0 + s, t, p, ws.yrow);
       __syncwarp();
-      w_mv(lane, p, n, ws.F, n, true, ws.a, ws.f);
+      q_mv(lane, p, n, ws.F, n, true, ws.a, ws.f);
       const int po = svd_update_pre(lane, n, p, ws);
       if (oct == s) po_mine = po;
     }
@@ -1149,7 +1173,7 @@ svd4_kernel(const WarpArgs wa, const int shared_doubles, const int series_double
       for (ElemIter it(lane, n, n); it.ok(); it.next())
         ws.t1[it.i + it.j * n] = ws.C[it.i + it.j * n] * ws.dcv[it.j];
       __syncwarp();
-      w_mv(lane, n, n, ws.t1, n, false, ws.v3, ws.v2);
+      q_mv(lane, n, n, ws.t1, n, false, ws.v3, ws.v2);
       for (int k = lane; k < n; k += 32) ws.th[k] = ws.m[k] + ws.v2[k];
       __syncwarp();
       store_view(lane, wa.theta, b, rows - 1, n, ws.th);
@@ -1170,8 +1194,8 @@ svd4_kernel(const WarpArgs wa, const int shared_doubles, const int series_double
         for (int k = lane; k < nn; k += 32) ws.C[k] = sp[2 * n + k];
         __syncwarp();
         if (bt.w_tv) add_status(s, svd_load_params_tv(lane, bt, ws, b, tobs, false));
-        w_mm(lane, n, n, n, ws.Wsq, n, false, ws.G, n, false, ws.t1, n);
-        w_mm(lane, n, n, n, ws.t1, n, false, ws.C, n, false, ws.t2, n);
+        q_mm(lane, n, n, n, ws.Wsq, n, false, ws.G, n, false, ws.t1, n);
+        q_mm(lane, n, n, n, ws.t1, n, false, ws.C, n, false, ws.t2, n);
         for (ElemIter it(lane, n, n); it.ok(); it.next()) {
           ws.stk[it.i + it.j * 2 * n] = ws.t2[it.i + it.j * n];
           ws.stk[n + it.i + it.j * 2 * n] = (it.i == it.j) ? 1.0 / ws.dcv[it.i] : 0.0;
@@ -1185,24 +1209,24 @@ svd4_kernel(const WarpArgs wa, const int shared_doubles, const int series_double
         const Slot q = slot(s);
         const Ws &ws = q.ws;
         load_z(lane, wa, b0 + s, r, rows, n, ws.v3);
-        w_mm(lane, n, n, n, ws.C, n, false, q.sV, n, false, ws.t5, n);  // uh
+        q_mm(lane, n, n, n, ws.C, n, false, q.sV, n, false, ws.t5, n);  // uh
         for (int k = lane; k < n; k += 32) ws.v1[k] = 1.0 / q.sS[k];    // dh
         __syncwarp();
-        w_mm(lane, n, n, n, ws.G, n, true, ws.Wsq, n, true, ws.t1, n);
-        w_mm(lane, n, n, n, ws.t1, n, false, ws.Wsq, n, false, ws.t2, n);  // gWinv
+        q_mm(lane, n, n, n, ws.G, n, true, ws.Wsq, n, true, ws.t1, n);
+        q_mm(lane, n, n, n, ws.t1, n, false, ws.Wsq, n, false, ws.t2, n);  // gWinv
         for (ElemIter it(lane, n, n); it.ok(); it.next())
           ws.t3[it.i + it.j * n] = ws.v1[it.i] * ws.t5[it.j + it.i * n];  // du
         __syncwarp();
-        w_mm(lane, n, n, n, ws.t3, n, true, ws.t3, n, false, ws.t4, n);
-        w_mm(lane, n, n, n, ws.t4, n, false, ws.t2, n, false, ws.t6, n);
+        q_mm(lane, n, n, n, ws.t3, n, true, ws.t3, n, false, ws.t4, n);
+        q_mm(lane, n, n, n, ws.t4, n, false, ws.t2, n, false, ws.t6, n);
         for (int k = lane; k < n; k += 32) ws.v2[k] = ws.th[k] - ws.a[k];
         __syncwarp();
-        w_mv(lane, n, n, ws.t6, n, false, ws.v2, ws.v4);
+        q_mv(lane, n, n, ws.t6, n, false, ws.v2, ws.v4);
         for (int k = lane; k < n; k += 32) ws.v4[k] = ws.m[k] + ws.v4[k];  // h
         for (ElemIter it(lane, n, n); it.ok(); it.next())
           ws.t1[it.i + it.j * n] = ws.t5[it.i + it.j * n] * ws.v1[it.j];
         __syncwarp();
-        w_mv(lane, n, n, ws.t1, n, false, ws.v3, ws.v2);
+        q_mv(lane, n, n, ws.t1, n, false, ws.v3, ws.v2);
         for (int k = lane; k < n; k += 32) ws.th[k] = ws.v4[k] + ws.v2[k];
         __syncwarp();
         store_view(lane, wa.theta, b0 + s, r, n, ws.th);
@@ -1232,19 +1256,25 @@ bool svd4_supported(int op, const Batch &bt) {
          !bt.ps_model && bt.dt_sb == 0;
 }
 
-template <int OP>
-cudaError_t launch_svd4(const WarpArgs &wa, cudaStream_t stream) {
+template <int OP, int NP>
+cudaError_t launch_svd4_np(const WarpArgs &wa, cudaStream_t stream) {
   const int n = wa.bt.n, p = wa.bt.p;
   const int shared_doubles = (int)((Ws::svd4_shared_doubles(n, p) + 1) & ~(size_t)1);
   const int series_doubles = (int)((Ws::svd4_series_doubles(n, p) + 1) & ~(size_t)1);
   const size_t smem = ((size_t)shared_doubles + (size_t)kQuad * series_doubles) * sizeof(double);
-  cudaError_t e = cudaFuncSetAttribute(svd4_kernel<OP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  cudaError_t e = cudaFuncSetAttribute(svd4_kernel<OP, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem);
   if (e != cudaSuccess) return e;
   const int64_t blocks = (wa.bt.B + kQuad - 1) / kQuad;
   if (blocks <= 0) return cudaSuccess;
-  svd4_kernel<OP><<<(unsigned)blocks, 32, smem, stream>>>(wa, shared_doubles, series_doubles);
+  svd4_kernel<OP, NP><<<(unsigned)blocks, 32, smem, stream>>>(wa, shared_doubles, series_doubles);
   return cudaGetLastError();
+}
+template <int OP>
+cudaError_t launch_svd4(const WarpArgs &wa, cudaStream_t stream) {
+  static const bool fixed8 = std::getenv("BDLM_SVD4_GENERIC") == nullptr;  // A/B switch
+  if (fixed8 && wa.bt.n == 8 && wa.bt.p == 8) return launch_svd4_np<OP, 8>(wa, stream);
+  return launch_svd4_np<OP, 0>(wa, stream);
 }
 
 template <int OP, int NT, int PT>
