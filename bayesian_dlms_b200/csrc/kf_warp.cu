@@ -40,16 +40,23 @@ struct Ws {
   // warp, only what must survive from one phase to the next is kept per series.  Four full
   // workspaces (41.7 KB) allow 5 warps per SM; this layout (23.6 KB) allows 9, which is what
   // hides the serial rotation-parameter chain of the joint SVDs.
-  static __host__ __device__ size_t svd4_shared_doubles(int n, int p) {
+  // shared_params: V, W (and their square-root factors) are the same for every series of the
+  // batch (BASELINE config 4 as a filter / sampler; not inside a Gibbs sweep with per-series
+  // draws): one copy per warp instead of four.
+  static __host__ __device__ size_t svd4_shared_doubles(int n, int p, bool shared_params) {
     const int L = imax(n, p), LL = L * L;
-    return (size_t)n * n + (size_t)n * p + 6 * (size_t)LL + 4 * (size_t)L + p + kScrDoubles + kIscrInts / 2;
+    const bool scr_in_t = 2 * LL >= kScrDoubles;  // the Jacobi scratch of the (cold) generic SVDs
+    return (size_t)n * n + (size_t)n * p + 6 * (size_t)LL + 4 * (size_t)L + p +
+           (scr_in_t ? 0 : kScrDoubles) + kIscrInts / 2 +
+           (shared_params ? 2 * (size_t)n * n + (size_t)p * p : 0);
   }
-  static __host__ __device__ size_t svd4_series_doubles(int n, int p) {
+  static __host__ __device__ size_t svd4_series_doubles(int n, int p, bool shared_params) {
     const int nn = n * n, L = imax(n, p);
-    return 2 * (size_t)nn + (size_t)p * p + 3 * (size_t)n + 2 * (size_t)nn + p + 2 * (size_t)n +
-           (size_t)imax((n + L) * n, L * L) + nn + n;
+    return (shared_params ? 0 : 2 * (size_t)nn + (size_t)p * p) + 3 * (size_t)n + 2 * (size_t)nn + p +
+           2 * (size_t)n + (size_t)imax((n + L) * n, L * L) + n;
   }
-  static __device__ Ws svd4(double *shared, double *series, int n, int p, double *&sV, double *&sS) {
+  static __device__ Ws svd4(double *shared, double *series, int n, int p, bool shared_params,
+                            double *&sV, double *&sS) {
     Ws w;
     const int nn = n * n, L = imax(n, p), LL = L * L;
     double *o = shared;
@@ -57,15 +64,20 @@ struct Ws {
     w.G = take(nn); w.F = take((size_t)n * p);
     w.t1 = take(LL); w.t2 = take(LL); w.t3 = take(LL); w.t4 = take(LL); w.t5 = take(LL); w.t6 = take(LL);
     w.v1 = take(L); w.v2 = take(L); w.v3 = take(L); w.v4 = take(L); w.yrow = take(p);
-    w.scr = take(kScrDoubles);
+    // w_jacobi_svd (initial state / per-step parameter transforms) works in t3, t4, t5 only:
+    // its dot-product scratch can sit in t1 | t2 when they are large enough
+    w.scr = (2 * LL >= kScrDoubles) ? w.t1 : take(kScrDoubles);
     w.iscr = reinterpret_cast<int *>(take(kIscrInts / 2));
+    if (shared_params) { w.W = take(nn); w.Wsq = take(nn); w.V = take((size_t)p * p); }
     o = series;
-    w.W = take(nn); w.Wsq = take(nn); w.V = take((size_t)p * p);
+    if (!shared_params) { w.W = take(nn); w.Wsq = take(nn); w.V = take((size_t)p * p); }
     w.m = take(n); w.a = take(n); w.th = take(n);
     w.C = take(nn); w.R = take(nn); w.f = take(p);
     w.dcv = take(n); w.drv = take(n);
     w.stk = take((size_t)imax((n + L) * n, LL));
-    sV = take(nn); sS = take(n);
+    // right singular vectors of the joint SVDs: written after every lane of the octet has pulled
+    // its column of the stack into registers, so they can overwrite the stack
+    sV = w.stk; sS = take(n);
     w.Q = nullptr; w.Sm = nullptr;
     w.total = 0;
     return w;
@@ -828,28 +840,10 @@ warp_kernel(const WarpArgs wa, const int ws_doubles) {
 // (16 rows) and of V (8 rows) in registers; partners exchange columns with width-8 shuffles.
 // No shared-memory traffic and no barrier inside a sweep, all 32 lanes busy.
 
-// Out-of-line products for the four-series kernel: its ~25 small-matrix products per series-step
-// were inlined copies of w_mm (the kernel was 30 k SASS instructions = 480 KB, and ncu showed 2.35
-// warps per issue-active cycle stalled on instruction fetch, profiles/r2_svd4_before_full.txt).
-// One copy, strides instead of transpose flags; same products summed in the same order.
-__device__ __noinline__ void q_mm(int lane, int ar, int ac, int bc, const double *A, int lda,
-                                  bool ta, const double *B, int ldb, bool tb, double *out, int ldo) {
-  const int a_si = ta ? lda : 1, a_sk = ta ? 1 : lda;
-  const int b_sk = tb ? ldb : 1, b_sj = tb ? 1 : ldb;
-  for (ElemIter it(lane, ar, bc); it.ok(); it.next()) {
-    const double *ap = A + it.i * a_si, *bp = B + it.j * b_sj;
-    double acc = ap[0] * bp[0];
-    for (int k = 1; k < ac; ++k) acc = acc + ap[k * a_sk] * bp[k * b_sk];
-    out[it.i + it.j * ldo] = acc;
-  }
-  __syncwarp();
-}
-__device__ __forceinline__ void q_mv(int lane, int ar, int ac, const double *A, int lda, bool ta,
-                                     const double *x, double *y) {
-  q_mm(lane, ar, ac, 1, A, lda, ta, x, ac, false, y, ar);
-}
-
 constexpr int kQuad = 4;     // series per warp
+__host__ __device__ inline bool svd4_shared_params(const Batch &bt) {
+  return bt.V.sb == 0 && bt.W.sb == 0 && !bt.v_tv && !bt.w_tv;
+}
 constexpr int kOctRows = 16; // max rows of a stacked matrix: (p + n) or 2n with n, p <= 8
 constexpr int kOctN = 8;
 
@@ -953,11 +947,11 @@ __device__ __forceinline__ void svd_advance_pre(int lane, int n, const Ws &ws, d
     __syncwarp();
     return;
   }
-  q_mv(lane, n, n, ws.G, n, false, ws.m, ws.a);
+  w_mv(lane, n, n, ws.G, n, false, ws.m, ws.a);
   for (ElemIter it(lane, n, n); it.ok(); it.next())
     ws.t1[it.i + it.j * n] = ws.dcv[it.i] * ws.C[it.j + it.i * n];
   __syncwarp();
-  q_mm(lane, n, n, n, ws.t1, n, false, ws.G, n, true, ws.t2, n);
+  w_mm(lane, n, n, n, ws.t1, n, false, ws.G, n, true, ws.t2, n);
   const double sq = sqrt(dt);
   for (ElemIter it(lane, n, n); it.ok(); it.next()) {
     ws.stk[it.i + it.j * 2 * n] = ws.t2[it.i + it.j * n];
@@ -981,9 +975,9 @@ __device__ __forceinline__ int svd_update_pre(int lane, int n, int p, const Ws &
   for (ElemIter it(lane, po, po); it.ok(); it.next())
     Vm[it.i + it.j * po] = ws.V[obs[it.i] + obs[it.j] * p];
   __syncwarp();
-  q_mv(lane, po, n, Fm, n, true, ws.a, ws.v1);  // fm
-  q_mm(lane, po, po, n, Vm, po, false, Fm, n, true, ws.t3, po);
-  q_mm(lane, po, n, n, ws.t3, po, false, ws.R, n, false, ws.t4, po);
+  w_mv(lane, po, n, Fm, n, true, ws.a, ws.v1);  // fm
+  w_mm(lane, po, po, n, Vm, po, false, Fm, n, true, ws.t3, po);
+  w_mm(lane, po, n, n, ws.t3, po, false, ws.R, n, false, ws.t4, po);
   const int r = po + n;
   for (ElemIter it(lane, r, n); it.ok(); it.next()) {
     const int i = it.i, j = it.j;
@@ -1008,20 +1002,20 @@ __device__ __forceinline__ void svd_update_post(int lane, int n, int p, const Ws
   for (ElemIter it(lane, po, po); it.ok(); it.next())
     Vm[it.i + it.j * po] = ws.V[obs[it.i] + obs[it.j] * p];
   __syncwarp();
-  q_mv(lane, po, n, Fm, n, true, ws.a, ws.v1);  // fm
+  w_mv(lane, po, n, Fm, n, true, ws.a, ws.v1);  // fm
   if (lane < po) ws.v1[lane] = ws.yrow[obs[lane]] - ws.v1[lane];  // e
   __syncwarp();
-  q_mm(lane, n, n, n, ws.R, n, false, sV, n, false, ws.C, n);  // uc = ur * V
-  q_mm(lane, n, po, po, Fm, n, false, Vm, po, true, ws.t3, n);
-  q_mm(lane, n, po, po, ws.t3, n, false, Vm, po, false, ws.t4, n);  // fv
+  w_mm(lane, n, n, n, ws.R, n, false, sV, n, false, ws.C, n);  // uc = ur * V
+  w_mm(lane, n, po, po, Fm, n, false, Vm, po, true, ws.t3, n);
+  w_mm(lane, n, po, po, ws.t3, n, false, Vm, po, false, ws.t4, n);  // fv
   for (int k = lane; k < n; k += 32) ws.dcv[k] = 1.0 / sS[k];
   __syncwarp();
   for (ElemIter it(lane, n, n); it.ok(); it.next())
     ws.t3[it.i + it.j * n] = ws.dcv[it.i] * ws.C[it.j + it.i * n];  // X = diag(dc) uc^T
   __syncwarp();
-  q_mm(lane, n, n, n, ws.t3, n, true, ws.t3, n, false, ws.t5, n);
-  q_mm(lane, n, n, po, ws.t5, n, false, ws.t4, n, false, ws.t6, n);  // gain
-  q_mv(lane, n, po, ws.t6, n, false, ws.v1, ws.v3);
+  w_mm(lane, n, n, n, ws.t3, n, true, ws.t3, n, false, ws.t5, n);
+  w_mm(lane, n, n, po, ws.t5, n, false, ws.t4, n, false, ws.t6, n);  // gain
+  w_mv(lane, n, po, ws.t6, n, false, ws.v1, ws.v3);
   for (int k = lane; k < n; k += 32) ws.m[k] = ws.a[k] + ws.v3[k];
   __syncwarp();
 }
@@ -1040,12 +1034,13 @@ svd4_kernel(const WarpArgs wa, const int shared_doubles, const int series_double
   const int nn = n * n, T = bt.T, ki = bt.keep_init, rows = T + ki;
   const int oct = lane >> 3;
   constexpr bool kSpill = OP == kOpSvdFfbs;
+  const bool shared_params = svd4_shared_params(bt);
   // series s of this warp: shared temporaries + its own state slice; series past the end of the
   // batch are skipped
   struct Slot { Ws ws; double *sV, *sS; };
   auto slot = [&](int s) {
     Slot q;
-    q.ws = Ws::svd4(smem, smem + shared_doubles + (size_t)s * series_doubles, n, p, q.sV, q.sS);
+    q.ws = Ws::svd4(smem, smem + shared_doubles + (size_t)s * series_doubles, n, p, shared_params, q.sV, q.sS);
     return q;
   };
   auto live = [&](int s) { return b0 + s < bt.B; };
@@ -1084,7 +1079,7 @@ svd4_kernel(const WarpArgs wa, const int shared_doubles, const int series_double
     for (int k = lane; k < n; k += 32) ws.dcv[k] = sqrt(ws.v1[k]);
     w_copy(lane, nn, ws.t4, ws.C);
     if (ki) {
-      q_mv(lane, p, n, ws.F, n, true, ws.m, ws.f);
+      w_mv(lane, p, n, ws.F, n, true, ws.m, ws.f);
       store_view(lane, wa.svd.m, b, 0, n, ws.m);
       store_view(lane, wa.svd.a, b, 0, n, ws.m);
       store_view(lane, wa.svd.dc, b, 0, n, ws.dcv);
@@ -1124,7 +1119,7 @@ svd4_kernel(const WarpArgs wa, const int shared_doubles, const int series_double
       const Ws ws = slot(s).ws;
       load_cview(lane, bt.y, b0 + s, t, p, ws.yrow);
       __syncwarp();
-      q_mv(lane, p, n, ws.F, n, true, ws.a, ws.f);
+      w_mv(lane, p, n, ws.F, n, true, ws.a, ws.f);
       const int po = svd_update_pre(lane, n, p, ws);
       if (oct == s) po_mine = po;
     }
@@ -1173,7 +1168,7 @@ svd4_kernel(const WarpArgs wa, const int shared_doubles, const int series_double
       for (ElemIter it(lane, n, n); it.ok(); it.next())
         ws.t1[it.i + it.j * n] = ws.C[it.i + it.j * n] * ws.dcv[it.j];
       __syncwarp();
-      q_mv(lane, n, n, ws.t1, n, false, ws.v3, ws.v2);
+      w_mv(lane, n, n, ws.t1, n, false, ws.v3, ws.v2);
       for (int k = lane; k < n; k += 32) ws.th[k] = ws.m[k] + ws.v2[k];
       __syncwarp();
       store_view(lane, wa.theta, b, rows - 1, n, ws.th);
@@ -1194,8 +1189,8 @@ svd4_kernel(const WarpArgs wa, const int shared_doubles, const int series_double
         for (int k = lane; k < nn; k += 32) ws.C[k] = sp[2 * n + k];
         __syncwarp();
         if (bt.w_tv) add_status(s, svd_load_params_tv(lane, bt, ws, b, tobs, false));
-        q_mm(lane, n, n, n, ws.Wsq, n, false, ws.G, n, false, ws.t1, n);
-        q_mm(lane, n, n, n, ws.t1, n, false, ws.C, n, false, ws.t2, n);
+        w_mm(lane, n, n, n, ws.Wsq, n, false, ws.G, n, false, ws.t1, n);
+        w_mm(lane, n, n, n, ws.t1, n, false, ws.C, n, false, ws.t2, n);
         for (ElemIter it(lane, n, n); it.ok(); it.next()) {
           ws.stk[it.i + it.j * 2 * n] = ws.t2[it.i + it.j * n];
           ws.stk[n + it.i + it.j * 2 * n] = (it.i == it.j) ? 1.0 / ws.dcv[it.i] : 0.0;
@@ -1209,24 +1204,24 @@ svd4_kernel(const WarpArgs wa, const int shared_doubles, const int series_double
         const Slot q = slot(s);
         const Ws &ws = q.ws;
         load_z(lane, wa, b0 + s, r, rows, n, ws.v3);
-        q_mm(lane, n, n, n, ws.C, n, false, q.sV, n, false, ws.t5, n);  // uh
+        w_mm(lane, n, n, n, ws.C, n, false, q.sV, n, false, ws.t5, n);  // uh
         for (int k = lane; k < n; k += 32) ws.v1[k] = 1.0 / q.sS[k];    // dh
         __syncwarp();
-        q_mm(lane, n, n, n, ws.G, n, true, ws.Wsq, n, true, ws.t1, n);
-        q_mm(lane, n, n, n, ws.t1, n, false, ws.Wsq, n, false, ws.t2, n);  // gWinv
+        w_mm(lane, n, n, n, ws.G, n, true, ws.Wsq, n, true, ws.t1, n);
+        w_mm(lane, n, n, n, ws.t1, n, false, ws.Wsq, n, false, ws.t2, n);  // gWinv
         for (ElemIter it(lane, n, n); it.ok(); it.next())
           ws.t3[it.i + it.j * n] = ws.v1[it.i] * ws.t5[it.j + it.i * n];  // du
         __syncwarp();
-        q_mm(lane, n, n, n, ws.t3, n, true, ws.t3, n, false, ws.t4, n);
-        q_mm(lane, n, n, n, ws.t4, n, false, ws.t2, n, false, ws.t6, n);
+        w_mm(lane, n, n, n, ws.t3, n, true, ws.t3, n, false, ws.t4, n);
+        w_mm(lane, n, n, n, ws.t4, n, false, ws.t2, n, false, ws.t6, n);
         for (int k = lane; k < n; k += 32) ws.v2[k] = ws.th[k] - ws.a[k];
         __syncwarp();
-        q_mv(lane, n, n, ws.t6, n, false, ws.v2, ws.v4);
+        w_mv(lane, n, n, ws.t6, n, false, ws.v2, ws.v4);
         for (int k = lane; k < n; k += 32) ws.v4[k] = ws.m[k] + ws.v4[k];  // h
         for (ElemIter it(lane, n, n); it.ok(); it.next())
           ws.t1[it.i + it.j * n] = ws.t5[it.i + it.j * n] * ws.v1[it.j];
         __syncwarp();
-        q_mv(lane, n, n, ws.t1, n, false, ws.v3, ws.v2);
+        w_mv(lane, n, n, ws.t1, n, false, ws.v3, ws.v2);
         for (int k = lane; k < n; k += 32) ws.th[k] = ws.v4[k] + ws.v2[k];
         __syncwarp();
         store_view(lane, wa.theta, b0 + s, r, n, ws.th);
@@ -1259,8 +1254,9 @@ bool svd4_supported(int op, const Batch &bt) {
 template <int OP, int NP>
 cudaError_t launch_svd4_np(const WarpArgs &wa, cudaStream_t stream) {
   const int n = wa.bt.n, p = wa.bt.p;
-  const int shared_doubles = (int)((Ws::svd4_shared_doubles(n, p) + 1) & ~(size_t)1);
-  const int series_doubles = (int)((Ws::svd4_series_doubles(n, p) + 1) & ~(size_t)1);
+  const bool sp = svd4_shared_params(wa.bt);
+  const int shared_doubles = (int)((Ws::svd4_shared_doubles(n, p, sp) + 1) & ~(size_t)1);
+  const int series_doubles = (int)((Ws::svd4_series_doubles(n, p, sp) + 1) & ~(size_t)1);
   const size_t smem = ((size_t)shared_doubles + (size_t)kQuad * series_doubles) * sizeof(double);
   cudaError_t e = cudaFuncSetAttribute(svd4_kernel<OP, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem);
