@@ -685,39 +685,83 @@ def scan_dist_leg(comm, eng, dev, rank, world, logT=24, reps=5):
                              "whole series, max over ranks; bar 1e-9",
            "exchange": "bdlm_comm_scan_filter_smooth, one process per GPU: 2 ncclAllGather of <= 16 "
                        "doubles per rank per call, issued by libbdlm.so"}
-    # ---- the same job from ONE process driving all N GPUs (a JVM host): peer-mailbox exchange
-    dist.barrier()
+    # ---- the same job from ONE process driving all N GPUs (a JVM host): peer-mailbox exchange.
+    # The other ranks wait on the CPU (c10d store), not in an NCCL barrier whose spinning kernel
+    # would share their GPU with this leg.
+    store = dist.distributed_c10d._get_default_store()
+    torch.cuda.synchronize()
     if rank == 0:
         try:
-            pc = Comm.single_process(list(range(world)))
-            models, chunks = [], []
-            for r in range(world):
-                lo_r, hi_r = shard_range(T, r, world)
-                models.append(Model.build(dlm.polynomial(2), T=hi_r - lo_r))
-                chunks.append(yfull[lo_r:hi_r].to(torch.device("cuda", r)).contiguous())
-            hp = pc.scan_setup(models, params, chunks)
-            pc.scan_run(hp); pc.scan_run(hp); pc.sync()
-            wall = []
-            for _ in range(reps):
-                pc.sync()
-                # the communicator's contexts run on their own streams: time with the host clock
-                # around enqueue + sync of all devices (includes launch latency, like the caller sees)
-                w0 = time.perf_counter()
-                pc.scan_run(hp)
-                pc.sync()
-                wall.append((time.perf_counter() - w0) * 1e3)
-            worst_p = max(float(worst_vs_one(hp["outs"][r], r).item()) for r in range(world))
-            res["single_process"] = {
-                "ms": float(np.median(wall)), "peer_mailboxes": pc.uses_peer_exchange,
-                "status": max(int(s_.item()) for s_ in hp["status"]), "max_rel_err": worst_p,
-                "timing": "host clock around enqueue + sync of all %d devices (median of %d)" % (world, reps),
-                "exchange": "aggregates stored into the peers' mailboxes over NVLink + flag "
-                            "(no NCCL call)" if pc.uses_peer_exchange else "NCCL all-gathers"}
-            pc.close()
+            res["single_process"] = scan_single_process(T, world, params, yfull, worst_vs_one, reps)
         except Exception as ex:
             res["single_process"] = {"error": repr(ex)}
+        store.set("bdlm_single_process_scan_done", "1")
+    else:
+        store.wait(["bdlm_single_process_scan_done"])
     dist.barrier()
     return res
+
+
+def scan_single_process(T, world, params, yfull, worst_vs_one, reps):
+    import torch
+    from bayesian_dlms_b200 import Model, dlm
+    from bayesian_dlms_b200.comm import Comm
+    from bayesian_dlms_b200.sharding import shard_range
+    out = {}
+    for peer in (True, False):
+        if peer:
+            os.environ.pop("BDLM_COMM_NO_PEER", None)
+        else:
+            os.environ["BDLM_COMM_NO_PEER"] = "1"
+        pc = Comm.single_process(list(range(world)))
+        os.environ.pop("BDLM_COMM_NO_PEER", None)
+        streams = []
+        for r, e in enumerate(pc.engines):   # contexts on torch streams so that torch events time them
+            st = torch.cuda.Stream(device=r)
+            streams.append(st)
+            e.ctx.set_stream(st.cuda_stream)
+        models, chunks = [], []
+        for r in range(world):
+            lo_r, hi_r = shard_range(T, r, world)
+            models.append(Model.build(dlm.polynomial(2), T=hi_r - lo_r))
+            chunks.append(yfull[lo_r:hi_r].to(torch.device("cuda", r)).contiguous())
+        for r in range(world):
+            torch.cuda.synchronize(r)
+        guards = [torch.cuda.stream(st) for st in streams]
+        for gd in guards:
+            gd.__enter__()
+        try:
+            hp = pc.scan_setup(models, params, chunks)
+            for _ in range(3):
+                pc.scan_run(hp)
+            pc.sync()
+            dev_ms, host_ms = [], []
+            for _ in range(reps):
+                pc.sync()
+                evs = []
+                for st in streams:
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(st)
+                    evs.append((e0, e1))
+                w0 = time.perf_counter()
+                pc.scan_run(hp)
+                for (e0, e1), st in zip(evs, streams):
+                    e1.record(st)
+                pc.sync()
+                host_ms.append((time.perf_counter() - w0) * 1e3)
+                dev_ms.append(max(e0.elapsed_time(e1) for e0, e1 in evs))
+        finally:
+            for gd in reversed(guards):
+                gd.__exit__(None, None, None)
+        worst_p = max(float(worst_vs_one(hp["outs"][r], r).item()) for r in range(world))
+        out["peer_mailboxes" if pc.uses_peer_exchange else "nccl_allgather"] = {
+            "ms": float(np.median(dev_ms)), "host_enqueue_plus_sync_ms": float(np.median(host_ms)),
+            "status": max(int(s_.item()) for s_ in hp["status"]), "max_rel_err": worst_p}
+        pc.close()
+    out["timing"] = "CUDA events on every device's stream, max over devices, median of %d" % reps
+    out["what"] = ("ONE process drives all %d GPUs through bdlm_comm_scan_filter_smooth; peer_mailboxes = "
+                   "aggregates stored into the peers' memory over NVLink + flag, no NCCL call" % world)
+    return out
 
 
 def loglik_dist_leg(comm, eng, dev, rank, world, B=1_000_000, T=1000):
