@@ -125,8 +125,77 @@ def _model_for_states(mod: Dlm, state_times: np.ndarray):
                  bool(g_tv), n, p, int(st.size - 1), None)
 
 
+def _prep_batch(mod, yss: Sequence[Sequence[Data]], ps):
+    """Batched overloads (last rows): ``yss`` holds one ``Vector[Data]`` per
+    series -- each with its OWN times (Dlm.scala:94) and, for filter / smoother calls, its own
+    length -- ``mod`` one ``Dlm`` or one per series (regression covariates), ``ps`` one
+    ``DlmParameters`` or one per series.  Short series are padded with ``None`` observations at
+    their last time (dt = 0 passes the state through, KalmanFilter.scala:277-279)."""
+    from .batch import build_batch_model
+    B = len(yss)
+    flat = [_dlm.flatten_data(ys) for ys in yss]
+    lens = np.array([t.size for t, _ in flat])
+    T, p = int(lens.max()), flat[0][1].shape[1]
+    times = np.empty((B, T))
+    y = np.full((B, T, p), np.nan)
+    for b, (t, yy) in enumerate(flat):
+        times[b, :t.size] = t
+        times[b, t.size:] = t[-1]
+        y[b, :t.size] = yy
+    same_grid = not isinstance(mod, (list, tuple)) and all(np.array_equal(times[0], times[b]) for b in range(1, B))
+    model = Model.build(mod, times[0]) if same_grid else build_batch_model(mod, times)
+    if isinstance(ps, DlmParameters):
+        params = dict(V=ps.v, W=ps.w, m0=ps.m0, C0=ps.c0)
+    else:
+        assert len(ps) == B
+        params = dict(V=np.stack([_dlm.cm(q.v) for q in ps]), W=np.stack([_dlm.cm(q.w) for q in ps]),
+                      m0=np.stack([q.m0 for q in ps]), C0=np.stack([_dlm.cm(q.c0) for q in ps]),
+                      per_series=("V", "W", "m0", "C0"))
+    return model, params, times, y, lens
+
+
 class KalmanFilter:
     """``KalmanFilter`` companion-object entry points (KalmanFilter.scala)."""
+
+    @staticmethod
+    def filterBatch(mod, yss: Sequence[Sequence[Data]], ps, keep_init: bool = True) -> List[List[KfState]]:
+        """``yss.map(ys => KalmanFilter(adv).filter(mod, ys, p))`` as ONE call on the GPU: every
+        series on its own (irregular) time grid and of its own length, per-series parameters when
+        ``ps`` is a sequence (the reference's "one model per sensor" loop, UoModel.scala:69-104)."""
+        model, params, times, y, lens = _prep_batch(mod, yss, ps)
+        out = default_engine().filter(model, params, y, layout=SERIES_MAJOR, keep_init=keep_init)
+        res = []
+        for b in range(len(yss)):
+            _raise_status(int(out["status"][b]))
+            L = int(lens[b]) + int(keep_init)
+            one = {k: out[k][b:b + 1, :L] for k in ("m", "C", "a", "R", "f", "Q")}
+            res.append(_kf_states(model, one, _row_times(times[b, :lens[b]], keep_init), keep_init))
+        return res
+
+    @staticmethod
+    def filterDlmBatch(mod, yss, ps) -> List[List[KfState]]:
+        """Batched ``KalmanFilter.filterDlm`` (:291-294): initial states dropped."""
+        return KalmanFilter.filterBatch(mod, yss, ps, keep_init=False)
+
+    @staticmethod
+    def filterSmoothBatch(mod, yss, ps):
+        """``filter`` followed by ``Smoothing.backwardsSmoother`` for every series in one fused call.
+        Returns (filtered, smoothed) lists of lists."""
+        model, params, times, y, lens = _prep_batch(mod, yss, ps)
+        out = default_engine().filter_smooth(model, params, y, layout=SERIES_MAJOR)
+        n = model.n
+        filt, sm = [], []
+        for b in range(len(yss)):
+            _raise_status(int(out["status"][b]))
+            L = int(lens[b]) + 1
+            tm = _row_times(times[b, :lens[b]], True)
+            one = {k: out[k][b:b + 1, :L] for k in ("m", "C", "a", "R", "f", "Q")}
+            ks = _kf_states(model, one, tm, True)
+            filt.append(ks)
+            sm.append([SmoothingState(float(tm[r]), out["s"][b, r].copy(),
+                                      _dlm.from_cm(out["S"][b, r], n, n).copy(), ks[r].at, ks[r].rt)
+                       for r in range(L)])
+        return filt, sm
 
     @staticmethod
     def filterDlm(mod: Dlm, ys: Sequence[Data], p: DlmParameters) -> List[KfState]:

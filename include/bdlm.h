@@ -109,8 +109,10 @@ enum { BDLM_PS_V = 1, BDLM_PS_W = 2, BDLM_PS_M0 = 4, BDLM_PS_C0 = 8,
         *  BDLM_PS_G:     G (with g_tv = 1) is laid out like y with k = n*n -- mod.g(dt_t) of each
         *                 series (seasonal models on per-series irregular grids,
         *                 AqMeshExample.scala:86-127).
-        * Ragged batches: pad a short series at the END with NaN observations at its last time
-        * (dt = 0: advState passes the state through, an all-missing update leaves it unchanged). */
+        * Ragged batches (filter, smoother, innovations likelihood): pad a short series at the END
+        * with NaN observations at its last time (dt = 0: advState passes the state through, an
+        * all-missing update leaves it unchanged, the smoother's recursion is the identity there).
+        * The backward SAMPLER and the transition-form likelihood are not padding-invariant. */
        BDLM_PS_TIMES = 16, BDLM_PS_F = 32, BDLM_PS_G = 64 };
 
 typedef struct bdlm_ctx bdlm_ctx;

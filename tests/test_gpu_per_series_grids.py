@@ -143,3 +143,35 @@ def test_ragged_batch_by_padding(eng):
         # the padded tail repeats the terminal state
         _exact(_np(out["m"])[b, L:], np.repeat(o["m"][L:L + 1], T - L + 1, 0), "padded m")
         assert H.rel_err(_np(out["s"])[b, :L + 1], s["s"]) < 1e-9
+
+
+def test_batched_overloads_of_the_mirror_api(eng):
+    """`yss.map(ys => KalmanFilter.filterDlm(mod, ys, p))` and filter + backwardsSmoother as ONE GPU
+    call (INTEGRATION.md batched overloads): series with their own irregular grids, their own
+    lengths and their own DlmParameters equal the one-series mirror calls exactly."""
+    from bayesian_dlms_b200 import Data, DlmParameters, KalmanFilter, Smoothing, polynomial
+    rng = np.random.default_rng(21)
+    mod = polynomial(2)
+    yss, ps = [], []
+    for b in range(9):
+        T = int(rng.integers(8, 30))
+        tm = np.cumsum(rng.choice([0.5, 1.0, 2.5], T)) + rng.uniform(0, 3)
+        obs = rng.standard_normal(T).cumsum()
+        yss.append([Data(float(tm[t]), np.array([None if rng.random() < 0.1 else float(obs[t])], dtype=object))
+                    for t in range(T)])
+        ps.append(DlmParameters(v=[[float(rng.uniform(1, 4))]], w=np.diag(rng.uniform(0.5, 2, 2)),
+                                m0=rng.standard_normal(2), c0=10 * np.eye(2)))
+    batch = KalmanFilter.filterDlmBatch(mod, yss, ps)
+    filt, sm = KalmanFilter.filterSmoothBatch(mod, yss, ps)
+    for b in range(len(yss)):
+        one = KalmanFilter.filterDlm(mod, yss[b], ps[b])
+        assert len(batch[b]) == len(one) == len(yss[b])
+        for x, y_ in zip(batch[b], one):
+            assert x.time == y_.time and np.array_equal(x.mt, y_.mt) and np.array_equal(x.ct, y_.ct)
+            assert np.array_equal(x.ft, y_.ft) and np.array_equal(x.qt, y_.qt)
+        f1 = KalmanFilter.filter(mod, yss[b], ps[b])
+        s1 = Smoothing.backwardsSmoother(mod)(f1)
+        assert len(sm[b]) == len(s1)
+        assert np.array_equal(sm[b][-1].mean, s1[-1].mean)     # terminal state through the padding
+        for x, y_ in zip(sm[b], s1):
+            assert H.rel_err(x.mean, y_.mean) < 1e-9 and H.rel_err(x.covariance, y_.covariance) < 1e-9
