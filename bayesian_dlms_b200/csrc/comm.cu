@@ -23,9 +23,13 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
+#include <memory>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -94,11 +98,52 @@ struct Local {
   unsigned long long *flags = nullptr;  // device [2][world]: mailbox epochs (peer exchange)
 };
 
+// One persistent host thread per local device: a single thread enqueuing ~20 launches per device
+// is the bottleneck of a multi-GPU call (measured at 8 GPUs: 0.64 ms of host enqueue for 0.2 ms of
+// kernels per device), and creating threads per call would cost as much again.
+struct Worker {
+  std::thread th;
+  std::mutex mu;
+  std::condition_variable cv;
+  std::function<int()> job;
+  int rc = 0;
+  bool pending = false, quit = false;
+  Worker() { th = std::thread([this] { loop(); }); }
+  ~Worker() {
+    { std::lock_guard<std::mutex> lk(mu); quit = true; }
+    cv.notify_all();
+    if (th.joinable()) th.join();
+  }
+  void loop() {
+    std::unique_lock<std::mutex> lk(mu);
+    for (;;) {
+      cv.wait(lk, [&] { return pending || quit; });
+      if (quit) return;
+      std::function<int()> j = job;
+      lk.unlock();
+      const int r = j();
+      lk.lock();
+      rc = r; pending = false;
+      cv.notify_all();
+    }
+  }
+  void submit(std::function<int()> j) {
+    { std::lock_guard<std::mutex> lk(mu); job = std::move(j); pending = true; }
+    cv.notify_all();
+  }
+  int wait() {
+    std::unique_lock<std::mutex> lk(mu);
+    cv.wait(lk, [&] { return !pending; });
+    return rc;
+  }
+};
+
 }  // namespace
 
 struct bdlm_comm {
   int world = 0;
   std::vector<Local> loc;
+  std::vector<std::unique_ptr<Worker>> workers;  // one per local device when there are several
   std::string err;
   bool peer = false;               // every local device can store into every other's mailbox
   unsigned long long epoch = 0;    // scan call counter (mailbox flags)
@@ -214,9 +259,8 @@ int for_each_local(bdlm_comm *m, Fn fn) {
   std::vector<int> rc(n, 0);
   if (n == 1) rc[0] = fn(0);
   else {
-    std::vector<std::thread> th;
-    for (int i = 0; i < n; ++i) th.emplace_back([&, i] { rc[i] = fn(i); });
-    for (auto &t : th) t.join();
+    for (int i = 0; i < n; ++i) m->workers[i]->submit([&fn, i] { return fn(i); });
+    for (int i = 0; i < n; ++i) rc[i] = m->workers[i]->wait();
   }
   int worst = 0, numeric = 0;
   for (int i = 0; i < n; ++i) {
@@ -255,6 +299,7 @@ int bdlm_comm_unique_id(void *id) {
 
 void bdlm_comm_destroy(bdlm_comm *m) {
   if (!m) return;
+  m->workers.clear();  // joins the worker threads
   for (Local &L : m->loc) {
     cudaSetDevice(L.device);
     if (L.ctx) bdlm_sync(L.ctx);
@@ -348,6 +393,8 @@ int bdlm_comm_create(const int32_t *devices, int32_t n_local, int32_t first_rank
       m->peers[pass].flag[r] = m->loc[r].flags + (size_t)pass * world;
     }
   }
+  if (n_local > 1)
+    for (int i = 0; i < n_local; ++i) m->workers.emplace_back(new Worker());
   *out = m;
   return 0;
 }
@@ -475,47 +522,38 @@ int bdlm_comm_scan_filter_smooth(bdlm_comm *m, const bdlm_problem *probs, const 
   if (!m) return cfail(nullptr, BDLM_E_ARG, "null communicator");
   if (!probs || !kfs || !sms) return cfail(m, BDLM_E_ARG, "null problem / output arrays");
   Nccl *nc = nccl();
-  const int nl = (int)m->loc.size(), W = m->world;
+  const int W = m->world;
   const int n = probs[0].n;
   if (n < 1 || n > 4) return cfail(m, BDLM_E_ARG, "scan path: n <= 4");
   const int ef = bdlm_scan_elem_doubles(n, 0), eb = bdlm_scan_elem_doubles(n, 1);
-  ++m->epoch;
-  auto fail_from = [&](int i, int rc) {
-    return cfail(m, rc, std::string("rank ") + std::to_string(m->loc[i].rank) + ": " + bdlm_last_error(m->loc[i].ctx));
-  };
-  for (int pass = 0; pass < 2; ++pass) {
-    const int e = pass ? eb : ef;
-    const ScanPeers *peers = m->peer ? &m->peers[pass] : nullptr;
-    for (int i = 0; i < nl; ++i) {
-      Local &L = m->loc[i];
+  const unsigned long long epoch = ++m->epoch;
+  // Every device's phases are enqueued by its own host thread: local scan -> exchange -> finish,
+  // forwards then backwards.  With peer mailboxes nothing on the host couples the devices (the
+  // finish kernels wait on flags in device memory); with NCCL every thread issues the all-gather
+  // of its own communicator rank.
+  return for_each_local(m, [&](int i) -> int {
+    Local &L = m->loc[i];
+    int32_t *st = status ? status[i] : nullptr;
+    for (int pass = 0; pass < 2; ++pass) {
+      const int e = pass ? eb : ef;
+      const ScanPeers *peers = m->peer ? &m->peers[pass] : nullptr;
       double *agg = L.agg + (size_t)pass * kMaxElem;
-      scan_set_peers(L.ctx, peers, m->epoch);
+      double *aggs = L.aggs + (size_t)pass * W * kMaxElem;
+      scan_set_peers(L.ctx, peers, epoch);
       int rc = pass ? bdlm_scan_dist_backward_local(L.ctx, &probs[i], L.rank, W, &kfs[i], &sms[i], agg)
                     : bdlm_scan_dist_forward_local(L.ctx, &probs[i], L.rank, W, agg);
-      if (rc) return fail_from(i, rc);
-    }
-    if (!m->peer) {
-      CNC(nc->GroupStart());
-      for (int i = 0; i < nl; ++i) {
-        Local &L = m->loc[i];
-        int r = nc->AllGather(L.agg + (size_t)pass * kMaxElem, L.aggs + (size_t)pass * W * kMaxElem,
-                              (size_t)e, kNcclFloat64, L.nc, ctx_stream(L.ctx));
-        if (r != 0) { nc->GroupEnd(); return cfail(m, BDLM_E_NCCL, std::string("ncclAllGather: ") + nc->GetErrorString(r)); }
+      if (!rc && !m->peer) {
+        const int r = nc->AllGather(agg, aggs, (size_t)e, kNcclFloat64, L.nc, ctx_stream(L.ctx));
+        if (r != 0) rc = BDLM_E_NCCL;
       }
-      CNC(nc->GroupEnd());
-    }
-    for (int i = 0; i < nl; ++i) {
-      Local &L = m->loc[i];
-      const double *aggs = L.aggs + (size_t)pass * W * kMaxElem;
-      int32_t *st = status ? status[i] : nullptr;
-      scan_set_peers(L.ctx, peers, m->epoch);
-      int rc = pass ? bdlm_scan_dist_backward_finish(L.ctx, &probs[i], L.rank, W, aggs, &kfs[i], &sms[i], st)
-                    : bdlm_scan_dist_forward_finish(L.ctx, &probs[i], L.rank, W, aggs, &kfs[i], st);
+      if (!rc)
+        rc = pass ? bdlm_scan_dist_backward_finish(L.ctx, &probs[i], L.rank, W, aggs, &kfs[i], &sms[i], st)
+                  : bdlm_scan_dist_forward_finish(L.ctx, &probs[i], L.rank, W, aggs, &kfs[i], st);
       scan_set_peers(L.ctx, nullptr, 0);
-      if (rc) return fail_from(i, rc);
+      if (rc) return rc;
     }
-  }
-  return 0;
+    return 0;
+  });
 }
 
 int bdlm_comm_sync(bdlm_comm *m) {

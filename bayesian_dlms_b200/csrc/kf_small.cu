@@ -106,7 +106,14 @@ template <> struct Occ<1> { static constexpr int kMinBlocks = 6; };
 #define BDLM_OCC2 5
 #endif
 template <> struct Occ<2> { static constexpr int kMinBlocks = BDLM_OCC2; };
-template <> struct Occ<3> { static constexpr int kMinBlocks = 2; };
+#ifndef BDLM_OCC3
+#define BDLM_OCC3 2
+#endif
+#ifndef BDLM_OCC4
+#define BDLM_OCC4 1
+#endif
+template <> struct Occ<3> { static constexpr int kMinBlocks = BDLM_OCC3; };
+template <> struct Occ<4> { static constexpr int kMinBlocks = BDLM_OCC4; };
 
 template <int N, bool REG, int MODE, bool RELOAD>
 __global__ void __launch_bounds__(128, Occ<N>::kMinBlocks)
