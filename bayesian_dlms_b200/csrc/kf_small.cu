@@ -107,7 +107,7 @@ template <> struct Occ<1> { static constexpr int kMinBlocks = 6; };
 #endif
 template <> struct Occ<2> { static constexpr int kMinBlocks = BDLM_OCC2; };
 #ifndef BDLM_OCC3
-#define BDLM_OCC3 2
+#define BDLM_OCC3 3
 #endif
 #ifndef BDLM_OCC4
 #define BDLM_OCC4 1
@@ -266,9 +266,14 @@ cudaError_t launch_t(const Batch &bt, const SmallModel<N> &mdl, const KfViews &k
                      const View &Sv, cudaStream_t stream, int *wave_series) {
   if (wave_series) {  // occupancy query only
     int blocks = 0, dev = 0, sms = 0;
+    const size_t qsmem = (MODE & kDoSmooth) ? sizeof(double) * kRing * (N + N * N) * kThreads : 0;
+    if (qsmem > 48 * 1024) {  // n = 4: 80 KB ring -- the query needs the opt-in limit raised first
+      cudaError_t ea = cudaFuncSetAttribute(kf_small_kernel<N, REG, MODE, RELOAD>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qsmem);
+      if (ea != cudaSuccess) return ea;
+    }
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-        &blocks, kf_small_kernel<N, REG, MODE, RELOAD>, kThreads,
-        (MODE & kDoSmooth) ? sizeof(double) * kRing * (N + N * N) * kThreads : 0);
+        &blocks, kf_small_kernel<N, REG, MODE, RELOAD>, kThreads, qsmem);
     if (e != cudaSuccess) return e;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
