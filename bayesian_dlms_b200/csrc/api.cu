@@ -754,7 +754,8 @@ int run_host_mode(bdlm_ctx *c, DevCall d, int64_t lo, int64_t hi) {
   // packed into one pinned block, ONE copy in, ONE copy out, everything on the context's stream.
   // The per-field pipeline below costs one cudaMemcpyAsync (5-10 us from pageable memory) per
   // field and three streams' worth of events, which dominates calls of this size.
-  if (lo == 0 && hi == B && per_series * (size_t)B + 256 * (fields.size() + 2) <= kTinyBytes) {
+  if (lo == 0 && hi == B &&
+      per_series * (size_t)B + 256 * (fields.size() + 2) <= std::min(kTinyBytes, c->staging_cap / 4)) {
     std::vector<size_t> off(fields.size());
     size_t in_end = 0, pos = 0;
     for (int pass = 0; pass < 2; ++pass) {  // inputs first, then outputs: two contiguous regions
