@@ -222,7 +222,10 @@ __host__ __device__ __forceinline__ void s_element_pred(const double *G, const d
 
 namespace {
 
-constexpr int kSub = 64;       // ROWS per thread (level 1); multiple of kGrp
+#ifndef BDLM_SCAN_SUB
+#define BDLM_SCAN_SUB 64
+#endif
+constexpr int kSub = BDLM_SCAN_SUB;  // ROWS per thread (level 1); multiple of kGrp
 constexpr int kGrp = 4;        // rows per vector group: 4 rows x K doubles = K 32-byte sectors
 constexpr int kScanBlock = 256;
 constexpr size_t kScanTableBytes = 64 << 10;
