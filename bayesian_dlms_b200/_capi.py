@@ -17,7 +17,7 @@ TIME_MAJOR, SERIES_MAJOR = 0, 1
 DEVICE, HOST = 0, 1
 PS_V, PS_W, PS_M0, PS_C0 = 1, 2, 4, 8
 PS_TIMES, PS_F, PS_G = 16, 32, 64   # Data.time / mod.f(time) / mod.g(dt) given per series
-TEXTBOOK_SMOOTHER, SVD_CONSISTENT_W = 1, 2
+TEXTBOOK_SMOOTHER, SVD_CONSISTENT_W, PARALLEL_IN_TIME = 1, 2, 4
 ST_SINGULAR, ST_NOTCONVERGED, ST_NOTPD, ST_NONFINITE, ST_TIMEOUT = 1, 2, 4, 8, 16
 E_ARG, E_EMPTY, E_CUDA, E_NODEVICE, E_NCCL = -1, -2, -3, -4, -5
 

@@ -326,13 +326,16 @@ class Engine:
     @_on_engine_stream
     def filter_smooth(self, model: Model, params: Dict, y, *, layout=TIME_MAJOR, keep_init=True,
                       want=KF_FIELDS + ("s", "S"), textbook=False, status=True, pinned=False,
-                      out: Optional[Dict] = None):
-        """Fused KalmanFilter(adv).filter + Smoothing.backwardsSmoother."""
+                      out: Optional[Dict] = None, parallel_in_time=False):
+        """Fused KalmanFilter(adv).filter + Smoothing.backwardsSmoother.  ``parallel_in_time``: ONE
+        long eligible series may run through the associative-scan kernels (1e-9 instead of
+        bit-for-bit; include/bdlm.h BDLM_PARALLEL_IN_TIME)."""
         mem, _ = _mem_and_ptr(y)
         B = self._batch_of(model, y, layout)
         rows = model.T + int(keep_init)
         pr, keep = self._problem(model, params, y, layout, keep_init,
-                                 capi.TEXTBOOK_SMOOTHER if textbook else 0, B, mem)
+                                 (capi.TEXTBOOK_SMOOTHER if textbook else 0) |
+                                 (capi.PARALLEL_IN_TIME if parallel_in_time else 0), B, mem)
         dims = self._kf_dims(model)
         if out is None:
             res, ko = self._outs(capi.KfOut, KF_FIELDS, want, y, layout, B, rows, dims, pinned)

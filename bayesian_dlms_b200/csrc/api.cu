@@ -50,6 +50,8 @@ struct bdlm_ctx {
   PinSlot pin[4];
   int pin_next = 0;
   char *bounce = nullptr;
+  char *pit_buf = nullptr;               // host-buffer staging of BDLM_PARALLEL_IN_TIME calls
+  size_t pit_bytes = 0;
   ScanPeers scan_peers{};                // scan_set_peers: mailbox exchange of the dist scan phases
   unsigned long long scan_epoch = 0;
 };
@@ -950,6 +952,7 @@ void bdlm_destroy(bdlm_ctx *c) {
   if (c->arena) cudaFree(c->arena);
   if (c->scan_table) cudaFree(c->scan_table);
   if (c->bounce) cudaFreeHost(c->bounce);
+  if (c->pit_buf) cudaFree(c->pit_buf);
   for (auto &sl : c->pin) {
     if (sl.host) cudaFreeHost(sl.host);
     if (sl.done) cudaEventDestroy(sl.done);
@@ -1043,12 +1046,62 @@ int bdlm_rts_smooth(bdlm_ctx *c, const bdlm_problem *p, const bdlm_kf_out *filt,
   return dispatch(c, d);
 }
 
+// BDLM_PARALLEL_IN_TIME: one long eligible series goes to the associative-scan kernels
+static bool pit_eligible(const bdlm_problem *p) {
+  return (p->compat & BDLM_PARALLEL_IN_TIME) && p->B == 1 && p->T >= 4096 && p->p == 1 && p->n <= 4 &&
+         !p->times && !p->f_tv && !p->g_tv && !p->per_series && !p->v_tv && !p->w_tv &&
+         (p->n == 1 || (p->compat & BDLM_TEXTBOOK_SMOOTHER));
+}
+
+static int pit_host(bdlm_ctx *c, const bdlm_problem *p, const bdlm_kf_out *kf,
+                    const bdlm_smooth_out *sm, int32_t *status) {
+  // stage y in, every requested field out, through a buffer of its own (the scan owns the arena)
+  const int64_t n = p->n, R = rows_of(*p);
+  const int64_t ks[8] = {n, n * n, n, n * n, 1, 1, n, n * n};
+  double *host[8] = {kf ? kf->m : nullptr, kf ? kf->C : nullptr, kf ? kf->a : nullptr, kf ? kf->R : nullptr,
+                     kf ? kf->f : nullptr, kf ? kf->Q : nullptr, sm->s, sm->S};
+  size_t off[9], pos = align_up(sizeof(double) * (size_t)p->T);
+  for (int i = 0; i < 8; ++i) { off[i] = pos; if (host[i]) pos = align_up(pos + sizeof(double) * (size_t)R * ks[i]); }
+  off[8] = pos; pos += 256;
+  CU(cudaSetDevice(c->device));
+  if (pos > c->pit_bytes) {
+    CU(cudaStreamSynchronize(c->stream));
+    if (c->pit_buf) CU(cudaFree(c->pit_buf));
+    c->pit_buf = nullptr; c->pit_bytes = 0;
+    CU(cudaMalloc(&c->pit_buf, pos));
+    c->pit_bytes = pos;
+  }
+  CU(cudaMemcpyAsync(c->pit_buf, p->y, sizeof(double) * (size_t)p->T, cudaMemcpyHostToDevice, c->stream));
+  bdlm_problem q = *p;
+  q.mem = BDLM_DEVICE;
+  q.y = reinterpret_cast<const double *>(c->pit_buf);
+  double *dev[8];
+  for (int i = 0; i < 8; ++i) dev[i] = host[i] ? reinterpret_cast<double *>(c->pit_buf + off[i]) : nullptr;
+  bdlm_kf_out dk = {dev[0], dev[1], dev[2], dev[3], dev[4], dev[5]};
+  bdlm_smooth_out ds = {dev[6], dev[7]};
+  int32_t *dst = status ? reinterpret_cast<int32_t *>(c->pit_buf + off[8]) : nullptr;
+  int rc = bdlm_scan_filter_smooth(c, &q, &dk, &ds, dst);
+  if (rc) return rc;
+  for (int i = 0; i < 8; ++i)
+    if (host[i])
+      CU(cudaMemcpyAsync(host[i], dev[i], sizeof(double) * (size_t)R * ks[i], cudaMemcpyDeviceToHost, c->stream));
+  if (status) CU(cudaMemcpyAsync(status, dst, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
 int bdlm_kf_filter_smooth(bdlm_ctx *c, const bdlm_problem *p, const bdlm_kf_out *kf,
                           const bdlm_smooth_out *sm, int32_t *status) {
   NvtxRange nvtx_("bdlm_kf_filter_smooth");
   int rc = validate(c, A_FILTER_SMOOTH, p);
   if (rc) return rc;
   if (!sm) return fail(c, BDLM_E_ARG, "null smoother output struct");
+  if (pit_eligible(p) && (sm->s || sm->S)) {
+    bdlm_problem q = *p;
+    q.compat &= ~BDLM_PARALLEL_IN_TIME;
+    return p->mem == BDLM_DEVICE ? bdlm_scan_filter_smooth(c, &q, kf, sm, status)
+                                 : pit_host(c, &q, kf, sm, status);
+  }
   DevCall d{}; d.op = A_FILTER_SMOOTH; d.pr = *p; if (kf) d.kf = *kf; d.sm = *sm;
   d.status = status;
   return dispatch(c, d);

@@ -91,8 +91,15 @@ enum {
 /* compat flags: default 0 = reference-verbatim behaviour (what parity is judged on) */
 enum {
   BDLM_TEXTBOOK_SMOOTHER = 1, /* S = C - B (R-S) B^T instead of Smoothing.scala:44's ... B */
-  BDLM_SVD_CONSISTENT_W = 2   /* SVD time update stacks W^{1/2} sqrt(dt) (DlmFsv.scala:213-217)
+  BDLM_SVD_CONSISTENT_W = 2,  /* SVD time update stacks W^{1/2} sqrt(dt) (DlmFsv.scala:213-217)
                                  instead of the raw W the filterDlm/ffbsDlm/Gibbs closures hold */
+  BDLM_PARALLEL_IN_TIME = 4   /* bdlm_kf_filter_smooth may run ONE long series (B = 1, T >= 4096,
+                                 p = 1, n <= 4, regular grid, time-invariant model, shared
+                                 parameters; n = 1 or BDLM_TEXTBOOK_SMOOTHER) through the
+                                 associative-scan kernels: T dependent steps of ~0.3 us each become a
+                                 few hundred microseconds, at 1e-9 relative instead of bit-for-bit
+                                 agreement with the sequential recursion -- hence opt-in.  Ignored
+                                 (sequential kernel) when the problem is not eligible. */
 };
 
 /* which params are per series (bit mask for bdlm_problem.per_series) */

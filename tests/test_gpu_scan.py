@@ -202,3 +202,50 @@ def test_device_side_protocol_emulated_ranks(n, world):
         got = torch.cat([d.out[k] for d in ranks]).cpu().numpy()
         assert got.shape == tuple(seq[k].shape)
         assert H.rel_err(got, seq[k].cpu().numpy()) < TOL, (k, world, H.rel_err(got, seq[k].cpu().numpy()))
+
+
+@pytest.mark.parametrize("n", [1, 2])
+@pytest.mark.parametrize("where", ["device", "host"])
+def test_opt_in_dispatch_of_one_long_series_to_the_scan(eng, n, where):
+    """BDLM_PARALLEL_IN_TIME on bdlm_kf_filter_smooth: one long series (here T = 50 000) takes the
+    associative-scan kernels -- 1e-9 against the sequential recursion -- from device or host
+    buffers; an ineligible problem (B = 3) silently keeps the sequential kernel, bit for bit."""
+    import time
+    import torch
+    from bayesian_dlms_b200 import Model, SERIES_MAJOR
+    mod, V, W, m0, C0 = _models()[n]
+    T = 50_000
+    rng = np.random.default_rng(3 + n)
+    y = rng.standard_normal((1, T, 1)).cumsum(axis=1) * 0.1
+    y[rng.random(y.shape) < 0.01] = np.nan
+    model = Model.build(mod, T=T)
+    params = dict(V=V, W=W, m0=m0, C0=C0)
+    yy = torch.from_numpy(y).cuda() if where == "device" else y
+    seq = eng.filter_smooth(model, params, yy, layout=SERIES_MAJOR, textbook=True)
+    eng.sync()
+    t0 = time.perf_counter()
+    seq = eng.filter_smooth(model, params, yy, layout=SERIES_MAJOR, textbook=True)
+    eng.sync()
+    t_seq = time.perf_counter() - t0
+    pit = eng.filter_smooth(model, params, yy, layout=SERIES_MAJOR, textbook=True, parallel_in_time=True)
+    eng.sync()
+    t0 = time.perf_counter()
+    pit = eng.filter_smooth(model, params, yy, layout=SERIES_MAJOR, textbook=True, parallel_in_time=True)
+    eng.sync()
+    t_pit = time.perf_counter() - t0
+    npy = lambda x: x.cpu().numpy() if hasattr(x, "cpu") else x  # noqa: E731
+    assert int(npy(pit["status"])[0]) == 0
+    for k in ("m", "C", "a", "R", "s", "S"):
+        assert H.rel_err(npy(pit[k]), npy(seq[k])) < TOL, (k, H.rel_err(npy(pit[k]), npy(seq[k])))
+    assert H.rel_err(npy(pit["f"])[:, 1:], npy(seq["f"])[:, 1:]) < TOL
+    print("T = %d, n = %d, %s buffers: sequential %.2f ms, parallel in time %.2f ms" %
+          (T, n, where, t_seq * 1e3, t_pit * 1e3))
+    assert t_pit < t_seq
+    # not eligible (three series): the flag is ignored, results are those of the sequential kernel
+    y3 = np.repeat(y[:, :5000], 3, axis=0).copy()
+    m3 = Model.build(mod, T=5000)
+    y3 = torch.from_numpy(y3).cuda() if where == "device" else y3
+    a = eng.filter_smooth(m3, params, y3, layout=SERIES_MAJOR, textbook=True)
+    b = eng.filter_smooth(m3, params, y3, layout=SERIES_MAJOR, textbook=True, parallel_in_time=True)
+    eng.sync()
+    assert np.array_equal(npy(a["S"]), npy(b["S"]))
