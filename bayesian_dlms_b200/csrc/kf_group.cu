@@ -394,12 +394,7 @@ group_kernel(const WarpArgs wa) {
       }
       // R = (G C) G^T + W dt
       double t1[N];
-      if (cx.act) {
-#pragma unroll
-        for (int i = 0; i < N; ++i) cx.S1[i + j * LD] = Ccol[i];
-      }
-      __syncwarp();
-      mm_sy<N, LD>(cx.SG, cx.S1 + j * LD, 1, t1);        // column j of G C
+      mm_sx<N, LD>(cx.SG, Ccol, t1);                      // column j of G C (C column in registers)
       __syncwarp();
       if (cx.act) {
 #pragma unroll
