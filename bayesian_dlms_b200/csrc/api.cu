@@ -53,7 +53,7 @@ struct bdlm_ctx {
   char *pit_buf = nullptr;               // host-buffer staging of BDLM_PARALLEL_IN_TIME calls
   size_t pit_bytes = 0;
   ScanPeers scan_peers{};                // scan_set_peers: mailbox exchange of the dist scan phases
-  unsigned long long scan_epoch = 0;
+  const unsigned long long *scan_epoch = nullptr;
 };
 
 static std::string g_create_err;
@@ -899,9 +899,9 @@ namespace bdlm {
 cudaStream_t ctx_stream(bdlm_ctx *c) { return c->stream; }
 void ctx_set_range(bdlm_ctx *c, int64_t lo, int64_t hi) { c->range_lo = lo; c->range_hi = lo < 0 ? -1 : hi; }
 void ctx_count_launches(bdlm_ctx *c, int64_t n) { c->launches += n; }
-void scan_set_peers(bdlm_ctx *c, const ScanPeers *peers, unsigned long long epoch) {
+void scan_set_peers(bdlm_ctx *c, const ScanPeers *peers, const unsigned long long *epoch_dev) {
   if (peers) c->scan_peers = *peers; else c->scan_peers.world = 0;
-  c->scan_epoch = epoch;
+  c->scan_epoch = epoch_dev;
 }
 }  // namespace bdlm
 
@@ -1388,7 +1388,7 @@ int bdlm_scan_dist_forward_local(bdlm_ctx *c, const bdlm_problem *p, int32_t ran
   rc = scan_fill(c, p, a, true);
   if (rc) return rc;
   a.phase = kScanDistLocal; a.agg_dev = agg_dev; a.workspace = c->arena;
-  a.rank = rank; a.world = world; a.peers = c->scan_peers; a.epoch = c->scan_epoch;
+  a.rank = rank; a.world = world; a.peers = c->scan_peers; a.epoch_dev = c->scan_epoch;
   { rc = scan_launch_fwd(c, a); if (rc) return rc; }
   return 0;
 }
@@ -1408,7 +1408,7 @@ int bdlm_scan_dist_forward_finish(bdlm_ctx *c, const bdlm_problem *p, int32_t ra
   rc = scan_fill(c, p, a, true);
   if (rc) return rc;
   a.phase = kScanDistFinish; a.aggs_dev = aggs_dev; a.rank = rank; a.world = world;
-  a.peers = c->scan_peers; a.epoch = c->scan_epoch;
+  a.peers = c->scan_peers; a.epoch_dev = c->scan_epoch;
   a.start = prior.data(); a.has_successor = rank < world - 1;
   a.kf = scan_kf_views(p, kf); a.status = status; a.workspace = c->arena;
   a.fuse_sagg = c->arena + ws;  // smoother level-1 aggregates for the backward phases
@@ -1435,7 +1435,7 @@ int bdlm_scan_dist_backward_local(bdlm_ctx *c, const bdlm_problem *p, int32_t ra
   a.kf = scan_kf_views(p, filt);
   a.s = mk_view(sm->s, p->layout, 0, 1, R, n); a.S = mk_view(sm->S, p->layout, 0, 1, R, n * n);
   a.agg_dev = agg_dev; a.rank = rank; a.world = world; a.workspace = c->arena + ws;
-  a.peers = c->scan_peers; a.epoch = c->scan_epoch;
+  a.peers = c->scan_peers; a.epoch_dev = c->scan_epoch;
   CU(launch_scan(a, c->stream, &c->launches));
   return 0;
 }
@@ -1457,7 +1457,7 @@ int bdlm_scan_dist_backward_finish(bdlm_ctx *c, const bdlm_problem *p, int32_t r
   a.kf = scan_kf_views(p, filt);
   a.s = mk_view(sm->s, p->layout, 0, 1, R, n); a.S = mk_view(sm->S, p->layout, 0, 1, R, n * n);
   a.aggs_dev = aggs_dev; a.rank = rank; a.world = world; a.status = status;
-  a.workspace = c->arena + ws; a.peers = c->scan_peers; a.epoch = c->scan_epoch;
+  a.workspace = c->arena + ws; a.peers = c->scan_peers; a.epoch_dev = c->scan_epoch;
   CU(launch_scan(a, c->stream, &c->launches));
   return 0;
 }

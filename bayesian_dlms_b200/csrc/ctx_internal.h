@@ -18,6 +18,6 @@ void ctx_set_range(bdlm_ctx *c, int64_t lo, int64_t hi);
 void ctx_count_launches(bdlm_ctx *c, int64_t n);
 // Peer mailboxes the bdlm_scan_dist_* calls of this context use until cleared (peers == nullptr).
 struct ScanPeers;
-void scan_set_peers(bdlm_ctx *c, const ScanPeers *peers, unsigned long long epoch);
+void scan_set_peers(bdlm_ctx *c, const ScanPeers *peers, const unsigned long long *epoch_dev);
 
 }  // namespace bdlm

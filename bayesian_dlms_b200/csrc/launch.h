@@ -117,10 +117,11 @@ struct ScanArgs {
   const double *aggs_dev;  // dist finish: device [world][elem doubles], all ranks' aggregates
   int rank, world;     // dist phases
   ScanPeers peers;     // dist phases: peer mailboxes instead of agg_dev + all-gather (world > 0)
-  unsigned long long epoch;  // value the mailbox flags take for this call
+  const unsigned long long *epoch_dev;  // device: this rank's call counter = the value its flags take
   void *table;         // device, scan_table_bytes(): y-independent parts of the level-1 aggregates
   int table_upload;    // 1 = (re)build the table for this model before the forward pass
 };
+cudaError_t launch_epoch_bump(unsigned long long *epoch_dev, cudaStream_t stream);
 size_t scan_table_bytes();
 size_t scan_workspace_bytes(int n, int64_t T);
 int scan_forward_elem_doubles(int n);

@@ -883,7 +883,7 @@ __global__ void copy_last_row(View fm, View fC, int64_t row, View sv, View Sv, d
 // flag[d][rank] = epoch.  One launch replaces the device-to-device copy + the NCCL all-gather.
 template <class E>
 __global__ void __launch_bounds__(64)
-publish_kernel(const E *src, const ScanPeers peers, int rank, unsigned long long epoch) {
+publish_kernel(const E *src, const ScanPeers peers, int rank, const unsigned long long *epoch_dev) {
   constexpr int kD = (int)(sizeof(E) / sizeof(double));
   const int d = blockIdx.x;
   const double *s = reinterpret_cast<const double *>(src);
@@ -893,7 +893,7 @@ publish_kernel(const E *src, const ScanPeers peers, int rank, unsigned long long
   __syncthreads();
   if (threadIdx.x == 0) {
     volatile unsigned long long *f = peers.flag[d] + rank;
-    *f = epoch;
+    *f = *epoch_dev;  // this device's call counter (bumped by epoch_bump_kernel at the start of a call)
   }
 }
 
@@ -902,7 +902,8 @@ publish_kernel(const E *src, const ScanPeers peers, int rank, unsigned long long
 constexpr int kPeerSpinMax = 1 << 24;
 template <class E>
 __device__ bool peer_wait_read(const ScanPeers &peers, int my_rank, int src_rank,
-                               unsigned long long epoch, E &out) {
+                               const unsigned long long *epoch_dev, E &out) {
+  const unsigned long long epoch = *epoch_dev;
   constexpr int kD = (int)(sizeof(E) / sizeof(double));
   volatile unsigned long long *f = peers.flag[my_rank] + src_rank;
   int spins = 0;
@@ -923,7 +924,7 @@ __device__ bool peer_wait_read(const ScanPeers &peers, int my_rank, int src_rank
 template <int N>
 __global__ void fold_forward_kernel(const FElem<N> *aggs, int rank, const StateArg<N> prior,
                                     FElem<N> *carry, const ScanPeers peers,
-                                    unsigned long long epoch, int32_t *status) {
+                                    const unsigned long long *epoch, int32_t *status) {
   FElem<N> e, t, in;
   f_state<N>(e, prior.v, prior.v + N);  // the state before the first observation of rank 0
   for (int r = 0; r < rank; ++r) {
@@ -940,7 +941,7 @@ __global__ void fold_forward_kernel(const FElem<N> *aggs, int rank, const StateA
 // its terminal state s_T = m_T, S_T = C_T.
 template <int N>
 __global__ void fold_backward_kernel(const SElem<N> *aggs, int rank, int world, SElem<N> *carry,
-                                     const ScanPeers peers, unsigned long long epoch,
+                                     const ScanPeers peers, const unsigned long long *epoch,
                                      int32_t *status) {
   SElem<N> e, t, in;
   bool ok = true;
@@ -1007,7 +1008,7 @@ cudaError_t scan_forward(const ScanArgs &a, cudaStream_t stream, int64_t *launch
     }
     if (local) {
       if (a.peers.world > 0) {  // straight into every peer's mailbox over NVLink
-        publish_kernel<FElem<N>><<<a.peers.world, 64, 0, stream>>>(X + M, a.peers, a.rank, a.epoch);
+        publish_kernel<FElem<N>><<<a.peers.world, 64, 0, stream>>>(X + M, a.peers, a.rank, a.epoch_dev);
         ++*launches;
         return cudaGetLastError();
       }
@@ -1018,7 +1019,7 @@ cudaError_t scan_forward(const ScanArgs &a, cudaStream_t stream, int64_t *launch
     // X still holds this rank's scanned prefixes from the local phase
     fold_forward_kernel<N><<<1, 1, 0, stream>>>(reinterpret_cast<const FElem<N> *>(a.aggs_dev),
                                                 a.rank, state_arg<N>(a.start), carry, a.peers,
-                                                a.epoch, a.status);
+                                                a.epoch_dev, a.status);
     ++*launches;
   }
   const bool vec = dense_aligned(a.kf.m, N) && dense_aligned(a.kf.C, N * N) &&
@@ -1084,7 +1085,7 @@ cudaError_t scan_backward(const ScanArgs &a, cudaStream_t stream, int64_t *launc
     }
     if (local) {
       if (a.peers.world > 0) {
-        publish_kernel<SElem<N>><<<a.peers.world, 64, 0, stream>>>(X, a.peers, a.rank, a.epoch);
+        publish_kernel<SElem<N>><<<a.peers.world, 64, 0, stream>>>(X, a.peers, a.rank, a.epoch_dev);
         ++*launches;
         return cudaGetLastError();
       }
@@ -1092,7 +1093,7 @@ cudaError_t scan_backward(const ScanArgs &a, cudaStream_t stream, int64_t *launc
     }
   } else if (a.has_successor) {
     fold_backward_kernel<N><<<1, 1, 0, stream>>>(reinterpret_cast<const SElem<N> *>(a.aggs_dev),
-                                                 a.rank, a.world, carry, a.peers, a.epoch, a.status);
+                                                 a.rank, a.world, carry, a.peers, a.epoch_dev, a.status);
     ++*launches;
   }
   const SElem<N> *cr = (finish && a.has_successor) ? carry : nullptr;
@@ -1112,6 +1113,12 @@ size_t scan_workspace_bytes(int n, int64_t T) {
   const int64_t M = (T + 1 + kSub - 1) / kSub + 2;
   const size_t elem = sizeof(double) * (3 * n * n + 2 * n);
   return elem * (size_t)(M + 1 + (M + 1) / kScanBlock * 2 + 24) + 8192;
+}
+
+__global__ void epoch_bump_kernel(unsigned long long *epoch_dev) { *epoch_dev = *epoch_dev + 1; }
+cudaError_t launch_epoch_bump(unsigned long long *epoch_dev, cudaStream_t stream) {
+  epoch_bump_kernel<<<1, 1, 0, stream>>>(epoch_dev);
+  return cudaGetLastError();
 }
 
 size_t scan_table_bytes() { return kScanTableBytes; }
