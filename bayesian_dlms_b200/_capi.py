@@ -39,7 +39,7 @@ SYMBOLS = [
     "bdlm_comm_unique_id", "bdlm_comm_create", "bdlm_comm_destroy", "bdlm_comm_last_error",
     "bdlm_comm_size", "bdlm_comm_local_size", "bdlm_comm_ctx", "bdlm_comm_sync",
     "bdlm_comm_uses_peer_exchange", "bdlm_comm_allreduce_sum", "bdlm_comm_allreduce_sum_device",
-    "bdlm_comm_kf_filter_smooth", "bdlm_comm_loglik", "bdlm_comm_ffbs", "bdlm_comm_svd_ffbs",
+    "bdlm_comm_kf_filter", "bdlm_comm_svd_filter", "bdlm_comm_kf_filter_smooth", "bdlm_comm_loglik", "bdlm_comm_ffbs", "bdlm_comm_svd_ffbs",
     "bdlm_comm_scan_filter_smooth",
 ]
 COMM_ID_BYTES = 128
@@ -184,6 +184,8 @@ def load():
     lib.bdlm_comm_allreduce_sum_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
     lib.bdlm_comm_kf_filter_smooth.argtypes = [C.c_void_p, PP, C.POINTER(KfOut), C.POINTER(SmoothOut),
                                                C.c_void_p]
+    lib.bdlm_comm_kf_filter.argtypes = [C.c_void_p, PP, C.POINTER(KfOut), C.c_void_p]
+    lib.bdlm_comm_svd_filter.argtypes = [C.c_void_p, PP, C.POINTER(SvdOut), C.c_void_p]
     lib.bdlm_comm_loglik.argtypes = [C.c_void_p, PP, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.bdlm_comm_ffbs.argtypes = [C.c_void_p, PP, C.c_void_p, C.c_void_p, C.POINTER(KfOut),
                                    C.POINTER(GibbsStats), C.c_void_p, C.POINTER(GibbsStats)]

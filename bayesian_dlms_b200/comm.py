@@ -125,6 +125,37 @@ class Comm:
         res["status"] = st
         return res
 
+    def filter(self, model: Model, params: Dict, y, *, layout=SERIES_MAJOR, keep_init=True,
+               want=KF_FIELDS):
+        """``bdlm_comm_kf_filter``: KalmanFilter.filterDlm / .filter over the devices."""
+        e = self._eng0()
+        with bound_engine(e):
+            mem, _ = _mem_and_ptr(y)
+            B = e._batch_of(model, y, layout)
+            rows = model.T + int(keep_init)
+            pr, keep = e._problem(model, params, y, layout, keep_init, 0, B, mem)
+            res, ko = e._outs(capi.KfOut, KF_FIELDS, want, y, layout, B, rows, e._kf_dims(model), False)
+            st, stp = e._status(y, B, True)
+        self._ck(capi.load().bdlm_comm_kf_filter(self._h, pr, ko, stp))
+        res["status"] = st
+        return res
+
+    def svd_filter(self, model: Model, params: Dict, y, *, layout=SERIES_MAJOR, keep_init=True,
+                   want=SVD_FIELDS, consistent_w=False):
+        """``bdlm_comm_svd_filter``: SvdFilter.filterDlm / .filter over the devices."""
+        e = self._eng0()
+        with bound_engine(e):
+            mem, _ = _mem_and_ptr(y)
+            B = e._batch_of(model, y, layout)
+            rows = model.T + int(keep_init)
+            pr, keep = e._problem(model, params, y, layout, keep_init,
+                                  capi.SVD_CONSISTENT_W if consistent_w else 0, B, mem)
+            res, so = e._outs(capi.SvdOut, SVD_FIELDS, want, y, layout, B, rows, e._svd_dims(model), False)
+            st, stp = e._status(y, B, True)
+        self._ck(capi.load().bdlm_comm_svd_filter(self._h, pr, so, stp))
+        res["status"] = st
+        return res
+
     def loglik(self, model: Model, params: Dict, y, *, layout=SERIES_MAJOR):
         """Per-series log-likelihoods + their sums over every series of every rank."""
         e = self._eng0()

@@ -456,6 +456,26 @@ int bdlm_comm_kf_filter_smooth(bdlm_comm *m, const bdlm_problem *p, const bdlm_k
   });
 }
 
+int bdlm_comm_kf_filter(bdlm_comm *m, const bdlm_problem *p, const bdlm_kf_out *out, int32_t *status) {
+  int rc = check_sharded(m, p);
+  if (rc) return rc;
+  const std::vector<int64_t> cut = cuts(m, p->B);
+  return for_each_local(m, [&](int i) {
+    ctx_set_range(m->loc[i].ctx, cut[i], cut[i + 1]);
+    return bdlm_kf_filter(m->loc[i].ctx, p, out, status);
+  });
+}
+
+int bdlm_comm_svd_filter(bdlm_comm *m, const bdlm_problem *p, const bdlm_svd_out *out, int32_t *status) {
+  int rc = check_sharded(m, p);
+  if (rc) return rc;
+  const std::vector<int64_t> cut = cuts(m, p->B);
+  return for_each_local(m, [&](int i) {
+    ctx_set_range(m->loc[i].ctx, cut[i], cut[i + 1]);
+    return bdlm_svd_filter(m->loc[i].ctx, p, out, status);
+  });
+}
+
 int bdlm_comm_loglik(bdlm_comm *m, const bdlm_problem *p, double *transition, double *innovations,
                      int32_t *status, double *sums) {
   int rc = check_sharded(m, p);

@@ -391,7 +391,11 @@ BDLM_API int32_t bdlm_comm_uses_peer_exchange(bdlm_comm *comm);
 BDLM_API int bdlm_comm_allreduce_sum(bdlm_comm *comm, double *values, int32_t count);
 /* Same on device memory of a one-device-per-process communicator; enqueue-only. */
 BDLM_API int bdlm_comm_allreduce_sum_device(bdlm_comm *comm, double *values_dev, int32_t count);
-/* bdlm_kf_filter_smooth over the communicator's devices. */
+/* bdlm_kf_filter / bdlm_svd_filter / bdlm_kf_filter_smooth over the communicator's devices. */
+BDLM_API int bdlm_comm_kf_filter(bdlm_comm *comm, const bdlm_problem *prob, const bdlm_kf_out *out,
+                                 int32_t *status);
+BDLM_API int bdlm_comm_svd_filter(bdlm_comm *comm, const bdlm_problem *prob, const bdlm_svd_out *out,
+                                  int32_t *status);
 BDLM_API int bdlm_comm_kf_filter_smooth(bdlm_comm *comm, const bdlm_problem *prob,
                                         const bdlm_kf_out *kf, const bdlm_smooth_out *sm,
                                         int32_t *status);

@@ -56,6 +56,12 @@ def test_sharded_host_batch_equals_one_call(eng, world):
             assert np.array_equal(ll1["transition"], ll["transition"])
             assert abs(ll["sum_transition"] - ll1["transition"].sum()) <= 1e-9 * abs(ll1["transition"].sum())
             assert abs(ll["sum_innovations"] - ll1["innovations"].sum()) <= 1e-9 * abs(ll1["innovations"].sum())
+        f1 = eng.filter(model, params, y, layout=SERIES_MAJOR, keep_init=False)
+        fN = comm.filter(model, params, y, layout=SERIES_MAJOR, keep_init=False)
+        assert np.array_equal(f1["C"], fN["C"]) and np.array_equal(f1["f"], fN["f"], equal_nan=True)
+        s1 = eng.svd_filter(model, params, y, layout=SERIES_MAJOR)
+        sN = comm.svd_filter(model, params, y, layout=SERIES_MAJOR)
+        assert np.array_equal(s1["uc"], sN["uc"]) and np.array_equal(s1["dc"], sN["dc"])
         # FFBS with injected normals: chains identical whatever the cut; pooled statistics
         mod13, V, W, m0, C0 = H.seasonal13()
         B, T = 37, 30
