@@ -590,7 +590,10 @@ int bdlm_comm_scan_filter_smooth(bdlm_comm *m, const bdlm_problem *probs, const 
   };
   return for_each_local(m, [&](int i) -> int {
     Local &L = m->loc[i];
-    if (!m->use_graph || m->peer) return enqueue(i);
+    static const bool graph_with_peers = std::getenv("BDLM_COMM_GRAPH_PEER") != nullptr;  // experiment
+    static const bool dbg = std::getenv("BDLM_COMM_DEBUG") != nullptr;
+    if (!m->use_graph || (m->peer && !graph_with_peers)) return enqueue(i);
+#define DBG(msg) do { if (dbg) { fprintf(stderr, "[comm dev %d] %s\n", L.device, msg); fflush(stderr); } } while (0)
     // the graph bakes in every pointer and scalar of the call: replay only an identical call
     const bdlm_problem &p = probs[i];
     std::vector<unsigned long long> key = {
@@ -612,9 +615,12 @@ int bdlm_comm_scan_filter_smooth(bdlm_comm *m, const bdlm_problem *probs, const 
     }
     if (L.graph_exec) {
       if (cudaSetDevice(L.device) != cudaSuccess) return BDLM_E_CUDA;
-      return cudaGraphLaunch(L.graph_exec, ctx_stream(L.ctx)) == cudaSuccess ? 0 : BDLM_E_CUDA;
+      DBG("replay");
+      const cudaError_t le = cudaGraphLaunch(L.graph_exec, ctx_stream(L.ctx));
+      DBG(le == cudaSuccess ? "replay launched" : cudaGetErrorString(le));
+      return le == cudaSuccess ? 0 : BDLM_E_CUDA;
     }
-    if (L.graph_seen++ == 0 || L.graph_seen < 0) return enqueue(i);  // first call: sizes workspaces, uploads tables
+    if (L.graph_seen++ == 0 || L.graph_seen < 0) { DBG("direct"); return enqueue(i); }  // first call: sizes workspaces, uploads tables
     // second identical call: capture it, instantiate, launch
     cudaStream_t stc = ctx_stream(L.ctx);
     if (cudaSetDevice(L.device) != cudaSuccess) return BDLM_E_CUDA;
@@ -623,9 +629,11 @@ int bdlm_comm_scan_filter_smooth(bdlm_comm *m, const bdlm_problem *probs, const 
       L.graph_seen = -1000000;  // capture not available on this stream: stay on direct launches
       return enqueue(i);
     }
+    DBG("capture begin");
     const int rc = enqueue(i);
     cudaGraph_t graph = nullptr;
     const cudaError_t ee = cudaStreamEndCapture(stc, &graph);
+    DBG(ee == cudaSuccess ? "capture end ok" : cudaGetErrorString(ee));
     if (rc != 0 || ee != cudaSuccess || !graph) {
       cudaGetLastError();
       if (graph) cudaGraphDestroy(graph);
@@ -641,7 +649,10 @@ int bdlm_comm_scan_filter_smooth(bdlm_comm *m, const bdlm_problem *probs, const 
     }
     cudaGraphDestroy(graph);
     L.graph_exec = exec;
-    return cudaGraphLaunch(exec, stc) == cudaSuccess ? 0 : BDLM_E_CUDA;
+    DBG("instantiated, first launch");
+    const cudaError_t fe = cudaGraphLaunch(exec, stc);
+    DBG(fe == cudaSuccess ? "first launch ok" : cudaGetErrorString(fe));
+    return fe == cudaSuccess ? 0 : BDLM_E_CUDA;
   });
 }
 

@@ -61,32 +61,39 @@ __host__ __device__ __forceinline__ void f_state(FElem<N> &e, const double *m, c
   for (int k = 0; k < N; ++k) { e.b[k] = m[k]; e.eta[k] = 0.0; }
 }
 
+// inverse of a small matrix for the combine operator (scan only: its contract is 1e-9, so the
+// closed forms for n <= 2 need not match dgesv's rounding)
+template <int N>
+__host__ __device__ __forceinline__ int small_inverse(const double (&Mx)[N * N], double (&inv)[N * N]) {
+  if (N == 1) {
+    inv[0] = 1.0 / Mx[0];
+    return Mx[0] == 0.0 ? BDLM_ST_SINGULAR : 0;
+  } else if (N == 2) {
+    const double det = Mx[0] * Mx[3] - Mx[2] * Mx[1];
+    const double r = 1.0 / det;
+    inv[0] = Mx[3] * r; inv[1] = -Mx[1] * r; inv[2] = -Mx[2] * r; inv[3] = Mx[0] * r;
+    return det == 0.0 ? BDLM_ST_SINGULAR : 0;
+  } else {
+    double Mc[N * N];
+#pragma unroll
+    for (int k = 0; k < N * N; ++k) { Mc[k] = Mx[k]; inv[k] = (k % (N + 1) == 0) ? 1.0 : 0.0; }
+    return lu_solve<N, N>(Mc, inv);
+  }
+}
+
 // out = ei (x) ej, ei earlier in time.  (Appendix C)
+// With C_i, J_j symmetric, (I + J_j C_i) = (I + C_i J_j)^T: ONE inverse serves both factors,
+//   X = A_j (I + C_i J_j)^-1,   Y = A_i^T (I + J_j C_i)^-1 = ((I + C_i J_j)^-1 A_i)^T.
 template <int N>
 __host__ __device__ __forceinline__ void f_combine(const FElem<N> &ei, const FElem<N> &ej,
                                                    FElem<N> &out) {
-  double CJ[N * N], Mt[N * N], X[N * N], JC[N * N], Nt[N * N], Y[N * N], t1[N * N], t2[N * N],
-      v1[N], v2[N];
-  // X = A_j (I + C_i J_j)^-1 :  X^T = (I + C_i J_j)^-T A_j^T
-  smm<N, N, N, false, false>(ei.C, ej.J, CJ);
+  double Mx[N * N], Minv[N * N], X[N * N], Y[N * N], t1[N * N], t2[N * N], v1[N], v2[N];
+  smm<N, N, N, false, false>(ei.C, ej.J, Mx);
 #pragma unroll
-  for (int j = 0; j < N; ++j)
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-      Mt[i + j * N] = ((i == j) ? 1.0 : 0.0) + CJ[j + i * N];  // (I + C_i J_j)^T
-      X[i + j * N] = ej.A[j + i * N];                            // A_j^T
-    }
-  lu_solve<N, N>(Mt, X);  // X := (I + C_i J_j)^-T A_j^T = (A_j M)^T
-  // Y^T = (I + J_j C_i)^-T A_i  ->  Y = A_i^T (I + J_j C_i)^-1
-  smm<N, N, N, false, false>(ej.J, ei.C, JC);
-#pragma unroll
-  for (int j = 0; j < N; ++j)
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-      Nt[i + j * N] = ((i == j) ? 1.0 : 0.0) + JC[j + i * N];
-      Y[i + j * N] = ei.A[i + j * N];
-    }
-  lu_solve<N, N>(Nt, Y);  // Y := (I + J_j C_i)^-T A_i = (A_i^T N)^T
+  for (int k = 0; k < N; ++k) Mx[k * (N + 1)] = 1.0 + Mx[k * (N + 1)];
+  small_inverse<N>(Mx, Minv);
+  smm<N, N, N, true, true>(Minv, ej.A, X);    // X := M^-T A_j^T = (A_j M^-1)^T
+  smm<N, N, N, false, false>(Minv, ei.A, Y);  // Y := M^-1 A_i = (A_i^T M^-T)^T
   // A = (A_j M) A_i
   smm<N, N, N, true, false>(X, ei.A, out.A);
   // b = (A_j M)(b_i + C_i eta_j) + b_j
@@ -200,17 +207,10 @@ template <int N>
 __host__ __device__ __forceinline__ void s_element_pred(const double *G, const double (&m)[N],
                                                         const double (&C)[N * N], const double (&a1)[N],
                                                         const double (&R1)[N * N], SElem<N> &e) {
-  double rhs[N * N], At[N * N], t1[N * N], t2[N * N], v[N];
-  smm<N, N, N, false, true>(G, C, rhs);
-#pragma unroll
-  for (int j = 0; j < N; ++j)
-#pragma unroll
-    for (int i = 0; i < N; ++i) At[i + j * N] = R1[j + i * N];
-  lu_solve<N, N>(At, rhs);
-#pragma unroll
-  for (int j = 0; j < N; ++j)
-#pragma unroll
-    for (int i = 0; i < N; ++i) e.E[i + j * N] = rhs[j + i * N];
+  double CGt[N * N], Rinv[N * N], t1[N * N], t2[N * N], v[N];
+  smm<N, N, N, false, true>(C, G, CGt);
+  small_inverse<N>(R1, Rinv);
+  smm<N, N, N, false, false>(CGt, Rinv, e.E);  // E = C G^T R1^-1
   smm<N, N, 1, false, false>(e.E, a1, v);
 #pragma unroll
   for (int k = 0; k < N; ++k) e.g[k] = m[k] - v[k];
@@ -511,46 +511,71 @@ __device__ __forceinline__ void scan_comb(const E &first, const E &second, E &o)
 // combine (two LU solves + ten products) is what this level costs.
 constexpr int kPer = 4;
 
+// Shared-memory staging of the thread totals is component-major ([k][thread]): an element is 10-56
+// doubles, so element-major rows would put every lane of a warp on the same banks.
+template <class E>
+__device__ __forceinline__ void sm_put(double *buf, int i, const E &e) {
+  constexpr int kD = (int)(sizeof(E) / sizeof(double));
+  const double *s = reinterpret_cast<const double *>(&e);
+#pragma unroll
+  for (int k = 0; k < kD; ++k) buf[k * kScanBlock + i] = s[k];
+}
+template <class E>
+__device__ __forceinline__ void sm_get(const double *buf, int i, E &e) {
+  constexpr int kD = (int)(sizeof(E) / sizeof(double));
+  double *d = reinterpret_cast<double *>(&e);
+#pragma unroll
+  for (int k = 0; k < kD; ++k) d[k] = buf[k * kScanBlock + i];
+}
+
 template <class E, bool IDXREV, bool OPREV>
 __global__ void __launch_bounds__(kScanBlock)
 block_scan_kernel(E *x, int64_t M, E *totals) {
   extern __shared__ unsigned char raw[];
-  E *buf0 = reinterpret_cast<E *>(raw), *buf1 = buf0 + kScanBlock;
+  constexpr int kD = (int)(sizeof(E) / sizeof(double));
+  double *buf0 = reinterpret_cast<double *>(raw), *buf1 = buf0 + kD * kScanBlock;
   const int tid = threadIdx.x;
   const int64_t base = (int64_t)blockIdx.x * (kScanBlock * kPer);
   const int64_t p0 = base + (int64_t)tid * kPer;
   const int cnt = (p0 >= M) ? 0 : (int)((M - p0 < kPer) ? (M - p0) : kPer);
   auto at = [&](int64_t p) -> E & { return x[IDXREV ? (M - 1 - p) : p]; };
   const bool act = cnt > 0;
+  E mine;  // this thread's running total (scan order)
   if (act) {
-    E run = at(p0), o;
-    for (int j = 1; j < cnt; ++j) { scan_comb<E, OPREV>(run, at(p0 + j), o); run = o; }
-    buf0[tid] = run;
+    E o;
+    mine = at(p0);
+    for (int j = 1; j < cnt; ++j) { scan_comb<E, OPREV>(mine, at(p0 + j), o); mine = o; }
+    sm_put<E>(buf0, tid, mine);
   }
   __syncthreads();
-  E *src = buf0, *dst = buf1;
+  double *src = buf0, *dst = buf1;
   for (int off = 1; off < kScanBlock; off <<= 1) {
     if (act) {
       if (tid >= off) {
-        E o;
-        scan_comb<E, OPREV>(src[tid - off], src[tid], o);
-        dst[tid] = o;
-      } else {
-        dst[tid] = src[tid];
+        E prev, o;
+        sm_get<E>(src, tid - off, prev);
+        scan_comb<E, OPREV>(prev, mine, o);
+        mine = o;
       }
+      sm_put<E>(dst, tid, mine);
     }
     __syncthreads();
-    E *t = src; src = dst; dst = t;
+    double *t = src; src = dst; dst = t;
   }
   if (act) {
     E run, o;
-    if (tid > 0) { scan_comb<E, OPREV>(src[tid - 1], at(p0), o); run = o; at(p0) = run; }
-    else run = at(p0);
+    if (tid > 0) {
+      E prev;
+      sm_get<E>(src, tid - 1, prev);
+      scan_comb<E, OPREV>(prev, at(p0), o); run = o; at(p0) = run;
+    } else {
+      run = at(p0);
+    }
     for (int j = 1; j < cnt; ++j) { scan_comb<E, OPREV>(run, at(p0 + j), o); run = o; at(p0 + j) = run; }
   }
   const int64_t left = M - base;  // positions in this block
   const int last = (int)(((left < kScanBlock * kPer ? left : kScanBlock * kPer) - 1) / kPer);
-  if (totals && tid == last) totals[blockIdx.x] = src[tid];
+  if (totals && tid == last) totals[blockIdx.x] = mine;
 }
 
 template <class E, bool IDXREV, bool OPREV>
@@ -618,7 +643,7 @@ __device__ __forceinline__ void fwd_row(const ScanModel<N> &md, const double (&W
     for (int k = 0; k < N; ++k) o.a[k] = an[k];
 #pragma unroll
     for (int k = 0; k < N * N; ++k) o.R[k] = Rn[k];
-    update<N>(md.F, md.V, yv, o.a, o.R, o.f, o.Q, m, C, st);
+    update<N, true>(md.F, md.V, yv, o.a, o.R, o.f, o.Q, m, C, st);
   }
 #pragma unroll
   for (int k = 0; k < N; ++k) o.m[k] = m[k];
@@ -756,9 +781,24 @@ template <int N>
 __device__ __forceinline__ void bwd_step(const ScanModel<N> &md, const double (&W)[N * N],
                                          const double (&m)[N], const double (&C)[N * N],
                                          double (&s)[N], double (&S)[N * N], int &st) {
-  double a1[N], R1[N * N];
+  // textbook RTS step (small_steps.cuh rts_step) with the gain formed from one explicit inverse:
+  //   B = C G^T R1^-1,  s = m + B (s - a1),  S = C - B (R1 - S) B^T
+  double a1[N], R1[N * N], CGt[N * N], Rinv[N * N], Bg[N * N], d[N], t[N], Dm[N * N], t1[N * N], t2[N * N];
   advance<N, true>(md.G, W, 1.0, m, C, a1, R1);
-  rts_step<N>(md.G, m, C, a1, R1, /*textbook=*/true, s, S, st);
+  smm<N, N, N, false, true>(C, md.G, CGt);
+  st |= small_inverse<N>(R1, Rinv);
+  smm<N, N, N, false, false>(CGt, Rinv, Bg);
+#pragma unroll
+  for (int i = 0; i < N; ++i) d[i] = s[i] - a1[i];
+  smm<N, N, 1, false, false>(Bg, d, t);
+#pragma unroll
+  for (int k = 0; k < N * N; ++k) Dm[k] = R1[k] - S[k];
+  smm<N, N, N, false, false>(Bg, Dm, t1);
+  smm<N, N, N, false, true>(t1, Bg, t2);
+#pragma unroll
+  for (int i = 0; i < N; ++i) s[i] = m[i] + t[i];
+#pragma unroll
+  for (int k = 0; k < N * N; ++k) S[k] = C[k] - t2[k];
 }
 template <int N, bool VEC>
 __device__ __forceinline__ void bwd_row(const ScanModel<N> &md, const double (&W)[N * N], const View &fm,

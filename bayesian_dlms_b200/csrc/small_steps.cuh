@@ -112,7 +112,8 @@ __host__ __device__ __forceinline__ void advance(const double *G, const double (
 }
 
 // oneStepPrediction (:311-321) + updateState (:64-94) for p = 1.
-template <int N>
+// RECIP (parallel-in-time scan only, 1e-9 contract): one reciprocal of Q instead of N divisions.
+template <int N, bool RECIP = false>
 __host__ __device__ __forceinline__ void update(const double *F, double V, double y,
                                        const double (&a)[N], const double (&R)[N * N],
                                        double &f, double &Q, double (&m)[N],
@@ -134,8 +135,14 @@ __host__ __device__ __forceinline__ void update(const double *F, double V, doubl
   double rhs[N], K[N], D[N * N], t1[N * N], t2[N], C2[N * N];
   smm<1, N, N, true, true>(F, R, rhs);  // F^T R^T
   if (Q == 0.0) st |= BDLM_ST_SINGULAR;
+  if (RECIP) {
+    const double rq = 1.0 / Q;
 #pragma unroll
-  for (int i = 0; i < N; ++i) K[i] = rhs[i] / Q;  // (Q^T \ (F^T R^T))^T  (:83)
+    for (int i = 0; i < N; ++i) K[i] = rhs[i] * rq;
+  } else {
+#pragma unroll
+    for (int i = 0; i < N; ++i) K[i] = rhs[i] / Q;  // (Q^T \ (F^T R^T))^T  (:83)
+  }
 #pragma unroll
   for (int i = 0; i < N; ++i) m[i] = a[i] + K[i] * e;
   smm<N, 1, N, false, true>(K, F, D);  // K F^T

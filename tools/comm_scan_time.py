@@ -21,6 +21,7 @@ from bayesian_dlms_b200.sharding import shard_range  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--logT", type=int, default=24)
 ap.add_argument("--reps", type=int, default=10)
+ap.add_argument("--only", choices=("nccl", "peer"), default=None)
 a = ap.parse_args()
 world = torch.cuda.device_count()
 T = 1 << a.logT
@@ -28,6 +29,8 @@ params = dict(V=[[3.0]], W=np.diag([2.0, 1.0]), m0=np.zeros(2), C0=100.0 * np.ey
 g = torch.Generator(device="cuda:0").manual_seed(20260105)
 yfull = torch.randn(T, generator=g, device="cuda:0", dtype=torch.float64).cumsum(0) * 0.1
 for peer in (False, True):
+    if a.only is not None and peer != (a.only == "peer"):
+        continue
     if peer:
         os.environ.pop("BDLM_COMM_NO_PEER", None)
     else:
