@@ -410,13 +410,31 @@ void build_fwd_table(const ScanModel<N> &md, FwdTable<N> &tb) {
   }
 }
 
+// (m, C) or (s, S) handed over by value: no host buffer outlives the call.
+template <int N>
+struct StateArg {
+  double v[N + N * N];
+};
+template <int N>
+StateArg<N> state_arg(const double *host) {
+  StateArg<N> s;
+  for (int k = 0; k < N + N * N; ++k) s.v[k] = host ? host[k] : 0.0;
+  return s;
+}
+
 template <int N, bool VEC>
 __global__ void __launch_bounds__(128)
 fwd_reduce_kernel(const ScanModel<N> md, const FwdTable<N> *__restrict__ tb,
                   const double *__restrict__ y, int64_t T, int64_t M, int keep_init,
-                  FElem<N> *agg /* [M + 1], slot 0 reserved for the start element */) {
+                  FElem<N> *agg /* [M + 1], slot 0 = the start element */,
+                  const StateArg<N> start, bool identity_start) {
   const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (c >= M) return;
+  if (c == 0) {  // slot 0: the state before the chunk, or the identity (aggregate-only phases)
+    FElem<N> e0;
+    if (identity_start) f_identity<N>(e0); else f_state<N>(e0, start.v, start.v + N);
+    agg[0] = e0;
+  }
   const int64_t rows = T + keep_init;
   const int64_t r0 = c * kSub, r1 = (r0 + kSub < rows) ? r0 + kSub : rows;
   const int64_t t0 = first_step(c, keep_init), t1 = r1 - keep_init;
@@ -595,8 +613,11 @@ add_prefix_kernel(E *x, int64_t M, const E *totals /* scanned, scan order */) {
   }
 }
 
+// defer_top: leave the top level's block prefixes unapplied -- the consumer (apply sweep) composes
+// scratch[block - 1] itself, which saves a read-modify-write pass over the whole element array.
 template <class E, bool IDXREV, bool OPREV>
-cudaError_t device_scan(E *x, int64_t M, E *scratch, cudaStream_t stream, int64_t *launches) {
+cudaError_t device_scan(E *x, int64_t M, E *scratch, cudaStream_t stream, int64_t *launches,
+                        bool defer_top = false) {
   if (M <= 1) return cudaSuccess;
   const int64_t per_block = kScanBlock * kPer;
   const int64_t nb = (M + per_block - 1) / per_block;
@@ -610,8 +631,10 @@ cudaError_t device_scan(E *x, int64_t M, E *scratch, cudaStream_t stream, int64_
   if (nb > 1) {
     e = device_scan<E, false, OPREV>(scratch, nb, scratch + nb, stream, launches);
     if (e != cudaSuccess) return e;
-    add_prefix_kernel<E, IDXREV, OPREV><<<(unsigned)nb, kScanBlock, 0, stream>>>(x, M, scratch);
-    ++*launches;
+    if (!defer_top) {
+      add_prefix_kernel<E, IDXREV, OPREV><<<(unsigned)nb, kScanBlock, 0, stream>>>(x, M, scratch);
+      ++*launches;
+    }
   }
   return cudaGetLastError();
 }
@@ -669,16 +692,23 @@ fwd_apply_kernel(const ScanModel<N> md, const double *__restrict__ y, int64_t T,
                  const FElem<N> *pre /* [M+1] inclusive scan with slot 0 = start */,
                  int keep_init, KfViews kf, int32_t *status,
                  SElem<N> *sagg /* FUSE: smoother level-1 aggregates */, int64_t nrows,
-                 const FElem<N> *carry /* multi-GPU: everything before this chunk, or nullptr */) {
+                 const FElem<N> *carry /* multi-GPU: everything before this chunk, or nullptr */,
+                 const FElem<N> *tot /* scanned level-2 block totals whose prefix `pre` still lacks, or nullptr */) {
   const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (c >= M) return;
   const int64_t rows = T + keep_init;
   const int64_t r0 = c * kSub, r1 = (r0 + kSub < rows) ? r0 + kSub : rows;
   double m[N], C[N * N], W[N * N], an[N], Rn[N * N];
   int st = 0;
-  if (carry) {  // the scan ran with an identity start: compose the carry on the fly
-    FElem<N> o;
-    f_combine<N>(*carry, pre[c], o);
+  const int64_t blk = c / (kScanBlock * kPer);  // level-2 block of scan position c
+  const bool use_tot = tot && blk > 0;
+  if (carry || use_tot) {
+    // the scan ran with an identity start (carry) and / or left its top-level block prefix to us:
+    // compose them on the fly; only (b, C) of the result is live, the rest folds away
+    FElem<N> left, o;
+    if (carry && use_tot) f_combine<N>(*carry, tot[blk - 1], left);
+    else left = carry ? *carry : tot[blk - 1];
+    f_combine<N>(left, pre[c], o);
 #pragma unroll
     for (int k = 0; k < N; ++k) m[k] = o.b[k];
 #pragma unroll
@@ -815,15 +845,24 @@ __global__ void __launch_bounds__(128, BDLM_SCAN_MINB)
 bwd_apply_kernel(const ScanModel<N> md, View fm, View fC, int64_t nrows, int64_t M,
                  const SElem<N> *suf /* [M+1] suffix-inclusive scan, slot M = terminal */,
                  View sv, View Sv, int32_t *status,
-                 const SElem<N> *carry /* multi-GPU: everything after this chunk, or nullptr */) {
+                 const SElem<N> *carry /* multi-GPU: everything after this chunk, or nullptr */,
+                 const SElem<N> *tot /* scanned level-2 block totals (scan order) `suf` still lacks, or nullptr */) {
   const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (c >= M) return;
   const int64_t r0 = c * kSub, r1 = (r0 + kSub < nrows) ? r0 + kSub : nrows;
   double W[N * N], s[N], S[N * N];
   int st = 0;
-  if (carry) {
+  const int64_t blk = (M - (c + 1)) / (kScanBlock * kPer);  // suffix scan: position = M - index
+  const bool use_tot = tot && blk > 0;
+  if (carry || use_tot) {
     SElem<N> o;
-    s_combine<N>(suf[c + 1], *carry, o);
+    if (carry && use_tot) {
+      SElem<N> mid;
+      s_combine<N>(suf[c + 1], tot[blk - 1], mid);  // later blocks of this chunk
+      s_combine<N>(mid, *carry, o);                  // later chunks
+    } else {
+      s_combine<N>(suf[c + 1], carry ? *carry : tot[blk - 1], o);
+    }
 #pragma unroll
     for (int k = 0; k < N * N; ++k) S[k] = o.L[k];
 #pragma unroll
@@ -877,23 +916,6 @@ bwd_apply_kernel(const ScanModel<N> md, View fm, View fC, int64_t nrows, int64_t
   if (status && st) atomicOr(status, st);
 }
 
-// (m, C) or (s, S) handed over by value: no host buffer outlives the call.
-template <int N>
-struct StateArg {
-  double v[N + N * N];
-};
-template <int N>
-StateArg<N> state_arg(const double *host) {
-  StateArg<N> s;
-  for (int k = 0; k < N + N * N; ++k) s.v[k] = host ? host[k] : 0.0;
-  return s;
-}
-template <int N>
-__global__ void set_f_start(FElem<N> *slot, const StateArg<N> mC, bool identity) {
-  FElem<N> e;
-  if (identity) f_identity<N>(e); else f_state<N>(e, mC.v, mC.v + N);
-  *slot = e;
-}
 template <int N>
 __global__ void set_s_terminal(SElem<N> *slot, const StateArg<N> sS, const double *sS_dev,
                                bool identity) {
@@ -903,8 +925,10 @@ __global__ void set_s_terminal(SElem<N> *slot, const StateArg<N> sS, const doubl
   else s_state<N>(e, sS.v, sS.v + N);
   *slot = e;
 }
+// last chunk: s_T = m_T, S_T = C_T go to the outputs and become the terminal element of the scan
 template <int N>
-__global__ void copy_last_row(View fm, View fC, int64_t row, View sv, View Sv, double *sS) {
+__global__ void terminal_from_last_row(View fm, View fC, int64_t row, View sv, View Sv, SElem<N> *slot) {
+  double sS[N + N * N];
   for (int k = 0; k < N; ++k) {
     const double v = fm.ptr[row * fm.sr + k * fm.sk];
     if (sv.ptr) sv.ptr[row * sv.sr + k * sv.sk] = v;
@@ -915,6 +939,9 @@ __global__ void copy_last_row(View fm, View fC, int64_t row, View sv, View Sv, d
     if (Sv.ptr) Sv.ptr[row * Sv.sr + k * Sv.sk] = v;
     sS[N + k] = v;
   }
+  SElem<N> e;
+  s_state<N>(e, sS, sS + N);
+  *slot = e;
 }
 
 // ---- peer-mailbox exchange of the chunk aggregates (single-process communicators, comm.cu) ----
@@ -1019,6 +1046,7 @@ cudaError_t scan_forward(const ScanArgs &a, cudaStream_t stream, int64_t *launch
   FElem<N> *X = reinterpret_cast<FElem<N> *>(a.workspace);       // [M + 1]
   FElem<N> *scratch = X + (M + 1);                                // block totals
   const unsigned blocks = (unsigned)((M + 127) / 128);
+  const int64_t nb = (M + 1 + kScanBlock * kPer - 1) / (kScanBlock * kPer);  // level-2 blocks over X
   FwdTable<N> *tb = reinterpret_cast<FwdTable<N> *>(a.table);
   if (a.table_upload) {  // model changed since the context last built it
     static_assert(sizeof(FwdTable<N>) <= kScanTableBytes, "table buffer too small");
@@ -1034,26 +1062,28 @@ cudaError_t scan_forward(const ScanArgs &a, cudaStream_t stream, int64_t *launch
     // reduce / dist local: chunk aggregate only (identity start); apply: prefix of
     // (start (x) aggregates), a.start = host (m, C) of the state before t = 0
     const bool ident = reduce || local;
-    set_f_start<N><<<1, 1, 0, stream>>>(X, state_arg<N>(ident ? nullptr : a.start), ident);
+    const StateArg<N> st0 = state_arg<N>(ident ? nullptr : a.start);
     if ((reinterpret_cast<uintptr_t>(a.y) & 31) == 0)
-      fwd_reduce_kernel<N, true><<<blocks, 128, 0, stream>>>(md, tb, a.y, T, M, a.keep_init, X);
+      fwd_reduce_kernel<N, true><<<blocks, 128, 0, stream>>>(md, tb, a.y, T, M, a.keep_init, X, st0, ident);
     else
-      fwd_reduce_kernel<N, false><<<blocks, 128, 0, stream>>>(md, tb, a.y, T, M, a.keep_init, X);
-    *launches += 2;
+      fwd_reduce_kernel<N, false><<<blocks, 128, 0, stream>>>(md, tb, a.y, T, M, a.keep_init, X, st0, ident);
+    ++*launches;
     CK(cudaGetLastError());
-    CK((device_scan<FElem<N>, false, false>(X, M + 1, scratch, stream, launches)));
+    CK((device_scan<FElem<N>, false, false>(X, M + 1, scratch, stream, launches, /*defer_top=*/true)));
+    // the whole chunk: last element of a one-block scan, else the last scanned block total
+    const FElem<N> *whole = nb > 1 ? scratch + (nb - 1) : X + M;
     if (reduce) {
-      CK(cudaMemcpyAsync(a.agg_out, X + M, sizeof(FElem<N>), cudaMemcpyDeviceToHost, stream));
+      CK(cudaMemcpyAsync(a.agg_out, whole, sizeof(FElem<N>), cudaMemcpyDeviceToHost, stream));
       return cudaStreamSynchronize(stream);
     }
     if (local) {
       if (a.peers.world > 0) {  // straight into every peer's mailbox over NVLink
-        publish_kernel<FElem<N>><<<a.peers.world, 64, 0, stream>>>(X + M, a.peers, a.rank, a.epoch_dev);
+        publish_kernel<FElem<N>><<<a.peers.world, 64, 0, stream>>>(whole, a.peers, a.rank, a.epoch_dev);
         ++*launches;
         return cudaGetLastError();
       }
       // stays on the device: the caller all-gathers it (NCCL) on the same stream
-      return cudaMemcpyAsync(a.agg_dev, X + M, sizeof(FElem<N>), cudaMemcpyDeviceToDevice, stream);
+      return cudaMemcpyAsync(a.agg_dev, whole, sizeof(FElem<N>), cudaMemcpyDeviceToDevice, stream);
     }
   } else {
     // X still holds this rank's scanned prefixes from the local phase
@@ -1071,9 +1101,10 @@ cudaError_t scan_forward(const ScanArgs &a, cudaStream_t stream, int64_t *launch
   SElem<N> *sagg = reinterpret_cast<SElem<N> *>(a.fuse_sagg);
   const int64_t nrows = T + a.keep_init - (a.has_successor ? 0 : 1);
   const FElem<N> *cr = finish ? carry : nullptr;
+  const FElem<N> *tot = nb > 1 ? scratch : nullptr;  // top-level block prefixes, composed by the sweep
 #define BDLM_FWD_APPLY(VEC_, FUSE_)                                                         \
   fwd_apply_kernel<N, VEC_, FUSE_><<<blocks, 128, 0, stream>>>(md, a.y, T, M, X, a.keep_init, \
-                                                               a.kf, a.status, sagg, nrows, cr)
+                                                               a.kf, a.status, sagg, nrows, cr, tot)
   if (vec && sagg) BDLM_FWD_APPLY(true, true);
   else if (vec) BDLM_FWD_APPLY(true, false);
   else if (sagg) BDLM_FWD_APPLY(false, true);
@@ -1095,6 +1126,7 @@ cudaError_t scan_backward(const ScanArgs &a, cudaStream_t stream, int64_t *launc
   SElem<N> *scratch = X + (M + 1);
   double *term_dev = reinterpret_cast<double *>(scratch + (M + 1) / kScanBlock * 2 + 8);
   const unsigned blocks = (unsigned)((M + 127) / 128);
+  const int64_t nb = (M + 1 + kScanBlock * kPer - 1) / (kScanBlock * kPer);  // level-2 blocks over X
   const bool reduce = a.phase == kScanReduce, local = a.phase == kScanDistLocal,
              finish = a.phase == kScanDistFinish;
   const StateArg<N> none = state_arg<N>(nullptr);
@@ -1107,9 +1139,7 @@ cudaError_t scan_backward(const ScanArgs &a, cudaStream_t stream, int64_t *launc
     } else if (a.has_successor) {
       set_s_terminal<N><<<1, 1, 0, stream>>>(X + M, state_arg<N>(a.start), nullptr, false);
     } else {  // last chunk: s_T = m_T, S_T = C_T (Smoothing.scala:59-61)
-      copy_last_row<N><<<1, 1, 0, stream>>>(a.kf.m, a.kf.C, rows - 1, a.s, a.S, term_dev);
-      set_s_terminal<N><<<1, 1, 0, stream>>>(X + M, none, term_dev, false);
-      ++*launches;
+      terminal_from_last_row<N><<<1, 1, 0, stream>>>(a.kf.m, a.kf.C, rows - 1, a.s, a.S, X + M);
     }
     ++*launches;
     if (M > 0 && !a.pre_reduced) {
@@ -1118,18 +1148,19 @@ cudaError_t scan_backward(const ScanArgs &a, cudaStream_t stream, int64_t *launc
       ++*launches;
     }
     CK(cudaGetLastError());
-    CK((device_scan<SElem<N>, true, true>(X, M + 1, scratch, stream, launches)));
+    CK((device_scan<SElem<N>, true, true>(X, M + 1, scratch, stream, launches, /*defer_top=*/true)));
+    const SElem<N> *whole = nb > 1 ? scratch + (nb - 1) : X;  // the whole chunk (suffix scan ends at index 0)
     if (reduce) {
-      CK(cudaMemcpyAsync(a.agg_out, X, sizeof(SElem<N>), cudaMemcpyDeviceToHost, stream));
+      CK(cudaMemcpyAsync(a.agg_out, whole, sizeof(SElem<N>), cudaMemcpyDeviceToHost, stream));
       return cudaStreamSynchronize(stream);
     }
     if (local) {
       if (a.peers.world > 0) {
-        publish_kernel<SElem<N>><<<a.peers.world, 64, 0, stream>>>(X, a.peers, a.rank, a.epoch_dev);
+        publish_kernel<SElem<N>><<<a.peers.world, 64, 0, stream>>>(whole, a.peers, a.rank, a.epoch_dev);
         ++*launches;
         return cudaGetLastError();
       }
-      return cudaMemcpyAsync(a.agg_dev, X, sizeof(SElem<N>), cudaMemcpyDeviceToDevice, stream);
+      return cudaMemcpyAsync(a.agg_dev, whole, sizeof(SElem<N>), cudaMemcpyDeviceToDevice, stream);
     }
   } else if (a.has_successor) {
     fold_backward_kernel<N><<<1, 1, 0, stream>>>(reinterpret_cast<const SElem<N> *>(a.aggs_dev),
@@ -1137,11 +1168,12 @@ cudaError_t scan_backward(const ScanArgs &a, cudaStream_t stream, int64_t *launc
     ++*launches;
   }
   const SElem<N> *cr = (finish && a.has_successor) ? carry : nullptr;
+  const SElem<N> *tot = nb > 1 ? scratch : nullptr;
   if (M > 0) {
     if (vec)
-      bwd_apply_kernel<N, true><<<blocks, 128, 0, stream>>>(md, a.kf.m, a.kf.C, nrows, M, X, a.s, a.S, a.status, cr);
+      bwd_apply_kernel<N, true><<<blocks, 128, 0, stream>>>(md, a.kf.m, a.kf.C, nrows, M, X, a.s, a.S, a.status, cr, tot);
     else
-      bwd_apply_kernel<N, false><<<blocks, 128, 0, stream>>>(md, a.kf.m, a.kf.C, nrows, M, X, a.s, a.S, a.status, cr);
+      bwd_apply_kernel<N, false><<<blocks, 128, 0, stream>>>(md, a.kf.m, a.kf.C, nrows, M, X, a.s, a.S, a.status, cr, tot);
     ++*launches;
   }
   return cudaGetLastError();
