@@ -23,6 +23,7 @@
 // Parity: equals the sequential kernel in textbook-smoother mode to 1e-9 relative (for n = 1
 // that is the reference itself); the apply phases reuse the sequential step code, so the
 // only difference is the rounding of the scanned start states.
+#include <cmath>
 #include <cstdlib>
 #include <vector>
 
@@ -228,7 +229,7 @@ namespace {
 constexpr int kSub = BDLM_SCAN_SUB;  // ROWS per thread (level 1); multiple of kGrp
 constexpr int kGrp = 4;        // rows per vector group: 4 rows x K doubles = K 32-byte sectors
 constexpr int kScanBlock = 256;
-constexpr size_t kScanTableBytes = 64 << 10;
+constexpr size_t kScanTableBytes = (size_t)(kSub > 64 ? 128 : 64) << 10;
 
 template <int N>
 struct ScanModel {
@@ -242,8 +243,8 @@ struct ScanModel {
 // piecemeal: the partially written lines of all resident threads (6 fields x 128 B x 2.6e5
 // threads at T = 2^24) exceed L2, so 8-byte stores were evicted half-filled and cost a DRAM
 // read-fill plus a second write (ncu: 245 MB read, 596 MB written for 470 MB of output).
-__device__ __forceinline__ int64_t first_step(int64_t c, int keep_init) {
-  const int64_t t = c * kSub - keep_init;
+__device__ __forceinline__ int64_t first_step(int64_t c, int keep_init, int sub) {
+  const int64_t t = c * (int64_t)sub - keep_init;
   return t < 0 ? 0 : t;
 }
 
@@ -427,7 +428,7 @@ __global__ void __launch_bounds__(128)
 fwd_reduce_kernel(const ScanModel<N> md, const FwdTable<N> *__restrict__ tb,
                   const double *__restrict__ y, int64_t T, int64_t M, int keep_init,
                   FElem<N> *agg /* [M + 1], slot 0 = the start element */,
-                  const StateArg<N> start, bool identity_start) {
+                  const StateArg<N> start, bool identity_start, int sub) {
   const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (c >= M) return;
   if (c == 0) {  // slot 0: the state before the chunk, or the identity (aggregate-only phases)
@@ -436,8 +437,8 @@ fwd_reduce_kernel(const ScanModel<N> md, const FwdTable<N> *__restrict__ tb,
     agg[0] = e0;
   }
   const int64_t rows = T + keep_init;
-  const int64_t r0 = c * kSub, r1 = (r0 + kSub < rows) ? r0 + kSub : rows;
-  const int64_t t0 = first_step(c, keep_init), t1 = r1 - keep_init;
+  const int64_t r0 = c * (int64_t)sub, r1 = (r0 + sub < rows) ? r0 + sub : rows;
+  const int64_t t0 = first_step(c, keep_init, sub), t1 = r1 - keep_init;
   double b[N], eta[N];
 #pragma unroll
   for (int i = 0; i < N; ++i) { b[i] = 0.0; eta[i] = 0.0; }
@@ -693,11 +694,12 @@ fwd_apply_kernel(const ScanModel<N> md, const double *__restrict__ y, int64_t T,
                  int keep_init, KfViews kf, int32_t *status,
                  SElem<N> *sagg /* FUSE: smoother level-1 aggregates */, int64_t nrows,
                  const FElem<N> *carry /* multi-GPU: everything before this chunk, or nullptr */,
-                 const FElem<N> *tot /* scanned level-2 block totals whose prefix `pre` still lacks, or nullptr */) {
+                 const FElem<N> *tot /* scanned level-2 block totals whose prefix `pre` still lacks, or nullptr */,
+                 int sub) {
   const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (c >= M) return;
   const int64_t rows = T + keep_init;
-  const int64_t r0 = c * kSub, r1 = (r0 + kSub < rows) ? r0 + kSub : rows;
+  const int64_t r0 = c * (int64_t)sub, r1 = (r0 + sub < rows) ? r0 + sub : rows;
   double m[N], C[N * N], W[N * N], an[N], Rn[N * N];
   int st = 0;
   const int64_t blk = c / (kScanBlock * kPer);  // level-2 block of scan position c
@@ -767,10 +769,10 @@ fwd_apply_kernel(const ScanModel<N> md, const double *__restrict__ y, int64_t T,
 template <int N, bool VEC>
 __global__ void __launch_bounds__(128)
 bwd_reduce_kernel(const ScanModel<N> md, View fm, View fC, int64_t nrows, int64_t M,
-                  SElem<N> *agg /* [M + 1], slot M reserved for the terminal element */) {
+                  SElem<N> *agg /* [M + 1], slot M reserved for the terminal element */, int sub) {
   const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (c >= M) return;
-  const int64_t r0 = c * kSub, r1 = (r0 + kSub < nrows) ? r0 + kSub : nrows;
+  const int64_t r0 = c * (int64_t)sub, r1 = (r0 + sub < nrows) ? r0 + sub : nrows;
   double W[N * N];
 #pragma unroll
   for (int k = 0; k < N * N; ++k) W[k] = md.W[k];
@@ -846,10 +848,11 @@ bwd_apply_kernel(const ScanModel<N> md, View fm, View fC, int64_t nrows, int64_t
                  const SElem<N> *suf /* [M+1] suffix-inclusive scan, slot M = terminal */,
                  View sv, View Sv, int32_t *status,
                  const SElem<N> *carry /* multi-GPU: everything after this chunk, or nullptr */,
-                 const SElem<N> *tot /* scanned level-2 block totals (scan order) `suf` still lacks, or nullptr */) {
+                 const SElem<N> *tot /* scanned level-2 block totals (scan order) `suf` still lacks, or nullptr */,
+                 int sub) {
   const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (c >= M) return;
-  const int64_t r0 = c * kSub, r1 = (r0 + kSub < nrows) ? r0 + kSub : nrows;
+  const int64_t r0 = c * (int64_t)sub, r1 = (r0 + sub < nrows) ? r0 + sub : nrows;
   double W[N * N], s[N], S[N * N];
   int st = 0;
   const int64_t blk = (M - (c + 1)) / (kScanBlock * kPer);  // suffix scan: position = M - index
@@ -1023,6 +1026,62 @@ __global__ void fold_backward_kernel(const SElem<N> *aggs, int rank, int world, 
   *carry = e;
 }
 
+// ---- rows per thread (level-1 granularity), chosen per call ------------------------------------
+// The two apply sweeps are register-heavy (3 resident blocks of 128 threads per SM for n = 2), so
+// their time goes in WAVES of `slots` blocks, each as long as one thread's `sub` rows; the level-2
+// scan costs per element, i.e. per T / sub.  A fixed 64 rows per thread left 2^22 rows with 512
+// blocks for 444 slots (a second, almost empty wave) and 2^21 rows with every thread serially
+// walking 64 rows on a 58 % occupied GPU.  Cost model fitted on B200 (profiles/r2_tuning.txt).
+template <int N>
+int apply_slots() {
+  static const int slots = [] {  // devices of one process are alike
+    int dev = 0, sms = 0, bf = 0, bb = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bf, fwd_apply_kernel<N, true, true>, 128, 0) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bb, bwd_apply_kernel<N, true>, 128, 0) != cudaSuccess) {
+      cudaGetLastError();
+      return 148 * 2;
+    }
+    const int b = bf < bb ? bf : bb;
+    return sms * (b < 1 ? 1 : b);
+  }();
+  return slots;
+}
+
+int scan_rows_per_thread(int n, int64_t T) {
+  static const int forced = [] {
+    const char *e = std::getenv("BDLM_SCAN_ROWS");  // A/B knob: fixed rows per thread
+    const int v = e ? std::atoi(e) : 0;
+    return (v >= kGrp && v <= kSub && v % kGrp == 0) ? v : 0;
+  }();
+  if (forced) return forced;
+  int slots = 444;
+  switch (n) {
+    case 1: slots = apply_slots<1>(); break;
+    case 2: slots = apply_slots<2>(); break;
+    case 3: slots = apply_slots<3>(); break;
+    case 4: slots = apply_slots<4>(); break;
+    default: break;
+  }
+  const double rows = (double)(T + 1);
+  int best = kSub;
+  double best_cost = 1e300;
+  // multiples of 16 rows only: a thread's run of every output field then starts on a 128-byte line
+  // even for n = 1 (8 bytes per row); 60 rows per thread cost n = 1 13 % (lines shared by two threads)
+  for (int sub = 16; sub <= kSub; sub += 16) {
+    const double blocks = std::ceil(rows / (sub * 128.0));
+    const double waves = blocks / slots;
+    // a partly filled last wave is cheaper than a full one where the sweep is throughput-bound,
+    // as long where it is latency-bound: take the middle
+    const double sweep = 3.1 * sub * 0.5 * (std::ceil(waves) + waves);  // us
+    const double level2 = 0.00057 * rows / sub;                         // us
+    const double cost = sweep + level2;
+    if (cost < best_cost) { best_cost = cost; best = sub; }
+  }
+  return best;
+}
+
 template <int N>
 ScanModel<N> make_model(const ScanArgs &a) {
   ScanModel<N> md;
@@ -1042,7 +1101,8 @@ static bool dense_aligned(const View &v, int64_t K) {
 template <int N>
 cudaError_t scan_forward(const ScanArgs &a, cudaStream_t stream, int64_t *launches) {
   const ScanModel<N> md = make_model<N>(a);
-  const int64_t T = a.T, M = (T + a.keep_init + kSub - 1) / kSub;
+  const int sub = scan_rows_per_thread(a.n, a.T);
+  const int64_t T = a.T, M = (T + a.keep_init + sub - 1) / sub;
   FElem<N> *X = reinterpret_cast<FElem<N> *>(a.workspace);       // [M + 1]
   FElem<N> *scratch = X + (M + 1);                                // block totals
   const unsigned blocks = (unsigned)((M + 127) / 128);
@@ -1064,9 +1124,9 @@ cudaError_t scan_forward(const ScanArgs &a, cudaStream_t stream, int64_t *launch
     const bool ident = reduce || local;
     const StateArg<N> st0 = state_arg<N>(ident ? nullptr : a.start);
     if ((reinterpret_cast<uintptr_t>(a.y) & 31) == 0)
-      fwd_reduce_kernel<N, true><<<blocks, 128, 0, stream>>>(md, tb, a.y, T, M, a.keep_init, X, st0, ident);
+      fwd_reduce_kernel<N, true><<<blocks, 128, 0, stream>>>(md, tb, a.y, T, M, a.keep_init, X, st0, ident, sub);
     else
-      fwd_reduce_kernel<N, false><<<blocks, 128, 0, stream>>>(md, tb, a.y, T, M, a.keep_init, X, st0, ident);
+      fwd_reduce_kernel<N, false><<<blocks, 128, 0, stream>>>(md, tb, a.y, T, M, a.keep_init, X, st0, ident, sub);
     ++*launches;
     CK(cudaGetLastError());
     CK((device_scan<FElem<N>, false, false>(X, M + 1, scratch, stream, launches, /*defer_top=*/true)));
@@ -1104,7 +1164,7 @@ cudaError_t scan_forward(const ScanArgs &a, cudaStream_t stream, int64_t *launch
   const FElem<N> *tot = nb > 1 ? scratch : nullptr;  // top-level block prefixes, composed by the sweep
 #define BDLM_FWD_APPLY(VEC_, FUSE_)                                                         \
   fwd_apply_kernel<N, VEC_, FUSE_><<<blocks, 128, 0, stream>>>(md, a.y, T, M, X, a.keep_init, \
-                                                               a.kf, a.status, sagg, nrows, cr, tot)
+                                                               a.kf, a.status, sagg, nrows, cr, tot, sub)
   if (vec && sagg) BDLM_FWD_APPLY(true, true);
   else if (vec) BDLM_FWD_APPLY(true, false);
   else if (sagg) BDLM_FWD_APPLY(false, true);
@@ -1121,7 +1181,8 @@ cudaError_t scan_backward(const ScanArgs &a, cudaStream_t stream, int64_t *launc
   // rows with a successor inside this chunk: all but the last, plus the last when the chunk
   // is followed by another one (has_successor)
   const int64_t nrows = a.has_successor ? rows : rows - 1;
-  const int64_t M = (nrows + kSub - 1) / kSub;
+  const int sub = scan_rows_per_thread(a.n, a.T);
+  const int64_t M = (nrows + sub - 1) / sub;
   SElem<N> *X = reinterpret_cast<SElem<N> *>(a.workspace);  // [M + 1]
   SElem<N> *scratch = X + (M + 1);
   double *term_dev = reinterpret_cast<double *>(scratch + (M + 1) / kScanBlock * 2 + 8);
@@ -1143,8 +1204,8 @@ cudaError_t scan_backward(const ScanArgs &a, cudaStream_t stream, int64_t *launc
     }
     ++*launches;
     if (M > 0 && !a.pre_reduced) {
-      if (vec) bwd_reduce_kernel<N, true><<<blocks, 128, 0, stream>>>(md, a.kf.m, a.kf.C, nrows, M, X);
-      else bwd_reduce_kernel<N, false><<<blocks, 128, 0, stream>>>(md, a.kf.m, a.kf.C, nrows, M, X);
+      if (vec) bwd_reduce_kernel<N, true><<<blocks, 128, 0, stream>>>(md, a.kf.m, a.kf.C, nrows, M, X, sub);
+      else bwd_reduce_kernel<N, false><<<blocks, 128, 0, stream>>>(md, a.kf.m, a.kf.C, nrows, M, X, sub);
       ++*launches;
     }
     CK(cudaGetLastError());
@@ -1171,9 +1232,9 @@ cudaError_t scan_backward(const ScanArgs &a, cudaStream_t stream, int64_t *launc
   const SElem<N> *tot = nb > 1 ? scratch : nullptr;
   if (M > 0) {
     if (vec)
-      bwd_apply_kernel<N, true><<<blocks, 128, 0, stream>>>(md, a.kf.m, a.kf.C, nrows, M, X, a.s, a.S, a.status, cr, tot);
+      bwd_apply_kernel<N, true><<<blocks, 128, 0, stream>>>(md, a.kf.m, a.kf.C, nrows, M, X, a.s, a.S, a.status, cr, tot, sub);
     else
-      bwd_apply_kernel<N, false><<<blocks, 128, 0, stream>>>(md, a.kf.m, a.kf.C, nrows, M, X, a.s, a.S, a.status, cr, tot);
+      bwd_apply_kernel<N, false><<<blocks, 128, 0, stream>>>(md, a.kf.m, a.kf.C, nrows, M, X, a.s, a.S, a.status, cr, tot, sub);
     ++*launches;
   }
   return cudaGetLastError();
@@ -1182,7 +1243,8 @@ cudaError_t scan_backward(const ScanArgs &a, cudaStream_t stream, int64_t *launc
 }  // namespace
 
 size_t scan_workspace_bytes(int n, int64_t T) {
-  const int64_t M = (T + 1 + kSub - 1) / kSub + 2;
+  const int sub = scan_rows_per_thread(n, T);
+  const int64_t M = (T + 1 + sub - 1) / sub + 2;
   const size_t elem = sizeof(double) * (3 * n * n + 2 * n);
   return elem * (size_t)(M + 1 + (M + 1) / kScanBlock * 2 + 24) + 8192;
 }
