@@ -61,28 +61,33 @@ struct Nccl {
   std::string err;
 };
 
-Nccl *nccl() {
-  static Nccl g;
-  static bool tried = false;
-  if (tried) return &g;
-  tried = true;
+void nccl_load(Nccl &g) {
   const char *names[] = {std::getenv("BDLM_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+  std::string why;
   for (const char *nm : names) {
     if (!nm || !*nm) continue;
     g.h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
     if (g.h) break;
+    const char *e = dlerror();  // one call: dlerror() clears the message it returns
+    if (e) why = e;
   }
-  if (!g.h) { g.err = std::string("cannot load NCCL (libnccl.so.2): ") + (dlerror() ? dlerror() : ""); return &g; }
+  if (!g.h) { g.err = "cannot load NCCL (libnccl.so.2): " + why; return; }
 #define SYM(field, name)                                                       \
   *reinterpret_cast<void **>(&g.field) = dlsym(g.h, name);                     \
-  if (!g.field) { g.err = std::string("NCCL symbol missing: ") + name; g.h = nullptr; return &g; }
+  if (!g.field) { g.err = std::string("NCCL symbol missing: ") + name; g.h = nullptr; return; }
   SYM(GetUniqueId, "ncclGetUniqueId") SYM(CommInitRank, "ncclCommInitRank")
   SYM(CommInitAll, "ncclCommInitAll") SYM(CommDestroy, "ncclCommDestroy")
   SYM(AllReduce, "ncclAllReduce") SYM(AllGather, "ncclAllGather")
   SYM(GroupStart, "ncclGroupStart") SYM(GroupEnd, "ncclGroupEnd")
   SYM(GetErrorString, "ncclGetErrorString")
 #undef SYM
-  return &g;
+}
+
+Nccl *nccl() {
+  // function-local static: initialised once, thread-safe (communicators may be created from
+  // several host threads)
+  static Nccl *g = [] { Nccl *x = new Nccl(); nccl_load(*x); return x; }();
+  return g;
 }
 
 constexpr int kMaxElem = 3 * 4 * 4 + 2 * 4;  // forward scan element at n = 4 (56 doubles)
@@ -283,6 +288,17 @@ int for_each_local(bdlm_comm *m, Fn fn) {
   return worst ? worst : numeric;
 }
 
+// The sub-batch [lo, hi) of the NEXT call on a context.  dispatch() consumes it, but a call that
+// fails validation never gets there: the guard clears it on every path, so a later direct call on
+// the same context (bdlm_comm_ctx) cannot inherit a stale shard.
+struct ShardRange {
+  bdlm_ctx *c;
+  ShardRange(bdlm_ctx *ctx, int64_t lo, int64_t hi) : c(ctx) { ctx_set_range(c, lo, hi); }
+  ~ShardRange() { ctx_set_range(c, -1, -1); }
+  ShardRange(const ShardRange &) = delete;
+  ShardRange &operator=(const ShardRange &) = delete;
+};
+
 int check_sharded(bdlm_comm *m, const bdlm_problem *p) {
   if (!m) return cfail(nullptr, BDLM_E_ARG, "null communicator");
   if (!p) return cfail(m, BDLM_E_ARG, "null problem");
@@ -451,7 +467,7 @@ int bdlm_comm_kf_filter_smooth(bdlm_comm *m, const bdlm_problem *p, const bdlm_k
   if (rc) return rc;
   const std::vector<int64_t> cut = cuts(m, p->B);
   return for_each_local(m, [&](int i) {
-    ctx_set_range(m->loc[i].ctx, cut[i], cut[i + 1]);
+    ShardRange shard_(m->loc[i].ctx, cut[i], cut[i + 1]);
     return bdlm_kf_filter_smooth(m->loc[i].ctx, p, kf, sm, status);
   });
 }
@@ -461,7 +477,7 @@ int bdlm_comm_kf_filter(bdlm_comm *m, const bdlm_problem *p, const bdlm_kf_out *
   if (rc) return rc;
   const std::vector<int64_t> cut = cuts(m, p->B);
   return for_each_local(m, [&](int i) {
-    ctx_set_range(m->loc[i].ctx, cut[i], cut[i + 1]);
+    ShardRange shard_(m->loc[i].ctx, cut[i], cut[i + 1]);
     return bdlm_kf_filter(m->loc[i].ctx, p, out, status);
   });
 }
@@ -471,7 +487,7 @@ int bdlm_comm_svd_filter(bdlm_comm *m, const bdlm_problem *p, const bdlm_svd_out
   if (rc) return rc;
   const std::vector<int64_t> cut = cuts(m, p->B);
   return for_each_local(m, [&](int i) {
-    ctx_set_range(m->loc[i].ctx, cut[i], cut[i + 1]);
+    ShardRange shard_(m->loc[i].ctx, cut[i], cut[i + 1]);
     return bdlm_svd_filter(m->loc[i].ctx, p, out, status);
   });
 }
@@ -482,7 +498,7 @@ int bdlm_comm_loglik(bdlm_comm *m, const bdlm_problem *p, double *transition, do
   if (rc) return rc;
   const std::vector<int64_t> cut = cuts(m, p->B);
   rc = for_each_local(m, [&](int i) {
-    ctx_set_range(m->loc[i].ctx, cut[i], cut[i + 1]);
+    ShardRange shard_(m->loc[i].ctx, cut[i], cut[i + 1]);
     return bdlm_loglik(m->loc[i].ctx, p, transition, innovations, status);
   });
   if (rc < 0 || !sums) return rc;
@@ -503,10 +519,13 @@ static int comm_ffbs(bdlm_comm *m, bool svd, const bdlm_problem *p, const double
   if (pooled && !stats) return cfail(m, BDLM_E_ARG, "pooled statistics need the per-chain stats arrays");
   const int n = p->n, pp = p->p;
   if (pooled && 2 * pp + n + n * n > kRedMax) return cfail(m, BDLM_E_ARG, "statistics too large");
+  if (pooled && ((pooled->ssy && !stats->ssy) || (pooled->ny && !stats->ny) ||
+                 (pooled->ssw && !stats->ssw) || (pooled->scatter && !stats->scatter)))
+    return cfail(m, BDLM_E_ARG, "pooled statistic requested without its per-chain array");
   const std::vector<int64_t> cut = cuts(m, p->B);
   // chains keep their GLOBAL Philox subsequence whatever the cut (ctx rng_first + index in the call)
   rc = for_each_local(m, [&](int i) {
-    ctx_set_range(m->loc[i].ctx, cut[i], cut[i + 1]);
+    ShardRange shard_(m->loc[i].ctx, cut[i], cut[i + 1]);
     return svd ? bdlm_svd_ffbs(m->loc[i].ctx, p, z, theta, filt, stats, status)
                : bdlm_ffbs(m->loc[i].ctx, p, z, theta, kf, stats, status);
   });
@@ -523,10 +542,7 @@ static int comm_ffbs(bdlm_comm *m, bool svd, const bdlm_problem *p, const double
   if (r2) return r2;
   off = 0;
   for (int f = 0; f < 4; ++f) {
-    if (dst[f]) {
-      if (!src[f]) return cfail(m, BDLM_E_ARG, "pooled statistic requested without its per-chain array");
-      std::memcpy(dst[f], tot.data() + off, sizeof(double) * sizes[f]);
-    }
+    if (dst[f]) std::memcpy(dst[f], tot.data() + off, sizeof(double) * sizes[f]);
     off += sizes[f];
   }
   return rc;
@@ -556,6 +572,8 @@ int bdlm_comm_scan_filter_smooth(bdlm_comm *m, const bdlm_problem *probs, const 
   const int W = m->world;
   const int n = probs[0].n;
   if (n < 1 || n > 4) return cfail(m, BDLM_E_ARG, "scan path: n <= 4");
+  for (size_t i = 1; i < m->loc.size(); ++i)
+    if (probs[i].n != n) return cfail(m, BDLM_E_ARG, "time-sharded scan: every chunk describes the same model (n differs)");
   const int ef = bdlm_scan_elem_doubles(n, 0), eb = bdlm_scan_elem_doubles(n, 1);
   // Every device's phases are enqueued by its own host thread: local scan -> exchange -> finish,
   // forwards then backwards.  With peer mailboxes nothing on the host couples the devices (the
