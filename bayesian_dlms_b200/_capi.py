@@ -32,7 +32,6 @@ SYMBOLS = [
     "bdlm_fp64_peak_tflops", "bdlm_scan_filter_smooth", "bdlm_scan_elem_doubles",
     "bdlm_scan_forward_reduce", "bdlm_scan_forward_apply", "bdlm_scan_backward_reduce",
     "bdlm_scan_backward_apply", "bdlm_scan_combine",
-    "bdlm_debug_set_pair_mode", "bdlm_debug_pair_filter_smooth_host",
     "bdlm_scan_dist_forward_local", "bdlm_scan_dist_forward_finish",
     "bdlm_scan_dist_backward_local", "bdlm_scan_dist_backward_finish",
     "bdlm_ar_filter", "bdlm_ar_ffbs", "bdlm_conjugate_filter", "bdlm_gibbs_draw",
@@ -154,9 +153,6 @@ def load():
     lib.bdlm_scan_backward_apply.argtypes = [C.c_void_p, PP, C.POINTER(KfOut), C.c_void_p,
                                              C.POINTER(SmoothOut), C.c_void_p]
     lib.bdlm_scan_combine.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
-    lib.bdlm_debug_set_pair_mode.argtypes = [C.c_int32]
-    lib.bdlm_debug_pair_filter_smooth_host.argtypes = (
-        [C.c_void_p, C.c_void_p, C.c_double] + [C.c_void_p] * 5 + [C.c_int32, C.c_int32] + [C.c_void_p] * 8)
     lib.bdlm_scan_dist_forward_local.argtypes = [C.c_void_p, PP, C.c_int32, C.c_int32, C.c_void_p]
     lib.bdlm_scan_dist_forward_finish.argtypes = [C.c_void_p, PP, C.c_int32, C.c_int32, C.c_void_p,
                                                   C.POINTER(KfOut), C.c_void_p]

@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libbdlm.so")
 SOURCES = ["api.cu", "kf_small.cu", "kf_warp.cu", "kf_group.cu", "transpose.cu", "peak.cu", "scan.cu",
-           "scalar_filters.cu", "gibbs_draw.cu", "ffbs_small.cu", "comm.cu", "kf_pair.cu"]
+           "scalar_filters.cu", "gibbs_draw.cu", "ffbs_small.cu", "comm.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-fvisibility=hidden", "--expt-relaxed-constexpr",

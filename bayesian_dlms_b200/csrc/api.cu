@@ -1233,22 +1233,6 @@ int bdlm_scan_combine(int32_t n, int32_t backward, const double *earlier, const 
   return 0;
 }
 
-int bdlm_debug_set_pair_mode(int32_t mode) {
-  if (mode < 0 || mode > 4) return BDLM_E_ARG;
-  set_pair_kernel_mode(mode);
-  return 0;
-}
-
-int bdlm_debug_pair_filter_smooth_host(const double *G, const double *F, double V, const double *W,
-                                       const double *m0, const double *C0, const double *dt,
-                                       const double *y, int32_t T, int32_t textbook, double *m,
-                                       double *C, double *a, double *R, double *f, double *Q,
-                                       double *s, double *S) {
-  if (!G || !F || !W || !m0 || !C0 || !y || T < 1 || !m || !C || !a || !R || !f || !Q || !s || !S)
-    return BDLM_E_ARG;
-  return pair_filter_smooth_host(G, F, V, W, m0, C0, dt, y, T, textbook, m, C, a, R, f, Q, s, S);
-}
-
 int bdlm_scan_forward_reduce(bdlm_ctx *c, const bdlm_problem *p, double *agg_host) {
   NvtxRange nvtx_("bdlm_scan_forward_reduce");
   int rc = scan_validate(c, p);

@@ -325,14 +325,7 @@ cudaError_t launch_kf_small(const Batch &bt, const double *hG, const double *hF,
     case 1: return launch_n<1>(bt, hG, hF, kf, sv, Sv, mode, stream, wave_series);
     case 2: return launch_n<2>(bt, hG, hF, kf, sv, Sv, mode, stream, wave_series);
     case 3: return launch_n<3>(bt, hG, hF, kf, sv, Sv, mode, stream, wave_series);
-    case 4: {
-      // opt-in: two lanes per series (kf_pair.cu); smoother-only calls that reload a, R stay here
-      const int pk = pair_kernel_mode();
-      const bool reload = mode == kDoSmooth && kf.a.ptr != nullptr && kf.R.ptr != nullptr;
-      if (pk && !reload)
-        return launch_kf_pair(pk, bt, hG, hF, kf, sv, Sv, do_filter, do_smooth, stream, wave_series);
-      return launch_n<4>(bt, hG, hF, kf, sv, Sv, mode, stream, wave_series);
-    }
+    case 4: return launch_n<4>(bt, hG, hF, kf, sv, Sv, mode, stream, wave_series);
     default: return cudaErrorInvalidValue;
   }
 }

@@ -11,21 +11,6 @@ cudaError_t launch_kf_small(const Batch &bt, const double *hG, const double *hF,
                             bool do_filter, bool do_smooth, cudaStream_t stream,
                             int *wave_series = nullptr);  // non-null: occupancy query only
 
-// kf_pair.cu: n = 4, p = 1 with two lanes per series (pair_steps.cuh).  pair_kernel_mode():
-// BDLM_KF_PAIR = 0 (kf_small.cu serves n = 4) | 1 (shuffle exchange) | 2 (shared-memory exchange)
-// at 3 resident blocks per SM, 3 | 4: the same at 4 blocks.
-int pair_kernel_mode();
-void set_pair_kernel_mode(int mode);
-cudaError_t launch_kf_pair(int pxk, const Batch &bt, const double *hG, const double *hF,
-                           const KfViews &kf, const View &sv, const View &Sv, bool do_filter,
-                           bool do_smooth, cudaStream_t stream, int *wave_series);
-// host build of the pair kernel's arithmetic for ONE series (keep_init = 1, rows = T + 1,
-// row-major [row][k] outputs, matrices column-major); dt == nullptr: regular grid
-int pair_filter_smooth_host(const double *G, const double *F, double V, const double *W,
-                            const double *m0, const double *C0, const double *dt, const double *y,
-                            int T, int textbook, double *m, double *C, double *a, double *R,
-                            double *f, double *Q, double *s, double *S);
-
 // kf_warp.cu: warp-per-series shared-memory kernels (n <= 48, p <= 32).
 struct SvdViews {
   View m, dc, uc, a, dr, ur, f;

@@ -354,24 +354,6 @@ BDLM_API int bdlm_scan_dist_backward_finish(bdlm_ctx *ctx, const bdlm_problem *p
 BDLM_API int bdlm_scan_combine(int32_t n, int32_t backward, const double *earlier,
                                const double *later, double *out);
 
-/* ---- n = 4 with two lanes per series (csrc/kf_pair.cu): selection and CPU pin -----------
- * bdlm_debug_set_pair_mode: 0 = n = 4, p = 1 filter / smoother calls run on the thread-per-series
- * kernel; 1 | 2 = on the two-lanes-per-series kernel with the shuffle | shared-memory exchange
- * (3 | 4: the same at four resident blocks per SM).  Process-wide; the initial value comes from
- * the environment variable BDLM_KF_PAIR.  Every mode computes the same bits.
- * bdlm_debug_pair_filter_smooth_host: HOST build of that kernel's arithmetic for one series (two
- * host threads stand in for the two lanes, the step functions are the ones the kernel inlines):
- * test infrastructure for pinning the split operation order against the oracle without a GPU.
- * Matrices column-major, outputs [T + 1][k] (row 0 = the initial state, f / Q = NaN there);
- * dt = NULL: regular grid.  Returns the status bits of the series. */
-BDLM_API int bdlm_debug_set_pair_mode(int32_t mode);
-BDLM_API int bdlm_debug_pair_filter_smooth_host(const double *G, const double *F, double V,
-                                                const double *W, const double *m0,
-                                                const double *C0, const double *dt,
-                                                const double *y, int32_t T, int32_t textbook,
-                                                double *m, double *C, double *a, double *R,
-                                                double *f, double *Q, double *s, double *S);
-
 /* ======================================================================================
  * Multi-GPU communicator (SURVEY.md 8b "Threading", 8e): one context per device, NCCL behind
  * one object.  Series and chains are independent -- the reference fits one model per sensor
