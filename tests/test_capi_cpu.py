@@ -160,3 +160,36 @@ def test_communicator_needs_a_gpu_and_says_so():
     assert lib.bdlm_comm_last_error(None)
     assert lib.bdlm_comm_create(devs, 1, 0, 2, None, C.byref(h)) == capi.E_ARG   # several processes need an id
     assert lib.bdlm_comm_size(None) == 0 and lib.bdlm_comm_ctx(None, 0) is None
+
+
+def test_null_and_bad_arguments_are_codes_not_crashes():
+    """No C++ exception and no segfault may cross the ABI (SURVEY.md 8b "Errors"): misuse that can
+    be detected before any device work returns BDLM_E_ARG, also without a GPU."""
+    lib = capi.load()
+    h = C.c_void_p()
+    devs = (C.c_int32 * 2)(0, 1)
+    # communicator construction: device list / rank range / missing rendezvous id
+    assert lib.bdlm_comm_create(None, 1, 0, 1, None, C.byref(h)) == capi.E_ARG and not h.value
+    assert lib.bdlm_comm_create(devs, 0, 0, 1, None, C.byref(h)) == capi.E_ARG
+    assert lib.bdlm_comm_create(devs, 2, 0, 1, None, C.byref(h)) == capi.E_ARG      # world < n_local
+    assert lib.bdlm_comm_create(devs, 1, 3, 2, None, C.byref(h)) == capi.E_ARG      # rank outside world
+    assert lib.bdlm_comm_create(devs, 1, 0, 2, None, C.byref(h)) == capi.E_ARG      # several processes, no id
+    assert b"bdlm_comm_unique_id" in lib.bdlm_comm_last_error(None)
+    assert lib.bdlm_comm_create(devs, 1, 0, 1, None, None) == capi.E_ARG
+    assert lib.bdlm_comm_unique_id(None) == capi.E_ARG
+    # calls on a null communicator / context
+    assert lib.bdlm_comm_sync(None) == capi.E_ARG
+    assert lib.bdlm_comm_allreduce_sum(None, None, 1) == capi.E_ARG
+    assert lib.bdlm_comm_kf_filter(None, None, None, None) == capi.E_ARG
+    assert lib.bdlm_comm_size(None) == 0 and lib.bdlm_comm_local_size(None) == 0
+    assert not lib.bdlm_comm_ctx(None, 0)
+    lib.bdlm_comm_destroy(None)
+    assert lib.bdlm_kf_filter(None, None, None, None) == capi.E_ARG
+    assert lib.bdlm_sync(None) == capi.E_ARG and lib.bdlm_set_rng(None, 1, 0, 0) == capi.E_ARG
+    assert lib.bdlm_launch_count(None) == 0
+    lib.bdlm_destroy(None)
+    # host-side helpers of the time-sharded scan
+    assert lib.bdlm_scan_elem_doubles(5, 0) == capi.E_ARG and lib.bdlm_scan_elem_doubles(0, 1) == capi.E_ARG
+    x = np.zeros(64)
+    assert lib.bdlm_scan_combine(5, 0, x.ctypes.data, x.ctypes.data, x.ctypes.data) == capi.E_ARG
+    assert lib.bdlm_scan_combine(2, 0, None, x.ctypes.data, x.ctypes.data) == capi.E_ARG
