@@ -93,3 +93,28 @@ def test_mirror_batch_padding_of_ragged_series():
     assert np.array_equal(times[1], [10.0, 10.0, 10.0]) and np.isnan(y[1, 1:, 0]).all() and np.isnan(y[0, 1, 0])
     assert "times" in model.per_series and params["per_series"] == ("V", "W", "m0", "C0")
     assert np.array_equal(params["W"][0], [1.0, 0.3, 0.2, 4.0])   # column-major
+
+
+def test_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver times beside the CUDA arm) runs without
+    a GPU and prints ONE JSON line with the contract's keys; its e2e repeats its own value (no
+    copies on a CPU run) and its cpu_baseline says what was timed."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference",
+                        "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["higher_is_better"] is True
+    assert d["metric"] == "filter+smoother series-steps/s" and d["unit"] == "series-steps/s"
+    assert d["dtype"] == "f64" and d["n_gpus"] == 1 and d["value"] > 0
+    assert d["config"]["workload"].startswith("config2: polynomial(2)")
+    assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["cores"] >= 1
+    assert d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0,
+                        "d2h_bytes_per_step": 0}
